@@ -1,0 +1,84 @@
+"""ctypes binding of ``libboxseg_b200.so`` (the C ABI declared in ``include/boxseg_b200.h``).
+
+The product path has NO fallback: if the shared library is missing or a call fails, an
+exception is raised.  Build with ``python -m boxinstseg_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libboxseg_b200.so')
+
+_lib = None
+
+c_p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_f = ctypes.c_float
+
+# name -> argtypes (all return int unless listed in _RESTYPE)
+SIGNATURES = {
+    'bxs_version': [],
+    'bxs_last_error': [],
+    'bxs_device_sm_count': [],
+    'bxs_flush_l2': [c_p, c_i64, c_p],
+    'bxs_pairwise_nlog_forward': [c_p, c_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_p],
+    'bxs_pairwise_nlog_backward': [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_p],
+    'bxs_boxinst_lab': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p],
+    'bxs_boxinst_similarity': [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_int, c_f, c_p],
+    'bxs_boxinst_rects': [c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p],
+    'bxs_boxinst_bitmasks': [c_p, c_p, c_i64, c_i64, c_i64, c_p],
+    'bxs_boxinst_loss_workspace_bytes': [c_i64, c_i64, c_i64],
+    'bxs_boxinst_loss_forward': [c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p],
+    'bxs_boxinst_loss_backward': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p],
+}
+_RESTYPE = {'bxs_last_error': ctypes.c_char_p, 'bxs_boxinst_loss_workspace_bytes': c_i64}
+
+_STATUS = {-1: 'invalid argument', -2: 'kernel launch failed', -3: 'unsupported shape', -4: 'no CUDA device'}
+
+
+class BoxSegError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f'{LIB_PATH} is missing: the CUDA extension is the product and there is no fallback. '
+                'Build it with `python -m boxinstseg_b200.build`.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so does not export it
+            fn.argtypes = args
+            fn.restype = _RESTYPE.get(name, c_int)
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        detail = lib().bxs_last_error().decode() if rc == -2 else ''
+        raise BoxSegError(f'{what}: {_STATUS.get(rc, rc)} {detail}'.strip())
+
+
+def ptr(t):
+    return None if t is None else c_p(t.data_ptr())
+
+
+def stream():
+    return c_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    """Same error behaviour as the reference's CHECK_INPUT (pairwise.cu:7-13)."""
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError('boxinstseg_b200: tensor must be a CUDA tensor')
+        if not t.is_contiguous():
+            raise RuntimeError('boxinstseg_b200: tensor must be contiguous')

@@ -1,0 +1,136 @@
+"""Fused BoxInst mask-loss operators (SURVEY.md section 8 rows a5, a6+a7+a8) on the C ABI.
+
+``boxinst_targets``  replaces CondInstMaskHead.get_targets / get_bitmasks_from_boxes
+                     (mmdet/models/dense_heads/condinst_head.py:1345-1448), entirely on the GPU.
+``boxinst_mask_loss`` replaces the arithmetic of CondInstMaskHead.loss (:1288-1343).
+
+Neither function synchronises the host with the device.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+
+@dataclass
+class BoxInstTargets:
+    edge_bits: Optional[torch.Tensor]   # uint8 [B,H,W]; bit c <=> similarity[c] >= thresh (size 3 only)
+    similarity: Optional[torch.Tensor]  # float32 [B,k*k-1,H,W] (only when requested)
+    rects: torch.Tensor                 # int32 [G,4] (j0,j1,i0,i1), inclusive, in loss-grid coordinates
+    gt_img: torch.Tensor                # int32 [G] image of each GT
+    num_gts: List[int]                  # per image
+    lab: torch.Tensor                   # float32 [B,3,H,W]
+    valid: torch.Tensor                 # uint8 [B,H,W]
+
+    def bitmasks(self):
+        """Dense float bitmasks, list of [G_i,H,W] -- API parity with the reference's `bitmasks`."""
+        G = self.rects.shape[0]
+        H, W = self.valid.shape[-2:]
+        out = torch.empty((G, H, W), dtype=torch.float32, device=self.rects.device)
+        if G:
+            with torch.cuda.device(out.device):
+                L.check(L.lib().bxs_boxinst_bitmasks(L.ptr(self.rects), L.ptr(out), G, H, W, L.stream()),
+                        'boxinst_bitmasks')
+        return list(torch.split(out, self.num_gts))
+
+
+def _norm_cfg(img_metas):
+    cfg = img_metas[0]['img_norm_cfg']
+    mean = np.ascontiguousarray(np.asarray(cfg['mean'], dtype=np.float32).reshape(3))
+    std = np.ascontiguousarray(np.asarray(cfg['std'], dtype=np.float32).reshape(3))
+    for m in img_metas[1:]:
+        c = m['img_norm_cfg']
+        if not (np.allclose(np.asarray(c['mean'], np.float32), mean) and np.allclose(np.asarray(c['std'], np.float32), std)):
+            raise NotImplementedError('per-image normalisation constants are not supported')
+    return mean, std
+
+
+def boxinst_targets(img, img_metas, gt_bboxes, stride=4, pairwise_size=3, pairwise_dilation=2,
+                    pairwise_color_thresh=0.3, bottom_pixels_removed=10, want_similarity=False):
+    """img [B,3,Hp,Wp] normalised RGB (float32, CUDA); gt_bboxes list of [G_i,4] xyxy."""
+    img = img.contiguous()
+    L.require_cuda(img)
+    if img.dtype != torch.float32:
+        img = img.float()
+    B, _, Hp, Wp = img.shape
+    assert Hp % stride == 0 and Wp % stride == 0, 'padded image must be divisible by the loss stride'
+    H, W = Hp // stride, Wp // stride
+    dev = img.device
+    hw = np.zeros((B, 2), dtype=np.int32)
+    removed = np.zeros(B, dtype=np.int32)
+    for i, m in enumerate(img_metas):
+        ih, iw = m['img_shape'][:2]
+        hw[i] = (ih, iw)
+        removed[i] = int(bottom_pixels_removed * float(ih) / float(m['ori_shape'][0]))
+    mean, std = _norm_cfg(img_metas)
+    meta_dev = torch.from_numpy(np.concatenate([hw.reshape(-1), removed])).to(dev, non_blocking=True)
+    hw_dev, removed_dev = meta_dev[:2 * B], meta_dev[2 * B:]
+    lab = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+    valid = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    lib = L.lib()
+    with torch.cuda.device(dev):
+        L.check(lib.bxs_boxinst_lab(L.ptr(img), L.ptr(hw_dev), L.ptr(removed_dev), mean.ctypes.data, std.ctypes.data,
+                                    L.ptr(lab), L.ptr(valid), B, Hp, Wp, stride, L.stream()), 'boxinst_lab')
+        K = pairwise_size * pairwise_size - 1
+        sim = torch.empty((B, K, H, W), dtype=torch.float32, device=dev) if (want_similarity or pairwise_size != 3) else None
+        bits = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if pairwise_size == 3 else None
+        L.check(lib.bxs_boxinst_similarity(L.ptr(lab), L.ptr(valid), L.ptr(sim), L.ptr(bits), B, H, W, pairwise_size,
+                                           pairwise_dilation, float(pairwise_color_thresh), L.stream()),
+                'boxinst_similarity')
+        num_gts = [int(b.shape[0]) for b in gt_bboxes]
+        G = sum(num_gts)
+        boxes = (torch.cat([b.reshape(-1, 4) for b in gt_bboxes]) if G else torch.zeros((0, 4), device=dev)).to(
+            device=dev, dtype=torch.float32).contiguous()
+        rects = torch.empty((G, 4), dtype=torch.int32, device=dev)
+        L.check(lib.bxs_boxinst_rects(L.ptr(boxes), L.ptr(rects), G, Hp, Wp, stride, L.stream()), 'boxinst_rects')
+        gt_img = torch.from_numpy(np.repeat(np.arange(B, dtype=np.int32), num_gts)).to(dev, non_blocking=True)
+    return BoxInstTargets(bits, sim, rects, gt_img, num_gts, lab, valid)
+
+
+class _BoxInstMaskLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mask_logits, edge_bits, rects, inst_gt, gt_img, iter_buf, warmup_iters, dilation):
+        logits = mask_logits.contiguous()
+        L.require_cuda(logits, edge_bits, rects, inst_gt, gt_img, iter_buf)
+        N, _, H, W = logits.shape
+        lib = L.lib()
+        ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N, H, W), dtype=torch.uint8, device=logits.device)
+        out = torch.empty(4, dtype=torch.float32, device=logits.device)
+        with torch.cuda.device(logits.device):
+            L.check(lib.bxs_boxinst_loss_forward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
+                                                 L.ptr(gt_img), L.ptr(iter_buf), float(warmup_iters), L.ptr(ws),
+                                                 L.ptr(out), N, H, W, dilation, L.stream()), 'boxinst_loss_forward')
+        ctx.save_for_backward(logits, edge_bits, rects, inst_gt, gt_img, ws)
+        ctx.dilation = dilation
+        aux = out[2:]
+        ctx.mark_non_differentiable(aux)
+        return out[0], out[1], aux
+
+    @staticmethod
+    def backward(ctx, g_prj, g_pair, _g_aux):
+        logits, edge_bits, rects, inst_gt, gt_img, ws = ctx.saved_tensors
+        N, _, H, W = logits.shape
+        g = torch.stack([g_prj.reshape(()), g_pair.reshape(())]).to(torch.float32)
+        g_logits = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            L.check(L.lib().bxs_boxinst_loss_backward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
+                                                      L.ptr(gt_img), L.ptr(ws), L.ptr(g), L.ptr(g_logits), N, H, W,
+                                                      ctx.dilation, L.stream()), 'boxinst_loss_backward')
+        return g_logits, None, None, None, None, None, None, None
+
+
+def boxinst_mask_loss(mask_logits, targets: BoxInstTargets, gt_inds, iter_buf, warmup_iters=10000,
+                      pairwise_dilation=2):
+    """(loss_prj, loss_pairwise) for mask_logits [N,1,H,W] float32; gt_inds [N] indexes the
+    concatenated GT list (as in condinst_head.py:1302,1316).  Requires pairwise_size == 3."""
+    if targets.edge_bits is None:
+        raise NotImplementedError('the fused loss is specialised to pairwise_size == 3')
+    if mask_logits.dtype != torch.float32:
+        mask_logits = mask_logits.float()        # @force_fp32(apply_to=('mask_logits',)), :1288
+    inst_gt = gt_inds.to(torch.int32).contiguous()
+    prj, pair, _ = _BoxInstMaskLoss.apply(mask_logits, targets.edge_bits, targets.rects, inst_gt, targets.gt_img,
+                                          iter_buf, warmup_iters, pairwise_dilation)
+    return prj, pair

@@ -1,0 +1,106 @@
+/*
+ * boxseg_b200 -- C ABI of the B200-native (sm_100a) box-supervised mask-loss hot path.
+ *
+ * This is the drop-in boundary: every entry point takes raw DEVICE
+ * pointers + sizes + the CUDA stream to launch on, allocates nothing, keeps no state and
+ * returns 0 or a negative bxs_status.  No torch types.  The Python package
+ * `boxinstseg_b200` binds it with ctypes and re-creates the reference's own operator
+ * signatures (mmdet/ops/pairwise, mmdet/ops/tree_filter, the LOSSES/HEADS classes) on top.
+ *
+ * For each entry point the reference interface it replaces is cited (paths relative to
+ * the reference checkout).  Tensors are dense, row-major ("contiguous"), fp32 unless noted.
+ */
+#ifndef BOXSEG_B200_H_
+#define BOXSEG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* bxs_stream_t; /* cudaStream_t */
+
+typedef enum {
+  BXS_OK = 0,
+  BXS_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, unsupported neighbourhood */
+  BXS_ERR_LAUNCH = -2,        /* cudaGetLastError() != cudaSuccess after the launch */
+  BXS_ERR_UNSUPPORTED = -3,   /* shape outside what the kernel was built for */
+  BXS_ERR_NO_DEVICE = -4
+} bxs_status;
+
+/* library identity / environment ---------------------------------------------------------- */
+int bxs_version(void);                       /* 10000*major + 100*minor + patch */
+const char* bxs_last_error(void);            /* text of the last CUDA error seen by this thread */
+int bxs_device_sm_count(void);               /* multiprocessor count of the current device */
+int bxs_flush_l2(void* scratch, int64_t bytes, bxs_stream_t stream); /* bench helper: overwrite scratch */
+
+/* ---------------------------------------------------------------------------------------
+ * a7  pairwise -log P(same label)            replaces pairwise_ext.pairwise_nlog_forward /
+ *     pairwise_nlog_backward   (mmdet/ops/pairwise/csrc/pairwise/bind.cpp:15-36,
+ *     kernels pairwise.cu:68-149, Python wrapper mmdet/ops/pairwise/pairwise.py:6-26)
+ * logits [B,1,H,W] -> out [B,k*k-1,H,W];  dtype: 0 = float32, 1 = float64.
+ * backward is a deterministic gather (no atomics): g_logits is fully overwritten.
+ * --------------------------------------------------------------------------------------- */
+int bxs_pairwise_nlog_forward(const void* logits, void* out, int64_t B, int64_t H, int64_t W,
+                              int size, int dilation, int dtype, bxs_stream_t stream);
+int bxs_pairwise_nlog_backward(const void* logits, const void* g_out, void* g_logits, int64_t B,
+                               int64_t H, int64_t W, int size, int dilation, int dtype,
+                               bxs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a5  BoxInst targets      replaces CondInstMaskHead.get_targets / get_bitmasks_from_boxes /
+ *     get_original_image / get_image_color_similarity
+ *     (mmdet/models/dense_heads/condinst_head.py:170-246, 1345-1448) incl. the host round trips
+ *     through mmcv.tensor2imgs and skimage.color.rgb2lab.
+ *
+ * bxs_boxinst_lab: img [B,3,Hp,Wp] normalised RGB -> lab [B,3,Hp/s,Wp/s] (float32) and
+ *   valid [B,Hp/s,Wp/s] (uint8).  img_hw [B,2] int32 = (img_h, img_w) of each image,
+ *   removed_rows [B] int32 = int(bottom_pixels_removed*img_h/ori_h) (host integers),
+ *   mean/std: 3 floats each (host pointers, read at call time).
+ * bxs_boxinst_similarity: lab, valid -> sim [B,k*k-1,H,W] float32 (may be NULL) and, for
+ *   size==3, edge_bits [B,H,W] uint8 with bit c = (sim[c] >= thresh) (may be NULL).
+ * bxs_boxinst_rects: boxes [G,4] float xyxy -> rects [G,4] int32 (j0,j1,i0,i1 inclusive grid
+ *   ranges of the centre-sampled bitmask; empty when j0>j1 or i0>i1); Python slice semantics
+ *   of condinst_head.py:1429-1432 are kept.
+ * bxs_boxinst_bitmasks: rects -> dense bitmasks [G,H,W] float32 (API parity only).
+ * --------------------------------------------------------------------------------------- */
+int bxs_boxinst_lab(const float* img, const int32_t* img_hw, const int32_t* removed_rows,
+                    const float* mean3_host, const float* std3_host, float* lab, uint8_t* valid,
+                    int64_t B, int64_t Hp, int64_t Wp, int stride, bxs_stream_t stream);
+int bxs_boxinst_similarity(const float* lab, const uint8_t* valid, float* sim, uint8_t* edge_bits,
+                           int64_t B, int64_t H, int64_t W, int size, int dilation, float thresh,
+                           bxs_stream_t stream);
+int bxs_boxinst_rects(const float* boxes, int32_t* rects, int64_t G, int64_t Hp, int64_t Wp,
+                      int stride, bxs_stream_t stream);
+int bxs_boxinst_bitmasks(const int32_t* rects, float* bitmasks, int64_t G, int64_t H, int64_t W,
+                         bxs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a6+a7+a8  fused BoxInst mask loss     replaces the arithmetic of CondInstMaskHead.loss
+ *     (condinst_head.py:1288-1343): sigmoid, compute_project_term (:134-143), pairwise_nlog,
+ *     colour-threshold weights and the normalised reduction, plus their backward.
+ *
+ * logits [N,1,H,W]; edge_bits [B,H,W]; rects [G,4]; inst_gt [N] int32 (GT of each instance);
+ * gt_img [G] int32 (image of each GT); iter_ptr: device float holding CondInstMaskHead._iter
+ * (after the increment); warmup_iters: pairwise_warmup.
+ * workspace: device scratch of bxs_boxinst_loss_workspace_bytes(N,H,W) bytes; it carries the
+ * arg-max positions and gradient coefficients from forward to backward.
+ * losses_out: device float[4] = {loss_prj, loss_pairwise, pairwise numerator, weight sum}.
+ * backward: g_losses device float[2] = upstream d/d loss_prj, d/d loss_pairwise;
+ * g_logits [N,1,H,W] fully overwritten (deterministic, no atomics).
+ * --------------------------------------------------------------------------------------- */
+int64_t bxs_boxinst_loss_workspace_bytes(int64_t N, int64_t H, int64_t W);
+int bxs_boxinst_loss_forward(const float* logits, const uint8_t* edge_bits, const int32_t* rects,
+                             const int32_t* inst_gt, const int32_t* gt_img, const float* iter_ptr,
+                             float warmup_iters, void* workspace, float* losses_out, int64_t N,
+                             int64_t H, int64_t W, int dilation, bxs_stream_t stream);
+int bxs_boxinst_loss_backward(const float* logits, const uint8_t* edge_bits, const int32_t* rects,
+                              const int32_t* inst_gt, const int32_t* gt_img, const void* workspace,
+                              const float* g_losses, float* g_logits, int64_t N, int64_t H,
+                              int64_t W, int dilation, bxs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOXSEG_B200_H_ */
