@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- mask-loss fwd+bwd ms/img (BoxInst R-50, 800x1024, batch 2/GPU) on N B200s.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line on
+rank 0.  N > 1 is launched by torchrun, one rank per GPU; the loss is per image so ranks are
+replicas (weak scaling, no data-path collective); rank times are combined with MAX.
+
+What one "step" is (config A of BASELINE.json, synthetic): the BoxInst mask
+loss of ONE batch -- 2 images of 3x800x1024, 8 GT boxes each, N=128 sampled instances, loss grid
+200x256 -- forward (projection + colour-pairwise terms) and backward (d/d mask_logits).
+  value : inputs and targets resident in HBM; timed = fused loss forward + backward kernels.
+  e2e   : through the public head API with HOST (pinned) buffers: H2D of image, logits, boxes ->
+          target building (LAB, similarity, rects) -> loss fwd+bwd -> D2H of the gradient + losses.
+L2 hygiene: the timed loop rotates over R input/gradient sets whose footprint (R x 52 MB) exceeds
+the 126 MB L2, so every step streams its logits from HBM.
+
+``--impl reference`` times the reference's own CPU path (the oracle port, torch-on-CPU with all
+host threads) on a bounded sample: ONE image (64 instances) of the same workload per step.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'mask_loss_fwd_bwd_ms_per_img'
+HP, WP, B_IMG, GTS, INST_PER_GT = 800, 1024, 2, 8, 8
+H, W, K_NEIGH = HP // 4, WP // 4, 8
+N_INST = B_IMG * GTS * INST_PER_GT
+ALGO_BYTES = 3 * N_INST * H * W * 4 + 2 * B_IMG * K_NEIGH * H * W * 4     # 85.2 MB / step
+ROTATE = 8
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                     nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap'}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f'nvml_unavailable:{type(e).__name__}')
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+def synthetic_case(seed, b_img=B_IMG):
+    from tests.helpers import boxinst_case
+    return boxinst_case(seed, B=b_img, hp=HP, wp=WP, gts_per_img=GTS, inst_per_gt=INST_PER_GT)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (oracle port, all host threads)
+# ------------------------------------------------------------------------------------------
+def cpu_step(case):
+    from oracle import boxinst as ob
+    sim, bms = ob.boxinst_targets(case['img'], case['metas'], case['gt_bboxes'])
+    x = case['logits'].clone().requires_grad_(True)
+    bm = torch.cat(bms)[case['gt_inds']][:, None]
+    prj, pair = ob.boxinst_mask_loss(x, sim[case['img_inds']], bm)
+    (prj + pair).backward()
+    return float(prj), float(pair)
+
+
+def run_cpu(steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    case = synthetic_case(1234, b_img=1)          # bounded sample: ONE image, 64 instances
+    for _ in range(warmup):
+        cpu_step(case)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(case)
+        ts.append(time.perf_counter() - t0)
+    ms_img = 1e3 * sum(ts) / len(ts)              # one image per step
+    return ms_img, cores, '1 image (3x800x1024, 8 GT, 64 instances, loss grid 200x256) per step: targets + loss fwd + bwd, torch CPU'
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    ms_img, cores, sample = run_cpu(max(args.steps, 1), args.warmup)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': ms_img, 'unit': 'ms/img', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_img, 'higher_is_better': False,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'BoxInst R-50 mask loss fwd+bwd, 800x1024, 8 GT/img, 64 inst/img (config A)'},
+            'cpu_baseline': {'value': ms_img, 'unit': 'ms/img', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': ms_img, 'unit': 'ms/img', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def main_cuda(args, rank, world, local_rank):
+    from boxinstseg_b200 import _lib
+    from boxinstseg_b200.models.dense_heads import CondInstMaskHead
+    from boxinstseg_b200.ops.boxinst import boxinst_mask_loss, boxinst_targets
+    _lib.lib()                                   # fail loudly if the CUDA extension is missing
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    case = synthetic_case(1234 + rank)
+    img = case['img'].to(dev)
+    boxes = [b.to(dev) for b in case['gt_bboxes']]
+    gt_inds = case['gt_inds'].to(dev)
+    it = torch.tensor([10000.0], device=dev)
+    targets = boxinst_targets(img, case['metas'], boxes)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    logit_sets = [case['logits'].to(dev)] + [torch.randn(N_INST, 1, H, W, device=dev, generator=gen) * 2
+                                             for _ in range(ROTATE - 1)]
+    logit_sets = [t.requires_grad_(True) for t in logit_sets]
+    ones = torch.ones((), device=dev)
+    grad_ring = [None] * ROTATE       # keeps the last R gradients alive so every step writes a fresh 26 MB
+
+    def step(i):
+        x = logit_sets[i % ROTATE]
+        prj, pair = boxinst_mask_loss(x, targets, gt_inds, it)
+        torch.autograd.backward([prj, pair], [ones, ones])
+        grad_ring[i % ROTATE], x.grad = x.grad, None
+        return prj, pair
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms_step = e0.elapsed_time(e1) / args.steps
+
+    # ---- e2e through the public head API with host buffers ----
+    head = CondInstMaskHead(in_channels=16, in_stride=8, out_stride=4, topk_per_img=64, max_proposals=-1,
+                            boxinst_enabled=True, pairwise_warmup=10000).to(dev)
+    head._iter.fill_(9999)
+    h_img = case['img'].pin_memory()
+    h_logits = case['logits'].pin_memory()
+    h_boxes = [b.pin_memory() for b in case['gt_bboxes']]
+    h_grad = torch.empty_like(case['logits']).pin_memory()
+    h_loss = torch.empty(2).pin_memory()
+    h2d = h_img.numel() * 4 + h_logits.numel() * 4 + sum(b.numel() * 4 for b in h_boxes)
+    d2h = h_grad.numel() * 4 + 8
+
+    def e2e_step():
+        d_img = h_img.to(dev, non_blocking=True)
+        d_logits = h_logits.to(dev, non_blocking=True).requires_grad_(True)
+        d_boxes = [b.to(dev, non_blocking=True) for b in h_boxes]
+        head._iter.fill_(9999)
+        losses = head.loss(d_img, case['metas'], d_logits, gt_inds, d_boxes, None, None)
+        torch.autograd.backward([losses['loss_prj'], losses['loss_pairwise']], [ones, ones])
+        h_grad.copy_(d_logits.grad, non_blocking=True)
+        h_loss.copy_(torch.stack([losses['loss_prj'].detach(), losses['loss_pairwise'].detach()]), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms_step, ms_e2e], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_e2e = t.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    achieved = ALGO_BYTES / (ms_step * 1e-3) / 1e9
+    cpu_ms, cores, sample = (None, None, None)
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_ms, cores, sample = run_cpu(3, 1)
+    line = {
+        'metric': METRIC, 'value': ms_step / B_IMG, 'unit': 'ms/img', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': False, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BoxInst R-50 mask loss fwd+bwd (config A): batch 2/GPU x (3,800,1024), 8 GT/img, '
+                               'N=128 instances, loss grid 200x256, pairwise 3x3 dil 2',
+                   'l2': f'inputs rotate over {ROTATE} logit/grad sets ({ROTATE * 52} MB > 126 MB L2)',
+                   'parallelism': f'replicas x{world} (loss is per image; no data-path collective)'},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': None, 'peak_source': peak_src,
+                     'note': 'whole step (4 fwd + 1 bwd kernels incl. launch gaps) against the 85.2 MB/step '
+                             'algorithmic figure of SURVEY 8d'},
+        'e2e': {'value': ms_e2e / B_IMG, 'unit': 'ms/img', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': 5 * args.steps,
+        'clocks': clocks,
+    }
+    if cpu_ms is not None:
+        line['cpu_baseline'] = {'value': cpu_ms, 'unit': 'ms/img', 'cores': cores, 'kind': 'port', 'sample': sample}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        main_reference(args, rank, world)
+    else:
+        main_cuda(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -33,8 +33,19 @@ SIGNATURES = {
     'bxs_boxinst_loss_workspace_bytes': [c_i64, c_i64, c_i64],
     'bxs_boxinst_loss_forward': [c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p],
     'bxs_boxinst_loss_backward': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p],
+    'bxs_condinst_head_forward': [c_p] * 6 + [c_i64] * 6 + [c_int] * 3 + [c_p],
+    'bxs_condinst_head_workspace_bytes': [c_i64] * 5,
+    'bxs_condinst_head_backward': [c_p] * 9 + [c_i64] * 6 + [c_int] * 3 + [c_p],
+    'bxs_projection_workspace_bytes': [c_i64] * 3,
+    'bxs_projection_loss_forward': [c_p] * 4 + [c_i64] * 3 + [c_f, c_f, c_p],
+    'bxs_projection_loss_backward': [c_p] * 3 + [c_i64] * 3 + [c_p],
+    'bxs_levelset_workspace_bytes': [c_i64],
+    'bxs_levelset_loss_forward': [c_p] * 5 + [c_i64] * 4 + [c_f, c_p],
+    'bxs_levelset_loss_backward': [c_p] * 7 + [c_i64] * 4 + [c_f, c_p],
+    'bxs_length_reg_forward': [c_p] * 3 + [c_i64] * 4 + [c_p],
+    'bxs_length_reg_backward': [c_p] * 3 + [c_i64] * 4 + [c_p],
 }
-_RESTYPE = {'bxs_last_error': ctypes.c_char_p, 'bxs_boxinst_loss_workspace_bytes': c_i64}
+_RESTYPE = {'bxs_projection_workspace_bytes': c_i64, 'bxs_levelset_workspace_bytes': c_i64, 'bxs_condinst_head_workspace_bytes': c_i64, 'bxs_last_error': ctypes.c_char_p, 'bxs_boxinst_loss_workspace_bytes': c_i64}
 
 _STATUS = {-1: 'invalid argument', -2: 'kernel launch failed', -3: 'unsupported shape', -4: 'no CUDA device'}
 

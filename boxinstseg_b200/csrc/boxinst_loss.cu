@@ -28,19 +28,22 @@ constexpr float kFastLimit = 40.f;
 constexpr float kDiceEps = 1e-5f;        // condinst_head.py:124
 
 struct Workspace {
-  // zeroed at the start of every forward
-  unsigned long long* row_packed;  // [N*H]  (score bits << 32) | ~x
-  unsigned long long* col_packed;  // [N*W]  (score bits << 32) | ~y
+  // zeroed at the start of every forward (fast path: up to zero_bytes_fast)
+  unsigned long long* col_packed;  // [N*W]  (key(max logit) << 32) | ~y
   unsigned long long* weight_sum;  // [1]    sum of weights (integer)
-  unsigned int* ticket;            // [1]
+  unsigned int* ticket;            // [1]    instances finalized
+  unsigned int* inst_ticket;       // [N]    strips finished per instance (fast path)
+  size_t zero_bytes_fast;
+  unsigned long long* row_packed;  // [N*H]  (key(max logit) << 32) | ~x  (atomics only on the generic path)
   size_t zero_bytes;
   // plain
   float* coef_row;     // [N*H] d loss_prj / d logit at the row arg-max
   float* coef_col;     // [N*W]
   int* row_arg;        // [N*H]
   int* col_arg;        // [N*W]
-  int* tile_prefix;    // [N+1]
-  float* pair_partial; // [N*tiles_full]
+  int* tile_prefix;    // [N+1]            generic path work list
+  float* pair_partial; // [N*max(tiles,H)] per tile (generic) / per row (fast) numerators
+  int* den_partial;    // [N*H]            per row weight counts (fast)
   float* inst_prj;     // [N]
   float* inst_num;     // [N]
   float* scale_pair;   // [1] warmup / max(weight_sum, 1)
@@ -54,10 +57,12 @@ inline Workspace carve(void* base, int64_t N, int64_t H, int64_t W) {
   char* p = (char*)base;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* r = p + off; off = align_up(off + bytes); return r; };
-  w.row_packed = (unsigned long long*)take(sizeof(unsigned long long) * N * H);
   w.col_packed = (unsigned long long*)take(sizeof(unsigned long long) * N * W);
   w.weight_sum = (unsigned long long*)take(sizeof(unsigned long long));
   w.ticket = (unsigned int*)take(sizeof(unsigned int));
+  w.inst_ticket = (unsigned int*)take(sizeof(unsigned int) * N);
+  w.zero_bytes_fast = off;
+  w.row_packed = (unsigned long long*)take(sizeof(unsigned long long) * N * H);
   w.zero_bytes = off;
   w.coef_row = (float*)take(sizeof(float) * N * H);
   w.coef_col = (float*)take(sizeof(float) * N * W);
@@ -65,7 +70,8 @@ inline Workspace carve(void* base, int64_t N, int64_t H, int64_t W) {
   w.col_arg = (int*)take(sizeof(int) * N * W);
   w.tile_prefix = (int*)take(sizeof(int) * (N + 1));
   const int64_t tiles_full = ceil_div(H, TH) * ceil_div(W, TW);
-  w.pair_partial = (float*)take(sizeof(float) * N * tiles_full);
+  w.pair_partial = (float*)take(sizeof(float) * N * (tiles_full > H ? tiles_full : H));
+  w.den_partial = (int*)take(sizeof(int) * N * H);
   w.inst_prj = (float*)take(sizeof(float) * N);
   w.inst_num = (float*)take(sizeof(float) * N);
   w.scale_pair = (float*)take(sizeof(float));
@@ -128,9 +134,20 @@ __global__ void __launch_bounds__(NT) prep_worklist(const int32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // forward 1: projection maxima.  grid (strips, N, panels); one warp per row.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long pack_max(float score, int index) {
-  return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xffffffffu - (unsigned)index);
+// Order-preserving map float -> uint (total order of the reals, -0 < +0), so maxima of LOGITS can
+// be combined with integer max / atomicMax.  The sigmoid is monotone, hence the arg-max of the
+// scores is the arg-max of the logits (first index on exact ties, like torch.max(dim)).
+__device__ __forceinline__ unsigned fkey(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ unsigned long long pack_key(unsigned key, int index) {
+  return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (unsigned)index);
+}
+__device__ __forceinline__ unsigned long long pack_max(float v, int index) { return pack_key(fkey(v), index); }
 
 template <int NCHUNK, int V>
 __global__ void __launch_bounds__(NT) prj_max_kernel(const float* __restrict__ logits, int H, int W,
@@ -148,7 +165,7 @@ __global__ void __launch_bounds__(NT) prj_max_kernel(const float* __restrict__ l
   float cbest[NCHUNK * V];
   int cy[NCHUNK * V];
 #pragma unroll
-  for (int i = 0; i < NCHUNK * V; ++i) { cbest[i] = -1.f; cy[i] = 0; }
+  for (int i = 0; i < NCHUNK * V; ++i) { cbest[i] = -INFINITY; cy[i] = -1; }
 
   for (int y = r0 + warp; y < r1; y += NWARP) {
     const float* row = img + (int64_t)y * W;
@@ -163,21 +180,21 @@ __global__ void __launch_bounds__(NT) prj_max_kernel(const float* __restrict__ l
         v[ch] = col < W ? __ldg(row + col) : 0.f;
       }
     }
-    float rbest = -1.f;
-    int rx = 0;
+    float rbest = -INFINITY;
+    int rx = -1;
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
 #pragma unroll
       for (int e = 0; e < V; ++e) {
         const int col = panel0 + (ch * 32 + lane) * V + e;
         if (col < W) {
-          const float s = sigmoid_fast(v[ch * V + e]);
-          if (s > rbest) { rbest = s; rx = col; }                       // ascending cols: first wins
-          if (s > cbest[ch * V + e]) { cbest[ch * V + e] = s; cy[ch * V + e] = y; }   // ascending rows
+          const float s = v[ch * V + e];
+          if (s > rbest || rx < 0) { rbest = s; rx = col; }             // ascending cols: first wins
+          if (s > cbest[ch * V + e] || cy[ch * V + e] < 0) { cbest[ch * V + e] = s; cy[ch * V + e] = y; }
         }
       }
     }
-    unsigned long long rp = rbest >= 0.f ? pack_max(rbest, rx) : 0ull;
+    unsigned long long rp = rx >= 0 ? pack_max(rbest, rx) : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       unsigned long long other = __shfl_xor_sync(kFull, rp, o);
@@ -189,7 +206,7 @@ __global__ void __launch_bounds__(NT) prj_max_kernel(const float* __restrict__ l
   for (int ch = 0; ch < NCHUNK; ++ch)
 #pragma unroll
     for (int e = 0; e < V; ++e)
-      s_col[warp][(ch * 32 + lane) * V + e] = cbest[ch * V + e] >= 0.f ? pack_max(cbest[ch * V + e], cy[ch * V + e]) : 0ull;
+      s_col[warp][(ch * 32 + lane) * V + e] = cy[ch * V + e] >= 0 ? pack_max(cbest[ch * V + e], cy[ch * V + e]) : 0ull;
   __syncthreads();
   for (int c = threadIdx.x; c < PANEL; c += NT) {
     unsigned long long best = 0ull;
@@ -306,17 +323,24 @@ __global__ void __launch_bounds__(NT) pair_fwd_kernel(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
-// finalize: dice terms, gradient coefficients, scalars (last CTA by ticket)
+// finalize: dice terms, gradient coefficients, scalars.  Executed by ONE CTA per instance (a
+// dedicated kernel on the generic path; the last CTA of the instance on the fast path); the CTA
+// that finalizes the last instance (global ticket) writes the scalars.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) finalize_kernel(const int32_t* __restrict__ rects,
-                                                      const int32_t* __restrict__ inst_gt, int N, int H, int W,
-                                                      Workspace ws, const float* __restrict__ iter_ptr,
-                                                      float warmup_iters, float* __restrict__ losses_out) {
-  __shared__ float s_red[NT / 32];
-  __shared__ float s_bc[4];
-  __shared__ bool s_last;
-  const int n = blockIdx.x;
-  const Rect r = load_rect(rects, inst_gt[n]);
+struct FinalizeShared {
+  float red[NT / 32];
+  int redi[NT / 32];
+  float bc[2];
+  bool last;
+};
+
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ void finalize_instance(const int n, const Rect r, const int N, const int H, const int W, const Workspace& ws,
+                                  const float* __restrict__ partial, const int npartial,
+                                  const int* __restrict__ den_partial, const int nden,
+                                  const float* __restrict__ iter_ptr, const float warmup_iters,
+                                  float* __restrict__ losses_out, FinalizeShared& sh) {
   const bool empty = rect_empty(r);
   const float inv_n = 1.f / (float)N;
   float inst_loss = 0.f;
@@ -329,24 +353,24 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const int32_t* __restrict_
     int* arg = axis == 0 ? ws.row_arg + (int64_t)n * H : ws.col_arg + (int64_t)n * W;
     float inter = 0.f, x2 = 0.f;
     for (int i = threadIdx.x; i < L; i += NT) {
-      const float s = __uint_as_float((unsigned)(packed[i] >> 32));
+      const float s = sigmoid_exact(fkey_inv((unsigned)(__ldcg(packed + i) >> 32)));
       const bool t = !empty && i >= lo && i <= hi;
       inter += t ? s : 0.f;
       x2 = fmaf(s, s, x2);
     }
-    inter = block_sum<float>(inter, s_red);
-    x2 = block_sum<float>(x2, s_red);
+    inter = block_sum<float>(inter, sh.red);
+    x2 = block_sum<float>(x2, sh.red);
     if (threadIdx.x == 0) {
       const float t2 = empty ? 0.f : (float)(max(min(hi, L - 1) - max(lo, 0) + 1, 0));
       const float u = x2 + t2 + kDiceEps;
-      s_bc[0] = inter; s_bc[1] = u;
+      sh.bc[0] = inter; sh.bc[1] = u;
       inst_loss += 1.f - 2.f * inter / u;
     }
     __syncthreads();
-    const float I = s_bc[0], U = s_bc[1];
+    const float I = sh.bc[0], U = sh.bc[1];
     for (int i = threadIdx.x; i < L; i += NT) {
-      const unsigned long long p = packed[i];
-      const float s = __uint_as_float((unsigned)(p >> 32));
+      const unsigned long long p = __ldcg(packed + i);
+      const float s = sigmoid_exact(fkey_inv((unsigned)(p >> 32)));
       const float t = (!empty && i >= lo && i <= hi) ? 1.f : 0.f;
       // d dice / d s = -2 t / U + 4 I s / U^2 ; through the sigmoid: * s (1 - s); mean over N
       coef[i] = inv_n * (-2.f * t / U + 4.f * I * s / (U * U)) * s * (1.f - s);
@@ -354,23 +378,27 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const int32_t* __restrict_
     }
     __syncthreads();
   }
-  // pairwise numerator of this instance: fixed-order sum of its tile partials
+  // pairwise numerator / weight count of this instance: fixed-order sums of its partials
   float num = 0.f;
-  for (int i = ws.tile_prefix[n] + threadIdx.x; i < ws.tile_prefix[n + 1]; i += NT) num += ws.pair_partial[i];
-  num = block_sum<float>(num, s_red);
+  for (int i = threadIdx.x; i < npartial; i += NT) num += __ldcg(partial + i);
+  num = block_sum<float>(num, sh.red);
+  int den = 0;
+  for (int i = threadIdx.x; i < nden; i += NT) den += __ldcg(den_partial + i);
+  den = block_sum<int>(den, sh.redi);
   if (threadIdx.x == 0) {
     ws.inst_prj[n] = inst_loss;
     ws.inst_num[n] = num;
+    if (den) atomicAdd(ws.weight_sum, (unsigned long long)den);
     __threadfence();
-    s_last = atomicAdd(ws.ticket, 1u) == (unsigned)(N - 1);
+    sh.last = atomicAdd(ws.ticket, 1u) == (unsigned)(N - 1);
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!sh.last) return;
   __threadfence();
   float prj = 0.f, pn = 0.f;
   for (int i = threadIdx.x; i < N; i += NT) { prj += __ldcg(ws.inst_prj + i); pn += __ldcg(ws.inst_num + i); }
-  prj = block_sum<float>(prj, s_red);
-  pn = block_sum<float>(pn, s_red);
+  prj = block_sum<float>(prj, sh.red);
+  pn = block_sum<float>(pn, sh.red);
   if (threadIdx.x == 0) {
     const float wsum = (float)__ldcg(ws.weight_sum);
     const float warm = fminf(iter_ptr[0] / warmup_iters, 1.f);
@@ -380,6 +408,273 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const int32_t* __restrict_
     losses_out[2] = pn;
     losses_out[3] = wsum;
     ws.scale_pair[0] = scale;
+  }
+}
+
+__global__ void __launch_bounds__(NT) finalize_kernel(const int32_t* __restrict__ rects,
+                                                      const int32_t* __restrict__ inst_gt, int N, int H, int W,
+                                                      Workspace ws, const float* __restrict__ iter_ptr,
+                                                      float warmup_iters, float* __restrict__ losses_out) {
+  __shared__ FinalizeShared sh;
+  const int n = blockIdx.x;
+  const int p0 = ws.tile_prefix[n], p1 = ws.tile_prefix[n + 1];
+  finalize_instance(n, load_rect(rects, inst_gt[n]), N, H, W, ws, ws.pair_partial + p0, p1 - p0, nullptr, 0,
+                    iter_ptr, warmup_iters, losses_out, sh);
+}
+
+// =========================================================================================
+// FAST PATH (W % 4 == 0, 16-byte aligned, W <= 512, dilation <= 4): no shared-memory tiles, no
+// work list.  One warp owns a full row; a lane owns NCHUNK groups of 4 consecutive pixels.
+// =========================================================================================
+constexpr int ROWS_PER_CTA = 16;            // 2 rows per warp, both in flight before any use
+
+template <int D>
+struct HaloRow {                             // logits / sigmoid pairs / edge bytes of col0-D .. col0+3+D
+  float s[4 + 2 * D], n[4 + 2 * D], x[4 + 2 * D];
+  unsigned e[4 + 2 * D];
+  bool ok[4 + 2 * D];
+};
+
+// loads one row segment with halo; `own` (may be null) are the 4 centre logits already in registers
+template <int D>
+__device__ __forceinline__ void load_halo_row(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H,
+                                              int W, int y, int col0, const float* own, HaloRow<D>& r) {
+  const bool yok = y >= 0 && y < H;
+  const float* row = img + (int64_t)y * W;
+  const uint8_t* brow = bits + (int64_t)y * W;
+  float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned cb = 0;
+  if (yok) {
+    if (own) c = make_float4(own[0], own[1], own[2], own[3]);
+    else c = __ldg(reinterpret_cast<const float4*>(row + col0));
+    cb = __ldg(reinterpret_cast<const unsigned*>(brow + col0));       // 4 edge bytes
+  }
+  r.x[D] = c.x; r.x[D + 1] = c.y; r.x[D + 2] = c.z; r.x[D + 3] = c.w;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { r.e[D + k] = (cb >> (8 * k)) & 0xffu; r.ok[D + k] = yok; }
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const int xl = col0 - D + k, xr = col0 + 4 + k;
+    r.ok[k] = yok && xl >= 0;
+    r.ok[D + 4 + k] = yok && xr < W;
+    r.x[k] = r.ok[k] ? __ldg(row + xl) : 0.f;
+    r.e[k] = r.ok[k] ? __ldg(brow + xl) : 0u;
+    r.x[D + 4 + k] = r.ok[D + 4 + k] ? __ldg(row + xr) : 0.f;
+    r.e[D + 4 + k] = r.ok[D + 4 + k] ? __ldg(brow + xr) : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < 4 + 2 * D; ++k) sigmoid_pair(r.x[k], r.s[k], r.n[k]);
+}
+
+__device__ __forceinline__ float pair_value(float xa, float sa, float na, float xb, float sb, float nb) {
+  if (fmaxf(fabsf(xa), fabsf(xb)) <= kFastLimit) return -__logf(sa * sb + na * nb);
+  return pair_nlog_logspace<float>(xa, xb, true);
+}
+__device__ __forceinline__ float pair_grad_a(float xa, float sa, float na, float xb, float sb, float nb) {
+  if (fmaxf(fabsf(xa), fabsf(xb)) <= kFastLimit) return -(sb - nb) * __frcp_rn(sa * sb + na * nb) * (sa * na);
+  return pair_nlog_grad_a_logspace<float>(xa, xb, true, pair_nlog_logspace<float>(xa, xb, true));
+}
+
+// pair terms of the 4 pixels (y, col0..col0+3) with their FORWARD neighbours (0,+D),(+D,-D),(+D,0),(+D,+D)
+template <int D>
+__device__ __forceinline__ void pair_chunk_fwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H,
+                                               int W, int y, int col0, const float* own, const Rect& r, float& acc,
+                                               int& wsum) {
+  if (col0 + 3 < r.i0 - D || col0 > r.i1 + D) return;
+  HaloRow<D> a, b;
+  load_halo_row<D>(img, bits, H, W, y, col0, own, a);
+  load_halo_row<D>(img, bits, H, W, y + D, col0, nullptr, b);
+  const bool ya = y >= r.j0 && y <= r.j1, yb = y + D >= r.j0 && y + D <= r.j1;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int x = col0 + e, k = D + e;                 // k indexes the halo arrays
+    const bool pin = ya && x >= r.i0 && x <= r.i1;
+    const unsigned ep = a.e[k];
+    if (pin) wsum += __popc(ep);
+#pragma unroll
+    for (int c = 4; c < 8; ++c) {
+      const HaloRow<D>& q = c == 4 ? a : b;
+      const int kq = c == 4 ? k + D : k + (c - 6) * D;
+      if (!q.ok[kq]) continue;
+      const int qx = col0 - D + kq;
+      const bool qin = (c == 4 ? ya : yb) && qx >= r.i0 && qx <= r.i1;
+      const int m = (pin ? (ep >> c) & 1u : 0u) + (qin ? (q.e[kq] >> (7 - c)) & 1u : 0u);
+      if (m) acc = fmaf((float)m, pair_value(a.x[k], a.s[k], a.n[k], q.x[kq], q.s[kq], q.n[kq]), acc);
+    }
+  }
+}
+
+template <int NCHUNK, int D>
+__global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restrict__ logits,
+                                                       const uint8_t* __restrict__ edge_bits,
+                                                       const int32_t* __restrict__ rects,
+                                                       const int32_t* __restrict__ inst_gt,
+                                                       const int32_t* __restrict__ gt_img, int N, int H, int W,
+                                                       Workspace ws, const float* __restrict__ iter_ptr,
+                                                       float warmup_iters, float* __restrict__ losses_out) {
+  constexpr int PANEL = NCHUNK * 128, NWARP = NT / 32;
+  __shared__ unsigned long long s_col[NWARP][PANEL];
+  __shared__ FinalizeShared sh;
+  const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = inst_gt[n];
+  const Rect r = load_rect(rects, g);
+  const float* img = logits + (int64_t)n * H * W;
+  const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
+  const int y0 = blockIdx.x * ROWS_PER_CTA + warp, y1 = y0 + NWARP;
+
+  float va[NCHUNK * 4], vb[NCHUNK * 4];
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch) {                 // all loads of both rows first (memory-level parallelism)
+    const int col0 = (ch * 32 + lane) * 4;
+    float4 qa = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), qb = qa;
+    if (col0 < W) {
+      if (y0 < H) qa = __ldg(reinterpret_cast<const float4*>(img + (int64_t)y0 * W + col0));
+      if (y1 < H) qb = __ldg(reinterpret_cast<const float4*>(img + (int64_t)y1 * W + col0));
+    }
+    va[ch * 4] = qa.x; va[ch * 4 + 1] = qa.y; va[ch * 4 + 2] = qa.z; va[ch * 4 + 3] = qa.w;
+    vb[ch * 4] = qb.x; vb[ch * 4 + 1] = qb.y; vb[ch * 4 + 2] = qb.z; vb[ch * 4 + 3] = qb.w;
+  }
+  // ---- row maxima (warp-wide integer redux on the order-preserving key) ----
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int y = half ? y1 : y0;
+    const float* v = half ? vb : va;
+    if (y < H) {                                         // warp-uniform
+      float m = v[0];
+#pragma unroll
+      for (int i = 1; i < NCHUNK * 4; ++i) m = fmaxf(m, v[i]);
+      const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
+      const float mv = fkey_inv(kmax);
+      int cand = 0x7fffffff;
+#pragma unroll
+      for (int i = NCHUNK * 4 - 1; i >= 0; --i)
+        if (v[i] == mv) cand = ((i >> 2) * 32 + lane) * 4 + (i & 3);
+      const int amin = __reduce_min_sync(kFull, cand);
+      if (lane == 0) ws.row_packed[(int64_t)n * H + y] = pack_key(kmax, amin == 0x7fffffff ? 0 : amin);
+    }
+  }
+  // ---- column maxima of this CTA's 16 rows ----
+#pragma unroll
+  for (int i = 0; i < NCHUNK * 4; ++i) {
+    const bool second = y1 < H && vb[i] > va[i];         // strict: the earlier row wins ties
+    const float cv = second ? vb[i] : va[i];
+    s_col[warp][((i >> 2) * 32 + lane) * 4 + (i & 3)] = y0 < H ? pack_key(fkey(cv), second ? y1 : y0) : 0ull;
+  }
+  // ---- pairwise terms: only rows whose pixel or forward neighbour can lie in the box ----
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int y = half ? y1 : y0;
+    if (y >= H) continue;
+    float acc = 0.f;
+    int wsum = 0;
+    if (!rect_empty(r) && y >= r.j0 - D && y <= r.j1) {   // warp-uniform
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int col0 = (ch * 32 + lane) * 4;
+        if (col0 < W) pair_chunk_fwd<D>(img, bits, H, W, y, col0, (half ? vb : va) + ch * 4, r, acc, wsum);
+      }
+      acc = warp_sum(acc);
+      wsum = warp_sum(wsum);
+    }
+    if (lane == 0) {
+      ws.pair_partial[(int64_t)n * H + y] = acc;
+      ws.den_partial[(int64_t)n * H + y] = wsum;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < PANEL; c += NT) {
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) best = s_col[w][c] > best ? s_col[w][c] : best;
+    if (best && c < W) atomicMax(ws.col_packed + (int64_t)n * W + c, best);
+  }
+  // ---- the last CTA of this instance finalizes it ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) sh.last = atomicAdd(ws.inst_ticket + n, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!sh.last) return;
+  __threadfence();
+  finalize_instance(n, r, N, H, W, ws, ws.pair_partial + (int64_t)n * H, H, ws.den_partial + (int64_t)n * H, H,
+                    iter_ptr, warmup_iters, losses_out, sh);
+}
+
+// gradient of the 4 pixels (y, col0..col0+3): gather over all 8 neighbours
+template <int D>
+__device__ __forceinline__ void pair_chunk_bwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H,
+                                               int W, int y, int col0, const Rect& r, float g_pair, float* out) {
+  HaloRow<D> rows[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) load_halo_row<D>(img, bits, H, W, y + (k - 1) * D, col0, nullptr, rows[k]);
+  bool yin[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { const int yy = y + (k - 1) * D; yin[k] = yy >= r.j0 && yy <= r.j1; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int x = col0 + e, k = D + e;
+    if (x >= W) continue;
+    const bool pin = yin[1] && x >= r.i0 && x <= r.i1;
+    const unsigned ep = rows[1].e[k];
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int cc = c < 4 ? c : c + 1;                  // skip the centre of the 3x3 stencil
+      const int ry = cc / 3, kq = k + (cc % 3 - 1) * D;
+      const HaloRow<D>& q = rows[ry];
+      if (!q.ok[kq]) continue;
+      const int qx = col0 - D + kq;
+      const bool qin = yin[ry] && qx >= r.i0 && qx <= r.i1;
+      const int m = (pin ? (ep >> c) & 1u : 0u) + (qin ? (q.e[kq] >> (7 - c)) & 1u : 0u);
+      if (m) acc = fmaf((float)m, pair_grad_a(rows[1].x[k], rows[1].s[k], rows[1].n[k], q.x[kq], q.s[kq], q.n[kq]), acc);
+    }
+    out[e] = fmaf(acc, g_pair, out[e]);
+  }
+}
+
+template <int NCHUNK, int D>
+__global__ void __launch_bounds__(NT, 3) bwd_rows_kernel(const float* __restrict__ logits,
+                                                      const uint8_t* __restrict__ edge_bits,
+                                                      const int32_t* __restrict__ rects,
+                                                      const int32_t* __restrict__ inst_gt,
+                                                      const int32_t* __restrict__ gt_img, int H, int W, Workspace ws,
+                                                      const float* __restrict__ g_losses,
+                                                      float* __restrict__ g_logits) {
+  constexpr int NWARP = NT / 32;
+  const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = inst_gt[n];
+  const Rect r = load_rect(rects, g);
+  const float g_prj = g_losses[0];
+  const float g_pair = g_losses[1] * ws.scale_pair[0];
+  const float* img = logits + (int64_t)n * H * W;
+  const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
+  const float* ccol = ws.coef_col + (int64_t)n * W;
+  const int* acol = ws.col_arg + (int64_t)n * W;
+  const bool have_box = !rect_empty(r);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int y = blockIdx.x * ROWS_PER_CTA + warp + half * NWARP;
+    if (y >= H) continue;
+    const int ra = ws.row_arg[(int64_t)n * H + y];
+    const float rc = ws.coef_row[(int64_t)n * H + y] * g_prj;
+    const bool row_in = have_box && y >= r.j0 - D && y <= r.j1 + D;     // warp-uniform
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      const int col0 = (ch * 32 + lane) * 4;
+      if (col0 >= W) continue;
+      float out[4] = {0.f, 0.f, 0.f, 0.f};
+      const int4 ac = __ldg(reinterpret_cast<const int4*>(acol + col0));
+      if ((unsigned)(ra - col0) < 4u) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (ra - col0 == e) out[e] += rc;
+      }
+      if (ac.x == y) out[0] += ccol[col0] * g_prj;
+      if (ac.y == y) out[1] += ccol[col0 + 1] * g_prj;
+      if (ac.z == y) out[2] += ccol[col0 + 2] * g_prj;
+      if (ac.w == y) out[3] += ccol[col0 + 3] * g_prj;
+      if (row_in && col0 + 3 >= r.i0 - D && col0 <= r.i1 + D) pair_chunk_bwd<D>(img, bits, H, W, y, col0, r, g_pair, out);
+      *reinterpret_cast<float4*>(g_logits + (int64_t)n * H * W + (int64_t)y * W + col0) =
+          make_float4(out[0], out[1], out[2], out[3]);
+    }
   }
 }
 
@@ -483,6 +778,41 @@ extern "C" int64_t bxs_boxinst_loss_workspace_bytes(int64_t N, int64_t H, int64_
   return (int64_t)carve(nullptr, N, H, W).total_bytes;
 }
 
+namespace bxs {
+namespace {
+inline bool fast_ok(const void* logits, const void* edge_bits, const void* out, int64_t W, int d) {
+  return (W % 4 == 0) && W <= 512 && d >= 1 && d <= 4 && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
+         ((reinterpret_cast<uintptr_t>(edge_bits) & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+}
+
+template <int NCHUNK>
+void launch_fwd_fast(int d, dim3 grid, cudaStream_t st, const float* logits, const uint8_t* edge_bits,
+                     const int32_t* rects, const int32_t* inst_gt, const int32_t* gt_img, int N, int H, int W,
+                     Workspace ws, const float* iter_ptr, float warmup_iters, float* losses_out) {
+#define BXS_CASE(DD)                                                                                          \
+  case DD:                                                                                                    \
+    fwd_fused_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, N, H, W, ws, \
+                                                      iter_ptr, warmup_iters, losses_out);                    \
+    break;
+  switch (d) { BXS_CASE(1) BXS_CASE(2) BXS_CASE(3) BXS_CASE(4) }
+#undef BXS_CASE
+}
+
+template <int NCHUNK>
+void launch_bwd_fast(int d, dim3 grid, cudaStream_t st, const float* logits, const uint8_t* edge_bits,
+                     const int32_t* rects, const int32_t* inst_gt, const int32_t* gt_img, int H, int W, Workspace ws,
+                     const float* g_losses, float* g_logits) {
+#define BXS_CASE(DD)                                                                                              \
+  case DD:                                                                                                        \
+    bwd_rows_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, H, W, ws, g_losses, \
+                                                     g_logits);                                                   \
+    break;
+  switch (d) { BXS_CASE(1) BXS_CASE(2) BXS_CASE(3) BXS_CASE(4) }
+#undef BXS_CASE
+}
+}  // namespace
+}  // namespace bxs
+
 extern "C" int bxs_boxinst_loss_forward(const float* logits, const uint8_t* edge_bits, const int32_t* rects,
                                         const int32_t* inst_gt, const int32_t* gt_img, const float* iter_ptr,
                                         float warmup_iters, void* workspace, float* losses_out, int64_t N,
@@ -493,10 +823,18 @@ extern "C" int bxs_boxinst_loss_forward(const float* logits, const uint8_t* edge
   cudaStream_t st = as_stream(stream);
   Workspace ws = carve(workspace, N, H, W);
   const int d = dilation;
+  if (fast_ok(logits, edge_bits, logits, W, d)) {
+    // one fused streaming kernel: maxima + in-box pair terms + per-instance finalize
+    cudaMemsetAsync(workspace, 0, ws.zero_bytes_fast, st);
+    dim3 grid((unsigned)ceil_div(H, ROWS_PER_CTA), (unsigned)N);
+    if (W <= 128) launch_fwd_fast<1>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
+    else if (W <= 256) launch_fwd_fast<2>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
+    else launch_fwd_fast<4>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
+    return check_launch();
+  }
+  // ---- generic path (any W / alignment / dilation): tile kernels over a device-built work list ----
   cudaMemsetAsync(workspace, 0, ws.zero_bytes, st);
   prep_worklist<<<1, NT, 0, st>>>(rects, inst_gt, (int)N, (int)H, (int)W, d, ws.tile_prefix);
-
-  // forward 1: ~4 CTAs per SM in flight, at least 8 rows (one per warp) per CTA
   const int sms = sm_count();
   int strips = (int)ceil_div((int64_t)sms * 4, N);
   strips = (int)std::max<int64_t>(1, std::min<int64_t>(strips, ceil_div(H, 8)));
@@ -514,8 +852,6 @@ extern "C" int bxs_boxinst_loss_forward(const float* logits, const uint8_t* edge
   }
   int rc = check_launch();
   if (rc) return rc;
-
-  // forward 2: persistent CTAs over the tile work list
   const size_t sm2 = (size_t)(TH + d) * (TW + 2 * d) * (3 * sizeof(float) + 1) + 16;
   pair_fwd_kernel<<<sms * 4, NT, sm2, st>>>(logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, d,
                                             ws.tile_prefix, ws.pair_partial, ws.weight_sum);
@@ -536,6 +872,13 @@ extern "C" int bxs_boxinst_loss_backward(const float* logits, const uint8_t* edg
   cudaStream_t st = as_stream(stream);
   Workspace ws = carve(const_cast<void*>(workspace), N, H, W);
   const int d = dilation;
+  if (fast_ok(logits, edge_bits, g_logits, W, d)) {
+    dim3 grid((unsigned)ceil_div(H, ROWS_PER_CTA), (unsigned)N);
+    if (W <= 128) launch_bwd_fast<1>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);
+    else if (W <= 256) launch_bwd_fast<2>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);
+    else launch_bwd_fast<4>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);
+    return check_launch();
+  }
   const size_t sm = (size_t)(TH + 2 * d) * (TW + 2 * d) * (3 * sizeof(float) + 1) + 16;
   dim3 grid((unsigned)ceil_div(W, TW), (unsigned)ceil_div(H, TH), (unsigned)N);
   const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_logits) & 15) == 0);

@@ -1,0 +1,98 @@
+"""``LevelsetLoss`` / ``region_levelset`` / ``length_regularization`` -- registry drop-ins for
+mmdet/models/losses/levelset_loss.py:7-60, computed by libboxseg_b200 (two-pass moments/energy
+kernels with an analytic backward; no [n,C,h,w] temporaries)."""
+import torch
+import torch.nn as nn
+
+from ... import _lib as L
+from ..builder import LOSSES, register
+
+
+class _LevelsetLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores2, targets, pixel_num, loss_weight):
+        s = scores2.contiguous().float()
+        t = targets.contiguous().float()
+        p = pixel_num.contiguous().float()
+        L.require_cuda(s, t, p)
+        n, two, h, w = s.shape
+        assert two == 2 and t.shape[0] == n and t.shape[-2:] == (h, w)
+        C = t.shape[1]
+        lib = L.lib()
+        loss = torch.empty(n, dtype=torch.float32, device=s.device)
+        ws = torch.empty(max(lib.bxs_levelset_workspace_bytes(n), 1), dtype=torch.uint8, device=s.device)
+        if n:
+            with torch.cuda.device(s.device):
+                L.check(lib.bxs_levelset_loss_forward(L.ptr(s), L.ptr(t), L.ptr(p), L.ptr(loss), L.ptr(ws), n, C, h, w,
+                                                      float(loss_weight), L.stream()), 'levelset_loss_forward')
+        ctx.save_for_backward(s, t, p, ws)
+        ctx.loss_weight = float(loss_weight)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        s, t, p, ws = ctx.saved_tensors
+        n, _, h, w = s.shape
+        C = t.shape[1]
+        need_s, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gs = torch.empty_like(s) if need_s else None
+        gt = torch.empty_like(t) if need_t else None
+        if n and (need_s or need_t):
+            with torch.cuda.device(s.device):
+                L.check(L.lib().bxs_levelset_loss_backward(L.ptr(s), L.ptr(t), L.ptr(p), L.ptr(ws),
+                                                           L.ptr(g_loss.contiguous().float()), L.ptr(gs), L.ptr(gt),
+                                                           n, C, h, w, ctx.loss_weight, L.stream()),
+                        'levelset_loss_backward')
+        return gs, gt, None, None
+
+
+class _LengthReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores):
+        s = scores.contiguous().float()
+        L.require_cuda(s)
+        n, C, h, w = s.shape
+        out = torch.empty(n, dtype=torch.float32, device=s.device)
+        ws = torch.empty(max(n, 1) * 64, dtype=torch.float32, device=s.device)
+        if n:
+            with torch.cuda.device(s.device):
+                L.check(L.lib().bxs_length_reg_forward(L.ptr(s), L.ptr(out), L.ptr(ws), n, C, h, w, L.stream()),
+                        'length_reg_forward')
+        ctx.save_for_backward(s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (s,) = ctx.saved_tensors
+        n, C, h, w = s.shape
+        g = torch.empty_like(s)
+        if n:
+            with torch.cuda.device(s.device):
+                L.check(L.lib().bxs_length_reg_backward(L.ptr(s), L.ptr(g_out.contiguous().float()), L.ptr(g), n, C, h,
+                                                        w, L.stream()), 'length_reg_backward')
+        return g
+
+
+class region_levelset(nn.Module):
+    """mask_score [n,2,h,w], lst_target [n,C,h,w] -> energy [n] (levelset_loss.py:21-44)."""
+
+    def forward(self, mask_score, lst_target):
+        ones = torch.ones(mask_score.shape[0], dtype=torch.float32, device=mask_score.device)
+        return _LevelsetLoss.apply(mask_score, lst_target, ones, 1.0)
+
+
+class length_regularization(nn.Module):
+    """levelset_loss.py:47-60 (defined by the reference, never called by its heads)."""
+
+    def forward(self, mask_score):
+        return _LengthReg.apply(mask_score)
+
+
+@register(LOSSES)
+class LevelsetLoss(nn.Module):
+    def __init__(self, loss_weight=1.0):
+        super().__init__()
+        self.loss_weight = loss_weight
+
+    def forward(self, mask_logits, targets, pixel_num):
+        return _LevelsetLoss.apply(mask_logits, targets, pixel_num, self.loss_weight)

@@ -100,6 +100,62 @@ int bxs_boxinst_loss_backward(const float* logits, const uint8_t* edge_bits, con
                               const float* g_losses, float* g_logits, int64_t N, int64_t H,
                               int64_t W, int dilation, bxs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * a1  CondInst dynamic mask head       replaces CondInstMaskHead.forward + parse_dynamic_params +
+ *     aligned_bilinear (mmdet/models/dense_heads/condinst_head.py:1120-1164, 146-167).
+ * feat [B,C,h,w]; params [N,P] laid out [W1(8 x cin) | W2(8x8) | W3(1x8) | b1 | b2 | b3] with
+ * cin = C + 2*rel_coors; coors [N,2] (x,y); soi [N] = sizes_of_interest[level_inds] as float;
+ * img_inds [N] int32; out [N,1,factor*h,factor*w].  dynamic_channels == 8, dynamic_convs == 3,
+ * C <= 32 (BXS_ERR_UNSUPPORTED otherwise).
+ * backward: g_out [N,1,fh,fw] -> g_feat [B,C,h,w] and g_params [N,P], both fully overwritten,
+ * deterministic (no atomics).  workspace: bxs_condinst_head_workspace_bytes(...) device bytes.
+ * --------------------------------------------------------------------------------------- */
+int bxs_condinst_head_forward(const float* feat, const float* params, const float* coors, const float* soi,
+                              const int32_t* img_inds, float* out, int64_t N, int64_t B, int64_t C,
+                              int64_t h, int64_t w, int64_t P, int in_stride, int factor, int rel_coors,
+                              bxs_stream_t stream);
+int64_t bxs_condinst_head_workspace_bytes(int64_t N, int64_t B, int64_t h, int64_t w, int64_t P);
+int bxs_condinst_head_backward(const float* feat, const float* params, const float* coors, const float* soi,
+                               const int32_t* img_inds, const float* g_out, float* g_feat, float* g_params,
+                               void* workspace, int64_t N, int64_t B, int64_t C, int64_t h, int64_t w,
+                               int64_t P, int in_stride, int factor, int rel_coors, bxs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a6 (dense)  box-projection dice loss on arbitrary maps     replaces BoxProjectionLoss.forward
+ *     (mmdet/models/losses/box_projection_loss.py:11-42; eps = 1e-5), DiscoBox mil_loss+dice_loss
+ *     (mmdet/models/dense_heads/discobox_head.py:542-562; eps = 2e-3).
+ * scores, targets [n,h,w] -> loss [n] = loss_weight * (dice(row profiles) + dice(col profiles)),
+ * dice = 1 - 2<x,t>/(|x|^2 + |t|^2 + eps).  backward: g_loss [n] -> g_scores [n,h,w] (gradient goes
+ * to the first arg-max of each row / column, as torch.max(dim) does).
+ * --------------------------------------------------------------------------------------- */
+int64_t bxs_projection_workspace_bytes(int64_t n, int64_t h, int64_t w);
+int bxs_projection_loss_forward(const float* scores, const float* targets, float* loss, void* workspace,
+                                int64_t n, int64_t h, int64_t w, float eps, float loss_weight,
+                                bxs_stream_t stream);
+int bxs_projection_loss_backward(const void* workspace, const float* g_loss, float* g_scores, int64_t n,
+                                 int64_t h, int64_t w, bxs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a9  region level-set energy        replaces LevelsetLoss / region_levelset
+ *     (mmdet/models/losses/levelset_loss.py:7-44).
+ * scores2 [n,2,h,w], targets [n,C,h,w] (C <= 8), pixel_num [n] -> loss [n] = w * E / pixel_num.
+ * backward writes g_scores2 and/or g_targets (either may be NULL).  workspace carries the
+ * region means from forward to backward: bxs_levelset_workspace_bytes(n).
+ * a10 length regulariser (levelset_loss.py:47-60): scores [n,C,h,w] -> out [n]; workspace n*64 floats.
+ * --------------------------------------------------------------------------------------- */
+int64_t bxs_levelset_workspace_bytes(int64_t n);
+int bxs_levelset_loss_forward(const float* scores2, const float* targets, const float* pixel_num, float* loss,
+                              void* workspace, int64_t n, int64_t C, int64_t h, int64_t w, float loss_weight,
+                              bxs_stream_t stream);
+int bxs_levelset_loss_backward(const float* scores2, const float* targets, const float* pixel_num,
+                               const void* workspace, const float* g_loss, float* g_scores2, float* g_targets,
+                               int64_t n, int64_t C, int64_t h, int64_t w, float loss_weight,
+                               bxs_stream_t stream);
+int bxs_length_reg_forward(const float* scores, float* out, void* workspace, int64_t n, int64_t C, int64_t h,
+                           int64_t w, bxs_stream_t stream);
+int bxs_length_reg_backward(const float* scores, const float* g_out, float* g_scores, int64_t n, int64_t C,
+                            int64_t h, int64_t w, bxs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,8 +91,9 @@ def projection_losses(scores, targets, eps=1e-5):
     scores/targets [n,1,H,W].  condinst_head.py:134-143 (BoxInst, then .mean()) and
     mmdet/models/losses/box_projection_loss.py:18-42 (BoxLevelset/Box2Mask, x loss_weight).
     """
-    col_s, col_t = scores.amax(dim=2), targets.amax(dim=2)     # profile over columns
-    row_s, row_t = scores.amax(dim=3), targets.amax(dim=3)     # profile over rows
+    # .max(dim)[0] (not amax): like the reference the gradient goes to ONE arg-max element
+    col_s, col_t = scores.max(dim=2)[0], targets.max(dim=2)[0]     # profile over columns
+    row_s, row_t = scores.max(dim=3)[0], targets.max(dim=3)[0]     # profile over rows
     return dice_1d(row_s, row_t, eps) + dice_1d(col_s, col_t, eps)
 
 

@@ -97,7 +97,7 @@ def disco_dice_loss(x, t):
 def disco_mil_loss(x, t):
     """x,t [n,h,w]: dice on the column profile + dice on the row profile.
     discobox_head.py:552-562."""
-    return disco_dice_loss(x.amax(2), t.amax(2)) + disco_dice_loss(x.amax(1), t.amax(1))
+    return disco_dice_loss(x.max(2)[0], t.max(2)[0]) + disco_dice_loss(x.max(1)[0], t.max(1)[0])
 
 
 def meanfield_kernel(feature_map, kernel_size=3, theta0=0.5, theta1=30.0, alpha0=3.0):
