@@ -44,8 +44,14 @@ SIGNATURES = {
     'bxs_levelset_loss_backward': [c_p] * 7 + [c_i64] * 4 + [c_f, c_p],
     'bxs_length_reg_forward': [c_p] * 3 + [c_i64] * 4 + [c_p],
     'bxs_length_reg_backward': [c_p] * 3 + [c_i64] * 4 + [c_p],
+    'bxs_lcm_workspace_bytes': [c_i64] * 3,
+    'bxs_lcm_forward': [c_p] * 5 + [c_i64] * 4 + [c_int, c_int, c_p],
+    'bxs_lcm_backward': [c_p] * 5 + [c_i64] * 3 + [c_int, c_int, c_p],
+    'bxs_meanfield_kernel': [c_p, c_p] + [c_i64] * 4 + [c_int, c_f, c_f, c_f, c_p],
+    'bxs_meanfield_workspace_bytes': [c_i64] * 3,
+    'bxs_meanfield_forward': [c_p] * 8 + [c_i64] * 3 + [c_int, c_int, c_p],
 }
-_RESTYPE = {'bxs_projection_workspace_bytes': c_i64, 'bxs_levelset_workspace_bytes': c_i64, 'bxs_condinst_head_workspace_bytes': c_i64, 'bxs_last_error': ctypes.c_char_p, 'bxs_boxinst_loss_workspace_bytes': c_i64}
+_RESTYPE = {'bxs_lcm_workspace_bytes': c_i64, 'bxs_meanfield_workspace_bytes': c_i64, 'bxs_projection_workspace_bytes': c_i64, 'bxs_levelset_workspace_bytes': c_i64, 'bxs_condinst_head_workspace_bytes': c_i64, 'bxs_last_error': ctypes.c_char_p, 'bxs_boxinst_loss_workspace_bytes': c_i64}
 
 _STATUS = {-1: 'invalid argument', -2: 'kernel launch failed', -3: 'unsupported shape', -4: 'no CUDA device'}
 

@@ -428,78 +428,111 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const int32_t* __restrict_
 // =========================================================================================
 constexpr int ROWS_PER_CTA = 16;            // 2 rows per warp, both in flight before any use
 
-template <int D>
-struct HaloRow {                             // logits / sigmoid pairs / edge bytes of col0-D .. col0+3+D
-  float s[4 + 2 * D], n[4 + 2 * D], x[4 + 2 * D];
-  unsigned e[4 + 2 * D];
-  bool ok[4 + 2 * D];
-};
-
-// loads one row segment with halo; `own` (may be null) are the 4 centre logits already in registers
-template <int D>
-__device__ __forceinline__ void load_halo_row(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H,
-                                              int W, int y, int col0, const float* own, HaloRow<D>& r) {
-  const bool yok = y >= 0 && y < H;
-  const float* row = img + (int64_t)y * W;
-  const uint8_t* brow = bits + (int64_t)y * W;
-  float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-  unsigned cb = 0;
-  if (yok) {
-    if (own) c = make_float4(own[0], own[1], own[2], own[3]);
-    else c = __ldg(reinterpret_cast<const float4*>(row + col0));
-    cb = __ldg(reinterpret_cast<const unsigned*>(brow + col0));       // 4 edge bytes
-  }
-  r.x[D] = c.x; r.x[D + 1] = c.y; r.x[D + 2] = c.z; r.x[D + 3] = c.w;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { r.e[D + k] = (cb >> (8 * k)) & 0xffu; r.ok[D + k] = yok; }
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    const int xl = col0 - D + k, xr = col0 + 4 + k;
-    r.ok[k] = yok && xl >= 0;
-    r.ok[D + 4 + k] = yok && xr < W;
-    r.x[k] = r.ok[k] ? __ldg(row + xl) : 0.f;
-    r.e[k] = r.ok[k] ? __ldg(brow + xl) : 0u;
-    r.x[D + 4 + k] = r.ok[D + 4 + k] ? __ldg(row + xr) : 0.f;
-    r.e[D + 4 + k] = r.ok[D + 4 + k] ? __ldg(brow + xr) : 0u;
-  }
-#pragma unroll
-  for (int k = 0; k < 4 + 2 * D; ++k) sigmoid_pair(r.x[k], r.s[k], r.n[k]);
-}
-
-__device__ __forceinline__ float pair_value(float xa, float sa, float na, float xb, float sb, float nb) {
-  if (fmaxf(fabsf(xa), fabsf(xb)) <= kFastLimit) return -__logf(sa * sb + na * nb);
+// ---- pair terms, lane-per-pixel: a warp walks the box columns [c_lo, c_hi] of one row in segments of
+// 32 lanes of which the inner 32-2D "own" a pixel; horizontal neighbours come from warp shuffles, the
+// row below is a second (L1-resident) load.  Out-of-image / out-of-box neighbours need no test at all:
+// their effective weight bits are zero by construction.
+__device__ __forceinline__ float pair_value(bool extreme, float xa, float sa, float na, float xb, float sb, float nb) {
+  if (!extreme) return -__logf(sa * sb + na * nb);
   return pair_nlog_logspace<float>(xa, xb, true);
 }
-__device__ __forceinline__ float pair_grad_a(float xa, float sa, float na, float xb, float sb, float nb) {
-  if (fmaxf(fabsf(xa), fabsf(xb)) <= kFastLimit) return -(sb - nb) * __frcp_rn(sa * sb + na * nb) * (sa * na);
+__device__ __forceinline__ float pair_grad_a(bool extreme, float xa, float sa, float na, float xb, float sb, float nb) {
+  if (!extreme) return -(sb - nb) * __frcp_rn(sa * sb + na * nb) * (sa * na);
   return pair_nlog_grad_a_logspace<float>(xa, xb, true, pair_nlog_logspace<float>(xa, xb, true));
 }
 
-// pair terms of the 4 pixels (y, col0..col0+3) with their FORWARD neighbours (0,+D),(+D,-D),(+D,0),(+D,+D)
+struct RowSeg {            // one lane's pixel of a row segment
+  float x, s, n;
+  unsigned eff;            // edge bits masked by "pixel lies in the box"
+  unsigned raw;            // unmasked edge bits
+};
+
+__device__ __forceinline__ RowSeg load_seg(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
+                                           int y, int x, const Rect& r) {
+  RowSeg v;
+  const bool in = y >= 0 && y < H && x >= 0 && x < W;
+  v.x = in ? __ldg(img + (int64_t)y * W + x) : 0.f;
+  v.raw = in ? (unsigned)__ldg(bits + (int64_t)y * W + x) : 0u;
+  v.eff = in_rect(r, y, x) ? v.raw : 0u;
+  sigmoid_pair(v.x, v.s, v.n);
+  return v;
+}
+
 template <int D>
-__device__ __forceinline__ void pair_chunk_fwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H,
-                                               int W, int y, int col0, const float* own, const Rect& r, float& acc,
-                                               int& wsum) {
-  if (col0 + 3 < r.i0 - D || col0 > r.i1 + D) return;
-  HaloRow<D> a, b;
-  load_halo_row<D>(img, bits, H, W, y, col0, own, a);
-  load_halo_row<D>(img, bits, H, W, y + D, col0, nullptr, b);
-  const bool ya = y >= r.j0 && y <= r.j1, yb = y + D >= r.j0 && y + D <= r.j1;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int x = col0 + e, k = D + e;                 // k indexes the halo arrays
-    const bool pin = ya && x >= r.i0 && x <= r.i1;
-    const unsigned ep = a.e[k];
-    if (pin) wsum += __popc(ep);
+__device__ __forceinline__ void pair_row_fwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
+                                             int y, const Rect& r, int lane, float& acc, int& wsum) {
+  const int c_lo = max(r.i0 - D, 0), c_hi = min(r.i1 + D, W - 1);
+  const bool owner_lane = lane >= D && lane < 32 - D;
+  for (int xs = c_lo - D; xs + D <= c_hi; xs += 32 - 2 * D) {
+    const int x = xs + lane;
+    const RowSeg a = load_seg(img, bits, H, W, y, x, r);
+    const RowSeg b = load_seg(img, bits, H, W, y + D, x, r);
+    const bool extreme = __any_sync(kFull, fmaxf(fabsf(a.x), fabsf(b.x)) > kFastLimit);
+    const bool owner = owner_lane && x <= c_hi;
+    if (owner) wsum += __popc(a.eff);
+    // c = 4: (y, x+D)   c = 5: (y+D, x-D)   c = 6: (y+D, x)   c = 7: (y+D, x+D)
 #pragma unroll
     for (int c = 4; c < 8; ++c) {
-      const HaloRow<D>& q = c == 4 ? a : b;
-      const int kq = c == 4 ? k + D : k + (c - 6) * D;
-      if (!q.ok[kq]) continue;
-      const int qx = col0 - D + kq;
-      const bool qin = (c == 4 ? ya : yb) && qx >= r.i0 && qx <= r.i1;
-      const int m = (pin ? (ep >> c) & 1u : 0u) + (qin ? (q.e[kq] >> (7 - c)) & 1u : 0u);
-      if (m) acc = fmaf((float)m, pair_value(a.x[k], a.s[k], a.n[k], q.x[kq], q.s[kq], q.n[kq]), acc);
+      float qx, qs, qn;
+      unsigned qe;
+      if (c == 4) {
+        qs = __shfl_down_sync(kFull, a.s, D); qn = __shfl_down_sync(kFull, a.n, D); qe = __shfl_down_sync(kFull, a.eff, D);
+        qx = extreme ? __shfl_down_sync(kFull, a.x, D) : 0.f;
+      } else if (c == 5) {
+        qs = __shfl_up_sync(kFull, b.s, D); qn = __shfl_up_sync(kFull, b.n, D); qe = __shfl_up_sync(kFull, b.eff, D);
+        qx = extreme ? __shfl_up_sync(kFull, b.x, D) : 0.f;
+      } else if (c == 6) {
+        qs = b.s; qn = b.n; qe = b.eff; qx = b.x;
+      } else {
+        qs = __shfl_down_sync(kFull, b.s, D); qn = __shfl_down_sync(kFull, b.n, D); qe = __shfl_down_sync(kFull, b.eff, D);
+        qx = extreme ? __shfl_down_sync(kFull, b.x, D) : 0.f;
+      }
+      const unsigned m = ((a.eff >> c) & 1u) + ((qe >> (7 - c)) & 1u);
+      if (owner && m) acc = fmaf((float)m, pair_value(extreme, a.x, a.s, a.n, qx, qs, qn), acc);
+    }
+  }
+}
+
+// gradient of one row's box pixels (lane-per-pixel); also adds the projection arg-max terms and stores
+template <int D>
+__device__ __forceinline__ void pair_row_bwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
+                                             int y, const Rect& r, int lane, float g_pair, int ra, float rc,
+                                             const int* __restrict__ acol, const float* __restrict__ ccol, float g_prj,
+                                             float* __restrict__ grow) {
+  const int c_lo = max(r.i0 - D, 0), c_hi = min(r.i1 + D, W - 1);
+  const bool owner_lane = lane >= D && lane < 32 - D;
+  for (int xs = c_lo - D; xs + D <= c_hi; xs += 32 - 2 * D) {
+    const int x = xs + lane;
+    const RowSeg t = load_seg(img, bits, H, W, y - D, x, r);
+    const RowSeg m0 = load_seg(img, bits, H, W, y, x, r);
+    const RowSeg u = load_seg(img, bits, H, W, y + D, x, r);
+    const bool extreme = __any_sync(kFull, fmaxf(fmaxf(fabsf(t.x), fabsf(m0.x)), fabsf(u.x)) > kFastLimit);
+    const bool owner = owner_lane && x <= c_hi;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int cc = c < 4 ? c : c + 1;
+      const int ry = cc / 3, sx = cc % 3 - 1;            // row 0: y-D, 1: y, 2: y+D ; sx: -1, 0, +1 (times D)
+      const RowSeg& src = ry == 0 ? t : (ry == 1 ? m0 : u);
+      float qx, qs, qn;
+      unsigned qe;
+      if (sx < 0) {
+        qs = __shfl_up_sync(kFull, src.s, D); qn = __shfl_up_sync(kFull, src.n, D); qe = __shfl_up_sync(kFull, src.eff, D);
+        qx = extreme ? __shfl_up_sync(kFull, src.x, D) : 0.f;
+      } else if (sx > 0) {
+        qs = __shfl_down_sync(kFull, src.s, D); qn = __shfl_down_sync(kFull, src.n, D); qe = __shfl_down_sync(kFull, src.eff, D);
+        qx = extreme ? __shfl_down_sync(kFull, src.x, D) : 0.f;
+      } else {
+        qs = src.s; qn = src.n; qe = src.eff; qx = src.x;
+      }
+      const unsigned m = ((m0.eff >> c) & 1u) + ((qe >> (7 - c)) & 1u);
+      if (owner && m) acc = fmaf((float)m, pair_grad_a(extreme, m0.x, m0.s, m0.n, qx, qs, qn), acc);
+    }
+    if (owner) {
+      float v = 0.f;
+      if (x == ra) v += rc;
+      if (acol[x] == y) v += ccol[x] * g_prj;
+      grow[x] = fmaf(acc, g_pair, v);
     }
   }
 }
@@ -568,11 +601,7 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
     float acc = 0.f;
     int wsum = 0;
     if (!rect_empty(r) && y >= r.j0 - D && y <= r.j1) {   // warp-uniform
-#pragma unroll
-      for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int col0 = (ch * 32 + lane) * 4;
-        if (col0 < W) pair_chunk_fwd<D>(img, bits, H, W, y, col0, (half ? vb : va) + ch * 4, r, acc, wsum);
-      }
+      pair_row_fwd<D>(img, bits, H, W, y, r, lane, acc, wsum);
       acc = warp_sum(acc);
       wsum = warp_sum(wsum);
     }
@@ -597,38 +626,6 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
   __threadfence();
   finalize_instance(n, r, N, H, W, ws, ws.pair_partial + (int64_t)n * H, H, ws.den_partial + (int64_t)n * H, H,
                     iter_ptr, warmup_iters, losses_out, sh);
-}
-
-// gradient of the 4 pixels (y, col0..col0+3): gather over all 8 neighbours
-template <int D>
-__device__ __forceinline__ void pair_chunk_bwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H,
-                                               int W, int y, int col0, const Rect& r, float g_pair, float* out) {
-  HaloRow<D> rows[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) load_halo_row<D>(img, bits, H, W, y + (k - 1) * D, col0, nullptr, rows[k]);
-  bool yin[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { const int yy = y + (k - 1) * D; yin[k] = yy >= r.j0 && yy <= r.j1; }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int x = col0 + e, k = D + e;
-    if (x >= W) continue;
-    const bool pin = yin[1] && x >= r.i0 && x <= r.i1;
-    const unsigned ep = rows[1].e[k];
-    float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int cc = c < 4 ? c : c + 1;                  // skip the centre of the 3x3 stencil
-      const int ry = cc / 3, kq = k + (cc % 3 - 1) * D;
-      const HaloRow<D>& q = rows[ry];
-      if (!q.ok[kq]) continue;
-      const int qx = col0 - D + kq;
-      const bool qin = yin[ry] && qx >= r.i0 && qx <= r.i1;
-      const int m = (pin ? (ep >> c) & 1u : 0u) + (qin ? (q.e[kq] >> (7 - c)) & 1u : 0u);
-      if (m) acc = fmaf((float)m, pair_grad_a(rows[1].x[k], rows[1].s[k], rows[1].n[k], q.x[kq], q.s[kq], q.n[kq]), acc);
-    }
-    out[e] = fmaf(acc, g_pair, out[e]);
-  }
 }
 
 template <int NCHUNK, int D>
@@ -657,10 +654,13 @@ __global__ void __launch_bounds__(NT, 3) bwd_rows_kernel(const float* __restrict
     const int ra = ws.row_arg[(int64_t)n * H + y];
     const float rc = ws.coef_row[(int64_t)n * H + y] * g_prj;
     const bool row_in = have_box && y >= r.j0 - D && y <= r.j1 + D;     // warp-uniform
+    const int c_lo = row_in ? max(r.i0 - D, 0) : W, c_hi = row_in ? min(r.i1 + D, W - 1) : -1;
+    float* grow = g_logits + (int64_t)n * H * W + (int64_t)y * W;
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
       const int col0 = (ch * 32 + lane) * 4;
       if (col0 >= W) continue;
+      if (col0 >= c_lo && col0 + 3 <= c_hi) continue;                   // fully inside the box span: pair pass writes it
       float out[4] = {0.f, 0.f, 0.f, 0.f};
       const int4 ac = __ldg(reinterpret_cast<const int4*>(acol + col0));
       if ((unsigned)(ra - col0) < 4u) {
@@ -671,15 +671,20 @@ __global__ void __launch_bounds__(NT, 3) bwd_rows_kernel(const float* __restrict
       if (ac.y == y) out[1] += ccol[col0 + 1] * g_prj;
       if (ac.z == y) out[2] += ccol[col0 + 2] * g_prj;
       if (ac.w == y) out[3] += ccol[col0 + 3] * g_prj;
-      if (row_in && col0 + 3 >= r.i0 - D && col0 <= r.i1 + D) pair_chunk_bwd<D>(img, bits, H, W, y, col0, r, g_pair, out);
-      *reinterpret_cast<float4*>(g_logits + (int64_t)n * H * W + (int64_t)y * W + col0) =
-          make_float4(out[0], out[1], out[2], out[3]);
+      if (col0 + 3 < c_lo || col0 > c_hi) {
+        *reinterpret_cast<float4*>(grow + col0) = make_float4(out[0], out[1], out[2], out[3]);
+      } else {                                                          // straddles the span boundary
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col0 + e < c_lo || col0 + e > c_hi) grow[col0 + e] = out[e];
+      }
     }
+    if (row_in) pair_row_bwd<D>(img, bits, H, W, y, r, lane, g_pair, ra, rc, acol, ccol, g_prj, grow);
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// backward: one tile kernel, every g_logits element written exactly once
+// generic-path backward: one tile kernel, every g_logits element written exactly once
 // ---------------------------------------------------------------------------------------
 template <bool VEC>
 __global__ void __launch_bounds__(NT) loss_bwd_kernel(const float* __restrict__ logits,

@@ -96,3 +96,52 @@ class LevelsetLoss(nn.Module):
 
     def forward(self, mask_logits, targets, pixel_num):
         return _LevelsetLoss.apply(mask_logits, targets, pixel_num, self.loss_weight)
+
+
+class _LCM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, imgs, phis, box, dilation, num_iter):
+        im = imgs.contiguous().float()
+        ph = phis.contiguous().float()
+        bx = box.contiguous().float()
+        L.require_cuda(im, ph, bx)
+        n, C, h, w = im.shape
+        assert ph.shape == (n, 1, h, w) and bx.shape == (n, 1, h, w)
+        lib = L.lib()
+        out = torch.zeros(1, dtype=torch.float32, device=im.device)
+        ws = torch.empty(max(lib.bxs_lcm_workspace_bytes(n, h, w), 4), dtype=torch.uint8, device=im.device)
+        if n:
+            with torch.cuda.device(im.device):
+                L.check(lib.bxs_lcm_forward(L.ptr(im), L.ptr(ph), L.ptr(bx), L.ptr(out), L.ptr(ws), n, C, h, w,
+                                            dilation, num_iter, L.stream()), 'lcm_forward')
+        ctx.save_for_backward(ph, bx, ws)
+        ctx.cfg = (dilation, num_iter)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        ph, bx, ws = ctx.saved_tensors
+        n, _, h, w = ph.shape
+        gp = torch.zeros_like(ph)
+        if n:
+            with torch.cuda.device(ph.device):
+                L.check(L.lib().bxs_lcm_backward(L.ptr(ph), L.ptr(bx), L.ptr(ws), L.ptr(g.reshape(1).contiguous().float()),
+                                                 L.ptr(gp), n, h, w, ctx.cfg[0], ctx.cfg[1], L.stream()), 'lcm_backward')
+        return None, gp, None, None, None
+
+
+class LocalConsistencyModule(nn.Module):
+    """levelset_loss.py:74-126: returns the refined phi (forward only helper kept for API parity;
+    the differentiable loss is ``LCM``)."""
+
+    def __init__(self, dilations, num_iter):
+        super().__init__()
+        assert len(dilations) == 1, 'the reference only ever uses dilations=[2]'
+        self.dilations = dilations
+        self.num_iter = num_iter
+        self.alpha = 0.3
+
+
+def LCM(imgs, pred_phis, box_targets):
+    """local consistency loss, levelset_loss.py:64-71 (num_iter=10, dilations=[2])."""
+    return _LCM.apply(imgs, pred_phis, box_targets, 2, 10)

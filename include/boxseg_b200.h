@@ -156,6 +156,38 @@ int bxs_length_reg_forward(const float* scores, float* out, void* workspace, int
 int bxs_length_reg_backward(const float* scores, const float* g_out, float* g_scores, int64_t n, int64_t C,
                             int64_t h, int64_t w, bxs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * a11  Local Consistency Module (Box2Mask)     replaces LCM / LocalConsistencyModule
+ *     (mmdet/models/losses/levelset_loss.py:64-126).
+ * imgs [n,C,h,w], phis [n,1,h,w], box [n,1,h,w] -> loss_out device float[1]
+ *   = sum |phi_T - phi_0| box / max(sum box, 1) after num_iter affinity-propagation rounds.
+ * workspace (bxs_lcm_workspace_bytes) carries affinity + phi_T to the backward, which writes
+ * g_phis [n,1,h,w] = g_loss * d loss / d phi_0 (deterministic gather form).
+ * --------------------------------------------------------------------------------------- */
+int64_t bxs_lcm_workspace_bytes(int64_t n, int64_t h, int64_t w);
+int bxs_lcm_forward(const float* imgs, const float* phis, const float* box, float* loss_out, void* workspace,
+                    int64_t n, int64_t C, int64_t h, int64_t w, int dilation, int num_iter, bxs_stream_t stream);
+int bxs_lcm_backward(const float* phis, const float* box, const void* workspace, const float* g_loss,
+                     float* g_phis, int64_t n, int64_t h, int64_t w, int dilation, int num_iter,
+                     bxs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a16  DiscoBox mean-field CRF (forward only, as in the reference)     replaces MeanField
+ *     (mmdet/models/dense_heads/discobox_head.py:585-651).
+ * bxs_meanfield_kernel: feature [B,C,h,w] -> K [B,k*k,h,w] bilateral kernel (incl. centre tap).
+ * bxs_meanfield_forward: x, targets [n,1,h,w]; obj_img [n] int32 (image of each object, may be NULL
+ *   when B == 1); neglog4_host = {-log U_fg(bit0), -log U_fg(bit1), -log U_bg(bit0), -log U_bg(bit1)}
+ *   (4 host floats computed by the caller with the reference's float32 arithmetic);
+ *   ret [n,1,h,w] in {0,1}, valid [n].  workspace: bxs_meanfield_workspace_bytes (large maps only).
+ * --------------------------------------------------------------------------------------- */
+int bxs_meanfield_kernel(const float* feature, float* K, int64_t B, int64_t C, int64_t h, int64_t w,
+                         int kernel_size, float two_theta0_sq, float two_theta1_sq, float alpha0,
+                         bxs_stream_t stream);
+int64_t bxs_meanfield_workspace_bytes(int64_t n, int64_t h, int64_t w);
+int bxs_meanfield_forward(const float* K, const int32_t* obj_img, const float* x, const float* targets,
+                          const float* neglog4_host, float* ret, float* valid, void* workspace, int64_t n,
+                          int64_t h, int64_t w, int kernel_size, int num_iter, bxs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,3 +109,65 @@ def test_length_regularization_grad():
     (g,) = torch.autograd.grad(out.sum(), sg)
     assert torch.allclose(out.cpu().double(), oracle_len(s.double()), rtol=1e-5)
     assert torch.allclose(g.cpu().double(), gref, atol=1e-6)
+
+
+# ------------------------------------------------------------------ a11 LCM
+def test_lcm_golden(golden):
+    from boxinstseg_b200.models.losses import LCM
+    g = golden('lcm')
+    phis = T(g['phis']).to(DEV).requires_grad_(True)
+    loss = LCM(T(g['imgs']).to(DEV), phis, T(g['box']).to(DEV))
+    assert abs(loss.item() - float(g['loss'])) <= 1e-4 * abs(float(g['loss']))
+    (gp,) = torch.autograd.grad(loss, phis)
+    assert torch.allclose(gp.cpu(), T(g['g_phis']), rtol=1e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize('n,h,w', [(3, 96, 96), (2, 17, 23), (2, 5, 4), (1, 200, 256)])
+def test_lcm_vs_oracle(n, h, w):
+    from boxinstseg_b200.models.losses import LCM
+    from oracle.levelset import lcm_loss
+    gen = torch.Generator().manual_seed(8)
+    imgs = torch.rand(n, 3, h, w, generator=gen)
+    phis = torch.rand(n, 1, h, w, generator=gen)
+    box = (torch.rand(n, 1, h, w, generator=gen) > 0.4).float() * torch.rand(n, 1, h, w, generator=gen)
+    p64 = phis.double().requires_grad_(True)
+    ref = lcm_loss(imgs.double(), p64, box.double())
+    (gref,) = torch.autograd.grad(ref * 1.7, p64)
+    pg = phis.to(DEV).requires_grad_(True)
+    out = LCM(imgs.to(DEV), pg, box.to(DEV))
+    (gp,) = torch.autograd.grad(out * 1.7, pg)
+    assert abs(out.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    assert rel_err(gp.cpu(), gref) < 1e-3
+    (gp2,) = torch.autograd.grad(LCM(imgs.to(DEV), pg, box.to(DEV)) * 1.7, pg)
+    assert torch.equal(gp, gp2)
+
+
+# ------------------------------------------------------------------ a16 mean field
+def test_meanfield_golden(golden):
+    from boxinstseg_b200.models.dense_heads import MeanField
+    g = golden('meanfield')
+    mf = MeanField(T(g['feature']).to(DEV), kernel_size=3, theta0=0.5, theta1=30, theta2=10, alpha0=2, iter=10, base=0.1)
+    assert torch.allclose(mf.kernel[0].flatten(1).cpu(), T(g['kernel'])[0], rtol=1e-5, atol=1e-9)
+    ps, va = mf(T(g['x']).to(DEV), T(g['targets']).to(DEV))
+    assert torch.equal(ps.cpu(), T(g['pseudo'])) and torch.equal(va.cpu(), T(g['valid']))     # binary output: exact
+
+
+@pytest.mark.parametrize('n,h,w,big', [(6, 50, 64, False), (3, 200, 256, False), (2, 330, 340, True)])
+def test_meanfield_vs_oracle(n, h, w, big):
+    from boxinstseg_b200.models.dense_heads import MeanField
+    from oracle.levelset import meanfield_forward, meanfield_kernel
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(4)
+    fm = F.interpolate(torch.randn(1, 3, max(h // 8, 2), max(w // 8, 2), generator=gen), size=(h, w), mode='bilinear')
+    fm = fm + torch.randn(1, 3, h, w, generator=gen) * 0.1
+    x = torch.rand(n, 1, h, w, generator=gen)
+    t = torch.zeros(n, 1, h, w)
+    for i in range(n):
+        t[i, 0, h // 6: h // 6 + h // 3 + i, w // 5: w // 5 + w // 2] = 1
+    k = meanfield_kernel(fm, 3, 0.5, 30.0, 2.0)
+    ps, va = meanfield_forward(k, x, t, 3, 10, 0.1)
+    mf = MeanField(fm.to(DEV), kernel_size=3, theta0=0.5, theta1=30, theta2=10, alpha0=2, iter=10, base=0.1)
+    gps, gva = mf(x.to(DEV), t.to(DEV))
+    mism = (gps.cpu() != ps).float().mean().item()
+    assert mism <= 2e-5, mism          # expf differs from the CPU libm by <= 2 ulp: exact ties may flip
+    assert torch.equal(gva.cpu(), va)
