@@ -50,8 +50,17 @@ SIGNATURES = {
     'bxs_meanfield_kernel': [c_p, c_p] + [c_i64] * 4 + [c_int, c_f, c_f, c_f, c_p],
     'bxs_meanfield_workspace_bytes': [c_i64] * 3,
     'bxs_meanfield_forward': [c_p] * 8 + [c_i64] * 3 + [c_int, c_int, c_p],
+    'bxs_mst_workspace_bytes': [c_i64] * 3,
+    'bxs_mst_forward': [c_p] * 4 + [c_i64] * 3 + [c_p],
+    'bxs_bfs_workspace_bytes': [c_i64] * 2,
+    'bxs_bfs_forward': [c_p] * 7 + [c_i64] * 2 + [c_int, c_p],
+    'bxs_tree_levels': [c_p] * 4 + [c_i64] * 2 + [c_p],
+    'bxs_refine_scratch_bytes': [c_i64] * 3,
+    'bxs_refine_forward': [c_p] * 13 + [c_i64] * 3 + [c_p],
+    'bxs_refine_backward_feature': [c_p] * 10 + [c_i64] * 3 + [c_p],
+    'bxs_refine_backward_weight': [c_p] * 14 + [c_i64] * 3 + [c_p],
 }
-_RESTYPE = {'bxs_lcm_workspace_bytes': c_i64, 'bxs_meanfield_workspace_bytes': c_i64, 'bxs_projection_workspace_bytes': c_i64, 'bxs_levelset_workspace_bytes': c_i64, 'bxs_condinst_head_workspace_bytes': c_i64, 'bxs_last_error': ctypes.c_char_p, 'bxs_boxinst_loss_workspace_bytes': c_i64}
+_RESTYPE = {'bxs_mst_workspace_bytes': c_i64, 'bxs_bfs_workspace_bytes': c_i64, 'bxs_refine_scratch_bytes': c_i64, 'bxs_lcm_workspace_bytes': c_i64, 'bxs_meanfield_workspace_bytes': c_i64, 'bxs_projection_workspace_bytes': c_i64, 'bxs_levelset_workspace_bytes': c_i64, 'bxs_condinst_head_workspace_bytes': c_i64, 'bxs_last_error': ctypes.c_char_p, 'bxs_boxinst_loss_workspace_bytes': c_i64}
 
 _STATUS = {-1: 'invalid argument', -2: 'kernel launch failed', -3: 'unsupported shape', -4: 'no CUDA device'}
 

@@ -1,0 +1,584 @@
+// a12-a15: learnable tree filter -- minimum spanning tree, breadth-first ordering, two-pass tree
+// aggregation (forward + both backwards).  Drop-in for mmdet/ops/tree_filter (tree_filter_cuda):
+//   mst_forward  (src/mst/mst.cu:86-117 + boruvka.cpp)  : in the reference this runs ON THE CPU (sync copy,
+//                one std::thread per tree); here Boruvka runs on the GPU with 64-bit (weight,index) keys and
+//                integer atomicMin, so the result is the unique MST of the strict total order -- the same
+//                edge SET as the reference's; edges are returned sorted by edge id (deterministic).
+//   bfs_forward  (src/bfs/bfs.cu:100-135)               : deterministic adjacency (sorted neighbours, no
+//                atomics-dependent order), one CTA per tree, block scans assign positions level by level;
+//                also emits the level boundaries the aggregation kernels use.
+//   refine_*     (src/refine/refine.cu:201-370)         : the reference walks a tree with a 64-thread
+//                wavefront polling shared flags (>= V/64 barriers, each behind a global-memory round trip).
+//                Here the order is level-contiguous, one CTA owns a (tree, channel), the running values
+//                live in SHARED memory (V floats) and each level is one barrier.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace bxs {
+namespace {
+
+constexpr int NT = 1024;
+constexpr unsigned long long kInf = ~0ull;
+
+__device__ __forceinline__ unsigned fkey(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// ---------------------------------------------------------------------------------------
+// MST (Boruvka)
+// ---------------------------------------------------------------------------------------
+struct MstWs {
+  unsigned long long* best;   // [B*V]
+  int* P;                     // [B*V] component label (always a root id)
+  int* Q;                     // [B*V] hook parents
+  uint8_t* in_tree;           // [B*E]
+  size_t total_bytes;
+};
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+inline MstWs carve_mst(void* base, int64_t B, int64_t E, int64_t V) {
+  MstWs w{};
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* r = p + off; off = align_up(off + bytes); return r; };
+  w.best = (unsigned long long*)take(8 * B * V);
+  w.P = (int*)take(4 * B * V);
+  w.Q = (int*)take(4 * B * V);
+  w.in_tree = (uint8_t*)take(B * E);
+  w.total_bytes = off;
+  return w;
+}
+
+__global__ void mst_init_kernel(MstWs ws, int64_t BV, int64_t BE, int V) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < BV; i += (int64_t)gridDim.x * blockDim.x) {
+    ws.P[i] = (int)(i % V);
+    ws.best[i] = kInf;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < BE; i += (int64_t)gridDim.x * blockDim.x)
+    ws.in_tree[i] = 0;
+}
+
+// every edge offers itself to the two components it connects
+__global__ void mst_min_edge_kernel(const int32_t* __restrict__ edge_index, const float* __restrict__ edge_weight,
+                                    MstWs ws, int E, int V) {
+  const int b = blockIdx.y;
+  const int32_t* ei = edge_index + (int64_t)b * E * 2;
+  const float* ew = edge_weight + (int64_t)b * E;
+  const int* P = ws.P + (int64_t)b * V;
+  unsigned long long* best = ws.best + (int64_t)b * V;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    const int cu = P[ei[2 * e]], cv = P[ei[2 * e + 1]];
+    if (cu == cv) continue;
+    const unsigned long long key = ((unsigned long long)fkey(ew[e]) << 32) | (unsigned)e;
+    atomicMin(best + cu, key);
+    atomicMin(best + cv, key);
+  }
+}
+
+// roots with an outgoing edge hook onto the component at its other end (2-cycles broken by id)
+__global__ void mst_hook_kernel(const int32_t* __restrict__ edge_index, MstWs ws, int E, int V) {
+  const int b = blockIdx.y;
+  const int32_t* ei = edge_index + (int64_t)b * E * 2;
+  const int* P = ws.P + (int64_t)b * V;
+  int* Q = ws.Q + (int64_t)b * V;
+  const unsigned long long* best = ws.best + (int64_t)b * V;
+  uint8_t* in_tree = ws.in_tree + (int64_t)b * E;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    int q = P[v];
+    if (q == v && best[v] != kInf) {
+      const int e = (int)(best[v] & 0xffffffffull);
+      const int cu = P[ei[2 * e]], cv = P[ei[2 * e + 1]];
+      const int other = cu == v ? cv : cu;
+      const bool mutual = best[other] == best[v];
+      if (!(mutual && v < other)) {
+        q = other;
+        in_tree[e] = 1;
+      }
+    }
+    Q[v] = q;
+  }
+}
+
+__global__ void mst_compress_kernel(MstWs ws, int V) {
+  const int b = blockIdx.y;
+  int* P = ws.P + (int64_t)b * V;
+  const int* Q = ws.Q + (int64_t)b * V;
+  unsigned long long* best = ws.best + (int64_t)b * V;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    int r = P[v];
+    while (Q[r] != r) r = Q[r];
+    P[v] = r;
+    best[v] = kInf;
+  }
+}
+
+// tree edges in ascending edge id; one CTA per tree
+__global__ void __launch_bounds__(NT) mst_compact_kernel(const int32_t* __restrict__ edge_index, MstWs ws,
+                                                         int32_t* __restrict__ edge_out, int E, int V) {
+  __shared__ int s_cnt[NT];
+  const int b = blockIdx.x;
+  const int32_t* ei = edge_index + (int64_t)b * E * 2;
+  const uint8_t* in_tree = ws.in_tree + (int64_t)b * E;
+  int32_t* out = edge_out + (int64_t)b * (V - 1) * 2;
+  const int per = (E + NT - 1) / NT;
+  const int lo = min(threadIdx.x * per, E), hi = min(lo + per, E);
+  int cnt = 0;
+  for (int e = lo; e < hi; ++e) cnt += in_tree[e];
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < NT; ++i) { const int v = s_cnt[i]; s_cnt[i] = run; run += v; }
+  }
+  __syncthreads();
+  int pos = s_cnt[threadIdx.x];
+  for (int e = lo; e < hi; ++e)
+    if (in_tree[e] && pos < V - 1) { out[2 * pos] = ei[2 * e]; out[2 * pos + 1] = ei[2 * e + 1]; ++pos; }
+}
+
+// ---------------------------------------------------------------------------------------
+// BFS ordering
+// ---------------------------------------------------------------------------------------
+struct BfsWs {
+  int* deg;        // [B*V]
+  int* adj;        // [B*V*4]
+  int* counts;     // [B*V] scratch of the level scan
+  size_t total_bytes;
+};
+inline BfsWs carve_bfs(void* base, int64_t B, int64_t V) {
+  BfsWs w{};
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* r = p + off; off = align_up(off + bytes); return r; };
+  w.deg = (int*)take(4 * B * V);
+  w.adj = (int*)take(16 * B * V);
+  w.counts = (int*)take(4 * B * V);
+  w.total_bytes = off;
+  return w;
+}
+
+__global__ void bfs_adj_kernel(const int32_t* __restrict__ tree, BfsWs ws, int V, int* __restrict__ err) {
+  const int b = blockIdx.y;
+  const int32_t* te = tree + (int64_t)b * (V - 1) * 2;
+  int* deg = ws.deg + (int64_t)b * V;
+  int* adj = ws.adj + (int64_t)b * V * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V - 1; i += gridDim.x * blockDim.x) {
+    const int u = te[2 * i], v = te[2 * i + 1];
+    const int su = atomicAdd(deg + u, 1), sv = atomicAdd(deg + v, 1);
+    if (su < 4) adj[u * 4 + su] = v; else *err = 1;
+    if (sv < 4) adj[v * 4 + sv] = u; else *err = 1;
+  }
+}
+
+__global__ void bfs_sort_adj_kernel(BfsWs ws, int64_t BV) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < BV; i += (int64_t)gridDim.x * blockDim.x) {
+    int* a = ws.adj + i * 4;
+    const int d = min(ws.deg[i], 4);
+    for (int x = 1; x < d; ++x)
+      for (int y = x; y > 0 && a[y] < a[y - 1]; --y) { const int t = a[y]; a[y] = a[y - 1]; a[y - 1] = t; }
+  }
+}
+
+// exclusive scan of `val` over the CTA (NT threads); returns the prefix, total in *total (all threads)
+__device__ __forceinline__ int block_excl_scan(int val, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = val;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < NT / 32 ? s_warp[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;                       // exclusive warp offsets
+    if (lane == 31) s_warp[32] = winc;             // grand total
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[wid] + inc - val;
+}
+
+// one CTA per tree.  Level l occupies positions [level_start[l], level_start[l+1]); children of a
+// vertex are contiguous and ordered by ascending vertex id; parents are non-decreasing in position.
+__global__ void __launch_bounds__(NT) bfs_block_kernel(BfsWs ws, int V, int32_t* __restrict__ sorted_index,
+                                                       int32_t* __restrict__ sorted_parent,
+                                                       int32_t* __restrict__ sorted_child,
+                                                       int32_t* __restrict__ level_start,
+                                                       int32_t* __restrict__ num_levels) {
+  __shared__ int s_warp[33];
+  const int b = blockIdx.x;
+  const int* deg = ws.deg + (int64_t)b * V;
+  const int* adj = ws.adj + (int64_t)b * V * 4;
+  int32_t* idx = sorted_index + (int64_t)b * V;
+  int32_t* par = sorted_parent + (int64_t)b * V;
+  int32_t* chd = sorted_child + (int64_t)b * V * 4;
+  int32_t* lvl = level_start + (int64_t)b * (V + 1);
+  for (int i = threadIdx.x; i < V * 4; i += NT) chd[i] = 0;
+  if (threadIdx.x == 0) { idx[0] = 0; par[0] = 0; lvl[0] = 0; }
+  __syncthreads();
+  int ls = 0, le = 1, level = 0;
+  while (ls < le) {
+    int next = le;                                  // first free position
+    for (int base = ls; base < le; base += NT) {    // frontier in chunks of NT positions
+      const int p = base + threadIdx.x;
+      int v = -1, pv = -1, cnt = 0;
+      if (p < le) {
+        v = idx[p];
+        pv = p == 0 ? -1 : idx[par[p]];
+        const int d = min(deg[v], 4);
+        for (int k = 0; k < d; ++k) cnt += adj[v * 4 + k] != pv;
+      }
+      int total;
+      const int off = block_excl_scan(cnt, s_warp, &total);
+      if (p < le) {
+        int q = next + off, k2 = 0;
+        const int d = min(deg[v], 4);
+        for (int k = 0; k < d; ++k) {
+          const int u = adj[v * 4 + k];
+          if (u == pv) continue;
+          idx[q] = u;
+          par[q] = p;
+          chd[p * 4 + k2++] = q;
+          ++q;
+        }
+      }
+      next += total;
+      __syncthreads();
+    }
+    ls = le;
+    le = next;
+    ++level;
+    if (threadIdx.x == 0) lvl[level] = ls;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) num_levels[b] = level;      // lvl[level] == number of reached vertices
+}
+
+// level boundaries from (level-contiguous) sorted_parent when they were not produced by bfs_block_kernel:
+// depth by pointer doubling, one CTA per tree, scratch in global memory
+__global__ void __launch_bounds__(NT) levels_from_parent_kernel(const int32_t* __restrict__ sorted_parent, int V,
+                                                                int* __restrict__ scratch,
+                                                                int32_t* __restrict__ level_start,
+                                                                int32_t* __restrict__ num_levels) {
+  const int b = blockIdx.x;
+  const int32_t* par = sorted_parent + (int64_t)b * V;
+  int* anc0 = scratch + (int64_t)b * 4 * V;
+  int* dep0 = anc0 + V;
+  int* anc1 = dep0 + V;
+  int* dep1 = anc1 + V;
+  int32_t* lvl = level_start + (int64_t)b * (V + 1);
+  for (int p = threadIdx.x; p < V; p += NT) { anc0[p] = p == 0 ? 0 : par[p]; dep0[p] = p == 0 ? 0 : 1; }
+  __syncthreads();
+  for (int step = 1; step < V; step <<= 1) {
+    for (int p = threadIdx.x; p < V; p += NT) {
+      const int a = anc0[p];
+      anc1[p] = anc0[a];
+      dep1[p] = dep0[p] + dep0[a];
+    }
+    __syncthreads();
+    int* t = anc0; anc0 = anc1; anc1 = t;
+    t = dep0; dep0 = dep1; dep1 = t;
+  }
+  for (int p = threadIdx.x; p < V; p += NT)
+    if (p == 0 || dep0[p] != dep0[p - 1]) lvl[dep0[p]] = p;
+  __syncthreads();
+  if (threadIdx.x == 0) { const int L = dep0[V - 1] + 1; lvl[L] = V; num_levels[b] = L; }
+}
+
+// ---------------------------------------------------------------------------------------
+// tree aggregation
+// ---------------------------------------------------------------------------------------
+struct TreeView {
+  const int32_t* idx;     // [V] position -> vertex
+  const int32_t* par;     // [V] position of the parent
+  const int32_t* chd;     // [V,4] positions of the children, 0 terminated
+  const int32_t* lvl;     // [L+1]
+  const float* w;         // [V] edge weight to the parent, position order (w[0] treated as 0)
+  int V, L;
+};
+
+// U[p] = in(p) + sum_children w[c] U[c], deepest level first.  `buf` (shared or global) is position indexed.
+template <class In>
+__device__ __forceinline__ void up_pass(const TreeView& t, In in, float* buf, float* __restrict__ save_up) {
+  for (int l = t.L - 1; l >= 0; --l) {
+    const int s = t.lvl[l], e = t.lvl[l + 1];
+    for (int p = s + threadIdx.x; p < e; p += NT) {
+      float acc = in(p);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = t.chd[p * 4 + k];
+        if (c <= 0) break;
+        acc = fmaf(buf[c], t.w[c], acc);
+      }
+      buf[p] = acc;
+      if (save_up) save_up[p] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// in place: A[0] = U[0]; A[p] = (1 - w^2) U[p] + w A[par]; writes vertex-ordered result
+__device__ __forceinline__ void down_pass(const TreeView& t, float* buf, float* __restrict__ out_vertex) {
+  if (threadIdx.x == 0 && out_vertex) out_vertex[t.idx[0]] = buf[0];
+  __syncthreads();
+  for (int l = 1; l < t.L; ++l) {
+    const int s = t.lvl[l], e = t.lvl[l + 1];
+    for (int p = s + threadIdx.x; p < e; p += NT) {
+      const float ew = t.w[p];
+      const float a = fmaf(buf[t.par[p]], ew, buf[p] * (1.f - ew * ew));
+      buf[p] = a;
+      if (out_vertex) out_vertex[t.idx[p]] = a;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ TreeView make_view(const float* w, const int32_t* idx, const int32_t* par, const int32_t* chd,
+                                              const int32_t* lvl, const int32_t* nlv, int b, int V) {
+  TreeView t;
+  t.idx = idx + (int64_t)b * V; t.par = par + (int64_t)b * V; t.chd = chd + (int64_t)b * V * 4;
+  t.lvl = lvl + (int64_t)b * (V + 1); t.w = w + (int64_t)b * V; t.V = V; t.L = nlv[b];
+  return t;
+}
+
+// MODE 0: forward (channel c < C: feature; c == C: normaliser with input 1)
+// MODE 1: backward wrt feature: input = g / Z
+template <int MODE, bool SMEM>
+__global__ void __launch_bounds__(NT) refine_updown_kernel(const float* __restrict__ feature, const float* __restrict__ w,
+                                                           const int32_t* __restrict__ idx, const int32_t* __restrict__ par,
+                                                           const int32_t* __restrict__ chd, const int32_t* __restrict__ lvl,
+                                                           const int32_t* __restrict__ nlv, const float* __restrict__ wsum,
+                                                           float* __restrict__ aggr, float* __restrict__ aggr_up,
+                                                           float* __restrict__ wsum_out, float* __restrict__ wsum_up,
+                                                           float* __restrict__ scratch, int C, int V) {
+  extern __shared__ float s_buf[];
+  const int b = blockIdx.x, c = blockIdx.y;
+  const TreeView t = make_view(w, idx, par, chd, lvl, nlv, b, V);
+  float* buf = SMEM ? s_buf : scratch + ((int64_t)b * (C + 1) + c) * V;
+  const bool norm = MODE == 0 && c == C;
+  const float* x = norm ? nullptr : feature + ((int64_t)b * C + c) * V;
+  const float* z = MODE == 1 ? wsum + (int64_t)b * V : nullptr;
+  float* save_up = MODE == 0 ? (norm ? wsum_up + (int64_t)b * V : aggr_up + ((int64_t)b * C + c) * V) : nullptr;
+  float* out_v = MODE == 0 ? (norm ? wsum_out + (int64_t)b * V : aggr + ((int64_t)b * C + c) * V)
+                           : aggr + ((int64_t)b * C + c) * V;     // MODE 1: aggr == grad_feature
+  const int32_t* ix = t.idx;
+  up_pass(t, [&](int p) { const int v = ix[p]; return norm ? 1.f : (MODE == 1 ? x[v] / z[v] : x[v]); }, buf, save_up);
+  down_pass(t, buf, out_v);
+}
+
+__global__ void refine_div_kernel(const float* __restrict__ aggr, const float* __restrict__ wsum, float* __restrict__ out,
+                                  int C, int V, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = i % V;
+    const int64_t b = i / ((int64_t)C * V);
+    out[i] = aggr[i] / wsum[b * V + v];
+  }
+}
+
+// backward wrt the edge weights (refine.cu:302-370): per channel
+//   gn = g / Z, fg = gn * out;  gnU = up(gn), fgU = up(fg)
+//   grad[p] += sweep(aggr_up_c, gnU, aggr_c)[p] - sweep(wsum_up, fgU, wsum)[p]
+// sweep: G[0] = gup[0]; for p > 0: grad = gup (outd[v_par] - w ind) + ind (G[par] - w gup); G = gup (1 - w^2) + G[par] w
+template <bool SMEM>
+__global__ void __launch_bounds__(NT) refine_bwd_weight_kernel(
+    const float* __restrict__ w, const int32_t* __restrict__ idx, const int32_t* __restrict__ par,
+    const int32_t* __restrict__ chd, const int32_t* __restrict__ lvl, const int32_t* __restrict__ nlv,
+    const float* __restrict__ out, const float* __restrict__ aggr, const float* __restrict__ aggr_up,
+    const float* __restrict__ wsum, const float* __restrict__ wsum_up, const float* __restrict__ g_out,
+    float* __restrict__ grad_w, float* __restrict__ scratch, int C, int V) {
+  extern __shared__ float s_buf[];
+  const int b = blockIdx.x;
+  const TreeView t = make_view(w, idx, par, chd, lvl, nlv, b, V);
+  float* buf = SMEM ? s_buf : scratch + (int64_t)b * V;
+  float* gw = grad_w + (int64_t)b * V;
+  const float* z = wsum + (int64_t)b * V;
+  const float* zu = wsum_up + (int64_t)b * V;
+  const int32_t* ix = t.idx;
+  for (int p = threadIdx.x; p < V; p += NT) gw[p] = 0.f;
+  __syncthreads();
+  for (int c = 0; c < C; ++c) {
+    const float* g = g_out + ((int64_t)b * C + c) * V;
+    const float* o = out + ((int64_t)b * C + c) * V;
+    const float* ag = aggr + ((int64_t)b * C + c) * V;
+    const float* au = aggr_up + ((int64_t)b * C + c) * V;
+    for (int phase = 0; phase < 2; ++phase) {
+      // phase 0: gup = up(g/Z), data = (aggr_up, aggr), sign +   phase 1: gup = up(g/Z * out), data = (wsum_up, wsum), sign -
+      up_pass(t, [&](int p) { const int v = ix[p]; const float gn = g[v] / z[v]; return phase ? gn * o[v] : gn; }, buf,
+              nullptr);
+      const float* ind = phase ? zu : au;
+      const float* outd = phase ? z : ag;
+      const float sign = phase ? -1.f : 1.f;
+      // top-down: buf[p] holds gup[p] until visited, then G[p]
+      for (int l = 1; l < t.L; ++l) {
+        const int s = t.lvl[l], e = t.lvl[l + 1];
+        for (int p = s + threadIdx.x; p < e; p += NT) {
+          const float ew = t.w[p], gup = buf[p], Gp = buf[t.par[p]], in_p = ind[p];
+          const float left = gup * (outd[ix[t.par[p]]] - ew * in_p);
+          const float right = in_p * (Gp - ew * gup);
+          gw[p] += sign * (left + right);
+          buf[p] = fmaf(Gp, ew, gup * (1.f - ew * ew));
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+inline int grid_for(int64_t total, int block) {
+  const int64_t g = ceil_div(total, block), cap = (int64_t)sm_count() * 8;
+  return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+constexpr size_t kMaxTreeSmem = 220 * 1024;
+
+}  // namespace
+}  // namespace bxs
+
+using namespace bxs;
+
+extern "C" int64_t bxs_mst_workspace_bytes(int64_t B, int64_t E, int64_t V) {
+  return (B <= 0 || E <= 0 || V <= 0) ? 0 : (int64_t)carve_mst(nullptr, B, E, V).total_bytes;
+}
+
+extern "C" int bxs_mst_forward(const int32_t* edge_index, const float* edge_weight, int32_t* edge_out, void* workspace,
+                               int64_t B, int64_t E, int64_t V, bxs_stream_t stream) {
+  if (!edge_index || !edge_weight || !edge_out || !workspace || B <= 0 || B >= 65536 || E <= 0 || V <= 1 ||
+      E >= (int64_t(1) << 31) || V >= (int64_t(1) << 31))
+    return BXS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  MstWs ws = carve_mst(workspace, B, E, V);
+  mst_init_kernel<<<grid_for(B * std::max(E, V), 256), 256, 0, st>>>(ws, B * V, B * E, (int)V);
+  int rounds = 0;
+  while ((int64_t(1) << rounds) < V) ++rounds;             // components at least halve per round
+  const dim3 ge((unsigned)std::min<int64_t>(ceil_div(E, 256), 1024), (unsigned)B);
+  const dim3 gv((unsigned)std::min<int64_t>(ceil_div(V, 256), 1024), (unsigned)B);
+  for (int r = 0; r < rounds; ++r) {
+    mst_min_edge_kernel<<<ge, 256, 0, st>>>(edge_index, edge_weight, ws, (int)E, (int)V);
+    mst_hook_kernel<<<gv, 256, 0, st>>>(edge_index, ws, (int)E, (int)V);
+    mst_compress_kernel<<<gv, 256, 0, st>>>(ws, (int)V);
+  }
+  mst_compact_kernel<<<(unsigned)B, NT, 0, st>>>(edge_index, ws, edge_out, (int)E, (int)V);
+  return check_launch();
+}
+
+extern "C" int64_t bxs_bfs_workspace_bytes(int64_t B, int64_t V) {
+  return (B <= 0 || V <= 0) ? 0 : (int64_t)carve_bfs(nullptr, B, V).total_bytes + 256;
+}
+
+// level_start [B, V+1] and num_levels [B] are extra outputs (may be NULL -> scratch inside the workspace is NOT
+// provided: pass real buffers whenever the result feeds bxs_refine_*).
+extern "C" int bxs_bfs_forward(const int32_t* tree_edges, int32_t* sorted_index, int32_t* sorted_parent,
+                               int32_t* sorted_child, int32_t* level_start, int32_t* num_levels, void* workspace,
+                               int64_t B, int64_t V, int max_adj, bxs_stream_t stream) {
+  if (!tree_edges || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels || !workspace ||
+      B <= 0 || B >= 65536 || V <= 1)
+    return BXS_ERR_INVALID_ARG;
+  if (max_adj != 4) return BXS_ERR_UNSUPPORTED;             // the reference only ever passes 4 (tree_filter.py:137)
+  cudaStream_t st = as_stream(stream);
+  BfsWs ws = carve_bfs(workspace, B, V);
+  int* err = (int*)((char*)workspace + ws.total_bytes);
+  cudaMemsetAsync(ws.deg, 0, sizeof(int) * B * V, st);
+  cudaMemsetAsync(err, 0, sizeof(int), st);
+  bfs_adj_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div(V, 256), 1024), (unsigned)B), 256, 0, st>>>(tree_edges, ws,
+                                                                                                         (int)V, err);
+  bfs_sort_adj_kernel<<<grid_for(B * V, 256), 256, 0, st>>>(ws, B * V);
+  bfs_block_kernel<<<(unsigned)B, NT, 0, st>>>(ws, (int)V, sorted_index, sorted_parent, sorted_child, level_start,
+                                               num_levels);
+  return check_launch();
+}
+
+extern "C" int bxs_tree_levels(const int32_t* sorted_parent, int32_t* level_start, int32_t* num_levels, void* scratch,
+                               int64_t B, int64_t V, bxs_stream_t stream) {
+  if (!sorted_parent || !level_start || !num_levels || !scratch || B <= 0 || V <= 0) return BXS_ERR_INVALID_ARG;
+  levels_from_parent_kernel<<<(unsigned)B, NT, 0, as_stream(stream)>>>(sorted_parent, (int)V, (int*)scratch, level_start,
+                                                                       num_levels);
+  return check_launch();
+}
+
+extern "C" int64_t bxs_refine_scratch_bytes(int64_t B, int64_t C, int64_t V) {
+  return (B <= 0 || C <= 0 || V <= 0) ? 0 : (int64_t)sizeof(float) * B * (C + 1) * V;
+}
+
+extern "C" int bxs_refine_forward(const float* feature, const float* edge_weight, const int32_t* sorted_index,
+                                  const int32_t* sorted_parent, const int32_t* sorted_child, const int32_t* level_start,
+                                  const int32_t* num_levels, float* feature_out, float* aggr, float* aggr_up, float* wsum,
+                                  float* wsum_up, void* scratch, int64_t B, int64_t C, int64_t V, bxs_stream_t stream) {
+  if (!feature || !edge_weight || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels ||
+      !feature_out || !aggr || !aggr_up || !wsum || !wsum_up || !scratch || B <= 0 || B >= 65536 || C <= 0 ||
+      C >= 65535 || V <= 0)
+    return BXS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  const size_t sm = V * sizeof(float);
+  const dim3 grid((unsigned)B, (unsigned)(C + 1));
+  if (sm <= kMaxTreeSmem) {
+    cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+    refine_updown_kernel<0, true><<<grid, NT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent, sorted_child,
+                                                        level_start, num_levels, nullptr, aggr, aggr_up, wsum, wsum_up,
+                                                        nullptr, (int)C, (int)V);
+  } else {
+    refine_updown_kernel<0, false><<<grid, NT, 0, st>>>(feature, edge_weight, sorted_index, sorted_parent, sorted_child,
+                                                        level_start, num_levels, nullptr, aggr, aggr_up, wsum, wsum_up,
+                                                        (float*)scratch, (int)C, (int)V);
+  }
+  refine_div_kernel<<<grid_for(B * C * V, 256), 256, 0, st>>>(aggr, wsum, feature_out, (int)C, (int)V, B * C * V);
+  return check_launch();
+}
+
+extern "C" int bxs_refine_backward_feature(const float* edge_weight, const int32_t* sorted_index,
+                                           const int32_t* sorted_parent, const int32_t* sorted_child,
+                                           const int32_t* level_start, const int32_t* num_levels, const float* wsum,
+                                           const float* grad_out, float* grad_feature, void* scratch, int64_t B, int64_t C,
+                                           int64_t V, bxs_stream_t stream) {
+  if (!edge_weight || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels || !wsum ||
+      !grad_out || !grad_feature || !scratch || B <= 0 || B >= 65536 || C <= 0 || C >= 65535 || V <= 0)
+    return BXS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  const size_t sm = V * sizeof(float);
+  const dim3 grid((unsigned)B, (unsigned)C);
+  if (sm <= kMaxTreeSmem) {
+    cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+    refine_updown_kernel<1, true><<<grid, NT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, sorted_child,
+                                                        level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
+                                                        nullptr, nullptr, (int)C, (int)V);
+  } else {
+    refine_updown_kernel<1, false><<<grid, NT, 0, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, sorted_child,
+                                                        level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
+                                                        nullptr, (float*)scratch, (int)C, (int)V);
+  }
+  return check_launch();
+}
+
+extern "C" int bxs_refine_backward_weight(const float* edge_weight, const int32_t* sorted_index,
+                                          const int32_t* sorted_parent, const int32_t* sorted_child,
+                                          const int32_t* level_start, const int32_t* num_levels, const float* feature_out,
+                                          const float* aggr, const float* aggr_up, const float* wsum, const float* wsum_up,
+                                          const float* grad_out, float* grad_weight, void* scratch, int64_t B, int64_t C,
+                                          int64_t V, bxs_stream_t stream) {
+  if (!edge_weight || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels || !feature_out ||
+      !aggr || !aggr_up || !wsum || !wsum_up || !grad_out || !grad_weight || !scratch || B <= 0 || B >= 65536 || C <= 0 ||
+      V <= 0)
+    return BXS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  const size_t sm = V * sizeof(float);
+  if (sm <= kMaxTreeSmem) {
+    cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+    refine_bwd_weight_kernel<true><<<(unsigned)B, NT, sm, st>>>(edge_weight, sorted_index, sorted_parent, sorted_child,
+                                                                level_start, num_levels, feature_out, aggr, aggr_up, wsum,
+                                                                wsum_up, grad_out, grad_weight, nullptr, (int)C, (int)V);
+  } else {
+    refine_bwd_weight_kernel<false><<<(unsigned)B, NT, 0, st>>>(edge_weight, sorted_index, sorted_parent, sorted_child,
+                                                                 level_start, num_levels, feature_out, aggr, aggr_up, wsum,
+                                                                 wsum_up, grad_out, grad_weight, (float*)scratch, (int)C,
+                                                                 (int)V);
+  }
+  return check_launch();
+}

@@ -1,0 +1,103 @@
+"""``MinimumSpanningTree`` and ``TreeFilter2D`` -- drop-ins for
+mmdet/ops/tree_filter/modules/tree_filter.py:9-150 (same constructor arguments and forward signatures).
+
+The grid-graph construction and the edge-weight arithmetic stay in torch, written so that the float32
+results are bit-identical to the reference's (near-ties decide the tree); only the
+tree selection / ordering / aggregation run in libboxseg_b200.
+"""
+import torch
+from torch import nn
+
+from ..functions.bfs import bfs
+from ..functions.mst import mst
+from ..functions.refine import refine
+
+
+def _squared_distance(a, b):
+    d = a - b
+    return (d * d).sum(dim=1)
+
+
+class MinimumSpanningTree(nn.Module):
+    def __init__(self, distance_func):
+        super().__init__()
+        self.distance_func = distance_func
+
+    @staticmethod
+    def _build_matrix_index(fm):
+        """int32 [B,E,2]: vertical edges (v, v+W) first, then horizontal (v, v+1); tree_filter.py:15-25."""
+        b, h, w = fm.shape[0], fm.shape[2], fm.shape[3]
+        ids = torch.arange(h * w, dtype=torch.int32, device=fm.device).view(h, w)
+        vert = torch.stack((ids[:-1], ids[1:]), dim=2).reshape(-1, 2)
+        hori = torch.stack((ids[:, :-1], ids[:, 1:]), dim=2).reshape(-1, 2)
+        return torch.cat((vert, hori), dim=0).unsqueeze(0).expand(b, -1, -1)
+
+    def _build_feature_weight(self, fm):
+        """distance along both grid directions + 1; tree_filter.py:27-34."""
+        b = fm.shape[0]
+        vert = self.distance_func(fm[:, :, :-1, :], fm[:, :, 1:, :]).reshape(b, -1)
+        hori = self.distance_func(fm[:, :, :, :-1], fm[:, :, :, 1:]).reshape(b, -1)
+        return torch.cat((vert, hori), dim=1) + 1
+
+    def _build_label_weight(self, fm):
+        """tree_filter.py:36-51 (never used by the heads; kept for API parity)."""
+        b = fm.shape[0]
+        diff = torch.cat((self.distance_func(fm[:, :, :-1, :], fm[:, :, 1:, :]).reshape(b, -1),
+                          self.distance_func(fm[:, :, :, :-1], fm[:, :, :, 1:]).reshape(b, -1)), dim=1)
+        both = torch.cat(((fm[:, :, :-1, :] + fm[:, :, 1:, :]).sum(1).reshape(b, -1),
+                          (fm[:, :, :, :-1] + fm[:, :, :, 1:]).sum(1).reshape(b, -1)), dim=1)
+        return diff * both
+
+    def forward(self, guide_in, label=None):
+        with torch.no_grad():
+            index = self._build_matrix_index(guide_in).contiguous()
+            weight = self._build_feature_weight(guide_in)
+            if label is not None:
+                sel = self._build_label_weight(label) > 0
+                weight[sel] = torch.sigmoid(weight[sel])
+            return mst(index, weight.contiguous(), guide_in.shape[2] * guide_in.shape[3])
+
+
+class TreeFilter2D(nn.Module):
+    def __init__(self, groups=1, sigma=0.02, distance_func=None, enable_log=False):
+        super().__init__()
+        self.groups = groups
+        self.enable_log = enable_log
+        self.distance_func = distance_func if distance_func is not None else self.norm2_distance
+        self.sigma = sigma
+
+    @staticmethod
+    def norm2_distance(fm_ref, fm_tar):
+        return _squared_distance(fm_ref, fm_tar)
+
+    @staticmethod
+    def batch_index_opr(data, index):
+        with torch.no_grad():
+            index = index.long().unsqueeze(1).expand(-1, data.shape[1], -1)
+        return torch.gather(data, 2, index)
+
+    def build_edge_weight(self, fm, sorted_index, sorted_parent, low_tree):
+        """w[pos] = exp(-dist(E(v_pos), E(v_par)) / (sigma if low_tree else 1)); tree_filter.py:91-108."""
+        b, c = fm.shape[0], fm.shape[1]
+        v = fm.shape[2] * fm.shape[3]
+        flat = fm.reshape(b, c, -1)
+        src = self.batch_index_opr(flat, sorted_index)
+        dst = self.batch_index_opr(src, sorted_parent)
+        src = src.reshape(-1, c // self.groups, v)
+        dst = dst.reshape(-1, c // self.groups, v)
+        dist = self.distance_func(src, dst)
+        return torch.exp(-dist / self.sigma) if low_tree else torch.exp(-dist)
+
+    def forward(self, feature_in, embed_in, tree, low_tree=True):
+        shape = feature_in.shape
+        sorted_index, sorted_parent, sorted_child = bfs(tree, 4)
+        edge_weight = self.build_edge_weight(embed_in, sorted_index, sorted_parent, low_tree)
+        feat = feature_in.reshape(shape[0] * self.groups, shape[1] // self.groups, -1).contiguous()
+        if self.groups > 1:                                  # tree_filter.py:110-120 (split_group)
+            from .. import tree_filter_cuda as _C
+            levels = _C.levels_of(sorted_index, sorted_parent)
+            rep = lambda t: t.repeat_interleave(self.groups, dim=0).contiguous()   # noqa: E731
+            sorted_index, sorted_parent, sorted_child = rep(sorted_index), rep(sorted_parent), rep(sorted_child)
+            setattr(sorted_index, '_bxs_levels', (rep(levels[0]), rep(levels[1])))
+        out = refine(feat, edge_weight, sorted_index, sorted_parent, sorted_child, low_tree)
+        return out.reshape(shape)

@@ -188,6 +188,49 @@ int bxs_meanfield_forward(const float* K, const int32_t* obj_img, const float* x
                           const float* neglog4_host, float* ret, float* valid, void* workspace, int64_t n,
                           int64_t h, int64_t w, int kernel_size, int num_iter, bxs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * a12-a15  tree filter      replaces the pybind module tree_filter_cuda
+ *     (mmdet/ops/tree_filter/src/tree_filter.cpp:7-13: mst_forward, bfs_forward, refine_forward,
+ *      refine_backward_feature, refine_backward_weight).
+ *
+ * bxs_mst_forward: edge_index int32 [B,E,2], edge_weight f32 [B,E] -> edge_out int32 [B,V-1,2]: the unique
+ *   minimum spanning tree under the strict total order (weight, edge id) -- the same edge SET the reference's
+ *   CPU Boruvka returns (src/mst/boruvka.cpp:74-80) -- emitted in ascending edge id.  Runs on the GPU.
+ * bxs_bfs_forward: tree edges -> sorted_index [B,V] (position -> vertex), sorted_parent [B,V] (position of
+ *   the parent, root 0), sorted_child [B,V,4] (positions, 0 terminated) exactly as src/bfs/bfs.cu:46-98 defines
+ *   them, plus level_start [B,V+1] / num_levels [B]: the order is level-contiguous and deterministic.
+ * bxs_tree_levels: recovers level_start / num_levels from a level-contiguous sorted_parent (scratch 16*B*V bytes).
+ * bxs_refine_forward: feature f32 [B,C,V] (vertex order), edge_weight f32 [B,V] (sorted order; entry 0 is
+ *   ignored = 0 and NOT overwritten, unlike refine.cu:43-46) -> feature_out, aggr [B,C,V], aggr_up [B,C,V],
+ *   wsum [B,V], wsum_up [B,V] (the five tensors of refine.cu:201-249).  scratch: bxs_refine_scratch_bytes.
+ * bxs_refine_backward_feature / _weight: refine.cu:251-370.
+ * --------------------------------------------------------------------------------------- */
+int64_t bxs_mst_workspace_bytes(int64_t B, int64_t E, int64_t V);
+int bxs_mst_forward(const int32_t* edge_index, const float* edge_weight, int32_t* edge_out, void* workspace,
+                    int64_t B, int64_t E, int64_t V, bxs_stream_t stream);
+int64_t bxs_bfs_workspace_bytes(int64_t B, int64_t V);
+int bxs_bfs_forward(const int32_t* tree_edges, int32_t* sorted_index, int32_t* sorted_parent,
+                    int32_t* sorted_child, int32_t* level_start, int32_t* num_levels, void* workspace,
+                    int64_t B, int64_t V, int max_adj, bxs_stream_t stream);
+int bxs_tree_levels(const int32_t* sorted_parent, int32_t* level_start, int32_t* num_levels, void* scratch,
+                    int64_t B, int64_t V, bxs_stream_t stream);
+int64_t bxs_refine_scratch_bytes(int64_t B, int64_t C, int64_t V);
+int bxs_refine_forward(const float* feature, const float* edge_weight, const int32_t* sorted_index,
+                       const int32_t* sorted_parent, const int32_t* sorted_child, const int32_t* level_start,
+                       const int32_t* num_levels, float* feature_out, float* aggr, float* aggr_up, float* wsum,
+                       float* wsum_up, void* scratch, int64_t B, int64_t C, int64_t V, bxs_stream_t stream);
+int bxs_refine_backward_feature(const float* edge_weight, const int32_t* sorted_index,
+                                const int32_t* sorted_parent, const int32_t* sorted_child,
+                                const int32_t* level_start, const int32_t* num_levels, const float* wsum,
+                                const float* grad_out, float* grad_feature, void* scratch, int64_t B, int64_t C,
+                                int64_t V, bxs_stream_t stream);
+int bxs_refine_backward_weight(const float* edge_weight, const int32_t* sorted_index,
+                               const int32_t* sorted_parent, const int32_t* sorted_child,
+                               const int32_t* level_start, const int32_t* num_levels, const float* feature_out,
+                               const float* aggr, const float* aggr_up, const float* wsum, const float* wsum_up,
+                               const float* grad_out, float* grad_weight, void* scratch, int64_t B, int64_t C,
+                               int64_t V, bxs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,132 @@
+"""GPU parity of the tree-filter ops (a12-a15): MST edge set bit-exact against the reference's Boruvka
+(golden fixtures + the Kruskal oracle), BFS validity, refine forward/backward against the C oracle and the
+float64 closed form."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+DEV = 'cuda:0'
+
+
+def _edge_ids(tree, h, w):
+    from oracle.tree import edges_to_ids
+    return edges_to_ids(tree.cpu().numpy(), h, w)
+
+
+def test_mst_golden(golden):
+    from boxinstseg_b200.ops.tree_filter import MinimumSpanningTree, TreeFilter2D
+    g = golden('tree')
+    gm = T(g['guide']).to(DEV)
+    mst = MinimumSpanningTree(TreeFilter2D.norm2_distance)
+    assert torch.equal(mst._build_feature_weight(gm).cpu(), T(g['edge_weight']))          # weights bit-identical
+    tree = mst(gm)
+    assert tree.dtype == torch.int32 and tree.shape == (3, 9 * 13 - 1, 2)
+    for b in range(3):
+        assert np.array_equal(_edge_ids(tree[b], 9, 13), g['mst_edge_ids'][b])            # reference Boruvka edge set
+
+
+@pytest.mark.parametrize('B,C,h,w,quant', [(2, 3, 40, 56, False), (3, 5, 25, 31, True), (1, 3, 200, 256, False),
+                                           (2, 1, 96, 96, True), (1, 2, 2, 2, False), (1, 2, 1, 7, False)])
+def test_mst_vs_oracle(B, C, h, w, quant):
+    from boxinstseg_b200.ops.tree_filter import MinimumSpanningTree, TreeFilter2D
+    from oracle import tree as ot
+    gen = torch.Generator().manual_seed(h * w)
+    gm = torch.randn(B, C, h, w, generator=gen)
+    if quant:
+        gm = torch.round(gm * 2) / 2                          # massive weight ties -> the (weight, id) order decides
+    tree = MinimumSpanningTree(TreeFilter2D.norm2_distance)(gm.to(DEV))
+    ei = ot.grid_edges(h, w)
+    ew = ot.grid_edge_weights(gm).numpy()
+    for b in range(B):
+        assert np.array_equal(_edge_ids(tree[b], h, w), ot.mst_edge_ids(ei, ew[b], h * w))
+
+
+def _check_bfs(idx, par, chd, tree, V):
+    i, p, c = idx.cpu().numpy(), par.cpu().numpy(), chd.cpu().numpy()
+    assert sorted(i.tolist()) == list(range(V)) and i[0] == 0 and p[0] == 0
+    assert np.all(p[1:] < np.arange(1, V)) and np.all(np.diff(p) >= 0)
+    edges = {tuple(sorted(e)) for e in tree.cpu().numpy().tolist()}
+    assert {tuple(sorted((int(i[k]), int(i[p[k]])))) for k in range(1, V)} == edges       # same tree
+    for pos in range(V):
+        kids = [k for k in c[pos] if k > 0]
+        assert all(p[k] == pos for k in kids) and len(kids) == int(np.sum(p[1:] == pos))
+
+
+def test_bfs_valid_and_deterministic():
+    from boxinstseg_b200.ops.tree_filter import MinimumSpanningTree, TreeFilter2D, bfs
+    gen = torch.Generator().manual_seed(1)
+    gm = torch.randn(3, 3, 30, 41, generator=gen).to(DEV)
+    tree = MinimumSpanningTree(TreeFilter2D.norm2_distance)(gm)
+    idx, par, chd = bfs(tree, 4)
+    for b in range(3):
+        _check_bfs(idx[b], par[b], chd[b], tree[b], 30 * 41)
+    idx2, par2, chd2 = bfs(tree, 4)
+    assert torch.equal(idx, idx2) and torch.equal(par, par2) and torch.equal(chd, chd2)   # the reference's order is racy
+    # level boundaries recomputed from sorted_parent agree with the ones bfs produced
+    from boxinstseg_b200.ops.tree_filter import tree_filter_cuda as _C
+    lvl, nlv = _C.levels_of(idx, par)
+    lvl2, nlv2 = _C.levels_of(idx.clone(), par)
+    assert torch.equal(nlv, nlv2)
+    for b in range(3):
+        L = int(nlv[b])
+        assert torch.equal(lvl[b, :L + 1], lvl2[b, :L + 1])
+
+
+def test_refine_golden_closed_form(golden):
+    from boxinstseg_b200.ops.tree_filter import MinimumSpanningTree, TreeFilter2D
+    g = golden('tree')
+    gm = T(g['guide']).to(DEV)
+    tree = MinimumSpanningTree(TreeFilter2D.norm2_distance)(gm)
+    out = TreeFilter2D(sigma=0.02)(T(g['feature']).to(DEV), gm, tree, low_tree=False)
+    assert torch.allclose(out.cpu().double(), T(g['filtered_high']), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('B,C,h,w,low', [(2, 1, 24, 30, True), (2, 1, 24, 30, False), (3, 4, 17, 9, False),
+                                         (1, 1, 200, 256, False), (2, 2, 96, 96, True), (1, 1, 250, 260, False)])
+def test_tree_filter_vs_oracle(B, C, h, w, low):
+    from boxinstseg_b200.ops.tree_filter import MinimumSpanningTree, TreeFilter2D
+    from oracle import tree as ot
+    gen = torch.Generator().manual_seed(7 + h)
+    guide = torch.randn(B, 3, h, w, generator=gen)
+    embed = torch.randn(B, 5, h, w, generator=gen) * (0.05 if low else 0.4)
+    feat = torch.rand(B, C, h, w, generator=gen)
+    gout = torch.randn(B, C, h, w, generator=gen)
+    tree_cpu = ot.mst(guide)
+    f_ref = feat.clone().requires_grad_(True)
+    e_ref = embed.clone().requires_grad_(True)
+    ref = ot.tree_filter(f_ref, e_ref, tree_cpu, low_tree=low)
+    gf_ref, ge_ref = torch.autograd.grad((ref * gout).sum(), [f_ref, e_ref], allow_unused=True)
+
+    tree = MinimumSpanningTree(TreeFilter2D.norm2_distance)(guide.to(DEV))
+    f = feat.to(DEV).requires_grad_(True)
+    e = embed.to(DEV).requires_grad_(True)
+    out = TreeFilter2D(sigma=0.02)(f, e, tree, low_tree=low)
+    gf, ge = torch.autograd.grad((out * gout.to(DEV)).sum(), [f, e], allow_unused=True)
+    assert rel_err(out.cpu(), ref.detach()) < 1e-4
+    assert rel_err(gf.cpu(), gf_ref) < 1e-4
+    if low:
+        assert ge is None and ge_ref is None              # low_tree: no gradient to the embedding (refine.py:36-37)
+    else:
+        assert rel_err(ge.cpu(), ge_ref) < 2e-3           # fp32 tree recursions, different (valid) BFS orders
+
+
+def test_box2mask_call_pattern():
+    """Box2Mask (box2mask_head.py:269-325): trees built once per image at 96x96 and repeated per query."""
+    from boxinstseg_b200.ops.tree_filter import MinimumSpanningTree, TreeFilter2D
+    gen = torch.Generator().manual_seed(11)
+    img = torch.randn(2, 3, 96, 96, generator=gen).to(DEV)
+    lst = torch.randn(2, 1, 96, 96, generator=gen).to(DEV).requires_grad_(True)
+    mst, tf = MinimumSpanningTree(TreeFilter2D.norm2_distance), TreeFilter2D()
+    t_img, t_lst = mst(img), mst(lst)
+    rep = torch.tensor([3, 2], device=DEV)
+    preds = torch.rand(5, 1, 96, 96, generator=gen).to(DEV).requires_grad_(True)
+    img_r, lst_r = img.repeat_interleave(rep, 0), lst.repeat_interleave(rep, 0)
+    s1 = tf(preds, img_r, t_img.repeat_interleave(rep, 0))
+    s2 = tf(s1, lst_r, t_lst.repeat_interleave(rep, 0), low_tree=False)
+    (s1.sum() + s2.sum()).backward()
+    assert torch.isfinite(preds.grad).all() and torch.isfinite(lst.grad).all()
+    assert 0.0 <= float(s2.min()) and float(s2.max()) <= 1.0 + 1e-5       # a normalised filter of values in [0,1]
