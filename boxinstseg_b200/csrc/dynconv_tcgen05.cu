@@ -1,0 +1,298 @@
+// a2 / a3 / a4: dense dynamic 1x1 convolution  out[b,i,p] = sum_c kernel[b,i,c] * feat[b,c,p]
+// (K = C = 256 channels) as a TMA-fed tcgen05 tensor-core kernel, TF32 inputs, FP32 accumulation in TMEM.
+// Replaces the F.conv2d / einsum calls at
+//   mmdet/models/dense_heads/box_solov2_head.py:209-211   (all S^2 cells, groups=B)
+//   mmdet/models/dense_heads/discobox_head.py:1219        (positive kernels of one image)
+//   mmdet/models/dense_heads/box2mask_head.py:345         (einsum 'bqc,bchw->bqhw')
+// which run as cuDNN/cuBLAS GEMMs (cuDNN convolutions use TF32 by default on Ampere and later).
+//
+// GEMM view per image:  D[M = pixels, N = kernels] = A[M, K] * B[N, K]^T
+//   A = feat^T : the pixel index is contiguous in memory -> "MN-major" operand, staged by TMA as
+//       [k-row][32 pixels] boxes with the 128-byte swizzle (canonical ((8,n),(8,k)) layout, LBO = 4 KB
+//       between 32-pixel groups, SBO = 1 KB between groups of 8 k-rows);
+//   B = kernel : K-major, [row = kernel][32 channels] boxes with the 128-byte swizzle (SBO = 1 KB);
+//   D          : 128 TMEM lanes (pixels) x N <= 128 fp32 columns, double buffered (256 columns).
+// The op is HBM bound (each feat tile is read once: 128 KB per 128 pixels; B stays resident in shared
+// memory for the whole CTA lifetime), so one CTA per SM streams pixel tiles:
+//   warp 0   : TMA producer (B once, then a 4-stage ring of 16 KB A stages)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (4 MMAs of K = 8 per stage)
+//   warps 2-5: epilogue -- tcgen05.ld 32x32b (one pixel per thread) and coalesced stores
+// synchronised with mbarriers only (full/empty per stage, tmem_full/tmem_empty per accumulator).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace bxs {
+namespace {
+
+constexpr int BLOCK_M = 128;        // pixels per tile (TMEM lanes)
+constexpr int BLOCK_N = 128;        // kernels per CTA (TMEM columns per accumulator)
+constexpr int BLOCK_K = 32;         // channels per stage = one 128-byte swizzle row of tf32
+constexpr int UMMA_K = 8;           // tf32: 32 bytes per instruction
+constexpr int MAX_KBLOCKS = 8;      // C <= 256
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;      // 16 KB
+constexpr int B_KBLOCK_BYTES = BLOCK_N * BLOCK_K * 4;     // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 2 * BLOCK_N;                    // 256 (power of two)
+
+struct SmemLayout {
+  alignas(1024) uint8_t a[STAGES][A_STAGE_BYTES];
+  alignas(1024) uint8_t b[MAX_KBLOCKS][B_KBLOCK_BYTES];
+  alignas(8) uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t b_full;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+
+// shared-memory matrix descriptor (SM100): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | swizzle-128B (2) << 61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, a_major MN (1) @15, b_major K (0) @16,
+// N >> 3 @17, M >> 4 @24
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// grid: (ctas_per_group, B * n_chunks).  CTA (x, g): image b = g / n_chunks, kernel chunk g % n_chunks,
+// pixel tiles x, x + gridDim.x, ...
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_constant__ CUtensorMap tm_kern,
+                    float* __restrict__ out, int C, int P, int I, int n_chunks) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout& S = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y / n_chunks, chunk = blockIdx.y % n_chunks;
+  const int kblocks = C / BLOCK_K;
+  const int tiles_m = (P + BLOCK_M - 1) / BLOCK_M;
+  const int n_here = min(BLOCK_N, ((I - chunk * BLOCK_N) + 15) / 16 * 16);     // multiple of 16, <= 128
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    mbar_init(&S.b_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                      // TMEM allocation by one full warp; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(&S.b_full, (uint32_t)kblocks * B_KBLOCK_BYTES);
+      for (int kb = 0; kb < kblocks; ++kb)
+        tma_load_2d(&tm_kern, &S.b_full, S.b[kb], kb * BLOCK_K, b * I + chunk * BLOCK_N);
+      int stage = 0, phase = 0;
+      for (int mt = blockIdx.x; mt < tiles_m; mt += gridDim.x) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&S.empty[stage], phase ^ 1);
+          mbar_expect_tx(&S.full[stage], A_STAGE_BYTES);
+#pragma unroll
+          for (int mg = 0; mg < BLOCK_M / 32; ++mg)
+            tma_load_2d(&tm_feat, &S.full[stage], S.a[stage] + mg * (BLOCK_K * 128), mt * BLOCK_M + mg * 32,
+                        b * C + kb * BLOCK_K);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(n_here);
+      mbar_wait(&S.b_full, 0);
+      tc_fence_after();
+      int stage = 0, phase = 0, t = 0;
+      for (int mt = blockIdx.x; mt < tiles_m; mt += gridDim.x, ++t) {
+        const int acc = t & 1;
+        mbar_wait(&S.tmem_empty[acc], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&S.full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(S.a[stage]);
+          const uint32_t b_base = smem_u32(S.b[kb]);
+#pragma unroll
+          for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4) {
+            // A (MN-major): 8 k-rows = one 1 KB swizzle atom per 32-pixel group; groups 4 KB apart
+            const uint64_t adesc = make_desc(a_base + k4 * 1024, BLOCK_K * 128, 1024);
+            // B (K-major): advance 32 bytes inside the 128-byte swizzled row; 8-row groups 1 KB apart
+            const uint64_t bdesc = make_desc(b_base + k4 * (UMMA_K * 4), 16, 1024);
+            umma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+          }
+          umma_commit(&S.empty[stage]);            // frees this A stage once the MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&S.tmem_full[acc]);            // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quarter = warp & 3;                  // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
+    int t = 0;
+    for (int mt = blockIdx.x; mt < tiles_m; mt += gridDim.x, ++t) {
+      const int acc = t & 1;
+      mbar_wait(&S.tmem_full[acc], (t >> 1) & 1);
+      tc_fence_after();
+      const int pixel = mt * BLOCK_M + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      float* dst = out + ((int64_t)b * I + chunk * BLOCK_N) * P + pixel;
+      for (int c0 = 0; c0 < n_here; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        if (pixel < P) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (chunk * BLOCK_N + c0 + j < I) dst[(int64_t)(c0 + j) * P] = __uint_as_float(r[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major [rows, cols] float32 matrix, box = [box_rows, 32 floats], 128-byte swizzle, zero fill out of bounds
+bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+}  // namespace bxs
+
+using namespace bxs;
+
+// feat [B,C,P], kernels [B,I,C] -> out [B,I,P] (all float32, contiguous).  Requirements of the TMA/UMMA path:
+// C % 32 == 0, C <= 256, P % 4 == 0, 16-byte aligned bases.  BXS_ERR_UNSUPPORTED otherwise.
+extern "C" int bxs_dynconv1x1_forward(const float* feat, const float* kernels, float* out, int64_t B, int64_t C, int64_t P,
+                                      int64_t I, bxs_stream_t stream) {
+  if (!feat || !kernels || !out || B <= 0 || C <= 0 || P <= 0 || I <= 0) return BXS_ERR_INVALID_ARG;
+  if (C % BLOCK_K || C > BLOCK_K * MAX_KBLOCKS || P % 4 || (reinterpret_cast<uintptr_t>(feat) & 15) ||
+      (reinterpret_cast<uintptr_t>(kernels) & 15) || B * C >= (int64_t(1) << 31) || B * I >= (int64_t(1) << 31))
+    return BXS_ERR_UNSUPPORTED;
+  CUtensorMap tm_feat, tm_kern;
+  if (!make_map(&tm_feat, feat, B * C, P, BLOCK_K) || !make_map(&tm_kern, kernels, B * I, C, BLOCK_N)) {
+    set_last_error(cudaErrorNotSupported);
+    return BXS_ERR_LAUNCH;
+  }
+  const int n_chunks = (int)ceil_div(I, BLOCK_N);
+  const int64_t groups = B * n_chunks;
+  if (groups > 65535) return BXS_ERR_UNSUPPORTED;
+  const int tiles_m = (int)ceil_div(P, BLOCK_M);
+  int per_group = (int)std::max<int64_t>(1, sm_count() / groups);
+  per_group = std::min(per_group, tiles_m);
+  const size_t smem = sizeof(SmemLayout) + 1024;
+  cudaFuncSetAttribute(dynconv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dynconv_tf32_kernel<<<dim3(per_group, (unsigned)groups), NUM_THREADS, smem, as_stream(stream)>>>(
+      tm_feat, tm_kern, out, (int)C, (int)P, (int)I, n_chunks);
+  return check_launch();
+}

@@ -231,6 +231,18 @@ int bxs_refine_backward_weight(const float* edge_weight, const int32_t* sorted_i
                                const float* grad_out, float* grad_weight, void* scratch, int64_t B, int64_t C,
                                int64_t V, bxs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * a2/a3/a4  dense dynamic 1x1 convolution on the 5th-gen tensor cores (tcgen05 + TMEM, TMA fed)
+ *     replaces F.conv2d(feature.view(1,B*C,h,w), kernel[B*S*S,C,1,1], groups=B)
+ *       (mmdet/models/dense_heads/box_solov2_head.py:209-211),
+ *     F.conv2d(mask_feat[1,C,h,w], kernels[I,C,1,1]) (mmdet/models/dense_heads/discobox_head.py:1219) and
+ *     einsum('bqc,bchw->bqhw') (mmdet/models/dense_heads/box2mask_head.py:345).
+ * feat [B,C,P] (P = h*w), kernels [B,I,C] -> out [B,I,P]; TF32 operands (as cuDNN's default for the
+ * reference's conv2d on Ampere+), FP32 accumulation.  C % 32 == 0, C <= 256, P % 4 == 0, 16-byte aligned.
+ * --------------------------------------------------------------------------------------- */
+int bxs_dynconv1x1_forward(const float* feat, const float* kernels, float* out, int64_t B, int64_t C, int64_t P,
+                           int64_t I, bxs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
