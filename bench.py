@@ -80,6 +80,14 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
 
 
+def reduce_max_over_ranks(values, dist, device):
+    """Per-rank timings -> MAX over ranks (the N>1 contract); identity without a process group."""
+    t = torch.tensor(values, device=device, dtype=torch.float64)
+    if dist is not None and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
 def synthetic_case(seed, b_img=B_IMG):
     from tests.helpers import boxinst_case
     return boxinst_case(seed, B=b_img, hp=HP, wp=WP, gts_per_img=GTS, inst_per_gt=INST_PER_GT)
@@ -99,7 +107,7 @@ def cpu_step(case):
 
 
 def run_cpu(steps, warmup):
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)      # torch CPU ops stop scaling (and oversubscribe) beyond this
     torch.set_num_threads(cores)
     case = synthetic_case(1234, b_img=1)          # bounded sample: ONE image, 64 instances
     for _ in range(warmup):
@@ -263,10 +271,7 @@ def main_cuda(args, rank, world, local_rank):
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop()
 
-    t = torch.tensor([ms_step, ms_e2e, ms_eager, us_fwd, us_bwd], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_e2e, ms_eager, us_fwd, us_bwd = t.tolist()
+    ms_step, ms_e2e, ms_eager, us_fwd, us_bwd = reduce_max_over_ranks([ms_step, ms_e2e, ms_eager, us_fwd, us_bwd], dist, dev)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -129,7 +129,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 // pixel tiles x, x + gridDim.x, ...
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_constant__ CUtensorMap tm_kern,
-                    float* __restrict__ out, int C, int P, int I, int n_chunks) {
+                    float* __restrict__ out, int C, int P, int I, int n_chunks, float* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,6 +153,16 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
+  if (dbg && warp >= 2) {                 // debug: poison the first 16 accumulator columns with 7.0
+    const uint32_t v = __float_as_uint(7.0f);
+    const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                 ::"r"(ta), "r"(v) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -190,6 +200,13 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
           tc_fence_after();
           const uint32_t a_base = smem_u32(S.a[stage]);
           const uint32_t b_base = smem_u32(S.b[kb]);
+          if (dbg && t == 0 && kb == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+            const float* fa = reinterpret_cast<const float*>(S.a[stage]);
+            const float* fb = reinterpret_cast<const float*>(S.b[kb]);
+            for (int i = 0; i < 64; ++i) { dbg[i] = fa[i]; dbg[64 + i] = fb[i]; }
+            dbg[128] = __uint_as_float(tmem_base); dbg[129] = __uint_as_float(idesc);
+            dbg[130] = __uint_as_float(a_base); dbg[131] = __uint_as_float(b_base);
+          }
 #pragma unroll
           for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4) {
             // A (MN-major): 8 k-rows = one 1 KB swizzle atom per 32-pixel group; groups 4 KB apart
@@ -218,6 +235,8 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
       for (int c0 = 0; c0 < n_here; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
+        if (dbg && t == 0 && c0 == 0 && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
+          for (int j = 0; j < 16; ++j) dbg[160 + (warp - 2) * 16 + j] = __uint_as_float(r[j]);
         if (pixel < P) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
@@ -273,6 +292,9 @@ using namespace bxs;
 
 // feat [B,C,P], kernels [B,I,C] -> out [B,I,P] (all float32, contiguous).  Requirements of the TMA/UMMA path:
 // C % 32 == 0, C <= 256, P % 4 == 0, 16-byte aligned bases.  BXS_ERR_UNSUPPORTED otherwise.
+static float* g_dbg = nullptr;
+extern "C" void bxs_dynconv1x1_set_debug(float* dbg) { g_dbg = dbg; }
+
 extern "C" int bxs_dynconv1x1_forward(const float* feat, const float* kernels, float* out, int64_t B, int64_t C, int64_t P,
                                       int64_t I, bxs_stream_t stream) {
   if (!feat || !kernels || !out || B <= 0 || C <= 0 || P <= 0 || I <= 0) return BXS_ERR_INVALID_ARG;
@@ -293,6 +315,6 @@ extern "C" int bxs_dynconv1x1_forward(const float* feat, const float* kernels, f
   const size_t smem = sizeof(SmemLayout) + 1024;
   cudaFuncSetAttribute(dynconv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dynconv_tf32_kernel<<<dim3(per_group, (unsigned)groups), NUM_THREADS, smem, as_stream(stream)>>>(
-      tm_feat, tm_kern, out, (int)C, (int)P, (int)I, n_chunks);
+      tm_feat, tm_kern, out, (int)C, (int)P, (int)I, n_chunks, g_dbg);
   return check_launch();
 }

@@ -1,0 +1,37 @@
+"""CPU: the registry surface -- classes build from the reference's own config dicts."""
+import torch
+
+
+def test_build_from_reference_config_kwargs():
+    from boxinstseg_b200.models import HEADS, LOSSES, build_head, build_loss
+    assert HEADS is LOSSES                                    # mmdet/models/builder.py:9-15: one registry
+    # configs/boxinst/boxinst_r50_fpn_1x_coco.py:54-71
+    head = build_head(dict(type='CondInstMaskHead', in_channels=16, in_stride=8, out_stride=4, dynamic_convs=3,
+                           dynamic_channels=8, disable_rel_coors=False, bbox_head_channels=256,
+                           sizes_of_interest=[64, 128, 256, 512, 1024], max_proposals=-1, topk_per_img=64,
+                           boxinst_enabled=True, bottom_pixels_removed=10, pairwise_size=3, pairwise_dilation=2,
+                           pairwise_color_thresh=0.3, pairwise_warmup=10000))
+    assert head.num_gen_params == 233 and head.param_conv.out_channels == 233
+    assert set(head.state_dict()) >= {'sizes_of_interest', '_iter', 'param_conv.weight', 'param_conv.bias'}
+    # configs/boxlevelset, configs/box2mask
+    assert build_loss(dict(type='BoxProjectionLoss', loss_weight=3.0)).loss_weight == 3.0
+    assert build_loss(dict(type='LevelsetLoss', loss_weight=1.0)).loss_weight == 1.0
+    assert build_head(dict(type='BoxSOLOv2Head', num_classes=80, in_channels=256)).num_classes == 80
+
+
+def test_empty_instances_follow_reference_branch():
+    from boxinstseg_b200.models import build_head
+    head = build_head(dict(type='CondInstMaskHead', in_channels=16, boxinst_enabled=True, max_proposals=-1, topk_per_img=64))
+    x = torch.zeros(0, 1, 8, 8, requires_grad=True)
+    out = head.loss(None, [], x, torch.zeros(0, dtype=torch.long), [], None, None)     # condinst_head.py:1306-1312
+    assert float(out['loss_prj']) == 0.0 and float(out['loss_pairwise']) == 0.0
+    assert float(head._iter) == 1.0
+
+
+def test_tree_filter_graph_construction_matches_oracle():
+    from boxinstseg_b200.ops.tree_filter import MinimumSpanningTree, TreeFilter2D
+    from oracle import tree as ot
+    fm = torch.randn(2, 3, 5, 7)
+    mst = MinimumSpanningTree(TreeFilter2D.norm2_distance)
+    assert (mst._build_matrix_index(fm)[0].numpy() == ot.grid_edges(5, 7)).all()
+    assert torch.equal(mst._build_feature_weight(fm), ot.grid_edge_weights(fm))
