@@ -159,6 +159,9 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
                  ::"r"(ta), "r"(v) : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    uint32_t rr[16];
+    tmem_ld16(ta, rr);
+    if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) dbg[224 + (warp - 2)] = __uint_as_float(rr[3]);   // poison read-back
   }
   tc_fence_before();
   __syncthreads();
@@ -247,6 +250,14 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
     }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (dbg && warp >= 2 && blockIdx.x == 0 && blockIdx.y == 0) {      // debug: read the accumulator again at kernel end
+    tc_fence_after();
+    uint32_t rr[16];
+    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16), rr);
+    if (lane == 0) for (int j = 0; j < 4; ++j) dbg[232 + (warp - 2) * 4 + j] = __uint_as_float(rr[j]);
   }
   tc_fence_before();
   __syncthreads();

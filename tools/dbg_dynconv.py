@@ -22,6 +22,7 @@ print('smem B[0:16]', d[64:80].tolist())
 print('kern[i=0,c=0:8]', kern[0, 0, :8].tolist())
 print('tmem_base %x idesc %x a_base %x b_base %x' % tuple(int(x) for x in d[128:132].view(torch.int32).tolist()))
 for wq in range(4): print('tmem warp', wq + 2, d[160 + 16 * wq:176 + 16 * wq].tolist())
+print('poison readback', d[224:228].tolist(), ' late read', d[232:248].tolist())
 ref = torch.einsum('bic,bchw->bihw', kern.double(), feat.double())
 print('ref[0,0:4,0,0]', ref[0, :4, 0, 0].tolist(), 'out', out[0, :4, 0, 0].tolist())
 print('out stats', out.min().item(), out.max().item(), 'ref max', ref.abs().max().item())
