@@ -422,11 +422,81 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const int32_t* __restrict_
                     iter_ptr, warmup_iters, losses_out, sh);
 }
 
+// Same arithmetic as finalize_instance, executed by ONE WARP (the fast path's last-arriving warp of an
+// instance), so no CTA barrier is involved in the tail of the forward kernel.
+__device__ void finalize_instance_warp(const int n, const Rect r, const int N, const int H, const int W, const Workspace& ws,
+                                       const float* __restrict__ iter_ptr, const float warmup_iters,
+                                       float* __restrict__ losses_out) {
+  const int lane = threadIdx.x & 31;
+  const bool empty = rect_empty(r);
+  const float inv_n = 1.f / (float)N;
+  float inst_loss = 0.f;
+  for (int axis = 0; axis < 2; ++axis) {
+    const int L = axis == 0 ? H : W;
+    const int lo = axis == 0 ? r.j0 : r.i0, hi = axis == 0 ? r.j1 : r.i1;
+    const unsigned long long* packed = (axis == 0 ? ws.row_packed + (int64_t)n * H : ws.col_packed + (int64_t)n * W);
+    float* coef = axis == 0 ? ws.coef_row + (int64_t)n * H : ws.coef_col + (int64_t)n * W;
+    int* arg = axis == 0 ? ws.row_arg + (int64_t)n * H : ws.col_arg + (int64_t)n * W;
+    float inter = 0.f, x2 = 0.f;
+    for (int i = lane; i < L; i += 32) {
+      const float s = sigmoid_exact(fkey_inv((unsigned)(__ldcg(packed + i) >> 32)));
+      inter += (!empty && i >= lo && i <= hi) ? s : 0.f;
+      x2 = fmaf(s, s, x2);
+    }
+    inter = warp_sum(inter);
+    x2 = warp_sum(x2);
+    const float t2 = empty ? 0.f : (float)(max(min(hi, L - 1) - max(lo, 0) + 1, 0));
+    const float U = x2 + t2 + kDiceEps, I = inter;
+    inst_loss += 1.f - 2.f * I / U;
+    for (int i = lane; i < L; i += 32) {
+      const unsigned long long p = __ldcg(packed + i);
+      const float s = sigmoid_exact(fkey_inv((unsigned)(p >> 32)));
+      const float t = (!empty && i >= lo && i <= hi) ? 1.f : 0.f;
+      coef[i] = inv_n * (-2.f * t / U + 4.f * I * s / (U * U)) * s * (1.f - s);
+      arg[i] = (int)(0xffffffffu - (unsigned)(p & 0xffffffffull));
+    }
+  }
+  float num = 0.f;
+  int den = 0;
+  for (int i = lane; i < H; i += 32) {
+    num += __ldcg(ws.pair_partial + (int64_t)n * H + i);
+    den += __ldcg(ws.den_partial + (int64_t)n * H + i);
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  bool last = false;
+  if (lane == 0) {
+    ws.inst_prj[n] = inst_loss;
+    ws.inst_num[n] = num;
+    if (den) atomicAdd(ws.weight_sum, (unsigned long long)den);
+    __threadfence();
+    last = atomicAdd(ws.ticket, 1u) == (unsigned)(N - 1);
+  }
+  last = __shfl_sync(kFull, last ? 1 : 0, 0) != 0;
+  if (!last) return;
+  __threadfence();
+  float prj = 0.f, pn = 0.f;
+  for (int i = lane; i < N; i += 32) { prj += __ldcg(ws.inst_prj + i); pn += __ldcg(ws.inst_num + i); }
+  prj = warp_sum(prj);
+  pn = warp_sum(pn);
+  if (lane == 0) {
+    const float wsum = (float)__ldcg(ws.weight_sum);
+    const float warm = fminf(iter_ptr[0] / warmup_iters, 1.f);
+    const float scale = warm / fmaxf(wsum, 1.f);
+    losses_out[0] = prj * inv_n;
+    losses_out[1] = pn * scale;
+    losses_out[2] = pn;
+    losses_out[3] = wsum;
+    ws.scale_pair[0] = scale;
+  }
+}
+
 // =========================================================================================
 // FAST PATH (W % 4 == 0, 16-byte aligned, W <= 512, dilation <= 4): no shared-memory tiles, no
 // work list.  One warp owns a full row; a lane owns NCHUNK groups of 4 consecutive pixels.
 // =========================================================================================
-constexpr int ROWS_PER_CTA = 16;            // 2 rows per warp, both in flight before any use
+constexpr int RPW = 3;                      // rows per warp, all in flight before any use
+constexpr int ROWS_PER_CTA = RPW * (NT / 32);
 
 // ---- pair terms, lane-per-pixel: a warp walks the box columns [c_lo, c_hi] of one row in segments of
 // 32 lanes of which the inner 32-2D "own" a pixel; horizontal neighbours come from warp shuffles, the
@@ -546,57 +616,74 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
                                                        Workspace ws, const float* __restrict__ iter_ptr,
                                                        float warmup_iters, float* __restrict__ losses_out) {
   constexpr int PANEL = NCHUNK * 128, NWARP = NT / 32;
-  __shared__ unsigned long long s_col[NWARP][PANEL];
-  __shared__ FinalizeShared sh;
+  __shared__ float s_val[NWARP][PANEL];
+  __shared__ int s_row[NWARP][PANEL];
   const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = inst_gt[n];
   const Rect r = load_rect(rects, g);
   const float* img = logits + (int64_t)n * H * W;
   const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
-  const int y0 = blockIdx.x * ROWS_PER_CTA + warp, y1 = y0 + NWARP;
+  const int ybase = blockIdx.x * ROWS_PER_CTA + warp;     // this warp's rows: ybase + k * NWARP
 
-  float va[NCHUNK * 4], vb[NCHUNK * 4];
+  float v[RPW][NCHUNK * 4];
 #pragma unroll
-  for (int ch = 0; ch < NCHUNK; ++ch) {                 // all loads of both rows first (memory-level parallelism)
-    const int col0 = (ch * 32 + lane) * 4;
-    float4 qa = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), qb = qa;
-    if (col0 < W) {
-      if (y0 < H) qa = __ldg(reinterpret_cast<const float4*>(img + (int64_t)y0 * W + col0));
-      if (y1 < H) qb = __ldg(reinterpret_cast<const float4*>(img + (int64_t)y1 * W + col0));
+  for (int k = 0; k < RPW; ++k) {                         // all loads first (memory-level parallelism)
+    const int y = ybase + k * NWARP;
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      const int col0 = (ch * 32 + lane) * 4;
+      float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (col0 < W && y < H) q = __ldg(reinterpret_cast<const float4*>(img + (int64_t)y * W + col0));
+      v[k][ch * 4] = q.x; v[k][ch * 4 + 1] = q.y; v[k][ch * 4 + 2] = q.z; v[k][ch * 4 + 3] = q.w;
     }
-    va[ch * 4] = qa.x; va[ch * 4 + 1] = qa.y; va[ch * 4 + 2] = qa.z; va[ch * 4 + 3] = qa.w;
-    vb[ch * 4] = qb.x; vb[ch * 4 + 1] = qb.y; vb[ch * 4 + 2] = qb.z; vb[ch * 4 + 3] = qb.w;
   }
   // ---- row maxima (warp-wide integer redux on the order-preserving key) ----
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int y = half ? y1 : y0;
-    const float* v = half ? vb : va;
+  for (int k = 0; k < RPW; ++k) {
+    const int y = ybase + k * NWARP;
     if (y < H) {                                         // warp-uniform
-      float m = v[0];
+      float m = v[k][0];
 #pragma unroll
-      for (int i = 1; i < NCHUNK * 4; ++i) m = fmaxf(m, v[i]);
+      for (int i = 1; i < NCHUNK * 4; ++i) m = fmaxf(m, v[k][i]);
       const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
       const float mv = fkey_inv(kmax);
       int cand = 0x7fffffff;
 #pragma unroll
       for (int i = NCHUNK * 4 - 1; i >= 0; --i)
-        if (v[i] == mv) cand = ((i >> 2) * 32 + lane) * 4 + (i & 3);
+        if (v[k][i] == mv) cand = ((i >> 2) * 32 + lane) * 4 + (i & 3);
       const int amin = __reduce_min_sync(kFull, cand);
       if (lane == 0) ws.row_packed[(int64_t)n * H + y] = pack_key(kmax, amin == 0x7fffffff ? 0 : amin);
     }
   }
-  // ---- column maxima of this CTA's 16 rows ----
+  // ---- column maxima of this warp's rows (strict '>' : the earlier row wins ties) ----
 #pragma unroll
   for (int i = 0; i < NCHUNK * 4; ++i) {
-    const bool second = y1 < H && vb[i] > va[i];         // strict: the earlier row wins ties
-    const float cv = second ? vb[i] : va[i];
-    s_col[warp][((i >> 2) * 32 + lane) * 4 + (i & 3)] = y0 < H ? pack_key(fkey(cv), second ? y1 : y0) : 0ull;
-  }
-  // ---- pairwise terms: only rows whose pixel or forward neighbour can lie in the box ----
+    float cv = v[0][i];
+    int cy = ybase;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int y = half ? y1 : y0;
+    for (int k = 1; k < RPW; ++k)
+      if (v[k][i] > cv) { cv = v[k][i]; cy = ybase + k * NWARP; }   // rows >= H hold -inf and never win
+    const int col = ((i >> 2) * 32 + lane) * 4 + (i & 3);
+    s_val[warp][col] = cv;
+    s_row[warp][col] = cy;
+  }
+  // ---- combine the column maxima of the CTA (balanced point: every warp has done the same work so far) ----
+  __syncthreads();
+  for (int c = threadIdx.x; c < PANEL; c += NT) {
+    float best = s_val[0][c];
+    int brow = s_row[0][c];
+#pragma unroll
+    for (int w = 1; w < NWARP; ++w) {
+      const float val = s_val[w][c];
+      const int row = s_row[w][c];
+      if (val > best || (val == best && row < brow)) { best = val; brow = row; }
+    }
+    if (c < W && brow < H) atomicMax(ws.col_packed + (int64_t)n * W + c, pack_key(fkey(best), brow));
+  }
+  // ---- pairwise terms: only rows whose pixel or forward neighbour can lie in the box (no CTA barrier below) ----
+#pragma unroll
+  for (int k = 0; k < RPW; ++k) {
+    const int y = ybase + k * NWARP;
     if (y >= H) continue;
     float acc = 0.f;
     int wsum = 0;
@@ -610,22 +697,15 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
       ws.den_partial[(int64_t)n * H + y] = wsum;
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < PANEL; c += NT) {
-    unsigned long long best = 0ull;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) best = s_col[w][c] > best ? s_col[w][c] : best;
-    if (best && c < W) atomicMax(ws.col_packed + (int64_t)n * W + c, best);
-  }
-  // ---- the last CTA of this instance finalizes it ----
+  // ---- the last WARP of this instance finalizes it ----
   __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) sh.last = atomicAdd(ws.inst_ticket + n, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!sh.last) return;
+  __syncwarp();
+  unsigned last = 0;
+  if (lane == 0) last = atomicAdd(ws.inst_ticket + n, 1u) == gridDim.x * NWARP - 1 ? 1u : 0u;
+  last = __shfl_sync(kFull, last, 0);
+  if (!last) return;
   __threadfence();
-  finalize_instance(n, r, N, H, W, ws, ws.pair_partial + (int64_t)n * H, H, ws.den_partial + (int64_t)n * H, H,
-                    iter_ptr, warmup_iters, losses_out, sh);
+  finalize_instance_warp(n, r, N, H, W, ws, iter_ptr, warmup_iters, losses_out);
 }
 
 template <int NCHUNK, int D>
@@ -647,12 +727,26 @@ __global__ void __launch_bounds__(NT, 3) bwd_rows_kernel(const float* __restrict
   const float* ccol = ws.coef_col + (int64_t)n * W;
   const int* acol = ws.col_arg + (int64_t)n * W;
   const bool have_box = !rect_empty(r);
+  const int y0 = blockIdx.x * ROWS_PER_CTA + warp;
+  // loop-invariant per lane: the column arg-max rows of its chunks; per row: arg-max column + coefficient
+  int4 ac[NCHUNK];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int y = blockIdx.x * ROWS_PER_CTA + warp + half * NWARP;
+  for (int ch = 0; ch < NCHUNK; ++ch) {
+    const int col0 = (ch * 32 + lane) * 4;
+    ac[ch] = col0 < W ? __ldg(reinterpret_cast<const int4*>(acol + col0)) : make_int4(-1, -1, -1, -1);
+  }
+  int ra[RPW];
+  float rc[RPW];
+#pragma unroll
+  for (int k = 0; k < RPW; ++k) {
+    const int y = y0 + k * NWARP;
+    ra[k] = y < H ? ws.row_arg[(int64_t)n * H + y] : -1;
+    rc[k] = y < H ? ws.coef_row[(int64_t)n * H + y] * g_prj : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < RPW; ++k) {
+    const int y = y0 + k * NWARP;
     if (y >= H) continue;
-    const int ra = ws.row_arg[(int64_t)n * H + y];
-    const float rc = ws.coef_row[(int64_t)n * H + y] * g_prj;
     const bool row_in = have_box && y >= r.j0 - D && y <= r.j1 + D;     // warp-uniform
     const int c_lo = row_in ? max(r.i0 - D, 0) : W, c_hi = row_in ? min(r.i1 + D, W - 1) : -1;
     float* grow = g_logits + (int64_t)n * H * W + (int64_t)y * W;
@@ -662,15 +756,14 @@ __global__ void __launch_bounds__(NT, 3) bwd_rows_kernel(const float* __restrict
       if (col0 >= W) continue;
       if (col0 >= c_lo && col0 + 3 <= c_hi) continue;                   // fully inside the box span: pair pass writes it
       float out[4] = {0.f, 0.f, 0.f, 0.f};
-      const int4 ac = __ldg(reinterpret_cast<const int4*>(acol + col0));
-      if ((unsigned)(ra - col0) < 4u) {
+      if ((unsigned)(ra[k] - col0) < 4u) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (ra - col0 == e) out[e] += rc;
+        for (int e = 0; e < 4; ++e) if (ra[k] - col0 == e) out[e] += rc[k];
       }
-      if (ac.x == y) out[0] += ccol[col0] * g_prj;
-      if (ac.y == y) out[1] += ccol[col0 + 1] * g_prj;
-      if (ac.z == y) out[2] += ccol[col0 + 2] * g_prj;
-      if (ac.w == y) out[3] += ccol[col0 + 3] * g_prj;
+      if (ac[ch].x == y) out[0] += ccol[col0] * g_prj;
+      if (ac[ch].y == y) out[1] += ccol[col0 + 1] * g_prj;
+      if (ac[ch].z == y) out[2] += ccol[col0 + 2] * g_prj;
+      if (ac[ch].w == y) out[3] += ccol[col0 + 3] * g_prj;
       if (col0 + 3 < c_lo || col0 > c_hi) {
         *reinterpret_cast<float4*>(grow + col0) = make_float4(out[0], out[1], out[2], out[3]);
       } else {                                                          // straddles the span boundary
@@ -679,7 +772,7 @@ __global__ void __launch_bounds__(NT, 3) bwd_rows_kernel(const float* __restrict
           if (col0 + e < c_lo || col0 + e > c_hi) grow[col0 + e] = out[e];
       }
     }
-    if (row_in) pair_row_bwd<D>(img, bits, H, W, y, r, lane, g_pair, ra, rc, acol, ccol, g_prj, grow);
+    if (row_in) pair_row_bwd<D>(img, bits, H, W, y, r, lane, g_pair, ra[k], rc[k], acol, ccol, g_prj, grow);
   }
 }
 

@@ -8,8 +8,10 @@
 //
 // GEMM view per image:  D[M = pixels, N = kernels] = A[M, K] * B[N, K]^T
 //   A = feat^T : the pixel index is contiguous in memory -> "MN-major" operand, staged by TMA as
-//       [k-row][32 pixels] boxes with the 128-byte swizzle (canonical ((8,n),(8,k)) layout, LBO = 4 KB
-//       between 32-pixel groups, SBO = 1 KB between groups of 8 k-rows);
+//       [k-row][32 pixels] boxes with the 128-byte swizzle on 32-BYTE atoms (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+//       <-> UMMA SWIZZLE_128B_BASE32B: the layout the tensor core requires for an MN-major 32-bit operand;
+//       the ordinary 128B swizzle silently yields zeros), LBO = 4 KB between 32-pixel groups, SBO = 512 B between
+//       groups of 4 k-rows;
 //   B = kernel : K-major, [row = kernel][32 channels] boxes with the 128-byte swizzle (SBO = 1 KB);
 //   D          : 128 TMEM lanes (pixels) x N <= 128 fp32 columns, double buffered (256 columns).
 // The op is HBM bound (each feat tile is read once: 128 KB per 128 pixels; B stays resident in shared
@@ -83,13 +85,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
 }
 
 // shared-memory matrix descriptor (SM100): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | swizzle-128B (2) << 61
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only swizzled layout the
+// tensor core accepts for an MN-major 32-bit operand)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -129,7 +133,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 // pixel tiles x, x + gridDim.x, ...
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_constant__ CUtensorMap tm_kern,
-                    float* __restrict__ out, int C, int P, int I, int n_chunks, float* __restrict__ dbg) {
+                    float* __restrict__ out, int C, int P, int I, int n_chunks) {
   extern __shared__ uint8_t smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,20 +157,6 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
-  if (dbg && warp >= 2) {                 // debug: poison the first 16 accumulator columns with 7.0
-    const uint32_t v = __float_as_uint(7.0f);
-    const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-                 ::"r"(ta), "r"(v) : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    uint32_t rr[16];
-    tmem_ld16(ta, rr);
-    if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) dbg[224 + (warp - 2)] = __uint_as_float(rr[3]);   // poison read-back
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -203,19 +193,13 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
           tc_fence_after();
           const uint32_t a_base = smem_u32(S.a[stage]);
           const uint32_t b_base = smem_u32(S.b[kb]);
-          if (dbg && t == 0 && kb == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-            const float* fa = reinterpret_cast<const float*>(S.a[stage]);
-            const float* fb = reinterpret_cast<const float*>(S.b[kb]);
-            for (int i = 0; i < 64; ++i) { dbg[i] = fa[i]; dbg[64 + i] = fb[i]; }
-            dbg[128] = __uint_as_float(tmem_base); dbg[129] = __uint_as_float(idesc);
-            dbg[130] = __uint_as_float(a_base); dbg[131] = __uint_as_float(b_base);
-          }
 #pragma unroll
           for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4) {
-            // A (MN-major): 8 k-rows = one 1 KB swizzle atom per 32-pixel group; groups 4 KB apart
-            const uint64_t adesc = make_desc(a_base + k4 * 1024, BLOCK_K * 128, 1024);
-            // B (K-major): advance 32 bytes inside the 128-byte swizzled row; 8-row groups 1 KB apart
-            const uint64_t bdesc = make_desc(b_base + k4 * (UMMA_K * 4), 16, 1024);
+            // A (MN-major, 128B swizzle with 32-byte atoms): 8 k-rows = two 512-byte atoms (SBO) per 32-pixel group;
+            // the 32-pixel groups (one TMA box each) are 4 KB apart (LBO)
+            const uint64_t adesc = make_desc(a_base + k4 * 1024, BLOCK_K * 128, 512, 1);
+            // B (K-major, 128B swizzle): advance 32 bytes inside the 128-byte swizzled row; 8-row groups 1 KB apart
+            const uint64_t bdesc = make_desc(b_base + k4 * (UMMA_K * 4), 16, 1024, 2);
             umma_tf32(tmem_d, adesc, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
           }
           umma_commit(&S.empty[stage]);            // frees this A stage once the MMAs have read it
@@ -238,8 +222,6 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
       for (int c0 = 0; c0 < n_here; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
-        if (dbg && t == 0 && c0 == 0 && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
-          for (int j = 0; j < 16; ++j) dbg[160 + (warp - 2) * 16 + j] = __uint_as_float(r[j]);
         if (pixel < P) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
@@ -250,14 +232,6 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);
     }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (dbg && warp >= 2 && blockIdx.x == 0 && blockIdx.y == 0) {      // debug: read the accumulator again at kernel end
-    tc_fence_after();
-    uint32_t rr[16];
-    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16), rr);
-    if (lane == 0) for (int j = 0; j < 4; ++j) dbg[232 + (warp - 2) * 4 + j] = __uint_as_float(rr[j]);
   }
   tc_fence_before();
   __syncthreads();
@@ -284,7 +258,7 @@ EncodeTiledFn encode_fn() {
 }
 
 // row-major [rows, cols] float32 matrix, box = [box_rows, 32 floats], 128-byte swizzle, zero fill out of bounds
-bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows) {
+bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -292,7 +266,7 @@ bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, i
   cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -303,9 +277,6 @@ using namespace bxs;
 
 // feat [B,C,P], kernels [B,I,C] -> out [B,I,P] (all float32, contiguous).  Requirements of the TMA/UMMA path:
 // C % 32 == 0, C <= 256, P % 4 == 0, 16-byte aligned bases.  BXS_ERR_UNSUPPORTED otherwise.
-static float* g_dbg = nullptr;
-extern "C" void bxs_dynconv1x1_set_debug(float* dbg) { g_dbg = dbg; }
-
 extern "C" int bxs_dynconv1x1_forward(const float* feat, const float* kernels, float* out, int64_t B, int64_t C, int64_t P,
                                       int64_t I, bxs_stream_t stream) {
   if (!feat || !kernels || !out || B <= 0 || C <= 0 || P <= 0 || I <= 0) return BXS_ERR_INVALID_ARG;
@@ -313,7 +284,8 @@ extern "C" int bxs_dynconv1x1_forward(const float* feat, const float* kernels, f
       (reinterpret_cast<uintptr_t>(kernels) & 15) || B * C >= (int64_t(1) << 31) || B * I >= (int64_t(1) << 31))
     return BXS_ERR_UNSUPPORTED;
   CUtensorMap tm_feat, tm_kern;
-  if (!make_map(&tm_feat, feat, B * C, P, BLOCK_K) || !make_map(&tm_kern, kernels, B * I, C, BLOCK_N)) {
+  if (!make_map(&tm_feat, feat, B * C, P, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map(&tm_kern, kernels, B * I, C, BLOCK_N, CU_TENSOR_MAP_SWIZZLE_128B)) {
     set_last_error(cudaErrorNotSupported);
     return BXS_ERR_LAUNCH;
   }
@@ -326,6 +298,6 @@ extern "C" int bxs_dynconv1x1_forward(const float* feat, const float* kernels, f
   const size_t smem = sizeof(SmemLayout) + 1024;
   cudaFuncSetAttribute(dynconv_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dynconv_tf32_kernel<<<dim3(per_group, (unsigned)groups), NUM_THREADS, smem, as_stream(stream)>>>(
-      tm_feat, tm_kern, out, (int)C, (int)P, (int)I, n_chunks, g_dbg);
+      tm_feat, tm_kern, out, (int)C, (int)P, (int)I, n_chunks);
   return check_launch();
 }
