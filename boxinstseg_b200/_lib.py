@@ -60,6 +60,7 @@ SIGNATURES = {
     'bxs_refine_backward_feature': [c_p] * 10 + [c_i64] * 3 + [c_p],
     'bxs_refine_backward_weight': [c_p] * 14 + [c_i64] * 3 + [c_p],
     'bxs_dynconv1x1_forward': [c_p] * 3 + [c_i64] * 4 + [c_p],
+    'bxs_upsampled_rowcol_max': [c_p] * 4 + [c_i64] * 5 + [c_int, c_p],
 }
 _RESTYPE = {'bxs_mst_workspace_bytes': c_i64, 'bxs_bfs_workspace_bytes': c_i64, 'bxs_refine_scratch_bytes': c_i64, 'bxs_lcm_workspace_bytes': c_i64, 'bxs_meanfield_workspace_bytes': c_i64, 'bxs_projection_workspace_bytes': c_i64, 'bxs_levelset_workspace_bytes': c_i64, 'bxs_condinst_head_workspace_bytes': c_i64, 'bxs_last_error': ctypes.c_char_p, 'bxs_boxinst_loss_workspace_bytes': c_i64}
 

@@ -495,7 +495,7 @@ __device__ void finalize_instance_warp(const int n, const Rect r, const int N, c
 // FAST PATH (W % 4 == 0, 16-byte aligned, W <= 512, dilation <= 4): no shared-memory tiles, no
 // work list.  One warp owns a full row; a lane owns NCHUNK groups of 4 consecutive pixels.
 // =========================================================================================
-constexpr int RPW = 3;                      // rows per warp, all in flight before any use
+constexpr int RPW = 2;                      // rows per warp, all in flight before any use
 constexpr int ROWS_PER_CTA = RPW * (NT / 32);
 
 // ---- pair terms, lane-per-pixel: a warp walks the box columns [c_lo, c_hi] of one row in segments of
@@ -607,6 +607,13 @@ __device__ __forceinline__ void pair_row_bwd(const float* __restrict__ img, cons
   }
 }
 
+// Both fast-path kernels use a HETEROGENEOUS grid per instance (blockIdx.y = instance):
+//   blockIdx.x <  strips : streaming role -- 16 rows of the map (2 per warp), full width
+//   blockIdx.x >= strips : pair role      -- sub-block s of PAIR_BLOCKS; its 8 warps take the rows of the box span
+//                                            round-robin, so pair work is divided evenly whatever the box size
+// The two roles touch disjoint outputs and overlap on the SMs (one is load/store bound, the other ALU bound).
+constexpr int PAIR_BLOCKS = 8;
+
 template <int NCHUNK, int D>
 __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restrict__ logits,
                                                        const uint8_t* __restrict__ edge_bits,
@@ -614,165 +621,180 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
                                                        const int32_t* __restrict__ inst_gt,
                                                        const int32_t* __restrict__ gt_img, int N, int H, int W,
                                                        Workspace ws, const float* __restrict__ iter_ptr,
-                                                       float warmup_iters, float* __restrict__ losses_out) {
+                                                       float warmup_iters, float* __restrict__ losses_out, int strips) {
   constexpr int PANEL = NCHUNK * 128, NWARP = NT / 32;
   __shared__ float s_val[NWARP][PANEL];
   __shared__ int s_row[NWARP][PANEL];
+  __shared__ FinalizeShared sh;
   const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = inst_gt[n];
   const Rect r = load_rect(rects, g);
   const float* img = logits + (int64_t)n * H * W;
-  const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
-  const int ybase = blockIdx.x * ROWS_PER_CTA + warp;     // this warp's rows: ybase + k * NWARP
+  // rows whose pixel or forward neighbour can lie in the box
+  const int p_lo = rect_empty(r) ? 0 : max(r.j0 - D, 0), p_hi = rect_empty(r) ? -1 : min(r.j1, H - 1);
 
-  float v[RPW][NCHUNK * 4];
+  if ((int)blockIdx.x < strips) {
+    // ================= streaming role: row / column maxima =================
+    const int ybase = blockIdx.x * ROWS_PER_CTA + warp;     // this warp's rows: ybase + k * NWARP
+    float v[RPW][NCHUNK * 4];
 #pragma unroll
-  for (int k = 0; k < RPW; ++k) {                         // all loads first (memory-level parallelism)
-    const int y = ybase + k * NWARP;
+    for (int k = 0; k < RPW; ++k) {                         // all loads first (memory-level parallelism)
+      const int y = ybase + k * NWARP;
 #pragma unroll
-    for (int ch = 0; ch < NCHUNK; ++ch) {
-      const int col0 = (ch * 32 + lane) * 4;
-      float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      if (col0 < W && y < H) q = __ldg(reinterpret_cast<const float4*>(img + (int64_t)y * W + col0));
-      v[k][ch * 4] = q.x; v[k][ch * 4 + 1] = q.y; v[k][ch * 4 + 2] = q.z; v[k][ch * 4 + 3] = q.w;
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int col0 = (ch * 32 + lane) * 4;
+        float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (col0 < W && y < H) q = __ldg(reinterpret_cast<const float4*>(img + (int64_t)y * W + col0));
+        v[k][ch * 4] = q.x; v[k][ch * 4 + 1] = q.y; v[k][ch * 4 + 2] = q.z; v[k][ch * 4 + 3] = q.w;
+      }
     }
-  }
-  // ---- row maxima (warp-wide integer redux on the order-preserving key) ----
 #pragma unroll
-  for (int k = 0; k < RPW; ++k) {
-    const int y = ybase + k * NWARP;
-    if (y < H) {                                         // warp-uniform
-      float m = v[k][0];
+    for (int k = 0; k < RPW; ++k) {                         // row maxima: integer redux on the order-preserving key
+      const int y = ybase + k * NWARP;
+      if (y < H) {                                          // warp-uniform
+        float m = v[k][0];
 #pragma unroll
-      for (int i = 1; i < NCHUNK * 4; ++i) m = fmaxf(m, v[k][i]);
-      const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
-      const float mv = fkey_inv(kmax);
-      int cand = 0x7fffffff;
+        for (int i = 1; i < NCHUNK * 4; ++i) m = fmaxf(m, v[k][i]);
+        const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
+        const float mv = fkey_inv(kmax);
+        int cand = 0x7fffffff;
 #pragma unroll
-      for (int i = NCHUNK * 4 - 1; i >= 0; --i)
-        if (v[k][i] == mv) cand = ((i >> 2) * 32 + lane) * 4 + (i & 3);
-      const int amin = __reduce_min_sync(kFull, cand);
-      if (lane == 0) ws.row_packed[(int64_t)n * H + y] = pack_key(kmax, amin == 0x7fffffff ? 0 : amin);
+        for (int i = NCHUNK * 4 - 1; i >= 0; --i)
+          if (v[k][i] == mv) cand = ((i >> 2) * 32 + lane) * 4 + (i & 3);
+        const int amin = __reduce_min_sync(kFull, cand);
+        if (lane == 0) ws.row_packed[(int64_t)n * H + y] = pack_key(kmax, amin == 0x7fffffff ? 0 : amin);
+      }
     }
-  }
-  // ---- column maxima of this warp's rows (strict '>' : the earlier row wins ties) ----
 #pragma unroll
-  for (int i = 0; i < NCHUNK * 4; ++i) {
-    float cv = v[0][i];
-    int cy = ybase;
+    for (int i = 0; i < NCHUNK * 4; ++i) {                  // column maxima (strict '>': the earlier row wins ties)
+      float cv = v[0][i];
+      int cy = ybase;
 #pragma unroll
-    for (int k = 1; k < RPW; ++k)
-      if (v[k][i] > cv) { cv = v[k][i]; cy = ybase + k * NWARP; }   // rows >= H hold -inf and never win
-    const int col = ((i >> 2) * 32 + lane) * 4 + (i & 3);
-    s_val[warp][col] = cv;
-    s_row[warp][col] = cy;
-  }
-  // ---- combine the column maxima of the CTA (balanced point: every warp has done the same work so far) ----
-  __syncthreads();
-  for (int c = threadIdx.x; c < PANEL; c += NT) {
-    float best = s_val[0][c];
-    int brow = s_row[0][c];
-#pragma unroll
-    for (int w = 1; w < NWARP; ++w) {
-      const float val = s_val[w][c];
-      const int row = s_row[w][c];
-      if (val > best || (val == best && row < brow)) { best = val; brow = row; }
+      for (int k = 1; k < RPW; ++k)
+        if (v[k][i] > cv) { cv = v[k][i]; cy = ybase + k * NWARP; }   // rows >= H hold -inf and never win
+      const int col = ((i >> 2) * 32 + lane) * 4 + (i & 3);
+      s_val[warp][col] = cv;
+      s_row[warp][col] = cy;
     }
-    if (c < W && brow < H) atomicMax(ws.col_packed + (int64_t)n * W + c, pack_key(fkey(best), brow));
-  }
-  // ---- pairwise terms: only rows whose pixel or forward neighbour can lie in the box (no CTA barrier below) ----
+    __syncthreads();
+    for (int c = threadIdx.x; c < PANEL; c += NT) {
+      float best = s_val[0][c];
+      int brow = s_row[0][c];
 #pragma unroll
-  for (int k = 0; k < RPW; ++k) {
-    const int y = ybase + k * NWARP;
-    if (y >= H) continue;
-    float acc = 0.f;
-    int wsum = 0;
-    if (!rect_empty(r) && y >= r.j0 - D && y <= r.j1) {   // warp-uniform
+      for (int w = 1; w < NWARP; ++w) {
+        const float val = s_val[w][c];
+        const int row = s_row[w][c];
+        if (val > best || (val == best && row < brow)) { best = val; brow = row; }
+      }
+      if (c < W && brow < H) atomicMax(ws.col_packed + (int64_t)n * W + c, pack_key(fkey(best), brow));
+    }
+  } else {
+    // ================= pair role: rows of the box span, round-robin over PAIR_BLOCKS * 8 warps =================
+    const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
+    const int gw = ((int)blockIdx.x - strips) * NWARP + warp;
+    for (int y = p_lo + gw; y <= p_hi; y += PAIR_BLOCKS * NWARP) {
+      float acc = 0.f;
+      int wsum = 0;
       pair_row_fwd<D>(img, bits, H, W, y, r, lane, acc, wsum);
       acc = warp_sum(acc);
       wsum = warp_sum(wsum);
-    }
-    if (lane == 0) {
-      ws.pair_partial[(int64_t)n * H + y] = acc;
-      ws.den_partial[(int64_t)n * H + y] = wsum;
+      if (lane == 0) {
+        ws.pair_partial[(int64_t)n * H + y] = acc;
+        ws.den_partial[(int64_t)n * H + y] = wsum;
+      }
     }
   }
-  // ---- the last WARP of this instance finalizes it ----
+  // ---- the last CTA of this instance (either role) finalizes it ----
   __threadfence();
-  __syncwarp();
-  unsigned last = 0;
-  if (lane == 0) last = atomicAdd(ws.inst_ticket + n, 1u) == gridDim.x * NWARP - 1 ? 1u : 0u;
-  last = __shfl_sync(kFull, last, 0);
-  if (!last) return;
+  __syncthreads();
+  if (threadIdx.x == 0) sh.last = atomicAdd(ws.inst_ticket + n, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!sh.last) return;
   __threadfence();
-  finalize_instance_warp(n, r, N, H, W, ws, iter_ptr, warmup_iters, losses_out);
+  const int np = max(p_hi - p_lo + 1, 0);
+  finalize_instance(n, r, N, H, W, ws, ws.pair_partial + (int64_t)n * H + p_lo, np, ws.den_partial + (int64_t)n * H + p_lo, np,
+                    iter_ptr, warmup_iters, losses_out, sh);
 }
 
 template <int NCHUNK, int D>
-__global__ void __launch_bounds__(NT, 3) bwd_rows_kernel(const float* __restrict__ logits,
+__global__ void __launch_bounds__(NT, 4) bwd_rows_kernel(const float* __restrict__ logits,
                                                       const uint8_t* __restrict__ edge_bits,
                                                       const int32_t* __restrict__ rects,
                                                       const int32_t* __restrict__ inst_gt,
                                                       const int32_t* __restrict__ gt_img, int H, int W, Workspace ws,
                                                       const float* __restrict__ g_losses,
-                                                      float* __restrict__ g_logits) {
+                                                      float* __restrict__ g_logits, int strips) {
   constexpr int NWARP = NT / 32;
   const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = inst_gt[n];
   const Rect r = load_rect(rects, g);
   const float g_prj = g_losses[0];
-  const float g_pair = g_losses[1] * ws.scale_pair[0];
-  const float* img = logits + (int64_t)n * H * W;
-  const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
   const float* ccol = ws.coef_col + (int64_t)n * W;
   const int* acol = ws.col_arg + (int64_t)n * W;
   const bool have_box = !rect_empty(r);
-  const int y0 = blockIdx.x * ROWS_PER_CTA + warp;
-  // loop-invariant per lane: the column arg-max rows of its chunks; per row: arg-max column + coefficient
-  int4 ac[NCHUNK];
-#pragma unroll
-  for (int ch = 0; ch < NCHUNK; ++ch) {
-    const int col0 = (ch * 32 + lane) * 4;
-    ac[ch] = col0 < W ? __ldg(reinterpret_cast<const int4*>(acol + col0)) : make_int4(-1, -1, -1, -1);
-  }
-  int ra[RPW];
-  float rc[RPW];
-#pragma unroll
-  for (int k = 0; k < RPW; ++k) {
-    const int y = y0 + k * NWARP;
-    ra[k] = y < H ? ws.row_arg[(int64_t)n * H + y] : -1;
-    rc[k] = y < H ? ws.coef_row[(int64_t)n * H + y] * g_prj : 0.f;
-  }
-#pragma unroll
-  for (int k = 0; k < RPW; ++k) {
-    const int y = y0 + k * NWARP;
-    if (y >= H) continue;
-    const bool row_in = have_box && y >= r.j0 - D && y <= r.j1 + D;     // warp-uniform
-    const int c_lo = row_in ? max(r.i0 - D, 0) : W, c_hi = row_in ? min(r.i1 + D, W - 1) : -1;
-    float* grow = g_logits + (int64_t)n * H * W + (int64_t)y * W;
+  // pixels that can receive a pairwise gradient: rows [q_lo, q_hi] x columns [c_lo, c_hi]
+  const int q_lo = have_box ? max(r.j0 - D, 0) : 0, q_hi = have_box ? min(r.j1 + D, H - 1) : -1;
+  const int s_lo = have_box ? max(r.i0 - D, 0) : W, s_hi = have_box ? min(r.i1 + D, W - 1) : -1;
+
+  if ((int)blockIdx.x < strips) {
+    // ================= streaming role: zeros + projection arg-max terms outside the box span =================
+    const int y0 = blockIdx.x * ROWS_PER_CTA + warp;
+    int4 ac[NCHUNK];                                        // loop invariant: column arg-max rows of this lane's chunks
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
       const int col0 = (ch * 32 + lane) * 4;
-      if (col0 >= W) continue;
-      if (col0 >= c_lo && col0 + 3 <= c_hi) continue;                   // fully inside the box span: pair pass writes it
-      float out[4] = {0.f, 0.f, 0.f, 0.f};
-      if ((unsigned)(ra[k] - col0) < 4u) {
+      ac[ch] = col0 < W ? __ldg(reinterpret_cast<const int4*>(acol + col0)) : make_int4(-1, -1, -1, -1);
+    }
+    int ra[RPW];
+    float rc[RPW];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (ra[k] - col0 == e) out[e] += rc[k];
-      }
-      if (ac[ch].x == y) out[0] += ccol[col0] * g_prj;
-      if (ac[ch].y == y) out[1] += ccol[col0 + 1] * g_prj;
-      if (ac[ch].z == y) out[2] += ccol[col0 + 2] * g_prj;
-      if (ac[ch].w == y) out[3] += ccol[col0 + 3] * g_prj;
-      if (col0 + 3 < c_lo || col0 > c_hi) {
-        *reinterpret_cast<float4*>(grow + col0) = make_float4(out[0], out[1], out[2], out[3]);
-      } else {                                                          // straddles the span boundary
+    for (int k = 0; k < RPW; ++k) {
+      const int y = y0 + k * NWARP;
+      ra[k] = y < H ? ws.row_arg[(int64_t)n * H + y] : -1;
+      rc[k] = y < H ? ws.coef_row[(int64_t)n * H + y] * g_prj : 0.f;
+    }
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (col0 + e < c_lo || col0 + e > c_hi) grow[col0 + e] = out[e];
+    for (int k = 0; k < RPW; ++k) {
+      const int y = y0 + k * NWARP;
+      if (y >= H) continue;
+      const bool row_in = y >= q_lo && y <= q_hi;           // warp-uniform
+      const int c_lo = row_in ? s_lo : W, c_hi = row_in ? s_hi : -1;
+      float* grow = g_logits + (int64_t)n * H * W + (int64_t)y * W;
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int col0 = (ch * 32 + lane) * 4;
+        if (col0 >= W) continue;
+        if (col0 >= c_lo && col0 + 3 <= c_hi) continue;     // fully inside the span: the pair role writes it
+        float out[4] = {0.f, 0.f, 0.f, 0.f};
+        if ((unsigned)(ra[k] - col0) < 4u) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (ra[k] - col0 == e) out[e] += rc[k];
+        }
+        if (ac[ch].x == y) out[0] += ccol[col0] * g_prj;
+        if (ac[ch].y == y) out[1] += ccol[col0 + 1] * g_prj;
+        if (ac[ch].z == y) out[2] += ccol[col0 + 2] * g_prj;
+        if (ac[ch].w == y) out[3] += ccol[col0 + 3] * g_prj;
+        if (col0 + 3 < c_lo || col0 > c_hi) {
+          *reinterpret_cast<float4*>(grow + col0) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {                                            // straddles the span boundary
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (col0 + e < c_lo || col0 + e > c_hi) grow[col0 + e] = out[e];
+        }
       }
     }
-    if (row_in) pair_row_bwd<D>(img, bits, H, W, y, r, lane, g_pair, ra[k], rc[k], acol, ccol, g_prj, grow);
+  } else {
+    // ================= pair role: gather-form gradient of the span pixels =================
+    const float g_pair = g_losses[1] * ws.scale_pair[0];
+    const float* img = logits + (int64_t)n * H * W;
+    const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
+    const int gw = ((int)blockIdx.x - strips) * NWARP + warp;
+    for (int y = q_lo + gw; y <= q_hi; y += PAIR_BLOCKS * NWARP) {
+      const int ra = ws.row_arg[(int64_t)n * H + y];
+      const float rc = ws.coef_row[(int64_t)n * H + y] * g_prj;
+      pair_row_bwd<D>(img, bits, H, W, y, r, lane, g_pair, ra, rc, acol, ccol, g_prj,
+                      g_logits + (int64_t)n * H * W + (int64_t)y * W);
+    }
   }
 }
 
@@ -890,7 +912,7 @@ void launch_fwd_fast(int d, dim3 grid, cudaStream_t st, const float* logits, con
 #define BXS_CASE(DD)                                                                                          \
   case DD:                                                                                                    \
     fwd_fused_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, N, H, W, ws, \
-                                                      iter_ptr, warmup_iters, losses_out);                    \
+                                                      iter_ptr, warmup_iters, losses_out, (int)grid.x - PAIR_BLOCKS); \
     break;
   switch (d) { BXS_CASE(1) BXS_CASE(2) BXS_CASE(3) BXS_CASE(4) }
 #undef BXS_CASE
@@ -903,7 +925,7 @@ void launch_bwd_fast(int d, dim3 grid, cudaStream_t st, const float* logits, con
 #define BXS_CASE(DD)                                                                                              \
   case DD:                                                                                                        \
     bwd_rows_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, H, W, ws, g_losses, \
-                                                     g_logits);                                                   \
+                                                     g_logits, (int)grid.x - PAIR_BLOCKS);                        \
     break;
   switch (d) { BXS_CASE(1) BXS_CASE(2) BXS_CASE(3) BXS_CASE(4) }
 #undef BXS_CASE
@@ -924,7 +946,7 @@ extern "C" int bxs_boxinst_loss_forward(const float* logits, const uint8_t* edge
   if (fast_ok(logits, edge_bits, logits, W, d)) {
     // one fused streaming kernel: maxima + in-box pair terms + per-instance finalize
     cudaMemsetAsync(workspace, 0, ws.zero_bytes_fast, st);
-    dim3 grid((unsigned)ceil_div(H, ROWS_PER_CTA), (unsigned)N);
+    dim3 grid((unsigned)ceil_div(H, ROWS_PER_CTA) + PAIR_BLOCKS, (unsigned)N);
     if (W <= 128) launch_fwd_fast<1>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
     else if (W <= 256) launch_fwd_fast<2>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
     else launch_fwd_fast<4>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
@@ -971,7 +993,7 @@ extern "C" int bxs_boxinst_loss_backward(const float* logits, const uint8_t* edg
   Workspace ws = carve(const_cast<void*>(workspace), N, H, W);
   const int d = dilation;
   if (fast_ok(logits, edge_bits, g_logits, W, d)) {
-    dim3 grid((unsigned)ceil_div(H, ROWS_PER_CTA), (unsigned)N);
+    dim3 grid((unsigned)ceil_div(H, ROWS_PER_CTA) + PAIR_BLOCKS, (unsigned)N);
     if (W <= 128) launch_bwd_fast<1>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);
     else if (W <= 256) launch_bwd_fast<2>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);
     else launch_bwd_fast<4>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);

@@ -465,3 +465,105 @@ extern "C" int bxs_length_reg_backward(const float* scores, const float* g_out, 
   length_bwd_kernel<<<blocks, NT, 0, as_stream(stream)>>>(scores, g_out, (int)C, (int)h, (int)w, total, g_scores);
   return check_launch();
 }
+
+// ---------------------------------------------------------------------------------------
+// projection profiles of a bilinearly UPSAMPLED map without materialising it.
+// BoxMatchingCost (mmdet/core/bbox/match_costs/match_cost.py:400-425) takes row / column maxima of the mask
+// predictions after Box2MaskHead._get_target_single upsampled them to the GT resolution
+// (box2mask_head.py:157-161: [100,1,1024,1024] = 420 MB per image per decoder layer).  Here every output pixel is
+// evaluated on the fly (PyTorch bilinear, align_corners=False) and reduced immediately.
+// ---------------------------------------------------------------------------------------
+namespace bxs {
+namespace {
+
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;        // area_pixel_compute_source_index, align_corners=False
+  src = src < 0.f ? 0.f : src;
+  i0 = min((int)src, in_size - 1);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+constexpr int UPK = 32;                                   // output columns per lane and panel -> panel = 1024 columns
+
+// grid (row groups, n), 256 threads; warp w handles output rows Y = group*rows_per_block + w, +8, ...
+__global__ void __launch_bounds__(NT) upsampled_rowcol_max_kernel(const float* __restrict__ x, int h, int w, int H, int W,
+                                                                  int rows_per_block, float sy, float sx,
+                                                                  unsigned* __restrict__ row_key,
+                                                                  unsigned* __restrict__ col_key) {
+  extern __shared__ float s_b[];                          // [8 warps][w] vertically blended low-res rows
+  const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* in = x + (int64_t)n * h * w;
+  float* b = s_b + warp * w;
+  const int y_begin = blockIdx.x * rows_per_block, y_end = min(y_begin + rows_per_block, H);
+  for (int panel0 = 0; panel0 < W; panel0 += 32 * UPK) {
+    float cmax[UPK];
+#pragma unroll
+    for (int k = 0; k < UPK; ++k) cmax[k] = -INFINITY;
+    for (int Y = y_begin + warp; Y < y_end; Y += NT / 32) {
+      int y0, y1;
+      float fy;
+      bilinear_src(Y, sy, h, y0, y1, fy);
+      for (int i = lane; i < w; i += 32)
+        b[i] = (1.f - fy) * __ldg(in + (int64_t)y0 * w + i) + fy * __ldg(in + (int64_t)y1 * w + i);
+      __syncwarp();
+      float rmax = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < UPK; ++k) {
+        const int X = panel0 + k * 32 + lane;
+        if (X < W) {
+          int x0, x1;
+          float fx;
+          bilinear_src(X, sx, w, x0, x1, fx);
+          const float v = (1.f - fx) * b[x0] + fx * b[x1];
+          rmax = fmaxf(rmax, v);
+          cmax[k] = fmaxf(cmax[k], v);
+        }
+      }
+      const unsigned rk = __reduce_max_sync(kFull, fkey(rmax));
+      if (lane == 0) atomicMax(row_key + (int64_t)n * H + Y, rk);      // several panels may contribute
+      __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < UPK; ++k) {
+      const int X = panel0 + k * 32 + lane;
+      if (X < W && cmax[k] > -INFINITY) atomicMax(col_key + (int64_t)n * W + X, fkey(cmax[k]));
+    }
+  }
+}
+
+__global__ void decode_keys_kernel(const unsigned* __restrict__ keys, float* __restrict__ out, int64_t total, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fkey_inv(keys[i]);
+    out[i] = act ? 1.f / (1.f + expf(-v)) : v;
+  }
+}
+
+}  // namespace
+}  // namespace bxs
+
+// x [n,h,w] -> row_prof [n,H], col_prof [n,W]: maxima over the (virtual) bilinear resize of x to H x W, optionally
+// followed by a sigmoid (monotone, so applied to the profiles).  H == h and W == w gives plain row/column maxima.
+// workspace: (n*H + n*W) * 4 bytes.
+extern "C" int bxs_upsampled_rowcol_max(const float* x, float* row_prof, float* col_prof, void* workspace, int64_t n,
+                                        int64_t h, int64_t w, int64_t H, int64_t W, int sigmoid_act, bxs_stream_t stream) {
+  if (!x || !row_prof || !col_prof || !workspace || n <= 0 || n >= 65536 || h <= 0 || w <= 0 || H <= 0 || W <= 0)
+    return BXS_ERR_INVALID_ARG;
+  if (w > 8192) return BXS_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  unsigned* row_key = (unsigned*)workspace;
+  unsigned* col_key = row_key + n * H;
+  cudaMemsetAsync(workspace, 0, sizeof(unsigned) * n * (H + W), st);
+  int groups = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(H, 8), ceil_div((int64_t)sm_count() * 4, n)));
+  const int rows = (int)ceil_div(H, groups);
+  groups = (int)ceil_div(H, rows);
+  const size_t sm = (size_t)(NT / 32) * w * sizeof(float);
+  if (sm > 48 * 1024) cudaFuncSetAttribute(upsampled_rowcol_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  upsampled_rowcol_max_kernel<<<dim3(groups, (unsigned)n), NT, sm, st>>>(x, (int)h, (int)w, (int)H, (int)W, rows,
+                                                                         (float)h / (float)H, (float)w / (float)W, row_key,
+                                                                         col_key);
+  const int64_t tr = n * H, tc = n * W;
+  decode_keys_kernel<<<(unsigned)std::min<int64_t>(ceil_div(tr, 256), 1024), 256, 0, st>>>(row_key, row_prof, tr, sigmoid_act);
+  decode_keys_kernel<<<(unsigned)std::min<int64_t>(ceil_div(tc, 256), 1024), 256, 0, st>>>(col_key, col_prof, tc, sigmoid_act);
+  return check_launch();
+}

@@ -243,6 +243,16 @@ int bxs_refine_backward_weight(const float* edge_weight, const int32_t* sorted_i
 int bxs_dynconv1x1_forward(const float* feat, const float* kernels, float* out, int64_t B, int64_t C, int64_t P,
                            int64_t I, bxs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ *   projection profiles of a bilinearly resized map, never materialised.
+ *     replaces, for BoxMatchingCost (mmdet/core/bbox/match_costs/match_cost.py:400-425), the F.interpolate of
+ *     the query masks to GT resolution (mmdet/models/dense_heads/box2mask_head.py:157-161) + max(dim).
+ * x [n,h,w] -> row_prof [n,H] (max over columns), col_prof [n,W] (max over rows) of resize(x, (H,W), bilinear,
+ * align_corners=False); sigmoid_act applies the (monotone) sigmoid to the profiles.  workspace: 4*n*(H+W) bytes.
+ * --------------------------------------------------------------------------------------- */
+int bxs_upsampled_rowcol_max(const float* x, float* row_prof, float* col_prof, void* workspace, int64_t n,
+                             int64_t h, int64_t w, int64_t H, int64_t W, int sigmoid_act, bxs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
