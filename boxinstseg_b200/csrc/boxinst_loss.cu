@@ -70,8 +70,9 @@ inline Workspace carve(void* base, int64_t N, int64_t H, int64_t W) {
   w.col_arg = (int*)take(sizeof(int) * N * W);
   w.tile_prefix = (int*)take(sizeof(int) * (N + 1));
   const int64_t tiles_full = ceil_div(H, TH) * ceil_div(W, TW);
-  w.pair_partial = (float*)take(sizeof(float) * N * (tiles_full > H ? tiles_full : H));
-  w.den_partial = (int*)take(sizeof(int) * N * H);
+  const int64_t per_inst = std::max<int64_t>(tiles_full, H * 24);      // generic: tiles; fast: H * SEG_MAX items
+  w.pair_partial = (float*)take(sizeof(float) * N * per_inst);
+  w.den_partial = (int*)take(sizeof(int) * N * per_inst);
   w.inst_prj = (float*)take(sizeof(float) * N);
   w.inst_num = (float*)take(sizeof(float) * N);
   w.scale_pair = (float*)take(sizeof(float));
@@ -422,75 +423,6 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const int32_t* __restrict_
                     iter_ptr, warmup_iters, losses_out, sh);
 }
 
-// Same arithmetic as finalize_instance, executed by ONE WARP (the fast path's last-arriving warp of an
-// instance), so no CTA barrier is involved in the tail of the forward kernel.
-__device__ void finalize_instance_warp(const int n, const Rect r, const int N, const int H, const int W, const Workspace& ws,
-                                       const float* __restrict__ iter_ptr, const float warmup_iters,
-                                       float* __restrict__ losses_out) {
-  const int lane = threadIdx.x & 31;
-  const bool empty = rect_empty(r);
-  const float inv_n = 1.f / (float)N;
-  float inst_loss = 0.f;
-  for (int axis = 0; axis < 2; ++axis) {
-    const int L = axis == 0 ? H : W;
-    const int lo = axis == 0 ? r.j0 : r.i0, hi = axis == 0 ? r.j1 : r.i1;
-    const unsigned long long* packed = (axis == 0 ? ws.row_packed + (int64_t)n * H : ws.col_packed + (int64_t)n * W);
-    float* coef = axis == 0 ? ws.coef_row + (int64_t)n * H : ws.coef_col + (int64_t)n * W;
-    int* arg = axis == 0 ? ws.row_arg + (int64_t)n * H : ws.col_arg + (int64_t)n * W;
-    float inter = 0.f, x2 = 0.f;
-    for (int i = lane; i < L; i += 32) {
-      const float s = sigmoid_exact(fkey_inv((unsigned)(__ldcg(packed + i) >> 32)));
-      inter += (!empty && i >= lo && i <= hi) ? s : 0.f;
-      x2 = fmaf(s, s, x2);
-    }
-    inter = warp_sum(inter);
-    x2 = warp_sum(x2);
-    const float t2 = empty ? 0.f : (float)(max(min(hi, L - 1) - max(lo, 0) + 1, 0));
-    const float U = x2 + t2 + kDiceEps, I = inter;
-    inst_loss += 1.f - 2.f * I / U;
-    for (int i = lane; i < L; i += 32) {
-      const unsigned long long p = __ldcg(packed + i);
-      const float s = sigmoid_exact(fkey_inv((unsigned)(p >> 32)));
-      const float t = (!empty && i >= lo && i <= hi) ? 1.f : 0.f;
-      coef[i] = inv_n * (-2.f * t / U + 4.f * I * s / (U * U)) * s * (1.f - s);
-      arg[i] = (int)(0xffffffffu - (unsigned)(p & 0xffffffffull));
-    }
-  }
-  float num = 0.f;
-  int den = 0;
-  for (int i = lane; i < H; i += 32) {
-    num += __ldcg(ws.pair_partial + (int64_t)n * H + i);
-    den += __ldcg(ws.den_partial + (int64_t)n * H + i);
-  }
-  num = warp_sum(num);
-  den = warp_sum(den);
-  bool last = false;
-  if (lane == 0) {
-    ws.inst_prj[n] = inst_loss;
-    ws.inst_num[n] = num;
-    if (den) atomicAdd(ws.weight_sum, (unsigned long long)den);
-    __threadfence();
-    last = atomicAdd(ws.ticket, 1u) == (unsigned)(N - 1);
-  }
-  last = __shfl_sync(kFull, last ? 1 : 0, 0) != 0;
-  if (!last) return;
-  __threadfence();
-  float prj = 0.f, pn = 0.f;
-  for (int i = lane; i < N; i += 32) { prj += __ldcg(ws.inst_prj + i); pn += __ldcg(ws.inst_num + i); }
-  prj = warp_sum(prj);
-  pn = warp_sum(pn);
-  if (lane == 0) {
-    const float wsum = (float)__ldcg(ws.weight_sum);
-    const float warm = fminf(iter_ptr[0] / warmup_iters, 1.f);
-    const float scale = warm / fmaxf(wsum, 1.f);
-    losses_out[0] = prj * inv_n;
-    losses_out[1] = pn * scale;
-    losses_out[2] = pn;
-    losses_out[3] = wsum;
-    ws.scale_pair[0] = scale;
-  }
-}
-
 // =========================================================================================
 // FAST PATH (W % 4 == 0, 16-byte aligned, W <= 512, dilation <= 4): no shared-memory tiles, no
 // work list.  One warp owns a full row; a lane owns NCHUNK groups of 4 consecutive pixels.
@@ -529,11 +461,10 @@ __device__ __forceinline__ RowSeg load_seg(const float* __restrict__ img, const 
 }
 
 template <int D>
-__device__ __forceinline__ void pair_row_fwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
-                                             int y, const Rect& r, int lane, float& acc, int& wsum) {
-  const int c_lo = max(r.i0 - D, 0), c_hi = min(r.i1 + D, W - 1);
+__device__ __forceinline__ void pair_seg_fwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
+                                             int y, int xs, int c_hi, const Rect& r, int lane, float& acc, int& wsum) {
   const bool owner_lane = lane >= D && lane < 32 - D;
-  for (int xs = c_lo - D; xs + D <= c_hi; xs += 32 - 2 * D) {
+  {
     const int x = xs + lane;
     const RowSeg a = load_seg(img, bits, H, W, y, x, r);
     const RowSeg b = load_seg(img, bits, H, W, y + D, x, r);
@@ -565,13 +496,12 @@ __device__ __forceinline__ void pair_row_fwd(const float* __restrict__ img, cons
 
 // gradient of one row's box pixels (lane-per-pixel); also adds the projection arg-max terms and stores
 template <int D>
-__device__ __forceinline__ void pair_row_bwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
-                                             int y, const Rect& r, int lane, float g_pair, int ra, float rc,
+__device__ __forceinline__ void pair_seg_bwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
+                                             int y, int xs, int c_hi, const Rect& r, int lane, float g_pair, int ra, float rc,
                                              const int* __restrict__ acol, const float* __restrict__ ccol, float g_prj,
                                              float* __restrict__ grow) {
-  const int c_lo = max(r.i0 - D, 0), c_hi = min(r.i1 + D, W - 1);
   const bool owner_lane = lane >= D && lane < 32 - D;
-  for (int xs = c_lo - D; xs + D <= c_hi; xs += 32 - 2 * D) {
+  {
     const int x = xs + lane;
     const RowSeg t = load_seg(img, bits, H, W, y - D, x, r);
     const RowSeg m0 = load_seg(img, bits, H, W, y, x, r);
@@ -607,35 +537,42 @@ __device__ __forceinline__ void pair_row_bwd(const float* __restrict__ img, cons
   }
 }
 
-// Both fast-path kernels use a HETEROGENEOUS grid per instance (blockIdx.y = instance):
-//   blockIdx.x <  strips : streaming role -- 16 rows of the map (2 per warp), full width
-//   blockIdx.x >= strips : pair role      -- sub-block s of PAIR_BLOCKS; its 8 warps take the rows of the box span
-//                                            round-robin, so pair work is divided evenly whatever the box size
-// The two roles touch disjoint outputs and overlap on the SMs (one is load/store bound, the other ALU bound).
-constexpr int PAIR_BLOCKS = 8;
+// Both fast-path kernels use a HETEROGENEOUS grid, blockIdx.x = instance, blockIdx.y = role:
+//   y <  PAIR_BLOCKS : pair role      -- the (row, 28-pixel segment) items of the box span, round-robin over
+//                                        PAIR_BLOCKS * 8 warps (scheduled first: they are the long, latency-bound CTAs)
+//   y >= PAIR_BLOCKS : streaming role -- 16 rows of the map (2 per warp), full width
+// The two roles touch disjoint outputs and overlap on the SMs (one is load/store bound, the other ALU/latency bound).
+constexpr int PAIR_BLOCKS = 16;
+constexpr int SEG_MAX = 24;                 // segments per row: ceil(W / (32 - 2D)) <= 22 for W <= 512, D <= 4
+
+struct Span { int y_lo, y_hi, c_lo, c_hi, nseg; };
+template <int D>
+__device__ __forceinline__ Span pair_span(const Rect& r, int H, int W, bool backward) {
+  Span s;
+  if (rect_empty(r)) { s.y_lo = 0; s.y_hi = -1; s.c_lo = 0; s.c_hi = -1; s.nseg = 0; return s; }
+  s.y_lo = max(r.j0 - D, 0);
+  s.y_hi = backward ? min(r.j1 + D, H - 1) : min(r.j1, H - 1);
+  s.c_lo = max(r.i0 - D, 0);
+  s.c_hi = min(r.i1 + D, W - 1);
+  s.nseg = (s.c_hi - s.c_lo + 1 + (32 - 2 * D) - 1) / (32 - 2 * D);
+  return s;
+}
 
 template <int NCHUNK, int D>
 __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restrict__ logits,
                                                        const uint8_t* __restrict__ edge_bits,
                                                        const int32_t* __restrict__ rects,
                                                        const int32_t* __restrict__ inst_gt,
-                                                       const int32_t* __restrict__ gt_img, int N, int H, int W,
-                                                       Workspace ws, const float* __restrict__ iter_ptr,
-                                                       float warmup_iters, float* __restrict__ losses_out, int strips) {
+                                                       const int32_t* __restrict__ gt_img, int H, int W, Workspace ws) {
   constexpr int PANEL = NCHUNK * 128, NWARP = NT / 32;
   __shared__ float s_val[NWARP][PANEL];
   __shared__ int s_row[NWARP][PANEL];
-  __shared__ FinalizeShared sh;
-  const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = inst_gt[n];
-  const Rect r = load_rect(rects, g);
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* img = logits + (int64_t)n * H * W;
-  // rows whose pixel or forward neighbour can lie in the box
-  const int p_lo = rect_empty(r) ? 0 : max(r.j0 - D, 0), p_hi = rect_empty(r) ? -1 : min(r.j1, H - 1);
 
-  if ((int)blockIdx.x < strips) {
+  if ((int)blockIdx.y >= PAIR_BLOCKS) {
     // ================= streaming role: row / column maxima =================
-    const int ybase = blockIdx.x * ROWS_PER_CTA + warp;     // this warp's rows: ybase + k * NWARP
+    const int ybase = ((int)blockIdx.y - PAIR_BLOCKS) * ROWS_PER_CTA + warp;     // this warp's rows: ybase + k * NWARP
     float v[RPW][NCHUNK * 4];
 #pragma unroll
     for (int k = 0; k < RPW; ++k) {                         // all loads first (memory-level parallelism)
@@ -689,31 +626,41 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
       if (c < W && brow < H) atomicMax(ws.col_packed + (int64_t)n * W + c, pack_key(fkey(best), brow));
     }
   } else {
-    // ================= pair role: rows of the box span, round-robin over PAIR_BLOCKS * 8 warps =================
+    // ================= pair role: (row, segment) items of the box span =================
+    const int g = inst_gt[n];
+    const Rect r = load_rect(rects, g);
     const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
-    const int gw = ((int)blockIdx.x - strips) * NWARP + warp;
-    for (int y = p_lo + gw; y <= p_hi; y += PAIR_BLOCKS * NWARP) {
+    const Span sp = pair_span<D>(r, H, W, false);
+    const int items = (sp.y_hi - sp.y_lo + 1) * sp.nseg;
+    for (int it = (int)blockIdx.y * NWARP + warp; it < items; it += PAIR_BLOCKS * NWARP) {
+      const int y = sp.y_lo + it / sp.nseg, seg = it % sp.nseg;
       float acc = 0.f;
       int wsum = 0;
-      pair_row_fwd<D>(img, bits, H, W, y, r, lane, acc, wsum);
+      pair_seg_fwd<D>(img, bits, H, W, y, sp.c_lo - D + seg * (32 - 2 * D), sp.c_hi, r, lane, acc, wsum);
       acc = warp_sum(acc);
       wsum = warp_sum(wsum);
       if (lane == 0) {
-        ws.pair_partial[(int64_t)n * H + y] = acc;
-        ws.den_partial[(int64_t)n * H + y] = wsum;
+        ws.pair_partial[(int64_t)n * H * SEG_MAX + it] = acc;
+        ws.den_partial[(int64_t)n * H * SEG_MAX + it] = wsum;
       }
     }
   }
-  // ---- the last CTA of this instance (either role) finalizes it ----
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) sh.last = atomicAdd(ws.inst_ticket + n, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!sh.last) return;
-  __threadfence();
-  const int np = max(p_hi - p_lo + 1, 0);
-  finalize_instance(n, r, N, H, W, ws, ws.pair_partial + (int64_t)n * H + p_lo, np, ws.den_partial + (int64_t)n * H + p_lo, np,
-                    iter_ptr, warmup_iters, losses_out, sh);
+}
+
+// one CTA per instance: dice terms, gradient coefficients, scalars (separate launch: no fences / tickets in the
+// streaming kernel)
+template <int D>
+__global__ void __launch_bounds__(NT) finalize_fast_kernel(const int32_t* __restrict__ rects,
+                                                           const int32_t* __restrict__ inst_gt, int N, int H, int W,
+                                                           Workspace ws, const float* __restrict__ iter_ptr,
+                                                           float warmup_iters, float* __restrict__ losses_out) {
+  __shared__ FinalizeShared sh;
+  const int n = blockIdx.x;
+  const Rect r = load_rect(rects, inst_gt[n]);
+  const Span sp = pair_span<D>(r, H, W, false);
+  const int items = (sp.y_hi - sp.y_lo + 1) * sp.nseg;
+  finalize_instance(n, r, N, H, W, ws, ws.pair_partial + (int64_t)n * H * SEG_MAX, items,
+                    ws.den_partial + (int64_t)n * H * SEG_MAX, items, iter_ptr, warmup_iters, losses_out, sh);
 }
 
 template <int NCHUNK, int D>
@@ -723,22 +670,19 @@ __global__ void __launch_bounds__(NT, 4) bwd_rows_kernel(const float* __restrict
                                                       const int32_t* __restrict__ inst_gt,
                                                       const int32_t* __restrict__ gt_img, int H, int W, Workspace ws,
                                                       const float* __restrict__ g_losses,
-                                                      float* __restrict__ g_logits, int strips) {
+                                                      float* __restrict__ g_logits) {
   constexpr int NWARP = NT / 32;
-  const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = inst_gt[n];
   const Rect r = load_rect(rects, g);
   const float g_prj = g_losses[0];
   const float* ccol = ws.coef_col + (int64_t)n * W;
   const int* acol = ws.col_arg + (int64_t)n * W;
-  const bool have_box = !rect_empty(r);
-  // pixels that can receive a pairwise gradient: rows [q_lo, q_hi] x columns [c_lo, c_hi]
-  const int q_lo = have_box ? max(r.j0 - D, 0) : 0, q_hi = have_box ? min(r.j1 + D, H - 1) : -1;
-  const int s_lo = have_box ? max(r.i0 - D, 0) : W, s_hi = have_box ? min(r.i1 + D, W - 1) : -1;
+  const Span sp = pair_span<D>(r, H, W, true);            // pixels that can receive a pairwise gradient
 
-  if ((int)blockIdx.x < strips) {
+  if ((int)blockIdx.y >= PAIR_BLOCKS) {
     // ================= streaming role: zeros + projection arg-max terms outside the box span =================
-    const int y0 = blockIdx.x * ROWS_PER_CTA + warp;
+    const int y0 = ((int)blockIdx.y - PAIR_BLOCKS) * ROWS_PER_CTA + warp;
     int4 ac[NCHUNK];                                        // loop invariant: column arg-max rows of this lane's chunks
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
@@ -757,8 +701,8 @@ __global__ void __launch_bounds__(NT, 4) bwd_rows_kernel(const float* __restrict
     for (int k = 0; k < RPW; ++k) {
       const int y = y0 + k * NWARP;
       if (y >= H) continue;
-      const bool row_in = y >= q_lo && y <= q_hi;           // warp-uniform
-      const int c_lo = row_in ? s_lo : W, c_hi = row_in ? s_hi : -1;
+      const bool row_in = y >= sp.y_lo && y <= sp.y_hi;     // warp-uniform
+      const int c_lo = row_in ? sp.c_lo : W, c_hi = row_in ? sp.c_hi : -1;
       float* grow = g_logits + (int64_t)n * H * W + (int64_t)y * W;
 #pragma unroll
       for (int ch = 0; ch < NCHUNK; ++ch) {
@@ -788,11 +732,12 @@ __global__ void __launch_bounds__(NT, 4) bwd_rows_kernel(const float* __restrict
     const float g_pair = g_losses[1] * ws.scale_pair[0];
     const float* img = logits + (int64_t)n * H * W;
     const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
-    const int gw = ((int)blockIdx.x - strips) * NWARP + warp;
-    for (int y = q_lo + gw; y <= q_hi; y += PAIR_BLOCKS * NWARP) {
+    const int items = (sp.y_hi - sp.y_lo + 1) * sp.nseg;
+    for (int it = (int)blockIdx.y * NWARP + warp; it < items; it += PAIR_BLOCKS * NWARP) {
+      const int y = sp.y_lo + it / sp.nseg, seg = it % sp.nseg;
       const int ra = ws.row_arg[(int64_t)n * H + y];
       const float rc = ws.coef_row[(int64_t)n * H + y] * g_prj;
-      pair_row_bwd<D>(img, bits, H, W, y, r, lane, g_pair, ra, rc, acol, ccol, g_prj,
+      pair_seg_bwd<D>(img, bits, H, W, y, sp.c_lo - D + seg * (32 - 2 * D), sp.c_hi, r, lane, g_pair, ra, rc, acol, ccol, g_prj,
                       g_logits + (int64_t)n * H * W + (int64_t)y * W);
     }
   }
@@ -909,10 +854,10 @@ template <int NCHUNK>
 void launch_fwd_fast(int d, dim3 grid, cudaStream_t st, const float* logits, const uint8_t* edge_bits,
                      const int32_t* rects, const int32_t* inst_gt, const int32_t* gt_img, int N, int H, int W,
                      Workspace ws, const float* iter_ptr, float warmup_iters, float* losses_out) {
-#define BXS_CASE(DD)                                                                                          \
-  case DD:                                                                                                    \
-    fwd_fused_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, N, H, W, ws, \
-                                                      iter_ptr, warmup_iters, losses_out, (int)grid.x - PAIR_BLOCKS); \
+#define BXS_CASE(DD)                                                                                             \
+  case DD:                                                                                                       \
+    fwd_fused_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, H, W, ws);      \
+    finalize_fast_kernel<DD><<<N, NT, 0, st>>>(rects, inst_gt, N, H, W, ws, iter_ptr, warmup_iters, losses_out); \
     break;
   switch (d) { BXS_CASE(1) BXS_CASE(2) BXS_CASE(3) BXS_CASE(4) }
 #undef BXS_CASE
@@ -925,7 +870,7 @@ void launch_bwd_fast(int d, dim3 grid, cudaStream_t st, const float* logits, con
 #define BXS_CASE(DD)                                                                                              \
   case DD:                                                                                                        \
     bwd_rows_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, H, W, ws, g_losses, \
-                                                     g_logits, (int)grid.x - PAIR_BLOCKS);                        \
+                                                     g_logits);                                                   \
     break;
   switch (d) { BXS_CASE(1) BXS_CASE(2) BXS_CASE(3) BXS_CASE(4) }
 #undef BXS_CASE
@@ -946,7 +891,7 @@ extern "C" int bxs_boxinst_loss_forward(const float* logits, const uint8_t* edge
   if (fast_ok(logits, edge_bits, logits, W, d)) {
     // one fused streaming kernel: maxima + in-box pair terms + per-instance finalize
     cudaMemsetAsync(workspace, 0, ws.zero_bytes_fast, st);
-    dim3 grid((unsigned)ceil_div(H, ROWS_PER_CTA) + PAIR_BLOCKS, (unsigned)N);
+    dim3 grid((unsigned)N, (unsigned)ceil_div(H, ROWS_PER_CTA) + PAIR_BLOCKS);
     if (W <= 128) launch_fwd_fast<1>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
     else if (W <= 256) launch_fwd_fast<2>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
     else launch_fwd_fast<4>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
@@ -993,7 +938,7 @@ extern "C" int bxs_boxinst_loss_backward(const float* logits, const uint8_t* edg
   Workspace ws = carve(const_cast<void*>(workspace), N, H, W);
   const int d = dilation;
   if (fast_ok(logits, edge_bits, g_logits, W, d)) {
-    dim3 grid((unsigned)ceil_div(H, ROWS_PER_CTA) + PAIR_BLOCKS, (unsigned)N);
+    dim3 grid((unsigned)N, (unsigned)ceil_div(H, ROWS_PER_CTA) + PAIR_BLOCKS);
     if (W <= 128) launch_bwd_fast<1>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);
     else if (W <= 256) launch_bwd_fast<2>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);
     else launch_bwd_fast<4>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);

@@ -171,12 +171,16 @@ __global__ void bfs_adj_kernel(const int32_t* __restrict__ tree, BfsWs ws, int V
   }
 }
 
+// ascending neighbour ids, unused slots = INT_MAX, so one 16-byte load per vertex describes its adjacency
 __global__ void bfs_sort_adj_kernel(BfsWs ws, int64_t BV) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < BV; i += (int64_t)gridDim.x * blockDim.x) {
     int* a = ws.adj + i * 4;
     const int d = min(ws.deg[i], 4);
-    for (int x = 1; x < d; ++x)
-      for (int y = x; y > 0 && a[y] < a[y - 1]; --y) { const int t = a[y]; a[y] = a[y - 1]; a[y - 1] = t; }
+    int v[4];
+    for (int x = 0; x < 4; ++x) v[x] = x < d ? a[x] : 0x7fffffff;
+    for (int x = 1; x < 4; ++x)
+      for (int y = x; y > 0 && v[y] < v[y - 1]; --y) { const int t = v[y]; v[y] = v[y - 1]; v[y - 1] = t; }
+    *reinterpret_cast<int4*>(a) = make_int4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -210,44 +214,51 @@ __device__ __forceinline__ int block_excl_scan(int val, int* s_warp, int* total)
 
 // one CTA per tree.  Level l occupies positions [level_start[l], level_start[l+1]); children of a
 // vertex are contiguous and ordered by ascending vertex id; parents are non-decreasing in position.
+// The frontier's (vertex, parent vertex) pairs are handed from level to level through shared memory, so a level
+// costs ONE dependent global load (the 16-byte adjacency record) plus a block scan.
 __global__ void __launch_bounds__(NT) bfs_block_kernel(BfsWs ws, int V, int32_t* __restrict__ sorted_index,
                                                        int32_t* __restrict__ sorted_parent,
                                                        int32_t* __restrict__ sorted_child,
                                                        int32_t* __restrict__ level_start,
                                                        int32_t* __restrict__ num_levels) {
   __shared__ int s_warp[33];
+  __shared__ int s_v[2][NT], s_pv[2][NT];
   const int b = blockIdx.x;
-  const int* deg = ws.deg + (int64_t)b * V;
-  const int* adj = ws.adj + (int64_t)b * V * 4;
+  const int4* adj = reinterpret_cast<const int4*>(ws.adj + (int64_t)b * V * 4);
+  int* pvert = ws.counts + (int64_t)b * V;           // parent VERTEX of each position (frontiers wider than NT)
   int32_t* idx = sorted_index + (int64_t)b * V;
   int32_t* par = sorted_parent + (int64_t)b * V;
   int32_t* chd = sorted_child + (int64_t)b * V * 4;
   int32_t* lvl = level_start + (int64_t)b * (V + 1);
-  for (int i = threadIdx.x; i < V * 4; i += NT) chd[i] = 0;
-  if (threadIdx.x == 0) { idx[0] = 0; par[0] = 0; lvl[0] = 0; }
+  for (int i = threadIdx.x; i < V; i += NT) reinterpret_cast<int4*>(chd)[i] = make_int4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { idx[0] = 0; par[0] = 0; lvl[0] = 0; pvert[0] = -1; s_v[0][0] = 0; s_pv[0][0] = -1; }
   __syncthreads();
-  int ls = 0, le = 1, level = 0;
+  int ls = 0, le = 1, level = 0, cur = 0;
   while (ls < le) {
     int next = le;                                  // first free position
     for (int base = ls; base < le; base += NT) {    // frontier in chunks of NT positions
       const int p = base + threadIdx.x;
       int v = -1, pv = -1, cnt = 0;
+      int4 a = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
       if (p < le) {
-        v = idx[p];
-        pv = p == 0 ? -1 : idx[par[p]];
-        const int d = min(deg[v], 4);
-        for (int k = 0; k < d; ++k) cnt += adj[v * 4 + k] != pv;
+        if (p - ls < NT) { v = s_v[cur][p - ls]; pv = s_pv[cur][p - ls]; }
+        else { v = idx[p]; pv = pvert[p]; }
+        a = __ldg(adj + v);
+        cnt = (a.x < V && a.x != pv) + (a.y < V && a.y != pv) + (a.z < V && a.z != pv) + (a.w < V && a.w != pv);
       }
       int total;
       const int off = block_excl_scan(cnt, s_warp, &total);
       if (p < le) {
         int q = next + off, k2 = 0;
-        const int d = min(deg[v], 4);
-        for (int k = 0; k < d; ++k) {
-          const int u = adj[v * 4 + k];
-          if (u == pv) continue;
+        const int nb[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int u = nb[k];
+          if (u >= V || u == pv) continue;
           idx[q] = u;
           par[q] = p;
+          pvert[q] = v;
+          if (q - le < NT) { s_v[cur ^ 1][q - le] = u; s_pv[cur ^ 1][q - le] = v; }
           chd[p * 4 + k2++] = q;
           ++q;
         }
@@ -257,6 +268,7 @@ __global__ void __launch_bounds__(NT) bfs_block_kernel(BfsWs ws, int V, int32_t*
     }
     ls = le;
     le = next;
+    cur ^= 1;
     ++level;
     if (threadIdx.x == 0) lvl[level] = ls;
     __syncthreads();
@@ -298,56 +310,139 @@ __global__ void __launch_bounds__(NT) levels_from_parent_kernel(const int32_t* _
 // ---------------------------------------------------------------------------------------
 // tree aggregation
 // ---------------------------------------------------------------------------------------
+// The recursion has one dependent step per tree level (~1700 levels for a 200x256 image MST), so the cost of a
+// level IS the kernel time.  Everything a level needs is therefore (a) made chain-free by parallel pre-passes
+// (values gathered into position order; child weights packed next to the child range) and (b) prefetched into
+// registers PF levels ahead, so that the per-level critical path is shared-memory read -> FMA -> write -> barrier.
+constexpr int PF = 4;                    // software-pipeline depth (levels in flight)
+
 struct TreeView {
   const int32_t* idx;     // [V] position -> vertex
   const int32_t* par;     // [V] position of the parent
-  const int32_t* chd;     // [V,4] positions of the children, 0 terminated
   const int32_t* lvl;     // [L+1]
   const float* w;         // [V] edge weight to the parent, position order (w[0] treated as 0)
+  const int32_t* cinfo;   // [V] first child position | (child count << 28)
+  const float4* cw;       // [V] weights of the (<= 4) children, in child order
   int V, L;
 };
 
-// U[p] = in(p) + sum_children w[c] U[c], deepest level first.  `buf` (shared or global) is position indexed.
-template <class In>
-__device__ __forceinline__ void up_pass(const TreeView& t, In in, float* buf, float* __restrict__ save_up) {
-  for (int l = t.L - 1; l >= 0; --l) {
-    const int s = t.lvl[l], e = t.lvl[l + 1];
-    for (int p = s + threadIdx.x; p < e; p += NT) {
-      float acc = in(p);
+// children are contiguous in position order (bfs_block_kernel); pack the range and the child weights per node
+__global__ void tree_pack_kernel(const float* __restrict__ w, const int32_t* __restrict__ chd, int32_t* __restrict__ cinfo,
+                                 float4* __restrict__ cw, int V, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / V;
+    const int32_t* c = chd + i * 4;
+    const float* wb = w + b * V;
+    int first = 0, n = 0;
+    float cv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = t.chd[p * 4 + k];
-        if (c <= 0) break;
-        acc = fmaf(buf[c], t.w[c], acc);
-      }
-      buf[p] = acc;
-      if (save_up) save_up[p] = acc;
+    for (int k = 0; k < 4; ++k) {
+      const int q = c[k];
+      if (q > 0 && n == k) { if (k == 0) first = q; cv[k] = wb[q]; ++n; }
     }
-    __syncthreads();
+    cinfo[i] = first | (n << 28);
+    cw[i] = make_float4(cv[0], cv[1], cv[2], cv[3]);
   }
 }
 
-// in place: A[0] = U[0]; A[p] = (1 - w^2) U[p] + w A[par]; writes vertex-ordered result
+struct UpNode { int s, e, ci; float4 cw; };
+struct DownNode { int s, e, par, idx; float w; };
+
+__device__ __forceinline__ UpNode fetch_up(const TreeView& t, int l) {
+  UpNode n;
+  n.s = n.e = 0; n.ci = 0; n.cw = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (l >= 0 && l < t.L) {
+    n.s = __ldg(t.lvl + l); n.e = __ldg(t.lvl + l + 1);
+    const int p = n.s + threadIdx.x;
+    if (p < n.e) { n.ci = __ldg(t.cinfo + p); n.cw = __ldg(t.cw + p); }
+  }
+  return n;
+}
+__device__ __forceinline__ DownNode fetch_down(const TreeView& t, int l) {
+  DownNode n;
+  n.s = n.e = 0; n.par = 0; n.idx = 0; n.w = 0.f;
+  if (l >= 1 && l < t.L) {
+    n.s = __ldg(t.lvl + l); n.e = __ldg(t.lvl + l + 1);
+    const int p = n.s + threadIdx.x;
+    if (p < n.e) { n.par = __ldg(t.par + p); n.idx = __ldg(t.idx + p); n.w = __ldg(t.w + p); }
+  }
+  return n;
+}
+
+__device__ __forceinline__ float up_node(float own, int ci, const float4& cw, const float* buf) {
+  const int first = ci & 0x0fffffff, n = ci >> 28;
+  float acc = own;
+  if (n > 0) acc = fmaf(buf[first], cw.x, acc);
+  if (n > 1) acc = fmaf(buf[first + 1], cw.y, acc);
+  if (n > 2) acc = fmaf(buf[first + 2], cw.z, acc);
+  if (n > 3) acc = fmaf(buf[first + 3], cw.w, acc);
+  return acc;
+}
+
+// buf[p] holds the node's own input on entry; on exit U[p] = in(p) + sum_children w[c] U[c].  Deepest level first.
+__device__ __forceinline__ void up_pass(const TreeView& t, float* buf, float* __restrict__ save_up) {
+  UpNode ring[PF];
+#pragma unroll
+  for (int j = 0; j < PF; ++j) ring[j] = fetch_up(t, t.L - 1 - j);
+  for (int l0 = t.L - 1; l0 >= 0; l0 -= PF) {
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int l = l0 - j;
+      if (l < 0) break;
+      const UpNode nd = ring[j];
+      ring[j] = fetch_up(t, l - PF);                        // refill this slot PF levels ahead
+      int p = nd.s + threadIdx.x;
+      if (p < nd.e) {
+        const float v = up_node(buf[p], nd.ci, nd.cw, buf);
+        buf[p] = v;
+        if (save_up) save_up[p] = v;
+      }
+      for (p += NT; p < nd.e; p += NT) {                    // wide levels: plenty of parallelism, plain loads
+        const float v = up_node(buf[p], __ldg(t.cinfo + p), __ldg(t.cw + p), buf);
+        buf[p] = v;
+        if (save_up) save_up[p] = v;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// in place: A[0] = U[0]; A[p] = (1 - w^2) U[p] + w A[par]; writes the vertex-ordered result
 __device__ __forceinline__ void down_pass(const TreeView& t, float* buf, float* __restrict__ out_vertex) {
   if (threadIdx.x == 0 && out_vertex) out_vertex[t.idx[0]] = buf[0];
+  DownNode ring[PF];
+#pragma unroll
+  for (int j = 0; j < PF; ++j) ring[j] = fetch_down(t, 1 + j);
   __syncthreads();
-  for (int l = 1; l < t.L; ++l) {
-    const int s = t.lvl[l], e = t.lvl[l + 1];
-    for (int p = s + threadIdx.x; p < e; p += NT) {
-      const float ew = t.w[p];
-      const float a = fmaf(buf[t.par[p]], ew, buf[p] * (1.f - ew * ew));
-      buf[p] = a;
-      if (out_vertex) out_vertex[t.idx[p]] = a;
+  for (int l0 = 1; l0 < t.L; l0 += PF) {
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int l = l0 + j;
+      if (l >= t.L) break;
+      const DownNode nd = ring[j];
+      ring[j] = fetch_down(t, l + PF);
+      int p = nd.s + threadIdx.x;
+      if (p < nd.e) {
+        const float a = fmaf(buf[nd.par], nd.w, buf[p] * (1.f - nd.w * nd.w));
+        buf[p] = a;
+        if (out_vertex) out_vertex[nd.idx] = a;
+      }
+      for (p += NT; p < nd.e; p += NT) {
+        const float ew = __ldg(t.w + p);
+        const float a = fmaf(buf[__ldg(t.par + p)], ew, buf[p] * (1.f - ew * ew));
+        buf[p] = a;
+        if (out_vertex) out_vertex[__ldg(t.idx + p)] = a;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
-__device__ __forceinline__ TreeView make_view(const float* w, const int32_t* idx, const int32_t* par, const int32_t* chd,
-                                              const int32_t* lvl, const int32_t* nlv, int b, int V) {
+__device__ __forceinline__ TreeView make_view(const float* w, const int32_t* idx, const int32_t* par, const int32_t* cinfo,
+                                              const float4* cw, const int32_t* lvl, const int32_t* nlv, int b, int V) {
   TreeView t;
-  t.idx = idx + (int64_t)b * V; t.par = par + (int64_t)b * V; t.chd = chd + (int64_t)b * V * 4;
-  t.lvl = lvl + (int64_t)b * (V + 1); t.w = w + (int64_t)b * V; t.V = V; t.L = nlv[b];
+  t.idx = idx + (int64_t)b * V; t.par = par + (int64_t)b * V; t.cinfo = cinfo + (int64_t)b * V;
+  t.cw = cw + (int64_t)b * V; t.lvl = lvl + (int64_t)b * (V + 1); t.w = w + (int64_t)b * V; t.V = V; t.L = nlv[b];
   return t;
 }
 
@@ -356,14 +451,15 @@ __device__ __forceinline__ TreeView make_view(const float* w, const int32_t* idx
 template <int MODE, bool SMEM>
 __global__ void __launch_bounds__(NT) refine_updown_kernel(const float* __restrict__ feature, const float* __restrict__ w,
                                                            const int32_t* __restrict__ idx, const int32_t* __restrict__ par,
-                                                           const int32_t* __restrict__ chd, const int32_t* __restrict__ lvl,
-                                                           const int32_t* __restrict__ nlv, const float* __restrict__ wsum,
-                                                           float* __restrict__ aggr, float* __restrict__ aggr_up,
-                                                           float* __restrict__ wsum_out, float* __restrict__ wsum_up,
-                                                           float* __restrict__ scratch, int C, int V) {
+                                                           const int32_t* __restrict__ cinfo, const float4* __restrict__ cw,
+                                                           const int32_t* __restrict__ lvl, const int32_t* __restrict__ nlv,
+                                                           const float* __restrict__ wsum, float* __restrict__ aggr,
+                                                           float* __restrict__ aggr_up, float* __restrict__ wsum_out,
+                                                           float* __restrict__ wsum_up, float* __restrict__ scratch, int C,
+                                                           int V) {
   extern __shared__ float s_buf[];
   const int b = blockIdx.x, c = blockIdx.y;
-  const TreeView t = make_view(w, idx, par, chd, lvl, nlv, b, V);
+  const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, b, V);
   float* buf = SMEM ? s_buf : scratch + ((int64_t)b * (C + 1) + c) * V;
   const bool norm = MODE == 0 && c == C;
   const float* x = norm ? nullptr : feature + ((int64_t)b * C + c) * V;
@@ -371,8 +467,12 @@ __global__ void __launch_bounds__(NT) refine_updown_kernel(const float* __restri
   float* save_up = MODE == 0 ? (norm ? wsum_up + (int64_t)b * V : aggr_up + ((int64_t)b * C + c) * V) : nullptr;
   float* out_v = MODE == 0 ? (norm ? wsum_out + (int64_t)b * V : aggr + ((int64_t)b * C + c) * V)
                            : aggr + ((int64_t)b * C + c) * V;     // MODE 1: aggr == grad_feature
-  const int32_t* ix = t.idx;
-  up_pass(t, [&](int p) { const int v = ix[p]; return norm ? 1.f : (MODE == 1 ? x[v] / z[v] : x[v]); }, buf, save_up);
+  for (int p = threadIdx.x; p < V; p += NT) {               // parallel gather of the inputs into position order
+    const int v = __ldg(t.idx + p);
+    buf[p] = norm ? 1.f : (MODE == 1 ? x[v] / z[v] : x[v]);
+  }
+  __syncthreads();
+  up_pass(t, buf, save_up);
   down_pass(t, buf, out_v);
 }
 
@@ -389,23 +489,26 @@ __global__ void refine_div_kernel(const float* __restrict__ aggr, const float* _
 //   gn = g / Z, fg = gn * out;  gnU = up(gn), fgU = up(fg)
 //   grad[p] += sweep(aggr_up_c, gnU, aggr_c)[p] - sweep(wsum_up, fgU, wsum)[p]
 // sweep: G[0] = gup[0]; for p > 0: grad = gup (outd[v_par] - w ind) + ind (G[par] - w gup); G = gup (1 - w^2) + G[par] w
+// `outd_par` [2][V] is the position-ordered gather outd[idx[par[p]]] for the two data sets (parallel pre-pass).
+struct SweepNode { int s, e, par; float w, ind, outp; };
+
 template <bool SMEM>
 __global__ void __launch_bounds__(NT) refine_bwd_weight_kernel(
     const float* __restrict__ w, const int32_t* __restrict__ idx, const int32_t* __restrict__ par,
-    const int32_t* __restrict__ chd, const int32_t* __restrict__ lvl, const int32_t* __restrict__ nlv,
-    const float* __restrict__ out, const float* __restrict__ aggr, const float* __restrict__ aggr_up,
-    const float* __restrict__ wsum, const float* __restrict__ wsum_up, const float* __restrict__ g_out,
-    float* __restrict__ grad_w, float* __restrict__ scratch, int C, int V) {
+    const int32_t* __restrict__ cinfo, const float4* __restrict__ cw, const int32_t* __restrict__ lvl,
+    const int32_t* __restrict__ nlv, const float* __restrict__ out, const float* __restrict__ aggr,
+    const float* __restrict__ aggr_up, const float* __restrict__ wsum, const float* __restrict__ wsum_up,
+    const float* __restrict__ g_out, float* __restrict__ grad_w, float* __restrict__ scratch, float* __restrict__ outd_par,
+    int C, int V) {
   extern __shared__ float s_buf[];
   const int b = blockIdx.x;
-  const TreeView t = make_view(w, idx, par, chd, lvl, nlv, b, V);
+  const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, b, V);
   float* buf = SMEM ? s_buf : scratch + (int64_t)b * V;
   float* gw = grad_w + (int64_t)b * V;
+  float* op = outd_par + (int64_t)b * V;
   const float* z = wsum + (int64_t)b * V;
   const float* zu = wsum_up + (int64_t)b * V;
-  const int32_t* ix = t.idx;
   for (int p = threadIdx.x; p < V; p += NT) gw[p] = 0.f;
-  __syncthreads();
   for (int c = 0; c < C; ++c) {
     const float* g = g_out + ((int64_t)b * C + c) * V;
     const float* o = out + ((int64_t)b * C + c) * V;
@@ -413,22 +516,52 @@ __global__ void __launch_bounds__(NT) refine_bwd_weight_kernel(
     const float* au = aggr_up + ((int64_t)b * C + c) * V;
     for (int phase = 0; phase < 2; ++phase) {
       // phase 0: gup = up(g/Z), data = (aggr_up, aggr), sign +   phase 1: gup = up(g/Z * out), data = (wsum_up, wsum), sign -
-      up_pass(t, [&](int p) { const int v = ix[p]; const float gn = g[v] / z[v]; return phase ? gn * o[v] : gn; }, buf,
-              nullptr);
       const float* ind = phase ? zu : au;
       const float* outd = phase ? z : ag;
       const float sign = phase ? -1.f : 1.f;
+      __syncthreads();
+      for (int p = threadIdx.x; p < V; p += NT) {           // parallel pre-pass: inputs and parent data, position order
+        const int v = __ldg(t.idx + p);
+        const float gn = g[v] / z[v];
+        buf[p] = phase ? gn * o[v] : gn;
+        op[p] = p == 0 ? 0.f : outd[__ldg(t.idx + __ldg(t.par + p))];
+      }
+      __syncthreads();
+      up_pass(t, buf, nullptr);
       // top-down: buf[p] holds gup[p] until visited, then G[p]
-      for (int l = 1; l < t.L; ++l) {
-        const int s = t.lvl[l], e = t.lvl[l + 1];
-        for (int p = s + threadIdx.x; p < e; p += NT) {
-          const float ew = t.w[p], gup = buf[p], Gp = buf[t.par[p]], in_p = ind[p];
-          const float left = gup * (outd[ix[t.par[p]]] - ew * in_p);
-          const float right = in_p * (Gp - ew * gup);
-          gw[p] += sign * (left + right);
-          buf[p] = fmaf(Gp, ew, gup * (1.f - ew * ew));
+      SweepNode ring[PF];
+      auto fetch = [&](int l) {
+        SweepNode n;
+        n.s = n.e = 0; n.par = 0; n.w = n.ind = n.outp = 0.f;
+        if (l >= 1 && l < t.L) {
+          n.s = __ldg(t.lvl + l); n.e = __ldg(t.lvl + l + 1);
+          const int p = n.s + threadIdx.x;
+          if (p < n.e) { n.par = __ldg(t.par + p); n.w = __ldg(t.w + p); n.ind = ind[p]; n.outp = op[p]; }
         }
-        __syncthreads();
+        return n;
+      };
+#pragma unroll
+      for (int j = 0; j < PF; ++j) ring[j] = fetch(1 + j);
+      for (int l0 = 1; l0 < t.L; l0 += PF) {
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+          const int l = l0 + j;
+          if (l >= t.L) break;
+          const SweepNode nd = ring[j];
+          ring[j] = fetch(l + PF);
+          int p = nd.s + threadIdx.x;
+          if (p < nd.e) {
+            const float gup = buf[p], Gp = buf[nd.par];
+            gw[p] += sign * (gup * (nd.outp - nd.w * nd.ind) + nd.ind * (Gp - nd.w * gup));
+            buf[p] = fmaf(Gp, nd.w, gup * (1.f - nd.w * nd.w));
+          }
+          for (p += NT; p < nd.e; p += NT) {
+            const float ew = __ldg(t.w + p), in_p = ind[p], gup = buf[p], Gp = buf[__ldg(t.par + p)];
+            gw[p] += sign * (gup * (op[p] - ew * in_p) + in_p * (Gp - ew * gup));
+            buf[p] = fmaf(Gp, ew, gup * (1.f - ew * ew));
+          }
+          __syncthreads();
+        }
       }
     }
   }
@@ -504,8 +637,36 @@ extern "C" int bxs_tree_levels(const int32_t* sorted_parent, int32_t* level_star
   return check_launch();
 }
 
+// scratch layout: cinfo int[B*V] | cw float4[B*V] | outd_par float[B*V] | global buffers float[B*(C+1)*V] (maps too large for smem)
+namespace bxs {
+namespace {
+struct RefineScratch {
+  int32_t* cinfo;
+  float4* cw;
+  float* outd_par;
+  float* bufs;
+  size_t total_bytes;
+};
+inline RefineScratch carve_refine(void* base, int64_t B, int64_t C, int64_t V) {
+  RefineScratch r{};
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* q = p + off; off = align_up(off + bytes); return q; };
+  r.cw = (float4*)take(16 * B * V);
+  r.cinfo = (int32_t*)take(4 * B * V);
+  r.outd_par = (float*)take(4 * B * V);
+  r.bufs = (float*)take(4 * B * (C + 1) * V);
+  r.total_bytes = off;
+  return r;
+}
+inline void pack_tree(const float* w, const int32_t* chd, const RefineScratch& rs, int64_t B, int64_t V, cudaStream_t st) {
+  tree_pack_kernel<<<grid_for(B * V, 256), 256, 0, st>>>(w, chd, rs.cinfo, rs.cw, (int)V, B * V);
+}
+}  // namespace
+}  // namespace bxs
+
 extern "C" int64_t bxs_refine_scratch_bytes(int64_t B, int64_t C, int64_t V) {
-  return (B <= 0 || C <= 0 || V <= 0) ? 0 : (int64_t)sizeof(float) * B * (C + 1) * V;
+  return (B <= 0 || C <= 0 || V <= 0) ? 0 : (int64_t)carve_refine(nullptr, B, C, V).total_bytes;
 }
 
 extern "C" int bxs_refine_forward(const float* feature, const float* edge_weight, const int32_t* sorted_index,
@@ -514,20 +675,22 @@ extern "C" int bxs_refine_forward(const float* feature, const float* edge_weight
                                   float* wsum_up, void* scratch, int64_t B, int64_t C, int64_t V, bxs_stream_t stream) {
   if (!feature || !edge_weight || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels ||
       !feature_out || !aggr || !aggr_up || !wsum || !wsum_up || !scratch || B <= 0 || B >= 65536 || C <= 0 ||
-      C >= 65535 || V <= 0)
+      C >= 65535 || V <= 0 || V >= (int64_t(1) << 28))
     return BXS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
+  RefineScratch rs = carve_refine(scratch, B, C, V);
+  pack_tree(edge_weight, sorted_child, rs, B, V, st);
   const size_t sm = V * sizeof(float);
   const dim3 grid((unsigned)B, (unsigned)(C + 1));
   if (sm <= kMaxTreeSmem) {
     cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
-    refine_updown_kernel<0, true><<<grid, NT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent, sorted_child,
+    refine_updown_kernel<0, true><<<grid, NT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, nullptr, aggr, aggr_up, wsum, wsum_up,
                                                         nullptr, (int)C, (int)V);
   } else {
-    refine_updown_kernel<0, false><<<grid, NT, 0, st>>>(feature, edge_weight, sorted_index, sorted_parent, sorted_child,
+    refine_updown_kernel<0, false><<<grid, NT, 0, st>>>(feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, nullptr, aggr, aggr_up, wsum, wsum_up,
-                                                        (float*)scratch, (int)C, (int)V);
+                                                        rs.bufs, (int)C, (int)V);
   }
   refine_div_kernel<<<grid_for(B * C * V, 256), 256, 0, st>>>(aggr, wsum, feature_out, (int)C, (int)V, B * C * V);
   return check_launch();
@@ -539,20 +702,23 @@ extern "C" int bxs_refine_backward_feature(const float* edge_weight, const int32
                                            const float* grad_out, float* grad_feature, void* scratch, int64_t B, int64_t C,
                                            int64_t V, bxs_stream_t stream) {
   if (!edge_weight || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels || !wsum ||
-      !grad_out || !grad_feature || !scratch || B <= 0 || B >= 65536 || C <= 0 || C >= 65535 || V <= 0)
+      !grad_out || !grad_feature || !scratch || B <= 0 || B >= 65536 || C <= 0 || C >= 65535 || V <= 0 ||
+      V >= (int64_t(1) << 28))
     return BXS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
+  RefineScratch rs = carve_refine(scratch, B, C, V);
+  pack_tree(edge_weight, sorted_child, rs, B, V, st);
   const size_t sm = V * sizeof(float);
   const dim3 grid((unsigned)B, (unsigned)C);
   if (sm <= kMaxTreeSmem) {
     cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
-    refine_updown_kernel<1, true><<<grid, NT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, sorted_child,
+    refine_updown_kernel<1, true><<<grid, NT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
                                                         nullptr, nullptr, (int)C, (int)V);
   } else {
-    refine_updown_kernel<1, false><<<grid, NT, 0, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, sorted_child,
+    refine_updown_kernel<1, false><<<grid, NT, 0, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
-                                                        nullptr, (float*)scratch, (int)C, (int)V);
+                                                        nullptr, rs.bufs, (int)C, (int)V);
   }
   return check_launch();
 }
@@ -565,20 +731,23 @@ extern "C" int bxs_refine_backward_weight(const float* edge_weight, const int32_
                                           int64_t V, bxs_stream_t stream) {
   if (!edge_weight || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels || !feature_out ||
       !aggr || !aggr_up || !wsum || !wsum_up || !grad_out || !grad_weight || !scratch || B <= 0 || B >= 65536 || C <= 0 ||
-      V <= 0)
+      V <= 0 || V >= (int64_t(1) << 28))
     return BXS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
+  RefineScratch rs = carve_refine(scratch, B, C, V);
+  pack_tree(edge_weight, sorted_child, rs, B, V, st);
   const size_t sm = V * sizeof(float);
   if (sm <= kMaxTreeSmem) {
     cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
-    refine_bwd_weight_kernel<true><<<(unsigned)B, NT, sm, st>>>(edge_weight, sorted_index, sorted_parent, sorted_child,
+    refine_bwd_weight_kernel<true><<<(unsigned)B, NT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                                 level_start, num_levels, feature_out, aggr, aggr_up, wsum,
-                                                                wsum_up, grad_out, grad_weight, nullptr, (int)C, (int)V);
+                                                                wsum_up, grad_out, grad_weight, nullptr, rs.outd_par,
+                                                                (int)C, (int)V);
   } else {
-    refine_bwd_weight_kernel<false><<<(unsigned)B, NT, 0, st>>>(edge_weight, sorted_index, sorted_parent, sorted_child,
+    refine_bwd_weight_kernel<false><<<(unsigned)B, NT, 0, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                                  level_start, num_levels, feature_out, aggr, aggr_up, wsum,
-                                                                 wsum_up, grad_out, grad_weight, (float*)scratch, (int)C,
-                                                                 (int)V);
+                                                                 wsum_up, grad_out, grad_weight, rs.bufs, rs.outd_par,
+                                                                 (int)C, (int)V);
   }
   return check_launch();
 }
