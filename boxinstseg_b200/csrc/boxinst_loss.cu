@@ -449,13 +449,15 @@ struct RowSeg {            // one lane's pixel of a row segment
   unsigned raw;            // unmasked edge bits
 };
 
+// x_ok / x_box are per-lane and computed once per segment; the row tests are warp-uniform
 __device__ __forceinline__ RowSeg load_seg(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
-                                           int y, int x, const Rect& r) {
+                                           int y, int x, bool x_ok, bool x_box, const Rect& r) {
   RowSeg v;
-  const bool in = y >= 0 && y < H && x >= 0 && x < W;
-  v.x = in ? __ldg(img + (int64_t)y * W + x) : 0.f;
-  v.raw = in ? (unsigned)__ldg(bits + (int64_t)y * W + x) : 0u;
-  v.eff = in_rect(r, y, x) ? v.raw : 0u;
+  const bool in = x_ok && y >= 0 && y < H;
+  const int64_t o = (int64_t)y * W + x;
+  v.x = in ? __ldg(img + o) : 0.f;
+  v.raw = in ? (unsigned)__ldg(bits + o) : 0u;
+  v.eff = (x_box && y >= r.j0 && y <= r.j1) ? v.raw : 0u;
   sigmoid_pair(v.x, v.s, v.n);
   return v;
 }
@@ -466,8 +468,9 @@ __device__ __forceinline__ void pair_seg_fwd(const float* __restrict__ img, cons
   const bool owner_lane = lane >= D && lane < 32 - D;
   {
     const int x = xs + lane;
-    const RowSeg a = load_seg(img, bits, H, W, y, x, r);
-    const RowSeg b = load_seg(img, bits, H, W, y + D, x, r);
+    const bool x_ok = x >= 0 && x < W, x_box = x >= r.i0 && x <= r.i1;
+    const RowSeg a = load_seg(img, bits, H, W, y, x, x_ok, x_box, r);
+    const RowSeg b = load_seg(img, bits, H, W, y + D, x, x_ok, x_box, r);
     const bool extreme = __any_sync(kFull, fmaxf(fabsf(a.x), fabsf(b.x)) > kFastLimit);
     const bool owner = owner_lane && x <= c_hi;
     if (owner) wsum += __popc(a.eff);
@@ -503,9 +506,10 @@ __device__ __forceinline__ void pair_seg_bwd(const float* __restrict__ img, cons
   const bool owner_lane = lane >= D && lane < 32 - D;
   {
     const int x = xs + lane;
-    const RowSeg t = load_seg(img, bits, H, W, y - D, x, r);
-    const RowSeg m0 = load_seg(img, bits, H, W, y, x, r);
-    const RowSeg u = load_seg(img, bits, H, W, y + D, x, r);
+    const bool x_ok = x >= 0 && x < W, x_box = x >= r.i0 && x <= r.i1;
+    const RowSeg t = load_seg(img, bits, H, W, y - D, x, x_ok, x_box, r);
+    const RowSeg m0 = load_seg(img, bits, H, W, y, x, x_ok, x_box, r);
+    const RowSeg u = load_seg(img, bits, H, W, y + D, x, x_ok, x_box, r);
     const bool extreme = __any_sync(kFull, fmaxf(fmaxf(fabsf(t.x), fabsf(m0.x)), fabsf(u.x)) > kFastLimit);
     const bool owner = owner_lane && x <= c_hi;
     float acc = 0.f;
@@ -631,9 +635,12 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
     const Rect r = load_rect(rects, g);
     const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
     const Span sp = pair_span<D>(r, H, W, false);
-    const int items = (sp.y_hi - sp.y_lo + 1) * sp.nseg;
-    for (int it = (int)blockIdx.y * NWARP + warp; it < items; it += PAIR_BLOCKS * NWARP) {
-      const int y = sp.y_lo + it / sp.nseg, seg = it % sp.nseg;
+    // warp gw owns segment (gw % nseg) of rows y_lo + gw / nseg, + rows_per_pass, ...  (one division per warp)
+    const int gw = (int)blockIdx.y * NWARP + warp;
+    const int rows_per_pass = sp.nseg > 0 ? (PAIR_BLOCKS * NWARP) / sp.nseg : 0;
+    const int seg = sp.nseg > 0 ? gw % sp.nseg : 0, r_sub = sp.nseg > 0 ? gw / sp.nseg : 0;
+    for (int y = sp.y_lo + r_sub; rows_per_pass > 0 && r_sub < rows_per_pass && y <= sp.y_hi; y += rows_per_pass) {
+      const int it = (y - sp.y_lo) * sp.nseg + seg;
       float acc = 0.f;
       int wsum = 0;
       pair_seg_fwd<D>(img, bits, H, W, y, sp.c_lo - D + seg * (32 - 2 * D), sp.c_hi, r, lane, acc, wsum);
@@ -647,20 +654,86 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
   }
 }
 
-// one CTA per instance: dice terms, gradient coefficients, scalars (separate launch: no fences / tickets in the
-// streaming kernel)
+// one 4-warp CTA per instance (separate launch: no fences / tickets in the streaming kernel).  The four
+// reductions of an instance are independent, so each gets its own warp and only warp shuffles are used:
+//   warp 0: row profile -> dice + row coefficients     warp 1: column profile -> dice + column coefficients
+//   warp 2: pairwise numerator (fixed order)           warp 3: weight count
 template <int D>
-__global__ void __launch_bounds__(NT) finalize_fast_kernel(const int32_t* __restrict__ rects,
-                                                           const int32_t* __restrict__ inst_gt, int N, int H, int W,
-                                                           Workspace ws, const float* __restrict__ iter_ptr,
-                                                           float warmup_iters, float* __restrict__ losses_out) {
-  __shared__ FinalizeShared sh;
-  const int n = blockIdx.x;
+__global__ void __launch_bounds__(128) finalize_fast_kernel(const int32_t* __restrict__ rects,
+                                                            const int32_t* __restrict__ inst_gt, int N, int H, int W,
+                                                            Workspace ws, const float* __restrict__ iter_ptr,
+                                                            float warmup_iters, float* __restrict__ losses_out) {
+  __shared__ float s_part[4];
+  __shared__ bool s_last;
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Rect r = load_rect(rects, inst_gt[n]);
-  const Span sp = pair_span<D>(r, H, W, false);
-  const int items = (sp.y_hi - sp.y_lo + 1) * sp.nseg;
-  finalize_instance(n, r, N, H, W, ws, ws.pair_partial + (int64_t)n * H * SEG_MAX, items,
-                    ws.den_partial + (int64_t)n * H * SEG_MAX, items, iter_ptr, warmup_iters, losses_out, sh);
+  const bool empty = rect_empty(r);
+  const float inv_n = 1.f / (float)N;
+  if (warp < 2) {
+    const int axis = warp;
+    const int L = axis == 0 ? H : W;
+    const int lo = axis == 0 ? r.j0 : r.i0, hi = axis == 0 ? r.j1 : r.i1;
+    const unsigned long long* packed = (axis == 0 ? ws.row_packed + (int64_t)n * H : ws.col_packed + (int64_t)n * W);
+    float* coef = axis == 0 ? ws.coef_row + (int64_t)n * H : ws.coef_col + (int64_t)n * W;
+    int* arg = axis == 0 ? ws.row_arg + (int64_t)n * H : ws.col_arg + (int64_t)n * W;
+    float inter = 0.f, x2 = 0.f;
+    for (int i = lane; i < L; i += 32) {
+      const float sv = sigmoid_exact(fkey_inv((unsigned)(packed[i] >> 32)));
+      inter += (!empty && i >= lo && i <= hi) ? sv : 0.f;
+      x2 = fmaf(sv, sv, x2);
+    }
+    inter = warp_sum(inter);
+    x2 = warp_sum(x2);
+    const float t2 = empty ? 0.f : (float)(max(min(hi, L - 1) - max(lo, 0) + 1, 0));
+    const float U = x2 + t2 + kDiceEps, I = inter;
+    for (int i = lane; i < L; i += 32) {
+      const unsigned long long p = packed[i];
+      const float sv = sigmoid_exact(fkey_inv((unsigned)(p >> 32)));
+      const float t = (!empty && i >= lo && i <= hi) ? 1.f : 0.f;
+      coef[i] = inv_n * (-2.f * t / U + 4.f * I * sv / (U * U)) * sv * (1.f - sv);
+      arg[i] = (int)(0xffffffffu - (unsigned)(p & 0xffffffffull));
+    }
+    if (lane == 0) s_part[axis] = 1.f - 2.f * I / U;
+  } else {
+    const Span sp = pair_span<D>(r, H, W, false);
+    const int items = (sp.y_hi - sp.y_lo + 1) * sp.nseg;
+    if (warp == 2) {
+      float num = 0.f;
+      for (int i = lane; i < items; i += 32) num += ws.pair_partial[(int64_t)n * H * SEG_MAX + i];
+      num = warp_sum(num);
+      if (lane == 0) s_part[2] = num;
+    } else {
+      int den = 0;
+      for (int i = lane; i < items; i += 32) den += ws.den_partial[(int64_t)n * H * SEG_MAX + i];
+      den = warp_sum(den);
+      if (lane == 0 && den) atomicAdd(ws.weight_sum, (unsigned long long)den);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ws.inst_prj[n] = s_part[0] + s_part[1];
+    ws.inst_num[n] = s_part[2];
+    __threadfence();
+    s_last = atomicAdd(ws.ticket, 1u) == (unsigned)(N - 1);
+  }
+  __syncthreads();
+  if (!s_last || warp != 0) return;
+  __threadfence();
+  float prj = 0.f, pn = 0.f;
+  for (int i = lane; i < N; i += 32) { prj += __ldcg(ws.inst_prj + i); pn += __ldcg(ws.inst_num + i); }
+  prj = warp_sum(prj);
+  pn = warp_sum(pn);
+  if (lane == 0) {
+    const float wsum = (float)__ldcg(ws.weight_sum);
+    const float warm = fminf(iter_ptr[0] / warmup_iters, 1.f);
+    const float scale = warm / fmaxf(wsum, 1.f);
+    losses_out[0] = prj * inv_n;
+    losses_out[1] = pn * scale;
+    losses_out[2] = pn;
+    losses_out[3] = wsum;
+    ws.scale_pair[0] = scale;
+  }
 }
 
 template <int NCHUNK, int D>
@@ -732,9 +805,10 @@ __global__ void __launch_bounds__(NT, 4) bwd_rows_kernel(const float* __restrict
     const float g_pair = g_losses[1] * ws.scale_pair[0];
     const float* img = logits + (int64_t)n * H * W;
     const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
-    const int items = (sp.y_hi - sp.y_lo + 1) * sp.nseg;
-    for (int it = (int)blockIdx.y * NWARP + warp; it < items; it += PAIR_BLOCKS * NWARP) {
-      const int y = sp.y_lo + it / sp.nseg, seg = it % sp.nseg;
+    const int gw = (int)blockIdx.y * NWARP + warp;
+    const int rows_per_pass = sp.nseg > 0 ? (PAIR_BLOCKS * NWARP) / sp.nseg : 0;
+    const int seg = sp.nseg > 0 ? gw % sp.nseg : 0, r_sub = sp.nseg > 0 ? gw / sp.nseg : 0;
+    for (int y = sp.y_lo + r_sub; rows_per_pass > 0 && r_sub < rows_per_pass && y <= sp.y_hi; y += rows_per_pass) {
       const int ra = ws.row_arg[(int64_t)n * H + y];
       const float rc = ws.coef_row[(int64_t)n * H + y] * g_prj;
       pair_seg_bwd<D>(img, bits, H, W, y, sp.c_lo - D + seg * (32 - 2 * D), sp.c_hi, r, lane, g_pair, ra, rc, acol, ccol, g_prj,
@@ -857,7 +931,7 @@ void launch_fwd_fast(int d, dim3 grid, cudaStream_t st, const float* logits, con
 #define BXS_CASE(DD)                                                                                             \
   case DD:                                                                                                       \
     fwd_fused_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, H, W, ws);      \
-    finalize_fast_kernel<DD><<<N, NT, 0, st>>>(rects, inst_gt, N, H, W, ws, iter_ptr, warmup_iters, losses_out); \
+    finalize_fast_kernel<DD><<<N, 128, 0, st>>>(rects, inst_gt, N, H, W, ws, iter_ptr, warmup_iters, losses_out); \
     break;
   switch (d) { BXS_CASE(1) BXS_CASE(2) BXS_CASE(3) BXS_CASE(4) }
 #undef BXS_CASE

@@ -18,7 +18,7 @@
 namespace bxs {
 namespace {
 
-constexpr int NT = 1024;
+constexpr int NT = 256;     // levels hold ~30 nodes on average: a small CTA keeps the per-level barrier and the idle-warp issue cost low
 constexpr unsigned long long kInf = ~0ull;
 
 __device__ __forceinline__ unsigned fkey(float f) {
