@@ -70,7 +70,7 @@ inline Workspace carve(void* base, int64_t N, int64_t H, int64_t W) {
   w.col_arg = (int*)take(sizeof(int) * N * W);
   w.tile_prefix = (int*)take(sizeof(int) * (N + 1));
   const int64_t tiles_full = ceil_div(H, TH) * ceil_div(W, TW);
-  const int64_t per_inst = std::max<int64_t>(tiles_full, H * 24);      // generic: tiles; fast: H * SEG_MAX items
+  const int64_t per_inst = std::max<int64_t>(tiles_full, 128);         // generic: tiles; fast: one per pair-role warp
   w.pair_partial = (float*)take(sizeof(float) * N * per_inst);
   w.den_partial = (int*)take(sizeof(int) * N * per_inst);
   w.inst_prj = (float*)take(sizeof(float) * N);
@@ -547,7 +547,7 @@ __device__ __forceinline__ void pair_seg_bwd(const float* __restrict__ img, cons
 //   y >= PAIR_BLOCKS : streaming role -- 16 rows of the map (2 per warp), full width
 // The two roles touch disjoint outputs and overlap on the SMs (one is load/store bound, the other ALU/latency bound).
 constexpr int PAIR_BLOCKS = 16;
-constexpr int SEG_MAX = 24;                 // segments per row: ceil(W / (32 - 2D)) <= 22 for W <= 512, D <= 4
+constexpr int PAIR_PARTS = PAIR_BLOCKS * 8;   // numerator / weight-count partials per instance (one per pair-role warp)
 
 struct Span { int y_lo, y_hi, c_lo, c_hi, nseg; };
 template <int D>
@@ -639,86 +639,110 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
     const int gw = (int)blockIdx.y * NWARP + warp;
     const int rows_per_pass = sp.nseg > 0 ? (PAIR_BLOCKS * NWARP) / sp.nseg : 0;
     const int seg = sp.nseg > 0 ? gw % sp.nseg : 0, r_sub = sp.nseg > 0 ? gw / sp.nseg : 0;
-    for (int y = sp.y_lo + r_sub; rows_per_pass > 0 && r_sub < rows_per_pass && y <= sp.y_hi; y += rows_per_pass) {
-      const int it = (y - sp.y_lo) * sp.nseg + seg;
-      float acc = 0.f;
-      int wsum = 0;
+    // per-lane accumulation over this warp's (static) item list, one shuffle tree and one store at the end:
+    // PAIR_BLOCKS * NWARP partials per instance, summed in fixed order by the finalize kernel
+    float acc = 0.f;
+    int wsum = 0;
+    for (int y = sp.y_lo + r_sub; rows_per_pass > 0 && r_sub < rows_per_pass && y <= sp.y_hi; y += rows_per_pass)
       pair_seg_fwd<D>(img, bits, H, W, y, sp.c_lo - D + seg * (32 - 2 * D), sp.c_hi, r, lane, acc, wsum);
-      acc = warp_sum(acc);
-      wsum = warp_sum(wsum);
-      if (lane == 0) {
-        ws.pair_partial[(int64_t)n * H * SEG_MAX + it] = acc;
-        ws.den_partial[(int64_t)n * H * SEG_MAX + it] = wsum;
-      }
+    acc = warp_sum(acc);
+    wsum = warp_sum(wsum);
+    if (lane == 0) {
+      ws.pair_partial[(int64_t)n * PAIR_PARTS + gw] = acc;
+      ws.den_partial[(int64_t)n * PAIR_PARTS + gw] = wsum;
     }
   }
 }
 
-// one 4-warp CTA per instance (separate launch: no fences / tickets in the streaming kernel).  The four
-// reductions of an instance are independent, so each gets its own warp and only warp shuffles are used:
+// Finalize (separate launch: no fences / tickets in the streaming kernel).  Each instance gets a group of four
+// warps whose reductions are independent and use warp shuffles only:
 //   warp 0: row profile -> dice + row coefficients     warp 1: column profile -> dice + column coefficients
 //   warp 2: pairwise numerator (fixed order)           warp 3: weight count
+// A CTA holds FIN_GROUPS instances so that only N / FIN_GROUPS CTAs touch the two same-address atomics
+// (weight sum, ticket) -- 128 serialised L2 atomics cost more than the arithmetic.
+constexpr int FIN_GROUPS = 4;
+
 template <int D>
-__global__ void __launch_bounds__(128) finalize_fast_kernel(const int32_t* __restrict__ rects,
-                                                            const int32_t* __restrict__ inst_gt, int N, int H, int W,
-                                                            Workspace ws, const float* __restrict__ iter_ptr,
-                                                            float warmup_iters, float* __restrict__ losses_out) {
-  __shared__ float s_part[4];
+__global__ void __launch_bounds__(FIN_GROUPS * 128) finalize_fast_kernel(const int32_t* __restrict__ rects,
+                                                                         const int32_t* __restrict__ inst_gt, int N, int H,
+                                                                         int W, Workspace ws,
+                                                                         const float* __restrict__ iter_ptr,
+                                                                         float warmup_iters, float* __restrict__ losses_out) {
+  __shared__ float s_part[FIN_GROUPS][4];
+  __shared__ int s_den[FIN_GROUPS];
   __shared__ bool s_last;
-  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const Rect r = load_rect(rects, inst_gt[n]);
-  const bool empty = rect_empty(r);
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3, group = threadIdx.x >> 7;
+  const int n = blockIdx.x * FIN_GROUPS + group;
   const float inv_n = 1.f / (float)N;
-  if (warp < 2) {
-    const int axis = warp;
-    const int L = axis == 0 ? H : W;
-    const int lo = axis == 0 ? r.j0 : r.i0, hi = axis == 0 ? r.j1 : r.i1;
-    const unsigned long long* packed = (axis == 0 ? ws.row_packed + (int64_t)n * H : ws.col_packed + (int64_t)n * W);
-    float* coef = axis == 0 ? ws.coef_row + (int64_t)n * H : ws.coef_col + (int64_t)n * W;
-    int* arg = axis == 0 ? ws.row_arg + (int64_t)n * H : ws.col_arg + (int64_t)n * W;
-    float inter = 0.f, x2 = 0.f;
-    for (int i = lane; i < L; i += 32) {
-      const float sv = sigmoid_exact(fkey_inv((unsigned)(packed[i] >> 32)));
-      inter += (!empty && i >= lo && i <= hi) ? sv : 0.f;
-      x2 = fmaf(sv, sv, x2);
-    }
-    inter = warp_sum(inter);
-    x2 = warp_sum(x2);
-    const float t2 = empty ? 0.f : (float)(max(min(hi, L - 1) - max(lo, 0) + 1, 0));
-    const float U = x2 + t2 + kDiceEps, I = inter;
-    for (int i = lane; i < L; i += 32) {
-      const unsigned long long p = packed[i];
-      const float sv = sigmoid_exact(fkey_inv((unsigned)(p >> 32)));
-      const float t = (!empty && i >= lo && i <= hi) ? 1.f : 0.f;
-      coef[i] = inv_n * (-2.f * t / U + 4.f * I * sv / (U * U)) * sv * (1.f - sv);
-      arg[i] = (int)(0xffffffffu - (unsigned)(p & 0xffffffffull));
-    }
-    if (lane == 0) s_part[axis] = 1.f - 2.f * I / U;
-  } else {
-    const Span sp = pair_span<D>(r, H, W, false);
-    const int items = (sp.y_hi - sp.y_lo + 1) * sp.nseg;
-    if (warp == 2) {
-      float num = 0.f;
-      for (int i = lane; i < items; i += 32) num += ws.pair_partial[(int64_t)n * H * SEG_MAX + i];
-      num = warp_sum(num);
-      if (lane == 0) s_part[2] = num;
+  if (n < N) {
+    const Rect r = load_rect(rects, inst_gt[n]);
+    const bool empty = rect_empty(r);
+    if (warp < 2) {
+      const int axis = warp;
+      const int L = axis == 0 ? H : W;
+      const int lo = axis == 0 ? r.j0 : r.i0, hi = axis == 0 ? r.j1 : r.i1;
+      const unsigned long long* packed = (axis == 0 ? ws.row_packed + (int64_t)n * H : ws.col_packed + (int64_t)n * W);
+      float* coef = axis == 0 ? ws.coef_row + (int64_t)n * H : ws.coef_col + (int64_t)n * W;
+      int* arg = axis == 0 ? ws.row_arg + (int64_t)n * H : ws.col_arg + (int64_t)n * W;
+      // the whole profile (L <= 512) sits in registers: all loads issue back to back, one latency round trip
+      constexpr int PER_LANE = 16;
+      unsigned long long pk[PER_LANE];
+#pragma unroll
+      for (int k = 0; k < PER_LANE; ++k) pk[k] = (k * 32 + lane < L) ? packed[k * 32 + lane] : 0ull;
+      float sv[PER_LANE];
+      float inter = 0.f, x2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < PER_LANE; ++k) {
+        const int i = k * 32 + lane;
+        sv[k] = i < L ? sigmoid_exact(fkey_inv((unsigned)(pk[k] >> 32))) : 0.f;
+        inter += (!empty && i >= lo && i <= hi) ? sv[k] : 0.f;
+        x2 = fmaf(sv[k], sv[k], x2);
+      }
+      inter = warp_sum(inter);
+      x2 = warp_sum(x2);
+      const float t2 = empty ? 0.f : (float)(max(min(hi, L - 1) - max(lo, 0) + 1, 0));
+      const float U = x2 + t2 + kDiceEps, I = inter;
+#pragma unroll
+      for (int k = 0; k < PER_LANE; ++k) {
+        const int i = k * 32 + lane;
+        if (i < L) {
+          const float t = (!empty && i >= lo && i <= hi) ? 1.f : 0.f;
+          coef[i] = inv_n * (-2.f * t / U + 4.f * I * sv[k] / (U * U)) * sv[k] * (1.f - sv[k]);
+          arg[i] = (int)(0xffffffffu - (unsigned)(pk[k] & 0xffffffffull));
+        }
+      }
+      if (lane == 0) s_part[group][axis] = 1.f - 2.f * I / U;
     } else {
-      int den = 0;
-      for (int i = lane; i < items; i += 32) den += ws.den_partial[(int64_t)n * H * SEG_MAX + i];
-      den = warp_sum(den);
-      if (lane == 0 && den) atomicAdd(ws.weight_sum, (unsigned long long)den);
+      if (warp == 2) {
+        float num = 0.f;
+#pragma unroll
+        for (int i = 0; i < PAIR_PARTS / 32; ++i) num += ws.pair_partial[(int64_t)n * PAIR_PARTS + i * 32 + lane];
+        num = warp_sum(num);
+        if (lane == 0) s_part[group][2] = num;
+      } else {
+        int den = 0;
+#pragma unroll
+        for (int i = 0; i < PAIR_PARTS / 32; ++i) den += ws.den_partial[(int64_t)n * PAIR_PARTS + i * 32 + lane];
+        den = warp_sum(den);
+        if (lane == 0) s_den[group] = den;
+      }
     }
+  } else if (lane == 0) {
+    if (warp == 3) s_den[group] = 0;
   }
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    ws.inst_prj[n] = s_part[0] + s_part[1];
-    ws.inst_num[n] = s_part[2];
+    int den = 0;
+    for (int gq = 0; gq < FIN_GROUPS; ++gq) {
+      const int m = blockIdx.x * FIN_GROUPS + gq;
+      if (m < N) { ws.inst_prj[m] = s_part[gq][0] + s_part[gq][1]; ws.inst_num[m] = s_part[gq][2]; den += s_den[gq]; }
+    }
+    if (den) atomicAdd(ws.weight_sum, (unsigned long long)den);
     __threadfence();
-    s_last = atomicAdd(ws.ticket, 1u) == (unsigned)(N - 1);
+    s_last = atomicAdd(ws.ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!s_last || warp != 0) return;
+  if (!s_last || threadIdx.x >= 32) return;
   __threadfence();
   float prj = 0.f, pn = 0.f;
   for (int i = lane; i < N; i += 32) { prj += __ldcg(ws.inst_prj + i); pn += __ldcg(ws.inst_num + i); }
@@ -919,8 +943,8 @@ extern "C" int64_t bxs_boxinst_loss_workspace_bytes(int64_t N, int64_t H, int64_
 
 namespace bxs {
 namespace {
-inline bool fast_ok(const void* logits, const void* edge_bits, const void* out, int64_t W, int d) {
-  return (W % 4 == 0) && W <= 512 && d >= 1 && d <= 4 && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
+inline bool fast_ok(const void* logits, const void* edge_bits, const void* out, int64_t H, int64_t W, int d) {
+  return (W % 4 == 0) && W <= 512 && H <= 512 && d >= 1 && d <= 4 && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
          ((reinterpret_cast<uintptr_t>(edge_bits) & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 }
 
@@ -931,7 +955,8 @@ void launch_fwd_fast(int d, dim3 grid, cudaStream_t st, const float* logits, con
 #define BXS_CASE(DD)                                                                                             \
   case DD:                                                                                                       \
     fwd_fused_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, H, W, ws);      \
-    finalize_fast_kernel<DD><<<N, 128, 0, st>>>(rects, inst_gt, N, H, W, ws, iter_ptr, warmup_iters, losses_out); \
+    finalize_fast_kernel<DD><<<(N + FIN_GROUPS - 1) / FIN_GROUPS, FIN_GROUPS * 128, 0, st>>>(                    \
+        rects, inst_gt, N, H, W, ws, iter_ptr, warmup_iters, losses_out);                                        \
     break;
   switch (d) { BXS_CASE(1) BXS_CASE(2) BXS_CASE(3) BXS_CASE(4) }
 #undef BXS_CASE
@@ -962,7 +987,7 @@ extern "C" int bxs_boxinst_loss_forward(const float* logits, const uint8_t* edge
   cudaStream_t st = as_stream(stream);
   Workspace ws = carve(workspace, N, H, W);
   const int d = dilation;
-  if (fast_ok(logits, edge_bits, logits, W, d)) {
+  if (fast_ok(logits, edge_bits, logits, H, W, d)) {
     // one fused streaming kernel: maxima + in-box pair terms + per-instance finalize
     cudaMemsetAsync(workspace, 0, ws.zero_bytes_fast, st);
     dim3 grid((unsigned)N, (unsigned)ceil_div(H, ROWS_PER_CTA) + PAIR_BLOCKS);
@@ -1011,7 +1036,7 @@ extern "C" int bxs_boxinst_loss_backward(const float* logits, const uint8_t* edg
   cudaStream_t st = as_stream(stream);
   Workspace ws = carve(const_cast<void*>(workspace), N, H, W);
   const int d = dilation;
-  if (fast_ok(logits, edge_bits, g_logits, W, d)) {
+  if (fast_ok(logits, edge_bits, g_logits, H, W, d)) {
     dim3 grid((unsigned)N, (unsigned)ceil_div(H, ROWS_PER_CTA) + PAIR_BLOCKS);
     if (W <= 128) launch_bwd_fast<1>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);
     else if (W <= 256) launch_bwd_fast<2>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)H, (int)W, ws, g_losses, g_logits);
