@@ -38,6 +38,16 @@ ALGO_BYTES = 3 * N_INST * H * W * 4 + 2 * B_IMG * K_NEIGH * H * W * 4     # SURV
 ROTATE = 8
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes per step from the committed ncu --set full capture (None when the summary is absent)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_traffic.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['step_dram_bytes'])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -294,7 +304,9 @@ def main_cuda(args, rank, world, local_rank):
                    'parallelism': f'replicas x{world} (loss is per image; no data-path collective)',
                    'aggregate_img_per_s': world * B_IMG / (ms_step * 1e-3)},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'peak_source': peak_src,
+                     'traffic': ncu_traffic_bytes(), 'traffic_source': 'profiles/r1_traffic.json (ncu --set full, dram read+write, '
+                                                                             'sum over the 3 kernels of one step)',
+                     'peak_source': peak_src,
                      'note': 'whole step = memset + fused forward kernel + finalize kernel + backward kernel, against the 85.2 MB/step '
                              'algorithmic figure of SURVEY 8d (29.5 MB fwd + 55.7 MB bwd)',
                      'kernels': {'fwd_fused_kernel+finalize': {'us': us_fwd, 'algo_mb': FWD_BYTES / 1e6, 'achieved': ach_f,
