@@ -294,7 +294,8 @@ def main_cuda(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         cpu_ms, cores, sample = run_cpu(2, 1)
     line = {
-        'metric': METRIC, 'value': ms_step / B_IMG * world / world, 'unit': 'ms/img', 'n_gpus': world,
+        'metric': METRIC, 'value': ms_step / (B_IMG * world),   # whole job: step time / images of all ranks
+        'unit': 'ms/img', 'n_gpus': world,
         'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': False, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'BoxInst R-50 mask loss fwd+bwd (config A): batch 2/GPU x (3,800,1024), 8 GT/img, '
@@ -313,7 +314,7 @@ def main_cuda(args, rank, world, local_rank):
                                                       'frac': ach_f / peak},
                                  'bwd_rows_kernel': {'us': us_bwd, 'algo_mb': BWD_BYTES / 1e6, 'achieved': ach_b,
                                                      'frac': ach_b / peak}}},
-        'e2e': {'value': ms_e2e / B_IMG, 'unit': 'ms/img', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'e2e': {'value': ms_e2e / (B_IMG * world), 'unit': 'ms/img', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': 3 * args.steps,        # fwd_fused_kernel + finalize_fast_kernel + bwd_rows_kernel per step
         'clocks': clocks,
     }
