@@ -449,95 +449,159 @@ struct RowSeg {            // one lane's pixel of a row segment
   unsigned raw;            // unmasked edge bits
 };
 
-// x_ok / x_box are per-lane and computed once per segment; the row tests are warp-uniform
-__device__ __forceinline__ RowSeg load_seg(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
-                                           int y, int x, bool x_ok, bool x_box, const Rect& r) {
-  RowSeg v;
+__device__ __forceinline__ float rcp_approx(float v) {
+  float o;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(o) : "f"(v));
+  return o;
+}
+
+// raw (x, bits) of one lane's pixel: issued one row ahead of its use so that the load latency hides behind
+// the pair arithmetic of the previous row
+struct RawSeg { float x; unsigned raw; };
+__device__ __forceinline__ RawSeg load_raw(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
+                                           int y, int x, bool x_ok) {
+  RawSeg v;
   const bool in = x_ok && y >= 0 && y < H;
   const int64_t o = (int64_t)y * W + x;
   v.x = in ? __ldg(img + o) : 0.f;
   v.raw = in ? (unsigned)__ldg(bits + o) : 0u;
-  v.eff = (x_box && y >= r.j0 && y <= r.j1) ? v.raw : 0u;
+  return v;
+}
+__device__ __forceinline__ RowSeg finish_seg(const RawSeg& w, int y, bool x_box, const Rect& r) {
+  RowSeg v;
+  v.x = w.x;
+  v.raw = w.raw;
+  v.eff = (x_box && y >= r.j0 && y <= r.j1) ? w.raw : 0u;
   sigmoid_pair(v.x, v.s, v.n);
   return v;
 }
 
+// The pair role walks CHAINS: rows y0, y0 + D, y0 + 2D, ... of one 32-lane column segment.  The row "below"
+// (y + D) of one step is the row "at" of the next, so every row of the chain is loaded and sigmoid-ed once,
+// and each unordered pair {p, q} is evaluated once (neighbours c = 4..7: right, below-left, below, below-right)
+// with multiplicity m = [edge bit of p towards q, p in box] + [edge bit of q towards p, q in box].
 template <int D>
-__device__ __forceinline__ void pair_seg_fwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
-                                             int y, int xs, int c_hi, const Rect& r, int lane, float& acc, int& wsum) {
-  const bool owner_lane = lane >= D && lane < 32 - D;
-  {
-    const int x = xs + lane;
-    const bool x_ok = x >= 0 && x < W, x_box = x >= r.i0 && x <= r.i1;
-    const RowSeg a = load_seg(img, bits, H, W, y, x, x_ok, x_box, r);
-    const RowSeg b = load_seg(img, bits, H, W, y + D, x, x_ok, x_box, r);
+struct Neigh { float x, s, n; unsigned e; };
+
+template <int D, int C>
+__device__ __forceinline__ Neigh<D> neighbour(const RowSeg& cur, const RowSeg& nxt, bool extreme, int lane, bool& valid) {
+  Neigh<D> q;
+  if (C == 4) {
+    q.s = __shfl_down_sync(kFull, cur.s, D); q.n = __shfl_down_sync(kFull, cur.n, D); q.e = __shfl_down_sync(kFull, cur.eff, D);
+    q.x = extreme ? __shfl_down_sync(kFull, cur.x, D) : 0.f;
+    valid = lane + D < 32;
+  } else if (C == 5) {
+    q.s = __shfl_up_sync(kFull, nxt.s, D); q.n = __shfl_up_sync(kFull, nxt.n, D); q.e = __shfl_up_sync(kFull, nxt.eff, D);
+    q.x = extreme ? __shfl_up_sync(kFull, nxt.x, D) : 0.f;
+    valid = lane >= D;
+  } else if (C == 6) {
+    q.s = nxt.s; q.n = nxt.n; q.e = nxt.eff; q.x = nxt.x;
+    valid = true;
+  } else {
+    q.s = __shfl_down_sync(kFull, nxt.s, D); q.n = __shfl_down_sync(kFull, nxt.n, D); q.e = __shfl_down_sync(kFull, nxt.eff, D);
+    q.x = extreme ? __shfl_down_sync(kFull, nxt.x, D) : 0.f;
+    valid = lane + D < 32;
+  }
+  return q;
+}
+
+// forward: sum of m * pair_value over the chain's owner pixels; wsum = weight count of the owner pixels
+template <int D>
+__device__ __forceinline__ void pair_chain_fwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
+                                               int y0, int nrows, int xs, int c_hi, const Rect& r, int lane, float& acc,
+                                               int& wsum) {
+  const int x = xs + lane;
+  const bool x_ok = x >= 0 && x < W, x_box = x >= r.i0 && x <= r.i1;
+  const bool owner = lane >= D && lane < 32 - D && x <= c_hi;
+  RowSeg a = finish_seg(load_raw(img, bits, H, W, y0, x, x_ok), y0, x_box, r);
+  RawSeg ahead = load_raw(img, bits, H, W, y0 + D, x, x_ok);
+  for (int k = 0; k < nrows; ++k) {
+    const int y = y0 + k * D;
+    const RowSeg b = finish_seg(ahead, y + D, x_box, r);
+    if (k + 1 < nrows) ahead = load_raw(img, bits, H, W, y + 2 * D, x, x_ok);
     const bool extreme = __any_sync(kFull, fmaxf(fabsf(a.x), fabsf(b.x)) > kFastLimit);
-    const bool owner = owner_lane && x <= c_hi;
     if (owner) wsum += __popc(a.eff);
-    // c = 4: (y, x+D)   c = 5: (y+D, x-D)   c = 6: (y+D, x)   c = 7: (y+D, x+D)
-#pragma unroll
-    for (int c = 4; c < 8; ++c) {
-      float qx, qs, qn;
-      unsigned qe;
-      if (c == 4) {
-        qs = __shfl_down_sync(kFull, a.s, D); qn = __shfl_down_sync(kFull, a.n, D); qe = __shfl_down_sync(kFull, a.eff, D);
-        qx = extreme ? __shfl_down_sync(kFull, a.x, D) : 0.f;
-      } else if (c == 5) {
-        qs = __shfl_up_sync(kFull, b.s, D); qn = __shfl_up_sync(kFull, b.n, D); qe = __shfl_up_sync(kFull, b.eff, D);
-        qx = extreme ? __shfl_up_sync(kFull, b.x, D) : 0.f;
-      } else if (c == 6) {
-        qs = b.s; qn = b.n; qe = b.eff; qx = b.x;
-      } else {
-        qs = __shfl_down_sync(kFull, b.s, D); qn = __shfl_down_sync(kFull, b.n, D); qe = __shfl_down_sync(kFull, b.eff, D);
-        qx = extreme ? __shfl_down_sync(kFull, b.x, D) : 0.f;
-      }
-      const unsigned m = ((a.eff >> c) & 1u) + ((qe >> (7 - c)) & 1u);
-      if (owner && m) acc = fmaf((float)m, pair_value(extreme, a.x, a.s, a.n, qx, qs, qn), acc);
+    float row = 0.f;
+#define BXS_FWD_PAIR(C)                                                                         \
+    {                                                                                           \
+      bool valid;                                                                               \
+      const Neigh<D> q = neighbour<D, C>(a, b, extreme, lane, valid);                           \
+      const unsigned m = ((a.eff >> C) & 1u) + ((q.e >> (7 - C)) & 1u);                         \
+      const float pv = pair_value(extreme, a.x, a.s, a.n, q.x, q.s, q.n);                       \
+      row = fmaf((float)m, pv, row);                                                            \
     }
+    BXS_FWD_PAIR(4) BXS_FWD_PAIR(5) BXS_FWD_PAIR(6) BXS_FWD_PAIR(7)
+#undef BXS_FWD_PAIR
+    if (owner) acc += row;
+    a = b;
   }
 }
 
-// gradient of one row's box pixels (lane-per-pixel); also adds the projection arg-max terms and stores
+// backward: gradient rows of the chain.  Each unordered pair yields the gradient of both of its pixels: the
+// one of the left/upper pixel stays in the lane, the one of the right/lower pixel travels by one shuffle
+// (same row) or through `carry` (row below -> next step).  The step before the chain (row y0 - D) only feeds
+// the carry.  Also adds the projection arg-max terms and stores the row.
 template <int D>
-__device__ __forceinline__ void pair_seg_bwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
-                                             int y, int xs, int c_hi, const Rect& r, int lane, float g_pair, int ra, float rc,
-                                             const int* __restrict__ acol, const float* __restrict__ ccol, float g_prj,
-                                             float* __restrict__ grow) {
-  const bool owner_lane = lane >= D && lane < 32 - D;
-  {
-    const int x = xs + lane;
-    const bool x_ok = x >= 0 && x < W, x_box = x >= r.i0 && x <= r.i1;
-    const RowSeg t = load_seg(img, bits, H, W, y - D, x, x_ok, x_box, r);
-    const RowSeg m0 = load_seg(img, bits, H, W, y, x, x_ok, x_box, r);
-    const RowSeg u = load_seg(img, bits, H, W, y + D, x, x_ok, x_box, r);
-    const bool extreme = __any_sync(kFull, fmaxf(fmaxf(fabsf(t.x), fabsf(m0.x)), fabsf(u.x)) > kFastLimit);
-    const bool owner = owner_lane && x <= c_hi;
-    float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int cc = c < 4 ? c : c + 1;
-      const int ry = cc / 3, sx = cc % 3 - 1;            // row 0: y-D, 1: y, 2: y+D ; sx: -1, 0, +1 (times D)
-      const RowSeg& src = ry == 0 ? t : (ry == 1 ? m0 : u);
-      float qx, qs, qn;
-      unsigned qe;
-      if (sx < 0) {
-        qs = __shfl_up_sync(kFull, src.s, D); qn = __shfl_up_sync(kFull, src.n, D); qe = __shfl_up_sync(kFull, src.eff, D);
-        qx = extreme ? __shfl_up_sync(kFull, src.x, D) : 0.f;
-      } else if (sx > 0) {
-        qs = __shfl_down_sync(kFull, src.s, D); qn = __shfl_down_sync(kFull, src.n, D); qe = __shfl_down_sync(kFull, src.eff, D);
-        qx = extreme ? __shfl_down_sync(kFull, src.x, D) : 0.f;
-      } else {
-        qs = src.s; qn = src.n; qe = src.eff; qx = src.x;
+__device__ __forceinline__ void pair_chain_bwd(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
+                                               int y0, int nrows, int xs, int c_hi, const Rect& r, int lane, float g_pair,
+                                               const int* __restrict__ row_arg, const float* __restrict__ coef_row,
+                                               const int* __restrict__ acol, const float* __restrict__ ccol, float g_prj,
+                                               float* __restrict__ ginst) {
+  const int x = xs + lane;
+  const bool x_ok = x >= 0 && x < W, x_box = x >= r.i0 && x <= r.i1;
+  const bool owner = lane >= D && lane < 32 - D && x <= c_hi;
+  const int acx = owner ? acol[x] : -1;
+  const float ccx = owner ? ccol[x] * g_prj : 0.f;
+  RowSeg cur = finish_seg(load_raw(img, bits, H, W, y0 - D, x, x_ok), y0 - D, x_box, r);
+  RawSeg ahead = load_raw(img, bits, H, W, y0, x, x_ok);
+  float carry = 0.f;
+  for (int k = -1; k < nrows; ++k) {
+    const int y = y0 + k * D;
+    const RowSeg nxt = finish_seg(ahead, y + D, x_box, r);
+    if (k + 1 < nrows) ahead = load_raw(img, bits, H, W, y + 2 * D, x, x_ok);
+    const bool extreme = __any_sync(kFull, fmaxf(fabsf(cur.x), fabsf(nxt.x)) > kFastLimit);
+    float acc = carry;
+    carry = 0.f;
+    const float sn_a = cur.s * cur.n, df_a = cur.s - cur.n;
+#define BXS_BWD_PAIR(C, GA, GQ)                                                                 \
+    float GA, GQ;                                                                               \
+    {                                                                                           \
+      bool valid;                                                                               \
+      const Neigh<D> q = neighbour<D, C>(cur, nxt, extreme, lane, valid);                       \
+      const unsigned m = valid ? ((cur.eff >> C) & 1u) + ((q.e >> (7 - C)) & 1u) : 0u;          \
+      if (!extreme) {                                                                           \
+        const float t = (float)m * rcp_approx(fmaf(cur.s, q.s, cur.n * q.n));                   \
+        GA = -(q.s - q.n) * t * sn_a;                                                           \
+        GQ = -df_a * t * (q.s * q.n);                                                           \
+      } else {                                                                                  \
+        GA = (float)m * pair_grad_a(true, cur.x, cur.s, cur.n, q.x, q.s, q.n);                  \
+        GQ = (float)m * pair_grad_a(true, q.x, q.s, q.n, cur.x, cur.s, cur.n);                  \
+      }                                                                                         \
+    }
+    if (k >= 0) {                                              // warp-uniform
+      BXS_BWD_PAIR(4, ga4, gq4)
+      const float from_left = __shfl_up_sync(kFull, gq4, D);  // pair (x - D, x): this lane is the right pixel
+      acc += ga4 + (lane >= D ? from_left : 0.f);
+    }
+    BXS_BWD_PAIR(5, ga5, gq5)
+    BXS_BWD_PAIR(6, ga6, gq6)
+    BXS_BWD_PAIR(7, ga7, gq7)
+#undef BXS_BWD_PAIR
+    {
+      const float to_left = __shfl_down_sync(kFull, gq5, D);  // lower-left pixel of lane + D is this lane's column
+      const float to_right = __shfl_up_sync(kFull, gq7, D);
+      carry = gq6 + (lane + D < 32 ? to_left : 0.f) + (lane >= D ? to_right : 0.f);
+    }
+    if (k >= 0) {
+      acc += ga5 + ga6 + ga7;
+      if (owner) {
+        float v = 0.f;
+        if (x == row_arg[y]) v += coef_row[y] * g_prj;
+        if (acx == y) v += ccx;
+        ginst[(int64_t)y * W + x] = fmaf(acc, g_pair, v);
       }
-      const unsigned m = ((m0.eff >> c) & 1u) + ((qe >> (7 - c)) & 1u);
-      if (owner && m) acc = fmaf((float)m, pair_grad_a(extreme, m0.x, m0.s, m0.n, qx, qs, qn), acc);
     }
-    if (owner) {
-      float v = 0.f;
-      if (x == ra) v += rc;
-      if (acol[x] == y) v += ccol[x] * g_prj;
-      grow[x] = fmaf(acc, g_pair, v);
-    }
+    cur = nxt;
   }
 }
 
@@ -560,6 +624,31 @@ __device__ __forceinline__ Span pair_span(const Rect& r, int H, int W, bool back
   s.c_hi = min(r.i1 + D, W - 1);
   s.nseg = (s.c_hi - s.c_lo + 1 + (32 - 2 * D) - 1) / (32 - 2 * D);
   return s;
+}
+
+// chain assignment of pair-role warp gw in [0, PAIR_PARTS): class p = row parity mod D, piece of `len` chain rows,
+// column segment seg.  At most one chain per warp: len is the smallest piece length (>= 4) that fits.
+struct Chain { int seg, y0, nrows; };
+template <int D>
+__device__ __forceinline__ Chain chain_of(const Span& sp, int gw) {
+  Chain c;
+  c.seg = 0; c.y0 = 0; c.nrows = 0;
+  if (sp.nseg <= 0) return c;
+  const int R = sp.y_hi - sp.y_lo + 1;
+  const int RC = (R + D - 1) / D;                        // chain rows of the longest class
+  const int pc_max = PAIR_PARTS / (D * sp.nseg);         // pieces per class that fit (>= 1: D * nseg <= 88)
+  const int len = max((RC + pc_max - 1) / pc_max, 4);
+  const int PC = (RC + len - 1) / len;
+  const int u = gw / sp.nseg;
+  const int p = u / PC, piece = u - p * PC;
+  if (p >= D) return c;
+  const int Rp = (R - p + D - 1) / D;                    // chain rows of class p
+  const int k0 = piece * len;
+  if (k0 >= Rp) return c;
+  c.seg = gw - u * sp.nseg;
+  c.y0 = sp.y_lo + p + D * k0;
+  c.nrows = min(len, Rp - k0);
+  return c;
 }
 
 template <int NCHUNK, int D>
@@ -635,16 +724,14 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
     const Rect r = load_rect(rects, g);
     const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
     const Span sp = pair_span<D>(r, H, W, false);
-    // warp gw owns segment (gw % nseg) of rows y_lo + gw / nseg, + rows_per_pass, ...  (one division per warp)
+    // one chain (rows of one parity class, one column segment) per warp; per-lane accumulation, one shuffle
+    // tree and one store at the end: PAIR_PARTS partials per instance, summed in fixed order by the finalize
     const int gw = (int)blockIdx.y * NWARP + warp;
-    const int rows_per_pass = sp.nseg > 0 ? (PAIR_BLOCKS * NWARP) / sp.nseg : 0;
-    const int seg = sp.nseg > 0 ? gw % sp.nseg : 0, r_sub = sp.nseg > 0 ? gw / sp.nseg : 0;
-    // per-lane accumulation over this warp's (static) item list, one shuffle tree and one store at the end:
-    // PAIR_BLOCKS * NWARP partials per instance, summed in fixed order by the finalize kernel
+    const Chain ch = chain_of<D>(sp, gw);
     float acc = 0.f;
     int wsum = 0;
-    for (int y = sp.y_lo + r_sub; rows_per_pass > 0 && r_sub < rows_per_pass && y <= sp.y_hi; y += rows_per_pass)
-      pair_seg_fwd<D>(img, bits, H, W, y, sp.c_lo - D + seg * (32 - 2 * D), sp.c_hi, r, lane, acc, wsum);
+    if (ch.nrows > 0)
+      pair_chain_fwd<D>(img, bits, H, W, ch.y0, ch.nrows, sp.c_lo - D + ch.seg * (32 - 2 * D), sp.c_hi, r, lane, acc, wsum);
     acc = warp_sum(acc);
     wsum = warp_sum(wsum);
     if (lane == 0) {
@@ -829,15 +916,11 @@ __global__ void __launch_bounds__(NT, 4) bwd_rows_kernel(const float* __restrict
     const float g_pair = g_losses[1] * ws.scale_pair[0];
     const float* img = logits + (int64_t)n * H * W;
     const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
-    const int gw = (int)blockIdx.y * NWARP + warp;
-    const int rows_per_pass = sp.nseg > 0 ? (PAIR_BLOCKS * NWARP) / sp.nseg : 0;
-    const int seg = sp.nseg > 0 ? gw % sp.nseg : 0, r_sub = sp.nseg > 0 ? gw / sp.nseg : 0;
-    for (int y = sp.y_lo + r_sub; rows_per_pass > 0 && r_sub < rows_per_pass && y <= sp.y_hi; y += rows_per_pass) {
-      const int ra = ws.row_arg[(int64_t)n * H + y];
-      const float rc = ws.coef_row[(int64_t)n * H + y] * g_prj;
-      pair_seg_bwd<D>(img, bits, H, W, y, sp.c_lo - D + seg * (32 - 2 * D), sp.c_hi, r, lane, g_pair, ra, rc, acol, ccol, g_prj,
-                      g_logits + (int64_t)n * H * W + (int64_t)y * W);
-    }
+    const Chain ch = chain_of<D>(sp, (int)blockIdx.y * NWARP + warp);
+    if (ch.nrows > 0)
+      pair_chain_bwd<D>(img, bits, H, W, ch.y0, ch.nrows, sp.c_lo - D + ch.seg * (32 - 2 * D), sp.c_hi, r, lane, g_pair,
+                        ws.row_arg + (int64_t)n * H, ws.coef_row + (int64_t)n * H, acol, ccol, g_prj,
+                        g_logits + (int64_t)n * H * W);
   }
 }
 
