@@ -47,6 +47,7 @@ struct Workspace {
   float* inst_prj;     // [N]
   float* inst_num;     // [N]
   float* scale_pair;   // [1] warmup / max(weight_sum, 1)
+  int* inst_rec;       // [N*16] per-instance record of the fast path (rectangle, image, span, chain split)
   size_t total_bytes;
 };
 
@@ -76,6 +77,7 @@ inline Workspace carve(void* base, int64_t N, int64_t H, int64_t W) {
   w.inst_prj = (float*)take(sizeof(float) * N);
   w.inst_num = (float*)take(sizeof(float) * N);
   w.scale_pair = (float*)take(sizeof(float));
+  w.inst_rec = (int*)take(sizeof(int) * 16 * N);
   w.total_bytes = off;
   return w;
 }
@@ -428,7 +430,8 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const int32_t* __restrict_
 // work list.  One warp owns a full row; a lane owns NCHUNK groups of 4 consecutive pixels.
 // =========================================================================================
 constexpr int RPW = 2;                      // rows per warp, all in flight before any use
-constexpr int ROWS_PER_CTA = RPW * (NT / 32);
+constexpr int PASSES = 2;                   // streaming CTAs repeat: the cross-warp column reduction is paid once per CTA
+constexpr int ROWS_PER_CTA = PASSES * RPW * (NT / 32);
 
 // ---- pair terms, lane-per-pixel: a warp walks the box columns [c_lo, c_hi] of one row in segments of
 // 32 lanes of which the inner 32-2D "own" a pixel; horizontal neighbours come from warp shuffles, the
@@ -448,12 +451,6 @@ struct RowSeg {            // one lane's pixel of a row segment
   unsigned eff;            // edge bits masked by "pixel lies in the box"
   unsigned raw;            // unmasked edge bits
 };
-
-__device__ __forceinline__ float rcp_approx(float v) {
-  float o;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(o) : "f"(v));
-  return o;
-}
 
 // raw (x, bits) of one lane's pixel: issued one row ahead of its use so that the load latency hides behind
 // the pair arithmetic of the previous row
@@ -626,22 +623,82 @@ __device__ __forceinline__ Span pair_span(const Rect& r, int H, int W, bool back
   return s;
 }
 
-// chain assignment of pair-role warp gw in [0, PAIR_PARTS): class p = row parity mod D, piece of `len` chain rows,
-// column segment seg.  At most one chain per warp: len is the smallest piece length (>= 4) that fits.
+__device__ __forceinline__ int div_small(int a, int b) {
+  return __float2int_rz((__int2float_rn(a) + 0.5f) * rcp_approx(__int2float_rn(b)));
+}
+
+// Per-instance record written by prep_fast_kernel (one 64-byte line): everything a CTA of either role needs to
+// know about its instance, so that its prologue is ONE load instead of the inst_gt -> rects -> gt_img chain plus
+// a dozen integer divisions per warp.
+struct InstRec {
+  Rect r;                          // box rectangle on the loss grid
+  int img, nseg, c_lo, c_hi;       // image index; column span [c_lo, c_hi] in nseg segments of 32 - 2D owner lanes
+  int y_lo, y_hi_f, y_hi_b, len_f; // row span (forward ends at j1, backward at j1 + D); chain piece lengths
+  int pc_f, len_b, pc_b, pad;      // pieces per parity class
+};
+__device__ __forceinline__ InstRec load_rec(const int* __restrict__ recs, int n) {
+  const int4* q = reinterpret_cast<const int4*>(recs + 16 * (int64_t)n);
+  const int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  InstRec v;
+  v.r = Rect{a.x, a.y, a.z, a.w};
+  v.img = b.x; v.nseg = b.y; v.c_lo = b.z; v.c_hi = b.w;
+  v.y_lo = c.x; v.y_hi_f = c.y; v.y_hi_b = c.z; v.len_f = c.w;
+  v.pc_f = d.x; v.len_b = d.y; v.pc_b = d.z; v.pad = 0;
+  return v;
+}
+__device__ __forceinline__ Span span_of(const InstRec& v, bool backward) {
+  return Span{v.y_lo, backward ? v.y_hi_b : v.y_hi_f, v.c_lo, v.c_hi, v.nseg};
+}
+
+// Chain split of one span: class p = row parity mod D, pieces of `len` chain rows, nseg column segments; at most
+// one chain per pair-role warp: len is the smallest piece length (>= 4) for which D * pc * nseg <= PAIR_PARTS.
+template <int D>
+__device__ __forceinline__ void chain_split(int rows, int nseg, int& len, int& pc) {
+  len = 4; pc = 0;
+  if (nseg <= 0 || rows <= 0) return;
+  const int RC = (rows + D - 1) / D;                     // chain rows of the longest class
+  const int pc_max = PAIR_PARTS / (D * nseg);            // >= 1: D * nseg <= 88
+  len = max((RC + pc_max - 1) / pc_max, 4);
+  pc = (RC + len - 1) / len;
+}
+
+// zeroes the accumulators of a forward pass and writes the instance records (replaces the memset node)
+template <int D>
+__global__ void __launch_bounds__(128) prep_fast_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ inst_gt,
+                                                        const int32_t* __restrict__ gt_img, int H, int W, Workspace ws) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < W; c += 128) ws.col_packed[(int64_t)n * W + c] = 0ull;
+  if (threadIdx.x < PAIR_PARTS) {
+    ws.pair_partial[(int64_t)n * PAIR_PARTS + threadIdx.x] = 0.f;
+    ws.den_partial[(int64_t)n * PAIR_PARTS + threadIdx.x] = 0;
+  }
+  if (threadIdx.x != 0) return;
+  if (n == 0) { *ws.weight_sum = 0ull; *ws.ticket = 0u; }
+  const int g = inst_gt[n];
+  const Rect r = load_rect(rects, g);
+  const Span f = pair_span<D>(r, H, W, false), b = pair_span<D>(r, H, W, true);
+  int len_f, pc_f, len_b, pc_b;
+  chain_split<D>(f.y_hi - f.y_lo + 1, f.nseg, len_f, pc_f);
+  chain_split<D>(b.y_hi - b.y_lo + 1, b.nseg, len_b, pc_b);
+  int4* q = reinterpret_cast<int4*>(ws.inst_rec + 16 * (int64_t)n);
+  q[0] = make_int4(r.j0, r.j1, r.i0, r.i1);
+  q[1] = make_int4(gt_img[g], f.nseg, f.c_lo, f.c_hi);
+  q[2] = make_int4(f.y_lo, f.y_hi, b.y_hi, len_f);
+  q[3] = make_int4(pc_f, len_b, pc_b, 0);
+}
+
+// chain of pair-role warp gw in [0, PAIR_PARTS).  The two divisions run on MUFU.RCP: for operands < 2^20,
+// floor((a + 0.5) / b) in fp32 is exact (error q * 2^-22 < 0.5 / b).
 struct Chain { int seg, y0, nrows; };
 template <int D>
-__device__ __forceinline__ Chain chain_of(const Span& sp, int gw) {
+__device__ __forceinline__ Chain chain_of(const Span& sp, int len, int pc, int gw) {
   Chain c;
   c.seg = 0; c.y0 = 0; c.nrows = 0;
-  if (sp.nseg <= 0) return c;
-  const int R = sp.y_hi - sp.y_lo + 1;
-  const int RC = (R + D - 1) / D;                        // chain rows of the longest class
-  const int pc_max = PAIR_PARTS / (D * sp.nseg);         // pieces per class that fit (>= 1: D * nseg <= 88)
-  const int len = max((RC + pc_max - 1) / pc_max, 4);
-  const int PC = (RC + len - 1) / len;
-  const int u = gw / sp.nseg;
-  const int p = u / PC, piece = u - p * PC;
+  if (pc <= 0) return c;
+  const int u = div_small(gw, sp.nseg);
+  const int p = div_small(u, pc), piece = u - p * pc;
   if (p >= D) return c;
+  const int R = sp.y_hi - sp.y_lo + 1;
   const int Rp = (R - p + D - 1) / D;                    // chain rows of class p
   const int k0 = piece * len;
   if (k0 >= Rp) return c;
@@ -661,50 +718,60 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
   __shared__ float s_val[NWARP][PANEL];
   __shared__ int s_row[NWARP][PANEL];
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int role = blockIdx.y;
   const float* img = logits + (int64_t)n * H * W;
 
-  if ((int)blockIdx.y >= PAIR_BLOCKS) {
+  if (role >= PAIR_BLOCKS) {
     // ================= streaming role: row / column maxima =================
-    const int ybase = ((int)blockIdx.y - PAIR_BLOCKS) * ROWS_PER_CTA + warp;     // this warp's rows: ybase + k * NWARP
-    float v[RPW][NCHUNK * 4];
+    const int ybase = (role - PAIR_BLOCKS) * ROWS_PER_CTA + warp;     // this warp's rows: ybase + k * NWARP
+    float cv[NCHUNK * 4];                                   // running column maxima of this lane's columns
+    int cy[NCHUNK * 4];
 #pragma unroll
-    for (int k = 0; k < RPW; ++k) {                         // all loads first (memory-level parallelism)
-      const int y = ybase + k * NWARP;
+    for (int i = 0; i < NCHUNK * 4; ++i) { cv[i] = -INFINITY; cy[i] = H; }
 #pragma unroll
-      for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int col0 = (ch * 32 + lane) * 4;
-        float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (col0 < W && y < H) q = __ldg(reinterpret_cast<const float4*>(img + (int64_t)y * W + col0));
-        v[k][ch * 4] = q.x; v[k][ch * 4 + 1] = q.y; v[k][ch * 4 + 2] = q.z; v[k][ch * 4 + 3] = q.w;
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int yp = ybase + ps * RPW * NWARP;
+      float v[RPW][NCHUNK * 4];
+#pragma unroll
+      for (int k = 0; k < RPW; ++k) {                       // all loads first (memory-level parallelism)
+        const int y = yp + k * NWARP;
+#pragma unroll
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+          const int col0 = (ch * 32 + lane) * 4;
+          float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          if (col0 < W && y < H) q = __ldg(reinterpret_cast<const float4*>(img + (int64_t)y * W + col0));
+          v[k][ch * 4] = q.x; v[k][ch * 4 + 1] = q.y; v[k][ch * 4 + 2] = q.z; v[k][ch * 4 + 3] = q.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < RPW; ++k) {                       // row maxima: integer redux on the order-preserving key
+        const int y = yp + k * NWARP;
+        if (y < H) {                                        // warp-uniform
+          float m = v[k][0];
+#pragma unroll
+          for (int i = 1; i < NCHUNK * 4; ++i) m = fmaxf(m, v[k][i]);
+          const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
+          const float mv = fkey_inv(kmax);
+          int cand = 0x7fffffff;
+#pragma unroll
+          for (int i = NCHUNK * 4 - 1; i >= 0; --i)
+            if (v[k][i] == mv) cand = ((i >> 2) * 32 + lane) * 4 + (i & 3);
+          const int amin = __reduce_min_sync(kFull, cand);
+          if (lane == 0) ws.row_packed[(int64_t)n * H + y] = pack_key(kmax, amin == 0x7fffffff ? 0 : amin);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NCHUNK * 4; ++i) {                // column maxima (strict '>': the earlier row wins ties;
+#pragma unroll
+        for (int k = 0; k < RPW; ++k)                       //  rows >= H hold -inf and never win)
+          if (v[k][i] > cv[i]) { cv[i] = v[k][i]; cy[i] = yp + k * NWARP; }
       }
     }
 #pragma unroll
-    for (int k = 0; k < RPW; ++k) {                         // row maxima: integer redux on the order-preserving key
-      const int y = ybase + k * NWARP;
-      if (y < H) {                                          // warp-uniform
-        float m = v[k][0];
-#pragma unroll
-        for (int i = 1; i < NCHUNK * 4; ++i) m = fmaxf(m, v[k][i]);
-        const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
-        const float mv = fkey_inv(kmax);
-        int cand = 0x7fffffff;
-#pragma unroll
-        for (int i = NCHUNK * 4 - 1; i >= 0; --i)
-          if (v[k][i] == mv) cand = ((i >> 2) * 32 + lane) * 4 + (i & 3);
-        const int amin = __reduce_min_sync(kFull, cand);
-        if (lane == 0) ws.row_packed[(int64_t)n * H + y] = pack_key(kmax, amin == 0x7fffffff ? 0 : amin);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NCHUNK * 4; ++i) {                  // column maxima (strict '>': the earlier row wins ties)
-      float cv = v[0][i];
-      int cy = ybase;
-#pragma unroll
-      for (int k = 1; k < RPW; ++k)
-        if (v[k][i] > cv) { cv = v[k][i]; cy = ybase + k * NWARP; }   // rows >= H hold -inf and never win
+    for (int i = 0; i < NCHUNK * 4; ++i) {
       const int col = ((i >> 2) * 32 + lane) * 4 + (i & 3);
-      s_val[warp][col] = cv;
-      s_row[warp][col] = cy;
+      s_val[warp][col] = cv[i];
+      s_row[warp][col] = cy[i];
     }
     __syncthreads();
     for (int c = threadIdx.x; c < PANEL; c += NT) {
@@ -720,14 +787,15 @@ __global__ void __launch_bounds__(NT, 4) fwd_fused_kernel(const float* __restric
     }
   } else {
     // ================= pair role: (row, segment) items of the box span =================
-    const int g = inst_gt[n];
-    const Rect r = load_rect(rects, g);
-    const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
-    const Span sp = pair_span<D>(r, H, W, false);
+    const InstRec rec = load_rec(ws.inst_rec, n);
+    if (role * NWARP >= D * rec.pc_f * rec.nseg) return;    // no chain for any warp of this CTA (partials pre-zeroed)
+    const Rect r = rec.r;
+    const uint8_t* bits = edge_bits + (int64_t)rec.img * H * W;
+    const Span sp = span_of(rec, false);
     // one chain (rows of one parity class, one column segment) per warp; per-lane accumulation, one shuffle
     // tree and one store at the end: PAIR_PARTS partials per instance, summed in fixed order by the finalize
-    const int gw = (int)blockIdx.y * NWARP + warp;
-    const Chain ch = chain_of<D>(sp, gw);
+    const int gw = role * NWARP + warp;
+    const Chain ch = chain_of<D>(sp, rec.len_f, rec.pc_f, gw);
     float acc = 0.f;
     int wsum = 0;
     if (ch.nrows > 0)
@@ -762,7 +830,7 @@ __global__ void __launch_bounds__(FIN_GROUPS * 128) finalize_fast_kernel(const i
   const int n = blockIdx.x * FIN_GROUPS + group;
   const float inv_n = 1.f / (float)N;
   if (n < N) {
-    const Rect r = load_rect(rects, inst_gt[n]);
+    const Rect r = load_rec(ws.inst_rec, n).r;
     const bool empty = rect_empty(r);
     if (warp < 2) {
       const int axis = warp;
@@ -857,34 +925,29 @@ __global__ void __launch_bounds__(NT, 4) bwd_rows_kernel(const float* __restrict
                                                       float* __restrict__ g_logits) {
   constexpr int NWARP = NT / 32;
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = inst_gt[n];
-  const Rect r = load_rect(rects, g);
+  const int role = blockIdx.y;
+  const InstRec rec = load_rec(ws.inst_rec, n);
+  if (role < PAIR_BLOCKS && role * NWARP >= D * rec.pc_b * rec.nseg) return;   // pair CTA without a chain
+  const Rect r = rec.r;
   const float g_prj = g_losses[0];
   const float* ccol = ws.coef_col + (int64_t)n * W;
   const int* acol = ws.col_arg + (int64_t)n * W;
-  const Span sp = pair_span<D>(r, H, W, true);            // pixels that can receive a pairwise gradient
+  const Span sp = span_of(rec, true);                     // pixels that can receive a pairwise gradient
 
-  if ((int)blockIdx.y >= PAIR_BLOCKS) {
+  if (role >= PAIR_BLOCKS) {
     // ================= streaming role: zeros + projection arg-max terms outside the box span =================
-    const int y0 = ((int)blockIdx.y - PAIR_BLOCKS) * ROWS_PER_CTA + warp;
+    const int y0 = (role - PAIR_BLOCKS) * ROWS_PER_CTA + warp;
     int4 ac[NCHUNK];                                        // loop invariant: column arg-max rows of this lane's chunks
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
       const int col0 = (ch * 32 + lane) * 4;
       ac[ch] = col0 < W ? __ldg(reinterpret_cast<const int4*>(acol + col0)) : make_int4(-1, -1, -1, -1);
     }
-    int ra[RPW];
-    float rc[RPW];
 #pragma unroll
-    for (int k = 0; k < RPW; ++k) {
-      const int y = y0 + k * NWARP;
-      ra[k] = y < H ? ws.row_arg[(int64_t)n * H + y] : -1;
-      rc[k] = y < H ? ws.coef_row[(int64_t)n * H + y] * g_prj : 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < RPW; ++k) {
+    for (int k = 0; k < PASSES * RPW; ++k) {
       const int y = y0 + k * NWARP;
       if (y >= H) continue;
+      const int ra = ws.row_arg[(int64_t)n * H + y];
       const bool row_in = y >= sp.y_lo && y <= sp.y_hi;     // warp-uniform
       const int c_lo = row_in ? sp.c_lo : W, c_hi = row_in ? sp.c_hi : -1;
       float* grow = g_logits + (int64_t)n * H * W + (int64_t)y * W;
@@ -893,16 +956,24 @@ __global__ void __launch_bounds__(NT, 4) bwd_rows_kernel(const float* __restrict
         const int col0 = (ch * 32 + lane) * 4;
         if (col0 >= W) continue;
         if (col0 >= c_lo && col0 + 3 <= c_hi) continue;     // fully inside the span: the pair role writes it
+        const bool hit = (ac[ch].x == y) | (ac[ch].y == y) | (ac[ch].z == y) | (ac[ch].w == y) |
+                         ((unsigned)(ra - col0) < 4u);
+        const bool outside = col0 + 3 < c_lo || col0 > c_hi;
+        if (!hit && outside) {                              // the common case: a plain zero store
+          *reinterpret_cast<float4*>(grow + col0) = make_float4(0.f, 0.f, 0.f, 0.f);
+          continue;
+        }
         float out[4] = {0.f, 0.f, 0.f, 0.f};
-        if ((unsigned)(ra[k] - col0) < 4u) {
+        if ((unsigned)(ra - col0) < 4u) {
+          const float rc = ws.coef_row[(int64_t)n * H + y] * g_prj;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) if (ra[k] - col0 == e) out[e] += rc[k];
+          for (int e = 0; e < 4; ++e) if (ra - col0 == e) out[e] += rc;
         }
         if (ac[ch].x == y) out[0] += ccol[col0] * g_prj;
         if (ac[ch].y == y) out[1] += ccol[col0 + 1] * g_prj;
         if (ac[ch].z == y) out[2] += ccol[col0 + 2] * g_prj;
         if (ac[ch].w == y) out[3] += ccol[col0 + 3] * g_prj;
-        if (col0 + 3 < c_lo || col0 > c_hi) {
+        if (outside) {
           *reinterpret_cast<float4*>(grow + col0) = make_float4(out[0], out[1], out[2], out[3]);
         } else {                                            // straddles the span boundary
 #pragma unroll
@@ -915,8 +986,8 @@ __global__ void __launch_bounds__(NT, 4) bwd_rows_kernel(const float* __restrict
     // ================= pair role: gather-form gradient of the span pixels =================
     const float g_pair = g_losses[1] * ws.scale_pair[0];
     const float* img = logits + (int64_t)n * H * W;
-    const uint8_t* bits = edge_bits + (int64_t)gt_img[g] * H * W;
-    const Chain ch = chain_of<D>(sp, (int)blockIdx.y * NWARP + warp);
+    const uint8_t* bits = edge_bits + (int64_t)rec.img * H * W;
+    const Chain ch = chain_of<D>(sp, rec.len_b, rec.pc_b, role * NWARP + warp);
     if (ch.nrows > 0)
       pair_chain_bwd<D>(img, bits, H, W, ch.y0, ch.nrows, sp.c_lo - D + ch.seg * (32 - 2 * D), sp.c_hi, r, lane, g_pair,
                         ws.row_arg + (int64_t)n * H, ws.coef_row + (int64_t)n * H, acol, ccol, g_prj,
@@ -1037,6 +1108,7 @@ void launch_fwd_fast(int d, dim3 grid, cudaStream_t st, const float* logits, con
                      Workspace ws, const float* iter_ptr, float warmup_iters, float* losses_out) {
 #define BXS_CASE(DD)                                                                                             \
   case DD:                                                                                                       \
+    prep_fast_kernel<DD><<<N, 128, 0, st>>>(rects, inst_gt, gt_img, H, W, ws);                                   \
     fwd_fused_kernel<NCHUNK, DD><<<grid, NT, 0, st>>>(logits, edge_bits, rects, inst_gt, gt_img, H, W, ws);      \
     finalize_fast_kernel<DD><<<(N + FIN_GROUPS - 1) / FIN_GROUPS, FIN_GROUPS * 128, 0, st>>>(                    \
         rects, inst_gt, N, H, W, ws, iter_ptr, warmup_iters, losses_out);                                        \
@@ -1072,7 +1144,6 @@ extern "C" int bxs_boxinst_loss_forward(const float* logits, const uint8_t* edge
   const int d = dilation;
   if (fast_ok(logits, edge_bits, logits, H, W, d)) {
     // one fused streaming kernel: maxima + in-box pair terms + per-instance finalize
-    cudaMemsetAsync(workspace, 0, ws.zero_bytes_fast, st);
     dim3 grid((unsigned)N, (unsigned)ceil_div(H, ROWS_PER_CTA) + PAIR_BLOCKS);
     if (W <= 128) launch_fwd_fast<1>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);
     else if (W <= 256) launch_fwd_fast<2>(d, grid, st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, (int)W, ws, iter_ptr, warmup_iters, losses_out);

@@ -72,10 +72,16 @@ __device__ __forceinline__ T pair_nlog_grad_a_logspace(T a, T b, bool has_b, T p
   return -(exp(lpb) - exp(lmb)) * exp(lpa + lma + pl);
 }
 
-// sigmoid pair (s, n) = (sigmoid(x), sigmoid(-x)), both accurate to fp32 relative precision.
+__device__ __forceinline__ float rcp_approx(float v) {      // MUFU.RCP, ~1 ulp
+  float o;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(o) : "f"(v));
+  return o;
+}
+
+// sigmoid pair (s, n) = (sigmoid(x), sigmoid(-x)), both accurate to a few ulp relative (no 1 - s cancellation).
 __device__ __forceinline__ void sigmoid_pair(float x, float& s, float& n) {
   float e = __expf(-fabsf(x));
-  float big = __frcp_rn(1.f + e);
+  float big = rcp_approx(1.f + e);
   float small = e * big;
   s = x >= 0.f ? big : small;
   n = x >= 0.f ? small : big;

@@ -7,11 +7,11 @@ MEAN = [123.675, 116.28, 103.53]
 STD = [58.395, 57.12, 57.375]
 
 
-def synth_image(gen, h, w, lowres=32):
-    """uint8-valued RGB [3,h,w] float32: low-frequency field + N(0,8) noise."""
+def synth_image(gen, h, w, lowres=32, noise=8.0):
+    """uint8-valued RGB [3,h,w] float32: low-frequency field + N(0,noise) noise."""
     coarse = torch.rand(1, 3, max(h // lowres, 2), max(w // lowres, 2), generator=gen) * 255
     img = F.interpolate(coarse, size=(h, w), mode='bilinear', align_corners=False)[0]
-    return (img + torch.randn(3, h, w, generator=gen) * 8).clamp(0, 255).floor()
+    return (img + torch.randn(3, h, w, generator=gen) * noise).clamp(0, 255).floor()
 
 
 def normalise(raw):
@@ -33,13 +33,13 @@ def synth_boxes(gen, num, hp, wp, lo=48, hi=400):
     return torch.stack([x1, y1, x1 + w, y1 + h], 1).float()
 
 
-def boxinst_case(seed, B, hp, wp, gts_per_img, inst_per_gt, logit_std=2.0, ragged=False):
+def boxinst_case(seed, B, hp, wp, gts_per_img, inst_per_gt, logit_std=2.0, ragged=False, lowres=32, noise=8.0):
     """Inputs of one BoxInst mask-loss step (config A when B=2, 800x1024, 8 GT, 8 inst/GT)."""
     gen = torch.Generator().manual_seed(seed)
     imgs, metas = [], []
     for b in range(B):
         ih, iw = (hp, wp) if not (ragged and b % 2) else (hp - 8 * (b % 3 + 1), wp - 12)
-        raw = synth_image(gen, ih, iw)
+        raw = synth_image(gen, ih, iw, lowres, noise)
         imgs.append(F.pad(normalise(raw), (0, wp - iw, 0, hp - ih)))
         metas.append(make_meta(ih, iw, ori_scale=1.0 if not ragged else 1.7))
     img = torch.stack(imgs)

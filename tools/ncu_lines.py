@@ -21,13 +21,13 @@ for r in rows[2:]:
 # locate the function in the disassembly
 want = mangled_hint + 'I' + ''.join(f'Li{t}E' for t in targs) if targs else mangled_hint
 start = next(i for i, l in enumerate(dis) if l.startswith('.text.') and want in l)
-lines, cur = [], 0
+lines, cur = [], ('', 0)
 for l in dis[start + 1:]:
     if l.startswith('.text.') or l.startswith('.section'):
         if lines: break
-    m = re.search(r'//## File ".*?", line (\d+)', l)
+    m = re.search(r'//## File "(.*?)", line (\d+)', l)
     if m:
-        cur = int(m.group(1)); continue
+        cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     if re.match(r'\s+/\*[0-9a-f]{4}\*/', l):
         lines.append(cur)
 print(f'{kname[:80]}\n sass rows ncu={len(body)} nvdisasm={len(lines)}')
@@ -36,9 +36,14 @@ inst, samp = collections.Counter(), collections.Counter()
 for i in range(n):
     inst[lines[i]] += int(body[i]['Instructions Executed'] or 0)
     samp[lines[i]] += int(body[i]['# Samples'] or 0)
-srcfile = [l.rstrip() for l in open(os.path.join(root, 'boxinstseg_b200/csrc', cub.split('.')[0] + '.cu'))]
+srcs = {}
+def text_of(key):
+    f, ln = key
+    if f not in srcs:
+        path = os.path.join(root, 'boxinstseg_b200/csrc', f)
+        srcs[f] = [l.rstrip() for l in open(path)] if os.path.exists(path) else []
+    return srcs[f][ln - 1].strip()[:100] if 0 < ln <= len(srcs[f]) else ''
 tot, ts = sum(inst.values()), sum(samp.values())
 print(f' total warp-instr {tot}, samples {ts}')
 for ln, c in inst.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 30):
-    text = srcfile[ln - 1].strip()[:100] if 0 < ln <= len(srcfile) else ''
-    print(f'{c:9d} {100*c/tot:5.1f}%  stall {100*samp[ln]/max(ts,1):5.1f}%  L{ln:4d}: {text}')
+    print(f'{c:9d} {100*c/tot:5.1f}%  stall {100*samp[ln]/max(ts,1):5.1f}%  {ln[0][:16]:16s}:{ln[1]:4d}: {text_of(ln)}')
