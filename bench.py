@@ -151,6 +151,7 @@ def main_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------
 FWD_BYTES = N_INST * H * W * 4 + B_IMG * K_NEIGH * H * W * 4            # read logits + similarity      (29.5 MB)
 BWD_BYTES = 2 * N_INST * H * W * 4 + B_IMG * K_NEIGH * H * W * 4        # re-read logits, write gradient (55.7 MB)
+ONEPASS_BYTES = 2 * N_INST * H * W * 4 + B_IMG * H * W                  # logits once + gradient once + edge bytes (52.5 MB)
 
 
 def main_cuda(args, rank, world, local_rank):
@@ -235,9 +236,12 @@ def main_cuda(args, rank, world, local_rank):
         mode = f'eager (graph capture failed: {type(e).__name__})'
         ms_step = ms_eager
 
-    # ---- per-kernel timing through the C ABI (same rotation) ----
+    # ---- per-call timing through the C ABI (same rotation): the single-pass schedule the step uses, and the
+    #      two-call kernels (forward-only / fallback path) for comparison ----
     inst_gt = gt_inds.to(torch.int32)
     ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N_INST, H, W), dtype=torch.uint8, device=dev)
+    ws1 = torch.empty(lib.bxs_boxinst_loss_fused_workspace_bytes(N_INST, H, W), dtype=torch.uint8, device=dev)
+    sched = torch.zeros(16, dtype=torch.uint8, device=dev)
     out4 = torch.empty(4, device=dev)
     g2 = torch.ones(2, device=dev)
     raw_x = [t.detach() for t in logit_sets]
@@ -253,9 +257,22 @@ def main_cuda(args, rank, world, local_rank):
         L.check(lib.bxs_boxinst_loss_backward(L.ptr(raw_x[i % ROTATE]), L.ptr(targets.edge_bits), L.ptr(targets.rects),
                                               L.ptr(inst_gt), L.ptr(targets.gt_img), L.ptr(ws), L.ptr(g2),
                                               L.ptr(raw_g[i % ROTATE]), N_INST, H, W, 2, st), 'bwd')
+
+    def raw_one_fwd(i):
+        L.check(lib.bxs_boxinst_loss_fused_forward(L.ptr(raw_x[i % ROTATE]), L.ptr(targets.edge_bits), L.ptr(targets.rects),
+                                                   L.ptr(inst_gt), L.ptr(targets.gt_img), L.ptr(it), 10000.0, L.ptr(ws1),
+                                                   L.ptr(sched), L.ptr(out4), L.ptr(raw_g[i % ROTATE]), N_INST, H, W, 2, st),
+                'fused fwd')
+
+    def raw_one_bwd(i):
+        L.check(lib.bxs_boxinst_loss_fused_backward(L.ptr(ws1), L.ptr(g2[0:1]), L.ptr(g2[1:2]), L.ptr(raw_g[i % ROTATE]),
+                                                    N_INST, H, W, st), 'fused bwd')
     raw_fwd(0)
     us_fwd = timed(raw_fwd, args.steps) * 1e3
     us_bwd = timed(raw_bwd, args.steps) * 1e3
+    raw_one_fwd(0)
+    us_one_fwd = timed(raw_one_fwd, args.steps) * 1e3
+    us_one_bwd = timed(raw_one_bwd, args.steps) * 1e3
 
     # ---- e2e through the public head API with host buffers ----
     head = CondInstMaskHead(in_channels=16, in_stride=8, out_stride=4, topk_per_img=64, max_proposals=-1,
@@ -305,7 +322,8 @@ def main_cuda(args, rank, world, local_rank):
     ms_e2e = timed_streams(e2e_step, args.steps)
     clocks = sampler.stop()
 
-    ms_step, ms_e2e, ms_eager, us_fwd, us_bwd = reduce_max_over_ranks([ms_step, ms_e2e, ms_eager, us_fwd, us_bwd], dist, dev)
+    ms_step, ms_e2e, ms_eager, us_fwd, us_bwd, us_one_fwd, us_one_bwd = reduce_max_over_ranks(
+        [ms_step, ms_e2e, ms_eager, us_fwd, us_bwd, us_one_fwd, us_one_bwd], dist, dev)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -330,17 +348,25 @@ def main_cuda(args, rank, world, local_rank):
                    'parallelism': f'replicas x{world} (loss is per image; no data-path collective)',
                    'aggregate_img_per_s': world * B_IMG / (ms_step * 1e-3)},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': ncu_traffic_bytes(), 'traffic_source': 'profiles/r1_traffic.json (ncu --set full, dram read+write, '
-                                                                             'sum over the 3 kernels of one step)',
+                     'traffic': ncu_traffic_bytes(),
+                     'traffic_source': 'profiles/r1_traffic.json (ncu --set full, dram read+write, sum over the kernels of one step)',
                      'peak_source': peak_src,
-                     'note': 'whole step = memset + fused forward kernel + finalize kernel + backward kernel, against the 85.2 MB/step '
-                             'algorithmic figure of SURVEY 8d (29.5 MB fwd + 55.7 MB bwd)',
-                     'kernels': {'fwd_fused_kernel+finalize': {'us': us_fwd, 'algo_mb': FWD_BYTES / 1e6, 'achieved': ach_f,
-                                                      'frac': ach_f / peak},
-                                 'bwd_rows_kernel': {'us': us_bwd, 'algo_mb': BWD_BYTES / 1e6, 'achieved': ach_b,
-                                                     'frac': ach_b / peak}}},
+                     'note': 'whole step (single-pass main kernel + finalize kernel + backward kernel, CUDA-graph replay) against '
+                             'the 85.2 MB/step ALGORITHMIC figure of SURVEY 8d (logits read in fwd and bwd + gradient written + '
+                             'similarity read twice); the single-pass schedule actually moves 52.6 MB (logits once, gradient '
+                             'once, edge bits), see kernels.single_pass',
+                     'kernels': {'single_pass_forward(main+finalize)': {
+                                     'us': us_one_fwd, 'moved_mb': ONEPASS_BYTES / 1e6,
+                                     'achieved_moved': ONEPASS_BYTES / (us_one_fwd * 1e-6) / 1e9,
+                                     'frac_moved': ONEPASS_BYTES / (us_one_fwd * 1e-6) / 1e9 / peak,
+                                     'achieved_algorithmic': ALGO_BYTES / (us_one_fwd * 1e-6) / 1e9},
+                                 'single_pass_backward(g=1 early exit)': {'us': us_one_bwd},
+                                 'two_call_forward(fwd_fused+finalize)': {'us': us_fwd, 'algo_mb': FWD_BYTES / 1e6, 'achieved': ach_f,
+                                                                          'frac': ach_f / peak},
+                                 'two_call_backward(bwd_rows)': {'us': us_bwd, 'algo_mb': BWD_BYTES / 1e6, 'achieved': ach_b,
+                                                                 'frac': ach_b / peak}}},
         'e2e': {'value': ms_e2e / (B_IMG * world), 'unit': 'ms/img', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-        'gpu_launches': 4 * args.steps,        # prep_fast + fwd_fused + finalize_fast + bwd_rows kernels per step
+        'gpu_launches': 3 * args.steps,        # onepass_main + onepass_finalize + onepass_backward kernels per step
         'clocks': clocks,
     }
     if cpu_ms is not None:

@@ -18,14 +18,12 @@
 //     scatter outside the box, gather-form pairwise gradient inside.  No atomics on floats.
 #include <algorithm>
 
-#include "common.cuh"
+#include "boxinst_common.cuh"
 
 namespace bxs {
 namespace {
 
 constexpr int TH = 16, TW = 64, NT = 256;
-constexpr float kFastLimit = 40.f;
-constexpr float kDiceEps = 1e-5f;        // condinst_head.py:124
 
 struct Workspace {
   // zeroed at the start of every forward (fast path: up to zero_bytes_fast)
@@ -82,16 +80,6 @@ inline Workspace carve(void* base, int64_t N, int64_t H, int64_t W) {
   return w;
 }
 
-struct Rect { int j0, j1, i0, i1; };
-
-__device__ __forceinline__ Rect load_rect(const int32_t* rects, int g) {
-  int4 r = *reinterpret_cast<const int4*>(rects + 4 * (int64_t)g);
-  return Rect{r.x, r.y, r.z, r.w};
-}
-__device__ __forceinline__ bool rect_empty(const Rect& r) { return r.j0 > r.j1 || r.i0 > r.i1; }
-__device__ __forceinline__ bool in_rect(const Rect& r, int y, int x) {
-  return y >= r.j0 && y <= r.j1 && x >= r.i0 && x <= r.i1;
-}
 
 // tiles (map aligned) that contain a pixel p for which pair (p, p+forward offset) can carry weight:
 // rows [j0-d, j1], cols [i0-d, i1+d], clipped to the map.
@@ -137,20 +125,6 @@ __global__ void __launch_bounds__(NT) prep_worklist(const int32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // forward 1: projection maxima.  grid (strips, N, panels); one warp per row.
 // ---------------------------------------------------------------------------------------
-// Order-preserving map float -> uint (total order of the reals, -0 < +0), so maxima of LOGITS can
-// be combined with integer max / atomicMax.  The sigmoid is monotone, hence the arg-max of the
-// scores is the arg-max of the logits (first index on exact ties, like torch.max(dim)).
-__device__ __forceinline__ unsigned fkey(float f) {
-  const unsigned b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float fkey_inv(unsigned k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-__device__ __forceinline__ unsigned long long pack_key(unsigned key, int index) {
-  return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (unsigned)index);
-}
-__device__ __forceinline__ unsigned long long pack_max(float v, int index) { return pack_key(fkey(v), index); }
 
 template <int NCHUNK, int V>
 __global__ void __launch_bounds__(NT) prj_max_kernel(const float* __restrict__ logits, int H, int W,
@@ -337,7 +311,6 @@ struct FinalizeShared {
   bool last;
 };
 
-__device__ __forceinline__ float sigmoid_exact(float x) { return 1.f / (1.f + expf(-x)); }
 
 __device__ void finalize_instance(const int n, const Rect r, const int N, const int H, const int W, const Workspace& ws,
                                   const float* __restrict__ partial, const int npartial,

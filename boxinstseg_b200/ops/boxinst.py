@@ -90,35 +90,101 @@ def boxinst_targets(img, img_metas, gt_bboxes, stride=4, pairwise_size=3, pairwi
     return BoxInstTargets(bits, sim, rects, gt_img, num_gts, lab, valid)
 
 
+# Scheduler state of the single-pass kernels (work-item counter + finalize ticket): zero before first use, left
+# zero by every call, owned by ONE stream at a time.  A pool of slots is created per device outside any graph
+# capture; eager calls take the slot of their stream, every captured call site takes a slot of its own (a captured
+# graph may be replayed on any stream, concurrently with eager work).
+_SCHED_SLOTS = 256
+_SCHED = {}     # device index -> dict(pool=tensor [slots, words], by_stream={}, next=int)
+
+
+def _sched_state(device):
+    words = max(int(L.lib().bxs_boxinst_loss_fused_sched_bytes()), 16) // 4
+    capturing = torch.cuda.is_current_stream_capturing()
+    st = _SCHED.get(device.index)
+    if st is None:
+        if capturing:           # first use ever is inside a capture: a graph-private, memset-initialised state
+            return torch.zeros(words, dtype=torch.int32, device=device)
+        st = dict(pool=torch.zeros((_SCHED_SLOTS, words), dtype=torch.int32, device=device), by_stream={}, next=0)
+        _SCHED[device.index] = st
+    if capturing:
+        if st['next'] >= _SCHED_SLOTS:
+            return torch.zeros(words, dtype=torch.int32, device=device)
+        slot, st['next'] = st['next'], st['next'] + 1
+        return st['pool'][slot]
+    key = torch.cuda.current_stream(device).cuda_stream
+    slot = st['by_stream'].get(key)
+    if slot is None:
+        if st['next'] >= _SCHED_SLOTS:
+            raise RuntimeError('boxinstseg_b200: out of scheduler-state slots (too many streams / captured graphs)')
+        slot, st['next'] = st['next'], st['next'] + 1
+        st['by_stream'][key] = slot
+    return st['pool'][slot]
+
+
 class _BoxInstMaskLoss(torch.autograd.Function):
+    """Two schedules of the same arithmetic.  When a gradient is wanted and the shape is inside the single-pass
+    envelope, forward runs `bxs_boxinst_loss_fused_forward` (logits read once, gradient written once) and backward
+    only converts for upstream gradients != 1; otherwise the two-call kernels (forward, then backward re-reading
+    the logits) are used.  A second backward through the same node (retain_graph) always takes the two-call
+    kernels, because the single-pass gradient buffer is converted in place."""
+
     @staticmethod
     def forward(ctx, mask_logits, edge_bits, rects, inst_gt, gt_img, iter_buf, warmup_iters, dilation):
         logits = mask_logits.contiguous()
         L.require_cuda(logits, edge_bits, rects, inst_gt, gt_img, iter_buf)
         N, _, H, W = logits.shape
         lib = L.lib()
-        ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N, H, W), dtype=torch.uint8, device=logits.device)
-        out = torch.empty(4, dtype=torch.float32, device=logits.device)
-        with torch.cuda.device(logits.device):
-            L.check(lib.bxs_boxinst_loss_forward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
-                                                 L.ptr(gt_img), L.ptr(iter_buf), float(warmup_iters), L.ptr(ws),
-                                                 L.ptr(out), N, H, W, dilation, L.stream()), 'boxinst_loss_forward')
-        ctx.save_for_backward(logits, edge_bits, rects, inst_gt, gt_img, ws)
-        ctx.dilation = dilation
+        dev = logits.device
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        fused = bool(ctx.needs_input_grad[0] and N > 0 and lib.bxs_boxinst_loss_fused_supported(N, H, W, dilation)
+                     and logits.data_ptr() % 16 == 0)
+        ctx.fused, ctx.dilation, ctx.calls = fused, dilation, 0
+        with torch.cuda.device(dev):
+            if fused:
+                ws = torch.empty(lib.bxs_boxinst_loss_fused_workspace_bytes(N, H, W), dtype=torch.uint8, device=dev)
+                g_logits = torch.empty_like(logits)
+                L.check(lib.bxs_boxinst_loss_fused_forward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
+                                                           L.ptr(gt_img), L.ptr(iter_buf), float(warmup_iters), L.ptr(ws),
+                                                           L.ptr(_sched_state(dev)), L.ptr(out), L.ptr(g_logits), N, H, W,
+                                                           dilation, L.stream()), 'boxinst_loss_fused_forward')
+                ctx.g_logits = g_logits
+            else:
+                ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N, H, W), dtype=torch.uint8, device=dev)
+                L.check(lib.bxs_boxinst_loss_forward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
+                                                     L.ptr(gt_img), L.ptr(iter_buf), float(warmup_iters), L.ptr(ws),
+                                                     L.ptr(out), N, H, W, dilation, L.stream()), 'boxinst_loss_forward')
+        ctx.save_for_backward(logits, edge_bits, rects, inst_gt, gt_img, ws, iter_buf)
+        ctx.warmup_iters = float(warmup_iters)
         aux = out[2:]
         ctx.mark_non_differentiable(aux)
         return out[0], out[1], aux
 
     @staticmethod
     def backward(ctx, g_prj, g_pair, _g_aux):
-        logits, edge_bits, rects, inst_gt, gt_img, ws = ctx.saved_tensors
+        logits, edge_bits, rects, inst_gt, gt_img, ws, iter_buf = ctx.saved_tensors
         N, _, H, W = logits.shape
-        g = torch.stack([g_prj.reshape(()), g_pair.reshape(())]).to(torch.float32)
-        g_logits = torch.empty_like(logits)
+        lib = L.lib()
+        ctx.calls += 1
+        g_prj = g_prj.reshape(()).to(torch.float32)
+        g_pair = g_pair.reshape(()).to(torch.float32)
         with torch.cuda.device(logits.device):
-            L.check(L.lib().bxs_boxinst_loss_backward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
-                                                      L.ptr(gt_img), L.ptr(ws), L.ptr(g), L.ptr(g_logits), N, H, W,
-                                                      ctx.dilation, L.stream()), 'boxinst_loss_backward')
+            if ctx.fused and ctx.calls == 1:
+                g_logits = ctx.g_logits
+                L.check(lib.bxs_boxinst_loss_fused_backward(L.ptr(ws), L.ptr(g_prj), L.ptr(g_pair), L.ptr(g_logits), N, H, W,
+                                                            L.stream()), 'boxinst_loss_fused_backward')
+                return g_logits, None, None, None, None, None, None, None
+            if ctx.fused:       # the in-place buffer is spent: recompute with the two-call kernels
+                ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N, H, W), dtype=torch.uint8, device=logits.device)
+                tmp = torch.empty(4, dtype=torch.float32, device=logits.device)
+                L.check(lib.bxs_boxinst_loss_forward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
+                                                     L.ptr(gt_img), L.ptr(iter_buf), ctx.warmup_iters, L.ptr(ws),
+                                                     L.ptr(tmp), N, H, W, ctx.dilation, L.stream()), 'boxinst_loss_forward')
+            g = torch.stack([g_prj, g_pair])
+            g_logits = torch.empty_like(logits)
+            L.check(lib.bxs_boxinst_loss_backward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
+                                                  L.ptr(gt_img), L.ptr(ws), L.ptr(g), L.ptr(g_logits), N, H, W,
+                                                  ctx.dilation, L.stream()), 'boxinst_loss_backward')
         return g_logits, None, None, None, None, None, None, None
 
 

@@ -101,6 +101,38 @@ int bxs_boxinst_loss_backward(const float* logits, const uint8_t* edge_bits, con
                               int64_t W, int dilation, bxs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * a6+a7+a8, single pass: the same loss (condinst_head.py:1288-1343) AND d/d logits from ONE
+ * read of the logits (boxinst_onepass.cu).  The pairwise normaliser is logit-independent and the
+ * projection term reaches only H + W arg-max positions per instance, so the dense gradient is
+ * written while the logits stream through the SM; HBM traffic = read logits once + write the
+ * gradient once.  Use when a gradient is wanted (training); the two-call API above remains for
+ * forward-only use and for shapes outside bxs_boxinst_loss_fused_supported().
+ *
+ * forward: computes losses_out (as above) and fills g_logits [N,1,H,W] with the RAW pairwise
+ *   gradient (zeros outside the box spans); g_logits is not a gradient yet.
+ * backward: g_prj / g_pair are device floats (upstream gradients); converts g_logits IN PLACE to
+ *   g_prj * d loss_prj/d logits + g_pair * d loss_pairwise/d logits (touches only the box spans
+ *   and the H + W arg-max positions of each instance).  Call it exactly once per forward.
+ * workspace: bxs_boxinst_loss_fused_workspace_bytes(N,H,W) bytes, no initial state needed.
+ * sched_state: bxs_boxinst_loss_fused_sched_bytes() bytes of device memory that MUST be zero
+ *   before the first call and is owned by one stream at a time (the kernels' work-item counter
+ *   and finalize ticket live there; each call leaves it zeroed again).
+ * Returns BXS_ERR_UNSUPPORTED outside the supported envelope (W % 4 == 0, W,H <= 512,
+ * 1 <= dilation <= 4, N <= 2048, 16-byte aligned logits / g_logits).
+ * --------------------------------------------------------------------------------------- */
+int bxs_boxinst_loss_fused_supported(int64_t N, int64_t H, int64_t W, int dilation);
+int64_t bxs_boxinst_loss_fused_workspace_bytes(int64_t N, int64_t H, int64_t W);
+int64_t bxs_boxinst_loss_fused_sched_bytes(void);
+int bxs_boxinst_loss_fused_forward(const float* logits, const uint8_t* edge_bits, const int32_t* rects,
+                                   const int32_t* inst_gt, const int32_t* gt_img, const float* iter_ptr,
+                                   float warmup_iters, void* workspace, void* sched_state,
+                                   float* losses_out, float* g_logits, int64_t N, int64_t H, int64_t W,
+                                   int dilation, bxs_stream_t stream);
+int bxs_boxinst_loss_fused_backward(const void* workspace, const float* g_prj, const float* g_pair,
+                                    float* g_logits, int64_t N, int64_t H, int64_t W,
+                                    bxs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * a1  CondInst dynamic mask head       replaces CondInstMaskHead.forward + parse_dynamic_params +
  *     aligned_bilinear (mmdet/models/dense_heads/condinst_head.py:1120-1164, 146-167).
  * feat [B,C,h,w]; params [N,P] laid out [W1(8 x cin) | W2(8x8) | W3(1x8) | b1 | b2 | b3] with

@@ -197,3 +197,124 @@ def test_fused_loss_full_size_properties(dev):
     assert rel_err(gx, gref) <= 1e-3
     # gradient is exactly zero where it must be: outside the dilated box and off the arg-max lines
     assert torch.isfinite(gx).all()
+
+
+# ------------------------------------------------------------------ a6+a7+a8 single-pass schedule (boxinst_onepass.cu)
+def _two_call(case, t, dev, dil, g_prj, g_pair, iters=10000.0):
+    """loss + gradient from the two-call kernels (forward, then backward re-reading the logits), through the C ABI."""
+    from boxinstseg_b200 import _lib as L
+    lib = L.lib()
+    x = case['logits'].to(dev).contiguous()
+    N, _, H, W = x.shape
+    ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N, H, W), dtype=torch.uint8, device=dev)
+    out = torch.empty(4, device=dev)
+    it = torch.tensor([iters], device=dev)
+    gi = case['gt_inds'].to(dev, torch.int32)
+    L.check(lib.bxs_boxinst_loss_forward(L.ptr(x), L.ptr(t.edge_bits), L.ptr(t.rects), L.ptr(gi), L.ptr(t.gt_img), L.ptr(it),
+                                         10000.0, L.ptr(ws), L.ptr(out), N, H, W, dil, L.stream()), 'fwd')
+    g = torch.tensor([g_prj, g_pair], device=dev)
+    gx = torch.empty_like(x)
+    L.check(lib.bxs_boxinst_loss_backward(L.ptr(x), L.ptr(t.edge_bits), L.ptr(t.rects), L.ptr(gi), L.ptr(t.gt_img), L.ptr(ws),
+                                          L.ptr(g), L.ptr(gx), N, H, W, dil, L.stream()), 'bwd')
+    return out, gx
+
+
+@pytest.mark.parametrize('cfg', [dict(B=2, hp=96, wp=160, gts_per_img=3, inst_per_gt=2, dil=2),       # H=24: one short strip + one full
+                                 dict(B=1, hp=200, wp=512, gts_per_img=4, inst_per_gt=3, dil=1),      # W=128, H=50
+                                 dict(B=2, hp=264, wp=1024, gts_per_img=3, inst_per_gt=4, dil=3),     # W=256, H=66
+                                 dict(B=1, hp=132, wp=2048, gts_per_img=5, inst_per_gt=2, dil=4),     # W=512 (4 chunks), H=33
+                                 dict(B=3, hp=128, wp=240, gts_per_img=6, inst_per_gt=40, dil=2)])    # N=720: many items per CTA
+def test_single_pass_matches_two_call_and_oracle(dev, cfg):
+    from boxinstseg_b200 import _lib as L
+    from boxinstseg_b200.ops.boxinst import boxinst_mask_loss, boxinst_targets
+    cfg = dict(cfg)
+    dil = cfg.pop('dil')
+    case = boxinst_case(21, logit_std=3.0, **cfg)
+    N, _, H, W = case['logits'].shape
+    assert L.lib().bxs_boxinst_loss_fused_supported(N, H, W, dil) == 1
+    t = boxinst_targets(case['img'].to(dev), case['metas'], [b.to(dev) for b in case['gt_bboxes']], pairwise_dilation=dil,
+                        want_similarity=True)
+    it = torch.tensor([10000.0], device=dev)
+    for g_prj, g_pair in [(1.0, 1.0), (0.75, 2.5)]:
+        x = case['logits'].to(dev).requires_grad_(True)
+        prj, pair = boxinst_mask_loss(x, t, case['gt_inds'].to(dev), it, pairwise_dilation=dil)
+        (gx,) = torch.autograd.grad(prj * g_prj + pair * g_pair, x)
+        out2, gx2 = _two_call(case, t, dev, dil, g_prj, g_pair)
+        assert abs(prj.item() - out2[0].item()) <= 1e-5 * abs(out2[0].item())
+        assert abs(pair.item() - out2[1].item()) <= 1e-5 * abs(out2[1].item()) + 1e-9
+        assert rel_err(gx, gx2) <= 1e-5
+        assert torch.allclose(gx, gx2, rtol=1e-4, atol=1e-9)
+    if N <= 64:                                                     # and against the float64 oracle where it is quick
+        from oracle import boxinst as ob
+        sim, bms = ob.boxinst_targets(case['img'], case['metas'], case['gt_bboxes'], dilation=dil)
+        x64 = case['logits'].double().requires_grad_(True)
+        bm = torch.cat(bms)[case['gt_inds']][:, None].double()
+        p64, q64 = ob.boxinst_mask_loss(x64, sim[case['img_inds']].double(), bm, dilation=dil)
+        (g64,) = torch.autograd.grad(p64 * 0.75 + q64 * 2.5, x64)
+        assert abs(prj.item() - p64.item()) <= 1e-4 * abs(p64.item())
+        assert abs(pair.item() - q64.item()) <= 1e-4 * abs(q64.item())
+        assert rel_err(gx.cpu(), g64) <= 1e-4
+
+
+def test_single_pass_retain_graph_and_no_grad(dev):
+    from boxinstseg_b200.ops.boxinst import boxinst_mask_loss, boxinst_targets
+    case = boxinst_case(33, B=2, hp=160, wp=256, gts_per_img=3, inst_per_gt=3, logit_std=2.0)
+    t = boxinst_targets(case['img'].to(dev), case['metas'], [b.to(dev) for b in case['gt_bboxes']])
+    it = torch.tensor([4000.0], device=dev)
+    gi = case['gt_inds'].to(dev)
+    x = case['logits'].to(dev).requires_grad_(True)
+    prj, pair = boxinst_mask_loss(x, t, gi, it)
+    (ga,) = torch.autograd.grad(prj * 3.0 + pair * 0.5, x, retain_graph=True)      # single-pass buffer, converted in place
+    ga = ga.clone()
+    (gb,) = torch.autograd.grad(prj * 3.0 + pair * 0.5, x, retain_graph=True)      # second call: two-call kernels
+    (gc,) = torch.autograd.grad(prj + pair, x)
+    _, g2 = _two_call(case, t, dev, 2, 3.0, 0.5, iters=4000.0)
+    _, g1 = _two_call(case, t, dev, 2, 1.0, 1.0, iters=4000.0)
+    assert torch.allclose(ga, g2, rtol=1e-4, atol=1e-9) and torch.equal(gb, g2) and torch.equal(gc, g1)
+    with torch.no_grad():                                                          # forward only: two-call forward kernel
+        p0, q0 = boxinst_mask_loss(case['logits'].to(dev), t, gi, it)
+    assert abs(p0.item() - prj.item()) <= 1e-6 * abs(prj.item()) and abs(q0.item() - pair.item()) <= 1e-6 * abs(pair.item())
+
+
+def test_single_pass_scheduler_state_is_reusable(dev):
+    """Back-to-back calls on two streams and a CUDA-graph replay: the work-item counter always returns to zero."""
+    from boxinstseg_b200.ops.boxinst import boxinst_mask_loss, boxinst_targets
+    case = boxinst_case(4, B=2, hp=320, wp=512, gts_per_img=4, inst_per_gt=8, logit_std=2.0)
+    t = boxinst_targets(case['img'].to(dev), case['metas'], [b.to(dev) for b in case['gt_bboxes']])
+    it = torch.tensor([10000.0], device=dev)
+    gi = case['gt_inds'].to(dev)
+    ones = torch.ones((), device=dev)
+
+    def run(x):
+        prj, pair = boxinst_mask_loss(x, t, gi, it)
+        torch.autograd.backward([prj, pair], [ones, ones])
+        return prj, pair
+
+    x = case['logits'].to(dev).requires_grad_(True)
+    run(x)
+    ref = x.grad.clone()
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    xs = [case['logits'].to(dev).requires_grad_(True) for _ in streams]
+    for _ in range(5):
+        for s_, xi in zip(streams, xs):
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                xi.grad = None
+                run(xi)
+    torch.cuda.synchronize()
+    assert torch.equal(xs[0].grad, ref) and torch.equal(xs[1].grad, ref)
+    xg = case['logits'].to(dev).requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run(xg)
+        xg.grad = None
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        prj, pair = run(xg)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(xg.grad, ref)

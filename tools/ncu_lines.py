@@ -11,7 +11,7 @@ src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-n
 rows = list(csv.reader(src.splitlines()))
 kname = rows[0][1]
 mangled_hint = re.search(r'::(\w+)<', kname).group(1)
-targs = re.findall(r'\(int\)(\d+)', kname.split('(const')[0])
+targs = re.findall(r'\((int|bool)\)(\d+)', kname.split('(const')[0])
 hdr = rows[1]
 body = []
 for r in rows[2:]:
@@ -19,7 +19,7 @@ for r in rows[2:]:
         break
     body.append(dict(zip(hdr, r)))
 # locate the function in the disassembly
-want = mangled_hint + 'I' + ''.join(f'Li{t}E' for t in targs) if targs else mangled_hint
+want = mangled_hint + 'I' + ''.join(('Li' if k == 'int' else 'Lb') + f'{t}E' for k, t in targs) if targs else mangled_hint
 start = next(i for i, l in enumerate(dis) if l.startswith('.text.') and want in l)
 lines, cur = [], ('', 0)
 for l in dis[start + 1:]:
