@@ -241,7 +241,7 @@ def main_cuda(args, rank, world, local_rank):
     inst_gt = gt_inds.to(torch.int32)
     ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N_INST, H, W), dtype=torch.uint8, device=dev)
     ws1 = torch.empty(lib.bxs_boxinst_loss_fused_workspace_bytes(N_INST, H, W), dtype=torch.uint8, device=dev)
-    sched = torch.zeros(16, dtype=torch.uint8, device=dev)
+    sched = torch.zeros(int(lib.bxs_boxinst_loss_fused_sched_bytes()), dtype=torch.uint8, device=dev)
     out4 = torch.empty(4, device=dev)
     g2 = torch.ones(2, device=dev)
     raw_x = [t.detach() for t in logit_sets]

@@ -35,8 +35,8 @@ constexpr int OP_MAX_N = 2048;      // instance records live in shared memory (1
 struct OpWorkspace {
   unsigned long long* row_packed;  // [N*H]    (key(max logit) << 32) | ~x
   unsigned long long* col_part;    // [N*S*W]  per strip (key(max logit) << 32) | ~y
-  float* num_part;                 // [N*S]    per strip pairwise numerator
-  int* den_part;                   // [N*S]    per strip weight count
+  float* num_part;                 // [N*MAXG] per chain group pairwise numerator
+  int* den_part;                   // [N*MAXG] per chain group weight count
   float* coef_row;                 // [N*H]    d loss_prj / d logit at the row arg-max
   float* coef_col;                 // [N*W]
   int* arg_row;                    // [N*H]
@@ -44,11 +44,23 @@ struct OpWorkspace {
   int* span;                       // [N*4]    y_lo, y_hi, c_lo, c_hi of the gradient span (y_lo > y_hi: none)
   float* inst_prj;                 // [N]
   float* inst_num;                 // [N]
+  int* inst_den;                   // [N]
   float* scale;                    // [1]      warmup / max(weight sum, 1)
   size_t total_bytes;
 };
 
 inline size_t op_align(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+constexpr int OP_LEN = 8;          // rows per pair-chain piece
+
+inline int64_t op_max_groups(int64_t H, int64_t W) {      // upper bound of ceil(chains / 8) for any box and dilation 1..4
+  int64_t best = 1;
+  for (int d = 1; d <= 4; ++d) {
+    const int64_t nseg = ceil_div(W, 32 - 2 * d) + 1, pc = ceil_div(ceil_div(H, d), OP_LEN) + 1;
+    best = std::max<int64_t>(best, ceil_div(d * pc * nseg, OP_NW));
+  }
+  return best;
+}
 
 inline OpWorkspace op_carve(void* base, int64_t N, int64_t H, int64_t W) {
   OpWorkspace w{};
@@ -58,8 +70,9 @@ inline OpWorkspace op_carve(void* base, int64_t N, int64_t H, int64_t W) {
   const int64_t S = ceil_div(H, OP_R);
   w.row_packed = (unsigned long long*)take(8 * N * H);
   w.col_part = (unsigned long long*)take(8 * N * S * W);
-  w.num_part = (float*)take(4 * N * S);
-  w.den_part = (int*)take(4 * N * S);
+  const int64_t G = op_max_groups(H, W);
+  w.num_part = (float*)take(4 * N * G);
+  w.den_part = (int*)take(4 * N * G);
   w.coef_row = (float*)take(4 * N * H);
   w.coef_col = (float*)take(4 * N * W);
   w.arg_row = (int*)take(4 * N * H);
@@ -67,6 +80,7 @@ inline OpWorkspace op_carve(void* base, int64_t N, int64_t H, int64_t W) {
   w.span = (int*)take(16 * N);
   w.inst_prj = (float*)take(4 * N);
   w.inst_num = (float*)take(4 * N);
+  w.inst_den = (int*)take(4 * N);
   w.scale = (float*)take(4);
   w.total_bytes = off;
   return w;
@@ -155,277 +169,385 @@ __device__ __forceinline__ void op_sigmoid_pair(float x, float& s, float& n) {
 }
 
 // ---------------------------------------------------------------------------------------
-// main kernel
+// pair chains
 // ---------------------------------------------------------------------------------------
-struct OpSched { unsigned next, done, ticket, pad; };
+// A chain is one warp walking rows y0, y0 + D, y0 + 2D, ... of one 32-lane column segment whose inner 32 - 2D
+// lanes own a pixel.  The row below (y + D) of one step is the row at of the next, so every row is loaded and
+// sigmoid-ed once, and each unordered pair {p, q} is evaluated once (q = right, below-left, below, below-right
+// of p) with multiplicity m = [edge bit of p towards q, p in box] + [edge bit of q towards p, q in box].  The
+// gradient of the left / upper pixel stays in the lane, the one of the other pixel travels by a shuffle (same
+// row) or through `carry` (row below -> next step).  The step before the chain (row y0 - D) only feeds the carry.
+struct PSeg { float x, s, n; unsigned e; };        // one lane's pixel: logit, sigmoid pair, box-masked edge bits
+struct PRaw { float x; unsigned e; };
+
+struct ChainGeom {                 // chain layout of one instance (pure function of its record)
+  int y_lo, rows, c_lo, c_hi, nseg, pc, nch;
+};
+template <int D>
+__device__ __forceinline__ ChainGeom chain_geom(const SRec& r, int H, int W) {
+  ChainGeom g;
+  const OpSpan sp = op_span<D>(r, H, W);
+  g.y_lo = sp.y_lo; g.rows = sp.y_hi - sp.y_lo + 1; g.c_lo = sp.c_lo; g.c_hi = sp.c_hi;
+  if (g.rows <= 0) { g.rows = 0; g.nseg = 0; g.pc = 0; g.nch = 0; return g; }
+  g.nseg = (sp.c_hi - sp.c_lo + 1 + (32 - 2 * D) - 1) / (32 - 2 * D);
+  g.pc = ((g.rows + D - 1) / D + OP_LEN - 1) / OP_LEN;        // pieces of the longest parity class
+  g.nch = D * g.pc * g.nseg;
+  return g;
+}
 
 template <int D>
-struct OpTile {
-  static constexpr int ROWS = OP_R + 2 * D;      // rows of one staged strip (halo above / strip / halo below)
-  static constexpr int TW = 64;                  // pitch of the pair tile: two columns per lane
-  static constexpr int TC = TW - 2 * D;          // owner columns per tile
+__device__ __forceinline__ void op_chain(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
+                                         int y0, int nrows, int xs, int c_hi, const SRec& r, int lane,
+                                         float* __restrict__ ginst, float& acc_lg, float& acc_slow, int& acc_w) {
+  const int x = xs + lane;
+  const bool x_ok = x >= 0 && x < W, x_box = x >= r.i0 && x <= r.i1;
+  const bool owner = lane >= D && lane < 32 - D && x <= c_hi;
+  const bool up_ok = lane >= D, dn_ok = lane + D < 32;       // the lane a shuffle by D reads from exists
+  auto load = [&](int y) {
+    PRaw v;
+    const bool in = x_ok && y >= 0 && y < H;
+    v.x = in ? __ldg(img + y * W + x) : 0.f;
+    v.e = (in && x_box && y >= r.j0 && y <= r.j1) ? (unsigned)__ldg(bits + y * W + x) : 0u;
+    return v;
+  };
+  auto finish = [&](const PRaw& w) {
+    PSeg v;
+    v.x = w.x; v.e = w.e;
+    op_sigmoid_pair(w.x, v.s, v.n);
+    return v;
+  };
+  PSeg cur = finish(load(y0 - D));
+  PRaw ahead = load(y0);
+  float carry = 0.f;
+  for (int k = -1; k < nrows; ++k) {
+    const int y = y0 + k * D;
+    const PSeg nxt = finish(ahead);
+    if (k + 1 < nrows) ahead = load(y + 2 * D);
+    const bool extreme = __any_sync(kFull, fmaxf(fabsf(cur.x), fabsf(nxt.x)) > kFastLimit);
+    const bool count = owner && k >= 0;
+    // neighbours: 4 = (y, x + D), 5 = (y + D, x - D), 6 = (y + D, x), 7 = (y + D, x + D)
+    const float s4 = __shfl_down_sync(kFull, cur.s, D), n4 = __shfl_down_sync(kFull, cur.n, D);
+    const unsigned e4 = __shfl_down_sync(kFull, cur.e, D);
+    const float s5 = __shfl_up_sync(kFull, nxt.s, D), n5 = __shfl_up_sync(kFull, nxt.n, D);
+    const unsigned e5 = __shfl_up_sync(kFull, nxt.e, D);
+    const float s7 = __shfl_down_sync(kFull, nxt.s, D), n7 = __shfl_down_sync(kFull, nxt.n, D);
+    const unsigned e7 = __shfl_down_sync(kFull, nxt.e, D);
+    const unsigned m4 = (dn_ok && k >= 0) ? ((cur.e >> 4) & 1u) + ((e4 >> 3) & 1u) : 0u;
+    const unsigned m5 = up_ok ? ((cur.e >> 5) & 1u) + ((e5 >> 2) & 1u) : 0u;
+    const unsigned m6 = ((cur.e >> 6) & 1u) + ((nxt.e >> 1) & 1u);
+    const unsigned m7 = dn_ok ? ((cur.e >> 7) & 1u) + (e7 & 1u) : 0u;
+    float ga, gq4, gq5, gq6, gq7;     // d/d this pixel (complete), d/d the neighbour (complete)
+    if (!extreme) {
+      const float dfa = cur.n - cur.s, sna = cur.s * cur.n;
+      float lg = 0.f, gs = 0.f;
+#define BXS_OP_PAIR(M, QS, QN, GQ)                                        \
+      {                                                                    \
+        const float den = fmaf(cur.s, QS, cur.n * QN);                     \
+        const float mf = (float)(M);                                       \
+        const float t = mf * rcp_approx(den);                              \
+        lg = fmaf(mf, op_lg2(den), lg);                                    \
+        gs = fmaf(QN - QS, t, gs);                                         \
+        GQ = dfa * t * (QS * QN);                                          \
+      }
+      BXS_OP_PAIR(m4, s4, n4, gq4)
+      BXS_OP_PAIR(m5, s5, n5, gq5)
+      BXS_OP_PAIR(m6, nxt.s, nxt.n, gq6)
+      BXS_OP_PAIR(m7, s7, n7, gq7)
+#undef BXS_OP_PAIR
+      ga = gs * sna;
+      if (count) acc_lg += lg;
+    } else {                           // a logit beyond +-40 in these two rows: log-space formulas
+      const float x4 = __shfl_down_sync(kFull, cur.x, D), x5 = __shfl_up_sync(kFull, nxt.x, D);
+      const float x7 = __shfl_down_sync(kFull, nxt.x, D);
+      float val = 0.f;
+      ga = 0.f;
+#define BXS_OP_SLOW(M, QX, GQ)                                                                  \
+      {                                                                                          \
+        GQ = 0.f;                                                                                \
+        if (M) {                                                                                 \
+          const float pl = pair_nlog_logspace<float>(cur.x, QX, true);                           \
+          val = fmaf((float)(M), pl, val);                                                       \
+          ga = fmaf((float)(M), pair_nlog_grad_a_logspace<float>(cur.x, QX, true, pl), ga);      \
+          GQ = (float)(M) * pair_nlog_grad_a_logspace<float>(QX, cur.x, true, pl);               \
+        }                                                                                        \
+      }
+      BXS_OP_SLOW(m4, x4, gq4)
+      BXS_OP_SLOW(m5, x5, gq5)
+      BXS_OP_SLOW(m6, nxt.x, gq6)
+      BXS_OP_SLOW(m7, x7, gq7)
+#undef BXS_OP_SLOW
+      if (count) acc_slow += val;
+    }
+    const float from_left = __shfl_up_sync(kFull, gq4, D);        // pair (x - D, x): this lane is the right pixel
+    const float to_left = __shfl_down_sync(kFull, gq5, D);        // lane + D's lower-left pixel is this lane's column
+    const float to_right = __shfl_up_sync(kFull, gq7, D);
+    if (count) {
+      acc_w += __popc(cur.e);
+      ginst[y * W + x] = (ga + carry) + from_left;                // owners have lane >= D: from_left is a real lane's value
+    }
+    carry = gq6 + (dn_ok ? to_left : 0.f) + (up_ok ? to_right : 0.f);
+    cur = nxt;
+  }
+}
+
+#ifdef BXS_OP_TRACE
+// diagnostic build only (tools/trace_onepass.py): per-CTA event log {globaltimer, tag}; 64 slots per CTA
+__device__ unsigned long long* g_op_trace = nullptr;
+__device__ __forceinline__ void op_trace(int& slot, unsigned long long tag) {
+  if (g_op_trace && slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_op_trace[(blockIdx.x * 64 + slot) * 2] = t;
+    g_op_trace[(blockIdx.x * 64 + slot) * 2 + 1] = tag;
+    ++slot;
+  }
+}
+#define OP_TRACE(tag) if (tid == 0) op_trace(trace_slot, (unsigned long long)(tag))
+#else
+#define OP_TRACE(tag)
+#endif
+
+struct OpSched { unsigned next, done, ticket, pad; };
+
+constexpr int OP_STAGES = 2;       // strips staged per CTA: one copy in flight while one strip is processed
+
+// Everything a thread needs to know about a work item, written by thread 0 when it issues the item.
+struct ItemInfo {
+  int kind;              // 0: stream item (n, strip s)   1: pair item (n, chain group s)   -1: the queue is empty
+  int n, s;
+  int ya, yb;            // stream: span rows inside the strip (ya > yb: none)
+  int c_lo, c_hi;        // span columns (float4-aligned)
+  int pad;
 };
 
+// One work queue (one atomic per item), two kinds of items:
+//   pair items    8 chains (one per warp) of one instance: pair terms, weight counts and the raw pairwise gradient of the
+//                 box span, straight from global memory (L2).  No shared memory, no barrier inside.  Long: queued first.
+//   stream items  one strip of 16 rows of one instance: ONE bulk copy into a shared-memory stage; row / column maxima and
+//                 the zero part of the gradient.  Short: they end the queue, so the dynamic scheduler has a short tail.
+// The copy of the next stream item is in flight while the current item is processed.
 // FULLW: W == NCHUNK * 128 (every lane of a row warp owns NCHUNK full float4 groups; W folds to a constant)
 template <int NCHUNK, int D, bool FULLW>
 __global__ void __launch_bounds__(OP_NT, NCHUNK <= 2 ? 4 : 2)
 onepass_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edge_bits,
                     const int32_t* __restrict__ rects, const int32_t* __restrict__ inst_gt,
-                    const int32_t* __restrict__ gt_img, int N, int H, int W_rt, int S, OpWorkspace ws,
+                    const int32_t* __restrict__ gt_img, int N, int H, int W_rt, int S, int MAXG, OpWorkspace ws,
                     OpSched* __restrict__ sched, float* __restrict__ g_logits) {
-  constexpr int ROWS = OpTile<D>::ROWS, TW = OpTile<D>::TW, TC = OpTile<D>::TC;
-  constexpr int TROWS_PER_WARP = (ROWS + OP_NW - 1) / OP_NW;
   const int W = FULLW ? NCHUNK * 128 : W_rt;
   extern __shared__ __align__(128) unsigned char op_smem[];
-  const int stage_floats = ROWS * W;
-  float* xbuf = reinterpret_cast<float*>(op_smem);                               // [2][ROWS][W]
-  float2* t_sn = reinterpret_cast<float2*>(xbuf + 2 * stage_floats);             // [ROWS][TW] (sigmoid, 1 - sigmoid)
-  uint8_t* t_e = reinterpret_cast<uint8_t*>(t_sn + ROWS * TW);                   // [ROWS][TW] effective edge bits
-  SRec* s_rec = reinterpret_cast<SRec*>(t_e + ROWS * TW);                        // [N]
-  __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ int s_item[2];
+  const int stage_floats = OP_R * W;
+  float* xbuf = reinterpret_cast<float*>(op_smem);                               // [OP_STAGES][OP_R][W]
+  SRec* s_rec = reinterpret_cast<SRec*>(xbuf + OP_STAGES * stage_floats);        // [N]
+  int* s_gpre = reinterpret_cast<int*>(s_rec + N);                               // [N + 1] prefix of chain-group counts
+  __shared__ __align__(8) uint64_t s_bar[OP_STAGES];
+  __shared__ __align__(16) ItemInfo s_info[OP_STAGES];
   __shared__ float s_redf[OP_NW];
   __shared__ int s_redi[OP_NW];
+  __shared__ int s_scan[OP_NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int total = N * S;
+#ifdef BXS_OP_TRACE
+  int trace_slot = 0;
+#endif
+  OP_TRACE(1);
+  // programmatic dependent launch: the finalize grid may be scheduled as soon as SM resources free up (it still waits
+  // for this grid's completion before reading its results)
+  asm volatile("griddepcontrol.launch_dependents;");
 
-  // strip `item` -> stage: ONE bulk copy; the D halo rows above / below ride along when the strip meets the box span
-  auto issue = [&](int item, int stage, bool force_halo) {
-    const int n = op_div(item, S), s = item - n * S, y0 = s * OP_R;
-    const int rows = min(OP_R, H - y0);
-    bool halo = force_halo;
-    if (!halo) {
-      const OpSpan sp = op_span<D>(s_rec[n], H, W);
-      halo = sp.y_lo <= sp.y_hi && y0 <= sp.y_hi && y0 + rows - 1 >= sp.y_lo;
+  // queue position v -> stage: the item's description for all threads and, for a stream item, ONE bulk copy
+  auto issue = [&](int v, int stage) {
+    ItemInfo info;
+    const int gtot = s_gpre[N];
+    info.ya = 1; info.yb = 0; info.c_lo = 4; info.c_hi = 3; info.pad = 0;
+    if (v < gtot) {
+      int lo = 0, hi = N;                          // largest n with s_gpre[n] <= v
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_gpre[mid] <= v) lo = mid; else hi = mid;
+      }
+      info.kind = 1; info.n = lo; info.s = v - s_gpre[lo];
+      s_info[stage] = info;
+      return;
     }
-    const int top = (halo && y0 >= D) ? D : 0;
-    const int bot = halo ? min(D, H - (y0 + rows)) : 0;
-    const uint32_t bytes = (uint32_t)(top + rows + bot) * (uint32_t)W * 4u;
+    const int u = v - gtot;
+    info.kind = 0;
+    info.n = op_div(u, S); info.s = u - info.n * S;
+    const int y0 = info.s * OP_R;
+    const int rows = min(OP_R, H - y0);
+    const OpSpan sp = op_span<D>(s_rec[info.n], H, W);
+    if (sp.y_lo <= sp.y_hi) { info.ya = max(y0, sp.y_lo); info.yb = min(y0 + rows - 1, sp.y_hi); }
+    info.c_lo = sp.c_lo; info.c_hi = sp.c_hi;
+    s_info[stage] = info;
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)W * 4u;
     op_mbar_expect_tx(&s_bar[stage], bytes);
-    op_bulk_g2s(xbuf + (size_t)stage * stage_floats + (size_t)(D - top) * W,
-                logits + ((int64_t)n * H + (y0 - top)) * W, bytes, &s_bar[stage]);
+    op_bulk_g2s(xbuf + (size_t)stage * stage_floats, logits + ((int64_t)info.n * H + y0) * W, bytes, &s_bar[stage]);
   };
 
-  unsigned fetched = 0;          // thread 0: next dynamic item (fetched one iteration ahead of its use)
+  unsigned fetched = 0;          // thread 0: next queue position (fetched one iteration ahead of its use)
   if (tid == 0) {
-    op_mbar_init(&s_bar[0], 1);
-    op_mbar_init(&s_bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < OP_STAGES; ++i) op_mbar_init(&s_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const int first = blockIdx.x;
-    s_item[0] = first;
-    if (first < total) issue(first, 0, true);
     fetched = gridDim.x + atomicAdd(&sched->next, 1u);
   }
   for (int n = tid; n < N; n += OP_NT) s_rec[n] = make_srec(rects, inst_gt, gt_img, n, H, W);
   __syncthreads();
+  {                              // exclusive prefix of the chain-group counts (block scan, 256 instances per round)
+    int run = 0;
+    for (int base = 0; base < N; base += OP_NT) {
+      const int n = base + tid;
+      const int cnt = n < N ? (chain_geom<D>(s_rec[n], H, W).nch + OP_NW - 1) / OP_NW : 0;
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) s_scan[warp] = inc;
+      __syncthreads();
+      int wbase = 0, tot = 0;
+#pragma unroll
+      for (int i = 0; i < OP_NW; ++i) { const int t = s_scan[i]; if (i < warp) wbase += t; tot += t; }
+      if (n < N) s_gpre[n] = run + wbase + inc - cnt;
+      run += tot;
+      if (base + OP_NT < N) __syncthreads();
+    }
+    if (tid == 0) s_gpre[N] = run;
+  }
+  __syncthreads();
+  const int total = s_gpre[N] + N * S;
+  if (tid == 0) issue(blockIdx.x, 0);             // gridDim.x <= N * S <= total (host)
+  __syncthreads();
 
-  for (int k = 0;; ++k) {
-    const int stage = k & 1;
-    const int item = s_item[stage];
-    if (item >= total) break;
-    if (tid == 0) {              // prefetch item k + 1 into the other stage (its readers finished before the last barrier)
-      const int nxt = (int)min(fetched, (unsigned)total);
-      s_item[stage ^ 1] = nxt;
-      if (nxt < total) {
-        issue(nxt, stage ^ 1, false);
+  unsigned phases = 0;           // mbarrier parity per stage (bit s): only stream items complete a phase
+  int stage = 0;
+  OP_TRACE(2);
+  for (;;) {
+    const ItemInfo it = s_info[stage];
+    if (it.kind < 0) break;
+    OP_TRACE(16 + it.kind + ((unsigned long long)it.n << 8));
+    if (tid == 0) {              // prefetch the next item into the other stage (its readers finished before the last barrier)
+      if (fetched < (unsigned)total) {
+        issue((int)fetched, stage ^ 1);
         fetched = gridDim.x + atomicAdd(&sched->next, 1u);
+      } else {
+        s_info[stage ^ 1].kind = -1;
       }
     }
-    const int n = op_div(item, S), s = item - n * S, y0 = s * OP_R;
-    const int rows = min(OP_R, H - y0);
-    const SRec rec = s_rec[n];
-    const OpSpan sp = op_span<D>(rec, H, W);
-    const int ya = max(y0, sp.y_lo), yb = min(y0 + rows - 1, sp.y_hi);
-    const bool has_pair = ya <= yb;
+    const int n = it.n;
     float* ginst = g_logits + (int64_t)n * H * W;
-    const uint8_t* bits = edge_bits + (int64_t)rec.img * H * W;
-    const int nrow = yb - ya + 1, trows = nrow + 2 * D;   // tile row tr <-> map row ya - D + tr <-> xbuf row (ya - y0) + tr
-
-    // edge bytes of the first pair tile: issued now, consumed after the streaming passes (hides the L2 latency)
-    unsigned eb[TROWS_PER_WARP][2];
-    auto load_bits = [&](int cx0, int ccols) {
+    if (it.kind == 0) {
+      // =============================== stream item: strip it.s of instance n ===============================
+      const int y0 = it.s * OP_R;
+      const int rows = min(OP_R, H - y0);
+      const int ya = it.ya, yb = it.yb;
+      op_mbar_wait(&s_bar[stage], (phases >> stage) & 1u);
+      phases ^= 1u << stage;
+      const float* xb = xbuf + (size_t)stage * stage_floats;       // strip row r at xb[r * W + col]
+      // ---- row maxima (one warp per row, the warp's rows unrolled together) + zero stores outside the span ----
 #pragma unroll
-      for (int j = 0; j < TROWS_PER_WARP; ++j) {
-        const int yy = ya - D + warp + j * OP_NW;
-        const bool rowok = warp + j * OP_NW < trows && yy >= rec.j0 && yy <= rec.j1;
+      for (int rr = 0; rr < OP_R / OP_NW; ++rr) {
+        const int r = warp + rr * OP_NW;
+        if (r < rows) {
+          const int y = y0 + r;
+          const float* row = xb + r * W;
+          float v[NCHUNK][4];
+          float cm[NCHUNK];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int xx = cx0 - D + lane + 32 * h;
-          eb[j][h] = (rowok && lane + 32 * h < ccols + 2 * D && xx >= rec.i0 && xx <= rec.i1) ? (unsigned)__ldg(bits + yy * W + xx) : 0u;
-        }
-      }
-    };
-    if (has_pair) load_bits(sp.c_lo, min(TC, sp.c_hi - sp.c_lo + 1));
-
-    op_mbar_wait(&s_bar[stage], (k >> 1) & 1);
-    const float* xb = xbuf + (size_t)stage * stage_floats;       // strip row r at xb[(D + r) * W + col]
-
-    // ---- row maxima (one warp per row) + zero stores outside the span ----
-    for (int r = warp; r < rows; r += OP_NW) {
-      const int y = y0 + r;
-      const float* row = xb + (D + r) * W;
-      float v[NCHUNK * 4];
-#pragma unroll
-      for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int col0 = (ch * 32 + lane) * 4;
-        float4 q;
-        if (FULLW || col0 < W) q = *reinterpret_cast<const float4*>(row + col0);
-        else q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        v[ch * 4] = q.x; v[ch * 4 + 1] = q.y; v[ch * 4 + 2] = q.z; v[ch * 4 + 3] = q.w;
-      }
-      float m = v[0];
-#pragma unroll
-      for (int i = 1; i < NCHUNK * 4; ++i) m = fmaxf(m, v[i]);
-      const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
-      const float mv = fkey_inv(kmax);
-      int cand = 0x7fffffff;
-#pragma unroll
-      for (int i = NCHUNK * 4 - 1; i >= 0; --i)
-        if (v[i] == mv) cand = ((i >> 2) * 32 + lane) * 4 + (i & 3);
-      const int amin = __reduce_min_sync(kFull, cand);
-      if (lane == 0) ws.row_packed[n * H + y] = pack_key(kmax, amin == 0x7fffffff ? 0 : amin);
-      float* grow = ginst + y * W + lane * 4;
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has_pair && y >= ya && y <= yb) {                      // warp-uniform: a span row
-#pragma unroll
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-          const int col0 = (ch * 32 + lane) * 4;
-          if ((FULLW || col0 < W) && (col0 < sp.c_lo || col0 > sp.c_hi)) *reinterpret_cast<float4*>(grow + ch * 128) = z;
-        }
-      } else {
-#pragma unroll
-        for (int ch = 0; ch < NCHUNK; ++ch)
-          if (FULLW || (ch * 32 + lane) * 4 < W) *reinterpret_cast<float4*>(grow + ch * 128) = z;
-      }
-    }
-    // ---- column maxima of the strip (one thread per column; first row wins ties) ----
-    for (int col = tid; col < W; col += OP_NT) {
-      const float* p = xb + D * W + col;
-      float best = p[0];
-      int brow = 0;
-      if (rows == OP_R) {
-#pragma unroll
-        for (int r = 1; r < OP_R; ++r) {
-          const float val = p[r * W];
-          if (val > best) { best = val; brow = r; }
-        }
-      } else {
-        for (int r = 1; r < rows; ++r) {
-          const float val = p[r * W];
-          if (val > best) { best = val; brow = r; }
-        }
-      }
-      ws.col_part[(n * S + s) * W + col] = pack_key(fkey(best), y0 + brow);
-    }
-
-    // ---- pair terms of the span rows [ya, yb]: tiles of TC owner columns, two columns per lane ----
-    float acc_v = 0.f;           // sum of w * lg2(denominator) (scaled by -ln 2 at the end)
-    float acc_slow = 0.f;        // slow-path values (natural log)
-    int acc_w = 0;
-    if (has_pair) {              // CTA-uniform
-      const int lr0 = ya - y0;
-      for (int cx0 = sp.c_lo; cx0 <= sp.c_hi; cx0 += TC) {
-        const int ccols = min(TC, sp.c_hi - cx0 + 1);
-        const int twc = ccols + 2 * D;
-        __syncthreads();                               // the previous tile has been consumed
-        bool ext = false;
-#pragma unroll
-        for (int j = 0; j < TROWS_PER_WARP; ++j) {
-          const int tr = warp + j * OP_NW;
-          if (tr < trows) {                            // warp-uniform
-            const int yy = ya - D + tr;
-            const bool rowok = yy >= 0 && yy < H;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int lc = lane + 32 * h, xx = cx0 - D + lc;
-              if (lc < twc) {
-                float sg = 1.f, ng = 1.f;              // outside the map: -log(s_a * 1 + n_a * 1) = 0 (padded neighbour)
-                if (rowok && xx >= 0 && xx < W) {
-                  const float x = xb[(lr0 + tr) * W + xx];
-                  op_sigmoid_pair(x, sg, ng);
-                  ext |= fabsf(x) > kFastLimit;
-                }
-                t_sn[tr * TW + lc] = make_float2(sg, ng);
-                t_e[tr * TW + lc] = (uint8_t)eb[j][h];
-              }
-            }
+          for (int ch = 0; ch < NCHUNK; ++ch) {
+            const int col0 = (ch * 32 + lane) * 4;
+            float4 q;
+            if (FULLW || col0 < W) q = *reinterpret_cast<const float4*>(row + col0);
+            else q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            v[ch][0] = q.x; v[ch][1] = q.y; v[ch][2] = q.z; v[ch][3] = q.w;
+            cm[ch] = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w));
           }
-        }
-        ext = __syncthreads_or(ext);
-        if (cx0 + TC <= sp.c_hi) load_bits(cx0 + TC, min(TC, sp.c_hi - cx0 - TC + 1));   // next tile's edge bytes
-        for (int ry = warp; ry < nrow; ry += OP_NW) {
-          const int y = ya + ry;
+          float m = cm[0];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cx = lane + 32 * h;
-            if (cx < ccols) {
-              const int ci = (ry + D) * TW + cx + D;
-              const float2 a = t_sn[ci];
-              const unsigned ea = t_e[ci];
-              const int x = cx0 + cx;
-              float g = 0.f;
-              if (!ext) {
-                float lg = 0.f;
+          for (int ch = 1; ch < NCHUNK; ++ch) m = fmaxf(m, cm[ch]);
+          const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
+          const float mv = fkey_inv(kmax);
+          // first chunk (lowest columns) that holds the maximum, first lane within it, first element within the lane
+          unsigned bal = __ballot_sync(kFull, cm[0] == mv);
+          int chunk = 0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  const int cc = c < 4 ? c : c + 1;
-                  const int dy = (cc / 3 - 1) * D, dx = (cc % 3 - 1) * D;
-                  const float2 q = t_sn[ci + dy * TW + dx];
-                  const unsigned eq = t_e[ci + dy * TW + dx];
-                  const bool pa = (ea & (1u << c)) != 0u, pq = (eq & (1u << (7 - c))) != 0u;
-                  const float den = fmaf(a.x, q.x, a.y * q.y);
-                  const float t = (q.y - q.x) * rcp_approx(den);
-                  const float l = op_lg2(den);
-                  lg += pa ? l : 0.f;
-                  g += pa ? t : 0.f;
-                  g += pq ? t : 0.f;
-                }
-                acc_v += lg;
-                g *= a.x * a.y;
-              } else {                                     // a logit beyond +-40 in the tile: log-space formulas
-                const float xa = xb[(lr0 + ry + D) * W + x];
+          for (int ch = 1; ch < NCHUNK; ++ch) {
+            const unsigned b = __ballot_sync(kFull, cm[ch] == mv);
+            if (bal == 0u) { bal = b; chunk = ch; }
+          }
+          if (lane == (bal ? __ffs(bal) - 1 : 0)) {                  // bal == 0 only for an all-NaN row: any in-range index
+            float w0 = v[0][0], w1 = v[0][1], w2 = v[0][2];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  const int cc = c < 4 ? c : c + 1;
-                  const int dy = (cc / 3 - 1) * D, dx = (cc % 3 - 1) * D;
-                  const unsigned eq = t_e[ci + dy * TW + dx];
-                  const unsigned wa = (ea >> c) & 1u;
-                  const unsigned mm = wa + ((eq >> (7 - c)) & 1u);
-                  if (mm) {
-                    const int qy = y + dy, qx = x + dx;
-                    const bool has_b = qy >= 0 && qy < H && qx >= 0 && qx < W;
-                    const float xq = has_b ? xb[(lr0 + ry + D) * W + x + dy * W + dx] : 0.f;
-                    const float pl = pair_nlog_logspace<float>(xa, xq, has_b);
-                    acc_slow = fmaf((float)wa, pl, acc_slow);
-                    g = fmaf((float)mm, pair_nlog_grad_a_logspace<float>(xa, xq, has_b, pl), g);
-                  }
-                }
-              }
-              acc_w += __popc(ea);
-              ginst[y * W + x] = g;
+            for (int ch = 1; ch < NCHUNK; ++ch)
+              if (chunk == ch) { w0 = v[ch][0]; w1 = v[ch][1]; w2 = v[ch][2]; }
+            const int e = w0 == mv ? 0 : (w1 == mv ? 1 : (w2 == mv ? 2 : 3));
+            ws.row_packed[n * H + y] = pack_key(kmax, min((chunk * 32 + lane) * 4 + e, W - 1));
+          }
+          float* grow = ginst + y * W + lane * 4;
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (y >= ya && y <= yb) {                                  // warp-uniform: a span row (the chains write the span)
+#pragma unroll
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+              const int col0 = (ch * 32 + lane) * 4;
+              if ((FULLW || col0 < W) && (col0 < it.c_lo || col0 > it.c_hi)) *reinterpret_cast<float4*>(grow + ch * 128) = z;
             }
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < NCHUNK; ++ch)
+              if (FULLW || (ch * 32 + lane) * 4 < W) *reinterpret_cast<float4*>(grow + ch * 128) = z;
           }
         }
       }
-      // per-strip partials: fixed-order block reduction
-      const float v = warp_sum(fmaf(acc_v, -0.69314718055994531f, acc_slow));
+      // ---- column maxima of the strip (one thread per column; first row wins ties) ----
+      for (int col = tid; col < W; col += OP_NT) {
+        const float* p = xb + col;
+        float best = p[0];
+        int brow = 0;
+        if (rows == OP_R) {
+#pragma unroll
+          for (int r = 1; r < OP_R; ++r) {
+            const float val = p[r * W];
+            if (val > best) { best = val; brow = r; }
+          }
+        } else {
+          for (int r = 1; r < rows; ++r) {
+            const float val = p[r * W];
+            if (val > best) { best = val; brow = r; }
+          }
+        }
+        ws.col_part[(n * S + it.s) * W + col] = pack_key(fkey(best), y0 + brow);
+      }
+    } else {
+      // =============================== pair item: chains 8 s .. 8 s + 7 of instance n ===============================
+      const SRec rec = s_rec[n];
+      const ChainGeom cg = chain_geom<D>(rec, H, W);
+      const int gw = it.s * OP_NW + warp;
+      float acc_lg = 0.f, acc_slow = 0.f;
+      int acc_w = 0;
+      if (gw < cg.nch) {                           // warp-uniform
+        const int u = op_div(gw, cg.nseg), seg = gw - u * cg.nseg;
+        const int p = op_div(u, cg.pc), piece = u - p * cg.pc;       // parity class, piece within the class
+        const int rows_p = (cg.rows - p + D - 1) / D;                // rows of class p
+        const int k0 = piece * OP_LEN;
+        if (k0 < rows_p)
+          op_chain<D>(logits + (int64_t)n * H * W, edge_bits + (int64_t)rec.img * H * W, H, W, cg.y_lo + p + D * k0,
+                      min(OP_LEN, rows_p - k0), cg.c_lo - D + seg * (32 - 2 * D), cg.c_hi, rec, lane, ginst, acc_lg, acc_slow,
+                      acc_w);
+      }
+      const float v = warp_sum(fmaf(acc_lg, -0.69314718055994531f, acc_slow));
       const int w = warp_sum(acc_w);
       if (lane == 0) { s_redf[warp] = v; s_redi[warp] = w; }
     }
-    __syncthreads();             // stage `stage` and the tile are free; s_item[stage ^ 1] is visible
-    if (tid == 0) {
+    __syncthreads();             // stage `stage` is free; the next s_info entries are visible; pair partials are in place
+    if (it.kind == 1 && tid == 0) {                // fixed-order sum over the 8 chains of the group
       float v = 0.f;
       int w = 0;
-      if (has_pair) {
 #pragma unroll
-        for (int i = 0; i < OP_NW; ++i) { v += s_redf[i]; w += s_redi[i]; }
-      }
-      ws.num_part[item] = v;
-      ws.den_part[item] = w;
+      for (int i = 0; i < OP_NW; ++i) { v += s_redf[i]; w += s_redi[i]; }
+      ws.num_part[n * MAXG + it.s] = v;
+      ws.den_part[n * MAXG + it.s] = w;
     }
+    stage ^= 1;
   }
+  OP_TRACE(3);
   // ---- scheduler reset by the last CTA (every fetch of a CTA precedes its `done` increment) ----
   if (tid == 0) {
     __threadfence();
@@ -445,15 +567,20 @@ onepass_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict_
 template <int D>
 __global__ void __launch_bounds__(OP_FIN_NT)
 onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ inst_gt,
-                        const int32_t* __restrict__ gt_img, int N, int H, int W, int S, OpWorkspace ws,
+                        const int32_t* __restrict__ gt_img, int N, int H, int W, int S, int MAXG, OpWorkspace ws,
                         OpSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
                         float* __restrict__ losses_out) {
   constexpr int NWF = OP_FIN_NT / 32;
   __shared__ float s_f[4][NWF];
-  __shared__ int s_i[NWF];
   __shared__ bool s_last;
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // independent loads first: this thread's row key, its column keys of every strip, weight counts, the record
+  // the record depends only on the targets: read it before waiting for the main grid (programmatic dependent launch)
+  asm volatile("griddepcontrol.launch_dependents;");
+  const SRec rec = make_srec(rects, inst_gt, gt_img, n, H, W);
+  const OpSpan sp = op_span<D>(rec, H, W);
+  const bool empty = rec.j0 > rec.j1;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // independent loads first: this thread's row key and its column keys of every strip
   const int row_i = tid, col_i = tid;                   // H, W <= 512 = OP_FIN_NT
   unsigned long long rp = 0ull, cp = 0ull;
   if (row_i < H) rp = ws.row_packed[n * H + row_i];
@@ -465,26 +592,15 @@ onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __rest
       cp = p > cp ? p : cp;
     }
   }
-  int den = 0;
-  for (int i = tid; i < N * S; i += OP_FIN_NT) den += ws.den_part[i];
-  float num = 0.f;
-  if (wid == 0 && lane < S) num = ws.num_part[n * S + lane];        // S <= 32
-  const float warm = fminf(iter_ptr[0] / warmup_iters, 1.f);
-  const SRec rec = make_srec(rects, inst_gt, gt_img, n, H, W);
-  const OpSpan sp = op_span<D>(rec, H, W);
-  const bool empty = rec.j0 > rec.j1;
-
   const float sr = row_i < H ? sigmoid_exact(fkey_inv((unsigned)(rp >> 32))) : 0.f;
   const float sc = col_i < W ? sigmoid_exact(fkey_inv((unsigned)(cp >> 32))) : 0.f;
   const bool tr = !empty && row_i >= rec.j0 && row_i <= rec.j1, tc = !empty && col_i >= rec.i0 && col_i <= rec.i1;
-  float r0 = warp_sum(tr ? sr : 0.f), r1 = warp_sum(sr * sr), r2 = warp_sum(tc ? sc : 0.f), r3 = warp_sum(sc * sc);
-  den = warp_sum(den);
-  if (lane == 0) { s_f[0][wid] = r0; s_f[1][wid] = r1; s_f[2][wid] = r2; s_f[3][wid] = r3; s_i[wid] = den; }
+  const float r0 = warp_sum(tr ? sr : 0.f), r1 = warp_sum(sr * sr), r2 = warp_sum(tc ? sc : 0.f), r3 = warp_sum(sc * sc);
+  if (lane == 0) { s_f[0][wid] = r0; s_f[1][wid] = r1; s_f[2][wid] = r2; s_f[3][wid] = r3; }
   __syncthreads();
   float Ir = 0.f, Xr = 0.f, Ic = 0.f, Xc = 0.f;
-  int wtot = 0;
 #pragma unroll
-  for (int i = 0; i < NWF; ++i) { Ir += s_f[0][i]; Xr += s_f[1][i]; Ic += s_f[2][i]; Xc += s_f[3][i]; wtot += s_i[i]; }
+  for (int i = 0; i < NWF; ++i) { Ir += s_f[0][i]; Xr += s_f[1][i]; Ic += s_f[2][i]; Xc += s_f[3][i]; }
   const float inv_n = 1.f / (float)N;
   const float Ur = Xr + (empty ? 0.f : (float)(rec.j1 - rec.j0 + 1)) + kDiceEps;
   const float Uc = Xc + (empty ? 0.f : (float)(rec.i1 - rec.i0 + 1)) + kDiceEps;
@@ -498,12 +614,17 @@ onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __rest
     ws.arg_col[n * W + col_i] = (int)(0xffffffffu - (unsigned)(cp & 0xffffffffull));
   }
   if (wid == 0) {
-    // fixed-order sum of the strip numerators (sequential over lanes -> same order as a serial loop)
-    float tot = 0.f;
-    for (int s = 0; s < S; ++s) tot += __shfl_sync(kFull, num, s);
+    // fixed-order sums of the chain-group partials of this instance (lane-strided, then a shuffle tree)
+    const int ng = (chain_geom<D>(rec, H, W).nch + OP_NW - 1) / OP_NW;
+    float num = 0.f;
+    int den = 0;
+    for (int g = lane; g < ng; g += 32) { num += ws.num_part[n * MAXG + g]; den += ws.den_part[n * MAXG + g]; }
+    num = warp_sum(num);
+    den = warp_sum(den);
     if (lane == 0) {
       ws.inst_prj[n] = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
-      ws.inst_num[n] = tot;
+      ws.inst_num[n] = num;
+      ws.inst_den[n] = den;
       reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
       __threadfence();
       s_last = atomicAdd(&sched->ticket, 1u) == (unsigned)(N - 1);
@@ -513,10 +634,14 @@ onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __rest
   if (!s_last || tid >= 32) return;
   __threadfence();
   float prj = 0.f, pn = 0.f;
-  for (int i = lane; i < N; i += 32) { prj += __ldcg(ws.inst_prj + i); pn += __ldcg(ws.inst_num + i); }
+  long long wtot = 0;
+  for (int i = lane; i < N; i += 32) { prj += __ldcg(ws.inst_prj + i); pn += __ldcg(ws.inst_num + i); wtot += __ldcg(ws.inst_den + i); }
   prj = warp_sum(prj);
   pn = warp_sum(pn);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wtot += __shfl_xor_sync(kFull, wtot, o);
   if (lane == 0) {
+    const float warm = fminf(iter_ptr[0] / warmup_iters, 1.f);
     const float scale = warm / fmaxf((float)wtot, 1.f);
     losses_out[0] = prj * inv_n;
     losses_out[1] = pn * scale;
@@ -539,6 +664,7 @@ onepass_backward_kernel(int H, int W, OpWorkspace ws, const float* __restrict__ 
   __shared__ float s_cr[512];
   const int n = blockIdx.x, tid = threadIdx.x;
   float* ginst = g_logits + (int64_t)n * H * W;
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // everything below may read the previous kernel's results
   const float gp = g_prj_p[0], gq = g_pair_p[0] * ws.scale[0];
   const int4 sp = reinterpret_cast<const int4*>(ws.span)[n];
   int ar = 0, ac = 0;
@@ -566,21 +692,32 @@ onepass_backward_kernel(int H, int W, OpWorkspace ws, const float* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+// launch with programmatic stream serialization: the kernel may start while its predecessor in the stream drains
+// (it calls griddepcontrol.wait before touching the predecessor's results)
+template <typename... KArgs, typename... Args>
+inline cudaError_t op_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline bool op_supported(int64_t N, int64_t H, int64_t W, int d) {
   return N > 0 && N <= OP_MAX_N && H > 0 && H <= 512 && W > 0 && W <= 512 && (W % 4 == 0) && d >= 1 && d <= 4;
 }
 
-template <int D>
 inline size_t op_smem_bytes(int64_t N, int64_t W) {
-  constexpr int ROWS = OpTile<D>::ROWS, TW = OpTile<D>::TW;
-  return (size_t)2 * ROWS * W * 4 + (size_t)ROWS * TW * 8 + (size_t)ROWS * TW + (size_t)N * sizeof(SRec);
+  return (size_t)OP_STAGES * OP_R * W * 4 + (size_t)N * sizeof(SRec) + (size_t)(N + 1) * 4;
 }
 
 template <int NCHUNK, int D, bool FULLW>
 int op_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bits, const int32_t* rects,
                    const int32_t* inst_gt, const int32_t* gt_img, int N, int H, int W, OpWorkspace ws, OpSched* sched,
                    float* g_logits) {
-  const size_t smem = op_smem_bytes<D>(N, W);
+  const size_t smem = op_smem_bytes(N, W);
   auto kern = onepass_main_kernel<NCHUNK, D, FULLW>;
   static thread_local size_t configured = 0;      // per instantiation
   static thread_local int occ_dev = -1, occ = 0;
@@ -603,9 +740,10 @@ int op_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bit
     occ_smem = smem;
   }
   const int S = (int)ceil_div(H, OP_R);
-  const int64_t total = (int64_t)N * S;
+  const int64_t total = (int64_t)N * S;           // stream items alone; pair items come on top
   const int grid = (int)std::min<int64_t>(total, (int64_t)sm_count() * occ);
-  kern<<<grid, OP_NT, smem, st>>>(logits, edge_bits, rects, inst_gt, gt_img, N, H, W, S, ws, sched, g_logits);
+  kern<<<grid, OP_NT, smem, st>>>(logits, edge_bits, rects, inst_gt, gt_img, N, H, W, S, (int)op_max_groups(H, W), ws, sched,
+                                  g_logits);
   return check_launch();
 }
 
@@ -613,6 +751,12 @@ int op_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bit
 }  // namespace bxs
 
 using namespace bxs;
+
+#ifdef BXS_OP_TRACE
+extern "C" int bxs_debug_set_trace(void* buf) {
+  return cudaMemcpyToSymbol(g_op_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int bxs_boxinst_loss_fused_supported(int64_t N, int64_t H, int64_t W, int dilation) {
   return op_supported(N, H, W, dilation) ? 1 : 0;
@@ -647,8 +791,8 @@ extern "C" int bxs_boxinst_loss_fused_forward(const float* logits, const uint8_t
                        : op_launch_main<NC, DD, false>(st, logits, edge_bits, rects, inst_gt, gt_img, (int)N, (int)H, \
                                                        (int)W, ws, sched, g_logits);                                \
   if (rc == BXS_OK) {                                                                                               \
-    onepass_finalize_kernel<DD><<<(unsigned)N, OP_FIN_NT, 0, st>>>(rects, inst_gt, gt_img, (int)N, (int)H, (int)W, S, \
-                                                                   ws, sched, iter_ptr, warmup_iters, losses_out);  \
+    op_launch_pdl(onepass_finalize_kernel<DD>, dim3((unsigned)N), dim3(OP_FIN_NT), 0, st, rects, inst_gt, gt_img, (int)N, \
+                  (int)H, (int)W, S, (int)op_max_groups(H, W), ws, sched, iter_ptr, warmup_iters, losses_out);      \
     rc = check_launch();                                                                                            \
   }
 #define BXS_OP_D(NC)                                                  \
@@ -671,6 +815,7 @@ extern "C" int bxs_boxinst_loss_fused_backward(const void* workspace, const floa
                                                bxs_stream_t stream) {
   if (!workspace || !g_prj || !g_pair || !g_logits || N <= 0 || H <= 0 || W <= 0) return BXS_ERR_INVALID_ARG;
   OpWorkspace ws = op_carve(const_cast<void*>(workspace), N, H, W);
-  onepass_backward_kernel<<<(unsigned)N, OP_FIN_NT, 0, as_stream(stream)>>>((int)H, (int)W, ws, g_prj, g_pair, g_logits);
+  op_launch_pdl(onepass_backward_kernel, dim3((unsigned)N), dim3(OP_FIN_NT), 0, as_stream(stream), (int)H, (int)W, ws, g_prj,
+                g_pair, g_logits);
   return check_launch();
 }

@@ -45,5 +45,7 @@ def text_of(key):
     return srcs[f][ln - 1].strip()[:100] if 0 < ln <= len(srcs[f]) else ''
 tot, ts = sum(inst.values()), sum(samp.values())
 print(f' total warp-instr {tot}, samples {ts}')
-for ln, c in inst.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 30):
+order = samp if (len(sys.argv) > 5 and sys.argv[5] == 'stall') else inst
+for ln, _c in order.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 30):
+    c = inst[ln]
     print(f'{c:9d} {100*c/tot:5.1f}%  stall {100*samp[ln]/max(ts,1):5.1f}%  {ln[0][:16]:16s}:{ln[1]:4d}: {text_of(ln)}')

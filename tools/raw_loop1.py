@@ -16,7 +16,7 @@ xs = [torch.randn(N_INST, 1, H, W, device=dev) * 2 for _ in range(R)]
 gls = [torch.empty_like(xs[0]) for _ in range(R)]
 inst_gt = case['gt_inds'].to(dev).to(torch.int32)
 ws = torch.empty(lib.bxs_boxinst_loss_fused_workspace_bytes(N_INST, H, W), dtype=torch.uint8, device=dev)
-sched = torch.zeros(16, dtype=torch.uint8, device=dev)
+sched = torch.zeros(int(lib.bxs_boxinst_loss_fused_sched_bytes()), dtype=torch.uint8, device=dev)
 out = torch.empty(4, device=dev); g = torch.ones(2, device=dev)
 def raw(i, st):
     x, gl = xs[i % R], gls[i % R]
