@@ -8,7 +8,8 @@ replicas (weak scaling, no data-path collective); rank times are combined with M
 What one "step" is (config A of BASELINE.json, synthetic): the BoxInst mask
 loss of ONE batch -- 2 images of 3x800x1024, 8 GT boxes each, N=128 sampled instances, loss grid
 200x256 -- forward (projection + colour-pairwise terms) and backward (d/d mask_logits).
-  value : inputs and targets resident in HBM; timed = fused loss forward + backward kernels.
+  value : inputs and targets resident in HBM; timed = the public autograd op, forward + backward (single-pass
+          schedule: onepass_main + onepass_finalize + onepass_backward kernels), replayed as a CUDA graph.
   e2e   : through the public head API with HOST (pinned) buffers: H2D of image, logits, boxes ->
           target building (LAB, similarity, rects) -> loss fwd+bwd -> D2H of the gradient + losses.
 L2 hygiene: the timed loop rotates over R input/gradient sets whose footprint (R x 52 MB) exceeds
@@ -172,6 +173,7 @@ def main_cuda(args, rank, world, local_rank):
     img = case['img'].to(dev)
     boxes = [b.to(dev) for b in case['gt_bboxes']]
     gt_inds = case['gt_inds'].to(dev)
+    gt_inds32 = gt_inds.to(torch.int32)       # instance -> GT indices are part of the (precomputed) targets
     it = torch.tensor([10000.0], device=dev)
     targets = boxinst_targets(img, case['metas'], boxes)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
@@ -183,7 +185,7 @@ def main_cuda(args, rank, world, local_rank):
 
     def step(i):
         x = logit_sets[i % ROTATE]
-        prj, pair = boxinst_mask_loss(x, targets, gt_inds, it)
+        prj, pair = boxinst_mask_loss(x, targets, gt_inds32, it)
         torch.autograd.backward([prj, pair], [ones, ones])
         grad_ring[i % ROTATE], x.grad = x.grad, None
         return prj, pair
@@ -210,7 +212,7 @@ def main_cuda(args, rank, world, local_rank):
 
     # ---- the same step (public autograd op, forward + backward) captured once per rotating input set
     #      into CUDA graphs: removes the ~0.2 ms/step of Python/autograd launch overhead ----
-    graphs, mode = [], 'cuda_graph'
+    graphs, mode, steps_timed = [], 'cuda_graph', args.steps
     try:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -221,24 +223,30 @@ def main_cuda(args, rank, world, local_rank):
                 logit_sets[i].grad = None
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        for i in range(ROTATE):
-            g = torch.cuda.CUDAGraph()
-            x = logit_sets[i]
+        # one graph = ROTATE consecutive steps over the rotating input sets (a training loop captures whole
+        # iterations the same way); the graph launch latency is amortised over its steps
+        g = torch.cuda.CUDAGraph()
+        for x in logit_sets:
             x.grad = None
-            with torch.cuda.graph(g):
-                prj, pair = boxinst_mask_loss(x, targets, gt_inds, it)
+        with torch.cuda.graph(g):
+            for i in range(ROTATE):
+                x = logit_sets[i]
+                prj, pair = boxinst_mask_loss(x, targets, gt_inds32, it)
                 torch.autograd.backward([prj, pair], [ones, ones])
-            graphs.append((g, prj, pair, x.grad))
-        for i in range(warm):
-            graphs[i % ROTATE][0].replay()
-        ms_step = timed(lambda i: graphs[i % ROTATE][0].replay(), args.steps)
+                graphs.append((prj, pair, x.grad))
+        for i in range(max(warm // ROTATE, 1)):
+            g.replay()
+        reps = max(args.steps // ROTATE, 1)
+        ms_step = timed(lambda i: g.replay(), reps) / ROTATE
+        steps_timed = reps * ROTATE
+        mode = f'cuda_graph ({ROTATE} steps per graph)'
     except Exception as e:  # noqa: BLE001
         mode = f'eager (graph capture failed: {type(e).__name__})'
         ms_step = ms_eager
 
     # ---- per-call timing through the C ABI (same rotation): the single-pass schedule the step uses, and the
     #      two-call kernels (forward-only / fallback path) for comparison ----
-    inst_gt = gt_inds.to(torch.int32)
+    inst_gt = gt_inds32
     ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N_INST, H, W), dtype=torch.uint8, device=dev)
     ws1 = torch.empty(lib.bxs_boxinst_loss_fused_workspace_bytes(N_INST, H, W), dtype=torch.uint8, device=dev)
     sched = torch.zeros(int(lib.bxs_boxinst_loss_fused_sched_bytes()), dtype=torch.uint8, device=dev)
@@ -248,31 +256,48 @@ def main_cuda(args, rank, world, local_rank):
     raw_g = [torch.empty_like(raw_x[0]) for _ in range(ROTATE)]
     st = L.stream()
 
-    def raw_fwd(i):
+    def raw_fwd(i, s_=None):
         L.check(lib.bxs_boxinst_loss_forward(L.ptr(raw_x[i % ROTATE]), L.ptr(targets.edge_bits), L.ptr(targets.rects),
                                              L.ptr(inst_gt), L.ptr(targets.gt_img), L.ptr(it), 10000.0, L.ptr(ws),
-                                             L.ptr(out4), N_INST, H, W, 2, st), 'fwd')
+                                             L.ptr(out4), N_INST, H, W, 2, s_ or st), 'fwd')
 
-    def raw_bwd(i):
+    def raw_bwd(i, s_=None):
         L.check(lib.bxs_boxinst_loss_backward(L.ptr(raw_x[i % ROTATE]), L.ptr(targets.edge_bits), L.ptr(targets.rects),
                                               L.ptr(inst_gt), L.ptr(targets.gt_img), L.ptr(ws), L.ptr(g2),
-                                              L.ptr(raw_g[i % ROTATE]), N_INST, H, W, 2, st), 'bwd')
+                                              L.ptr(raw_g[i % ROTATE]), N_INST, H, W, 2, s_ or st), 'bwd')
 
-    def raw_one_fwd(i):
+    def raw_one_fwd(i, s_=None):
         L.check(lib.bxs_boxinst_loss_fused_forward(L.ptr(raw_x[i % ROTATE]), L.ptr(targets.edge_bits), L.ptr(targets.rects),
                                                    L.ptr(inst_gt), L.ptr(targets.gt_img), L.ptr(it), 10000.0, L.ptr(ws1),
-                                                   L.ptr(sched), L.ptr(out4), L.ptr(raw_g[i % ROTATE]), N_INST, H, W, 2, st),
+                                                   L.ptr(sched), L.ptr(out4), L.ptr(raw_g[i % ROTATE]), N_INST, H, W, 2, s_ or st),
                 'fused fwd')
 
-    def raw_one_bwd(i):
+    def raw_one_bwd(i, s_=None):
         L.check(lib.bxs_boxinst_loss_fused_backward(L.ptr(ws1), L.ptr(g2[0:1]), L.ptr(g2[1:2]), L.ptr(raw_g[i % ROTATE]),
-                                                    N_INST, H, W, st), 'fused bwd')
-    raw_fwd(0)
-    us_fwd = timed(raw_fwd, args.steps) * 1e3
-    us_bwd = timed(raw_bwd, args.steps) * 1e3
-    raw_one_fwd(0)
-    us_one_fwd = timed(raw_one_fwd, args.steps) * 1e3
-    us_one_bwd = timed(raw_one_bwd, args.steps) * 1e3
+                                                    N_INST, H, W, s_ or st), 'fused bwd')
+    def graph_us(fn):
+        """device time per call: ROTATE calls captured in one CUDA graph (no host launch overhead), replayed"""
+        for i in range(ROTATE):
+            fn(i)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cur = L.stream()
+            for i in range(ROTATE):
+                fn(i, cur)
+        g.replay()
+        reps = max(args.steps // ROTATE, 1)
+        return timed(lambda i: g.replay(), reps) * 1e3 / ROTATE
+
+    us_fwd = graph_us(raw_fwd)
+    us_bwd = graph_us(raw_bwd)
+    us_one_fwd = graph_us(raw_one_fwd)
+
+    def raw_one_both(i, s_=None):
+        raw_one_fwd(i, s_)
+        raw_one_bwd(i, s_)
+    us_one_step = graph_us(raw_one_both)
+    us_one_bwd = us_one_step - us_one_fwd
 
     # ---- e2e through the public head API with host buffers ----
     head = CondInstMaskHead(in_channels=16, in_stride=8, out_stride=4, topk_per_img=64, max_proposals=-1,
@@ -322,8 +347,8 @@ def main_cuda(args, rank, world, local_rank):
     ms_e2e = timed_streams(e2e_step, args.steps)
     clocks = sampler.stop()
 
-    ms_step, ms_e2e, ms_eager, us_fwd, us_bwd, us_one_fwd, us_one_bwd = reduce_max_over_ranks(
-        [ms_step, ms_e2e, ms_eager, us_fwd, us_bwd, us_one_fwd, us_one_bwd], dist, dev)
+    ms_step, ms_e2e, ms_eager, us_fwd, us_bwd, us_one_fwd, us_one_bwd, us_one_step = reduce_max_over_ranks(
+        [ms_step, ms_e2e, ms_eager, us_fwd, us_bwd, us_one_fwd, us_one_bwd, us_one_step], dist, dev)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -338,7 +363,7 @@ def main_cuda(args, rank, world, local_rank):
     line = {
         'metric': METRIC, 'value': ms_step / (B_IMG * world),   # whole job: step time / images of all ranks
         'unit': 'ms/img', 'n_gpus': world,
-        'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': False, 'scaling': 'weak',
+        'steps': steps_timed, 'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': False, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'BoxInst R-50 mask loss fwd+bwd (config A): batch 2/GPU x (3,800,1024), 8 GT/img, '
                                'N=128 instances, loss grid 200x256, pairwise 3x3 dil 2',
@@ -349,24 +374,30 @@ def main_cuda(args, rank, world, local_rank):
                    'aggregate_img_per_s': world * B_IMG / (ms_step * 1e-3)},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': ncu_traffic_bytes(),
-                     'traffic_source': 'profiles/r1_traffic.json (ncu --set full, dram read+write, sum over the kernels of one step)',
+                     'traffic_source': 'profiles/r1_traffic.json (ncu --set full, dram read+write per launch, summed over the '
+                                       'kernels of one step)',
                      'peak_source': peak_src,
-                     'note': 'whole step (single-pass main kernel + finalize kernel + backward kernel, CUDA-graph replay) against '
-                             'the 85.2 MB/step ALGORITHMIC figure of SURVEY 8d (logits read in fwd and bwd + gradient written + '
-                             'similarity read twice); the single-pass schedule actually moves 52.6 MB (logits once, gradient '
-                             'once, edge bits), see kernels.single_pass',
-                     'kernels': {'single_pass_forward(main+finalize)': {
+                     'note': 'headline = the WHOLE step (onepass_main + onepass_finalize + onepass_backward kernels, CUDA-graph '
+                             'replay through the public autograd op) against the 85.2 MB/step ALGORITHMIC figure of SURVEY 8d '
+                             '(logits read in fwd and in bwd + gradient written + similarity read twice).  The single-pass '
+                             'schedule moves 52.5 MB (logits once, gradient once, edge bytes): see kernels.*; the dominant '
+                             'kernel is onepass_main_kernel (its share of the step: profiles/r1_launches_bench.csv)',
+                     'kernels': {'single_pass_forward(onepass_main+onepass_finalize)': {
                                      'us': us_one_fwd, 'moved_mb': ONEPASS_BYTES / 1e6,
                                      'achieved_moved': ONEPASS_BYTES / (us_one_fwd * 1e-6) / 1e9,
                                      'frac_moved': ONEPASS_BYTES / (us_one_fwd * 1e-6) / 1e9 / peak,
-                                     'achieved_algorithmic': ALGO_BYTES / (us_one_fwd * 1e-6) / 1e9},
-                                 'single_pass_backward(g=1 early exit)': {'us': us_one_bwd},
+                                     'achieved_algorithmic': ALGO_BYTES / (us_one_fwd * 1e-6) / 1e9,
+                                     'frac_algorithmic': ALGO_BYTES / (us_one_fwd * 1e-6) / 1e9 / peak},
+                                 'single_pass_backward(onepass_backward, in place)': {'us': us_one_bwd},
+                                 'single_pass_step_c_abi': {'us': us_one_step, 'achieved_algorithmic': ALGO_BYTES / (us_one_step * 1e-6) / 1e9,
+                                                            'frac_algorithmic': ALGO_BYTES / (us_one_step * 1e-6) / 1e9 / peak},
                                  'two_call_forward(fwd_fused+finalize)': {'us': us_fwd, 'algo_mb': FWD_BYTES / 1e6, 'achieved': ach_f,
                                                                           'frac': ach_f / peak},
                                  'two_call_backward(bwd_rows)': {'us': us_bwd, 'algo_mb': BWD_BYTES / 1e6, 'achieved': ach_b,
-                                                                 'frac': ach_b / peak}}},
+                                                                 'frac': ach_b / peak}},
+                     'timing': 'per-call numbers: 8 rotating calls captured in one CUDA graph, CUDA events around replays'},
         'e2e': {'value': ms_e2e / (B_IMG * world), 'unit': 'ms/img', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-        'gpu_launches': 3 * args.steps,        # onepass_main + onepass_finalize + onepass_backward kernels per step
+        'gpu_launches': 3 * steps_timed,        # onepass_main + onepass_finalize + onepass_backward kernels per step
         'clocks': clocks,
     }
     if cpu_ms is not None:

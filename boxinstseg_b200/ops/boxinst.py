@@ -140,6 +140,7 @@ class _BoxInstMaskLoss(torch.autograd.Function):
         fused = bool(ctx.needs_input_grad[0] and N > 0 and lib.bxs_boxinst_loss_fused_supported(N, H, W, dilation)
                      and logits.data_ptr() % 16 == 0)
         ctx.fused, ctx.dilation, ctx.calls = fused, dilation, 0
+        ctx.set_materialize_grads(False)          # no zero-fill kernels for unused / non-differentiable outputs
         with torch.cuda.device(dev):
             if fused:
                 ws = torch.empty(lib.bxs_boxinst_loss_fused_workspace_bytes(N, H, W), dtype=torch.uint8, device=dev)
@@ -166,8 +167,13 @@ class _BoxInstMaskLoss(torch.autograd.Function):
         N, _, H, W = logits.shape
         lib = L.lib()
         ctx.calls += 1
-        g_prj = g_prj.reshape(()).to(torch.float32)
-        g_pair = g_pair.reshape(()).to(torch.float32)
+        if g_prj is None and g_pair is None:
+            return (None,) * 8
+        zero = None
+        if g_prj is None or g_pair is None:
+            zero = torch.zeros((), dtype=torch.float32, device=logits.device)
+        g_prj = zero if g_prj is None else g_prj.reshape(()).to(torch.float32)
+        g_pair = zero if g_pair is None else g_pair.reshape(()).to(torch.float32)
         with torch.cuda.device(logits.device):
             if ctx.fused and ctx.calls == 1:
                 g_logits = ctx.g_logits
@@ -196,7 +202,7 @@ def boxinst_mask_loss(mask_logits, targets: BoxInstTargets, gt_inds, iter_buf, w
         raise NotImplementedError('the fused loss is specialised to pairwise_size == 3')
     if mask_logits.dtype != torch.float32:
         mask_logits = mask_logits.float()        # @force_fp32(apply_to=('mask_logits',)), :1288
-    inst_gt = gt_inds.to(torch.int32).contiguous()
+    inst_gt = gt_inds if (gt_inds.dtype == torch.int32 and gt_inds.is_contiguous()) else gt_inds.to(torch.int32).contiguous()
     prj, pair, _ = _BoxInstMaskLoss.apply(mask_logits, targets.edge_bits, targets.rects, inst_gt, targets.gt_img,
                                           iter_buf, warmup_iters, pairwise_dilation)
     return prj, pair
