@@ -165,7 +165,18 @@ def main_cuda(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL announces its version on stdout at communicator creation; the contract is ONE JSON line there
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     sampler = ClockSampler(local_rank)
     sampler.start()                              # NVML initialisation happens long before the timed regions
 

@@ -9,11 +9,14 @@
 // (transposed so that the 8 output channels of one input channel are two LDS.128 broadcasts).
 //   forward : CTA = (instance, 16x32 low-res tile + 1px apron); low-res logits live only in shared
 //             memory; the CTA writes the upsampled 32x64 output tile directly (float4 stores).
-//   backward: CTA = (image, 8x32 low-res tile) looping over the instances of that image, so
-//             d/d mask_feat is accumulated in registers across instances and written once (no
-//             atomics, deterministic); d/d params is an outer-product reduction over the tile in
+//   backward: CTA = (image, 8x32 low-res tile, instance group) looping over every GS-th instance of
+//             that image, so d/d mask_feat is accumulated in registers across the group's instances and
+//             written once per group (no atomics); the GS group partials are summed in a fixed order by a
+//             second kernel (deterministic).  d/d params is an outer-product reduction over the tile in
 //             shared memory -> per-tile partials -> a fixed-order second-stage sum.
 // Layout of params[n] (condinst_head.py:1079-1088,1122-1123): [W1(8xCIN) | W2(8x8) | W3(1x8) | b1 | b2 | b3]
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace bxs {
@@ -199,7 +202,8 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ coors, const float* __restrict__ soi,
                                                       const float* __restrict__ g_out, const int* __restrict__ order,
                                                       const int* __restrict__ start, float* __restrict__ g_feat,
-                                                      float* __restrict__ g_params_partial, HeadDims d, int tiles) {
+                                                      float* __restrict__ g_params_partial, HeadDims d, int tiles,
+                                                      int groups) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SB = SmemBwd<CMAX>;
   constexpr int PIT_IN = SB::PIT_IN;
@@ -227,7 +231,8 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(const float* __restrict__ 
       if (c < d.C) fin[2 + c] = __ldg(feat_img + c * plane + pix);
   }
 
-  for (int it = start[b]; it < start[b + 1]; ++it) {
+  const int grp = blockIdx.z;                      // this CTA handles instances start[b] + grp, + groups, ...
+  for (int it = start[b] + grp; it < start[b + 1]; it += groups) {
     const int n = order[it];
     __syncthreads();                               // previous instance fully consumed
     load_params(S.sp, params, coors, soi, n, d);
@@ -312,10 +317,23 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(const float* __restrict__ 
   }
   if (live) {
     const int64_t plane = (int64_t)d.h * d.w, pix = (int64_t)y * d.w + x;
-    float* gf = g_feat + (int64_t)b * d.C * plane;
+    // groups == 1: g_feat itself; else partial [grp][B][C][h*w] (g_feat then points at the partial buffer)
+    float* gf = g_feat + ((int64_t)grp * d.B + b) * d.C * plane;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
       if (c < d.C) gf[c * plane + pix] = gfeat[c];
+  }
+}
+
+// g_feat[i] = sum over groups of partial[g][i], fixed order
+__global__ void feat_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ g_feat, int64_t n4, int groups) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = partial[i];
+    for (int g = 1; g < groups; ++g) {
+      const float4 v = partial[g * n4 + i];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    g_feat[i] = a;
   }
 }
 
@@ -362,9 +380,21 @@ extern "C" int bxs_condinst_head_forward(const float* feat, const float* params,
   return check_launch();
 }
 
+namespace bxs {
+namespace {
+constexpr int kMaxGroups = 8;
+// instance groups per image of the backward grid: enough CTAs for ~4 per SM, at most kMaxGroups
+inline int bwd_groups(int64_t N, int64_t B, int64_t tiles) {
+  const int64_t want = ceil_div((int64_t)sm_count() * 4, tiles * B);
+  return (int)std::max<int64_t>(1, std::min<int64_t>({want, (int64_t)kMaxGroups, ceil_div(N, B)}));
+}
+}  // namespace
+}  // namespace bxs
+
 extern "C" int64_t bxs_condinst_head_workspace_bytes(int64_t N, int64_t B, int64_t h, int64_t w, int64_t P) {
   const int64_t tiles = ceil_div(h, BTY) * ceil_div(w, BTX);
-  return (N + B + 1) * 4 + 256 + N * tiles * P * 4;
+  const int64_t cin = (P - (CH * CH + 3 * CH + 1)) / CH;            // >= mask_feat channels
+  return (N + B + 1) * 4 + 512 + N * tiles * P * 4 + (int64_t)kMaxGroups * B * cin * h * w * 4 + 16;
 }
 
 extern "C" int bxs_condinst_head_backward(const float* feat, const float* params, const float* coors, const float* soi,
@@ -381,13 +411,18 @@ extern "C" int bxs_condinst_head_backward(const float* feat, const float* params
   int* order = (int*)workspace;
   int* start = order + N;
   float* partial = (float*)((char*)workspace + ((N + B + 1) * 4 + 255) / 256 * 256);
+  float* feat_partial = (float*)((char*)partial + ((size_t)N * tiles * P * 4 + 255) / 256 * 256);
+  const int groups = bwd_groups(N, B, tiles);
+  const bool vec4 = ((B * C * h * w) % 4 == 0) && ((reinterpret_cast<uintptr_t>(g_feat) & 15) == 0);
+  const int use_groups = vec4 ? groups : 1;
+  float* gf_target = use_groups > 1 ? feat_partial : g_feat;
   group_by_image<<<1, 256, (B + 1) * sizeof(int), st>>>(img_inds, (int)N, (int)B, order, start);
 #define BXS_LAUNCH_BWD(CM)                                                                                   \
   do {                                                                                                       \
     cudaFuncSetAttribute(head_bwd_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
                          (int)sizeof(SmemBwd<CM>));                                                          \
-    head_bwd_kernel<CM><<<dim3(tiles, (unsigned)B), NT, sizeof(SmemBwd<CM>), st>>>(                          \
-        feat, params, coors, soi, g_out, order, start, g_feat, partial, d, tiles);                           \
+    head_bwd_kernel<CM><<<dim3(tiles, (unsigned)B, (unsigned)use_groups), NT, sizeof(SmemBwd<CM>), st>>>(    \
+        feat, params, coors, soi, g_out, order, start, gf_target, partial, d, tiles, use_groups);            \
   } while (0)
   if (C <= 8) BXS_LAUNCH_BWD(8);
   else if (C <= 16) BXS_LAUNCH_BWD(16);
@@ -398,5 +433,10 @@ extern "C" int bxs_condinst_head_backward(const float* feat, const float* params
   // images without instances never write their partials: zero-fill is not needed because every
   // instance belongs to exactly one image and that image's CTAs write all of its tiles.
   params_reduce_kernel<<<(unsigned)ceil_div(N * P, 256), 256, 0, st>>>(partial, g_params, (int)N, tiles, (int)P);
+  if (use_groups > 1) {
+    const int64_t n4 = B * C * h * w / 4;
+    feat_reduce_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n4, 256), (int64_t)sm_count() * 8), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(feat_partial), reinterpret_cast<float4*>(g_feat), n4, use_groups);
+  }
   return check_launch();
 }
