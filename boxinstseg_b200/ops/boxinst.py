@@ -149,13 +149,18 @@ class _BoxInstMaskLoss(torch.autograd.Function):
                                                            L.ptr(gt_img), L.ptr(iter_buf), float(warmup_iters), L.ptr(ws),
                                                            L.ptr(_sched_state(dev)), L.ptr(out), L.ptr(g_logits), N, H, W,
                                                            dilation, L.stream()), 'boxinst_loss_fused_forward')
-                ctx.g_logits = g_logits
             else:
+                g_logits = None
                 ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N, H, W), dtype=torch.uint8, device=dev)
                 L.check(lib.bxs_boxinst_loss_forward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
                                                      L.ptr(gt_img), L.ptr(iter_buf), float(warmup_iters), L.ptr(ws),
                                                      L.ptr(out), N, H, W, dilation, L.stream()), 'boxinst_loss_forward')
-        ctx.save_for_backward(logits, edge_bits, rects, inst_gt, gt_img, ws, iter_buf)
+        # the gradient buffer rides along as a saved tensor (not a ctx attribute): autograd releases saved tensors right
+        # after backward returns, so AccumulateGrad sees a sole owner and adopts the buffer instead of cloning 26 MB
+        if g_logits is None:
+            ctx.save_for_backward(logits, edge_bits, rects, inst_gt, gt_img, ws, iter_buf)
+        else:
+            ctx.save_for_backward(logits, edge_bits, rects, inst_gt, gt_img, ws, iter_buf, g_logits)
         ctx.warmup_iters = float(warmup_iters)
         aux = out[2:]
         ctx.mark_non_differentiable(aux)
@@ -163,7 +168,8 @@ class _BoxInstMaskLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_prj, g_pair, _g_aux):
-        logits, edge_bits, rects, inst_gt, gt_img, ws, iter_buf = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        logits, edge_bits, rects, inst_gt, gt_img, ws, iter_buf = saved[:7]
         N, _, H, W = logits.shape
         lib = L.lib()
         ctx.calls += 1
@@ -176,7 +182,8 @@ class _BoxInstMaskLoss(torch.autograd.Function):
         g_pair = zero if g_pair is None else g_pair.reshape(()).to(torch.float32)
         with torch.cuda.device(logits.device):
             if ctx.fused and ctx.calls == 1:
-                g_logits = ctx.g_logits
+                g_logits = saved[7]
+                del saved
                 L.check(lib.bxs_boxinst_loss_fused_backward(L.ptr(ws), L.ptr(g_prj), L.ptr(g_pair), L.ptr(g_logits), N, H, W,
                                                             L.stream()), 'boxinst_loss_fused_backward')
                 return g_logits, None, None, None, None, None, None, None
