@@ -12,11 +12,13 @@
 //       span, and -- inside the span -- the pair terms and the RAW (unscaled) pairwise gradient,
 //       gathered from a (sigmoid, 1 - sigmoid, edge bits) tile.  HBM traffic: logits read once,
 //       gradient written once.
-//   onepass_finalize_kernel   one CTA per instance: dice terms and their gradient coefficients, the
-//       global weight sum; the last CTA writes the losses.  Does not touch the gradient.
-//   onepass_backward_kernel   one CTA per instance, in place: the (small) box span of the gradient is
-//       scaled by g_pair * warmup / weights and the projection terms are added at the H + W arg-max
-//       positions.
+//   onepass_finalize_kernel   one CTA per instance: dice terms and their gradient coefficients; scales
+//       the (small) box span of the gradient by warmup / weights (the weight total is an integer
+//       atomic sum of the main kernel) and adds the projection terms at the H + W arg-max positions
+//       for upstream gradients (1, 1); the last CTA writes the losses.
+//   onepass_backward_kernel   returns at once when the upstream gradients are (1, 1) (the result is in
+//       place); otherwise converts the gradient in place, exactly (the pairwise part at the arg-max
+//       positions is kept in the workspace).
 //
 // Everything is summed in a fixed order: results do not depend on which CTA processed which strip.
 #include <algorithm>
@@ -44,7 +46,8 @@ struct OpWorkspace {
   int* span;                       // [N*4]    y_lo, y_hi, c_lo, c_hi of the gradient span (y_lo > y_hi: none)
   float* inst_prj;                 // [N]
   float* inst_num;                 // [N]
-  int* inst_den;                   // [N]
+  float* sv_row;                   // [N*H]    scaled pairwise gradient at the row arg-max position
+  float* sv_col;                   // [N*W]
   float* scale;                    // [1]      warmup / max(weight sum, 1)
   size_t total_bytes;
 };
@@ -80,7 +83,8 @@ inline OpWorkspace op_carve(void* base, int64_t N, int64_t H, int64_t W) {
   w.span = (int*)take(16 * N);
   w.inst_prj = (float*)take(4 * N);
   w.inst_num = (float*)take(4 * N);
-  w.inst_den = (int*)take(4 * N);
+  w.sv_row = (float*)take(4 * N * H);
+  w.sv_col = (float*)take(4 * N * W);
   w.scale = (float*)take(4);
   w.total_bytes = off;
   return w;
@@ -307,7 +311,7 @@ __device__ __forceinline__ void op_trace(int& slot, unsigned long long tag) {
 #define OP_TRACE(tag)
 #endif
 
-struct OpSched { unsigned next, done, ticket, pad; };
+struct OpSched { unsigned next, done, ticket, pad; unsigned long long wtot, pad2; };   // wtot: total weight count of the step
 
 constexpr int OP_STAGES = 2;       // strips staged per CTA: one copy in flight while one strip is processed
 
@@ -544,6 +548,7 @@ onepass_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict_
       for (int i = 0; i < OP_NW; ++i) { v += s_redf[i]; w += s_redi[i]; }
       ws.num_part[n * MAXG + it.s] = v;
       ws.den_part[n * MAXG + it.s] = w;
+      if (w) atomicAdd(&sched->wtot, (unsigned long long)w);      // integer: order-independent, deterministic
     }
     stage ^= 1;
   }
@@ -569,9 +574,11 @@ __global__ void __launch_bounds__(OP_FIN_NT)
 onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ inst_gt,
                         const int32_t* __restrict__ gt_img, int N, int H, int W, int S, int MAXG, OpWorkspace ws,
                         OpSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
-                        float* __restrict__ losses_out) {
+                        float* __restrict__ losses_out, float* __restrict__ g_logits) {
   constexpr int NWF = OP_FIN_NT / 32;
   __shared__ float s_f[4][NWF];
+  __shared__ float s_coef[1024];      // rows [0, H), columns [512, 512 + W)
+  __shared__ int s_arg[1024];
   __shared__ bool s_last;
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // the record depends only on the targets: read it before waiting for the main grid (programmatic dependent launch)
@@ -580,7 +587,10 @@ onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __rest
   const OpSpan sp = op_span<D>(rec, H, W);
   const bool empty = rec.j0 > rec.j1;
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // independent loads first: this thread's row key and its column keys of every strip
+  float* ginst = g_logits + (unsigned)(n * H * W);
+  // independent loads first: the step's weight total, this thread's row key and its column keys of every strip
+  const unsigned long long wtot = *reinterpret_cast<volatile unsigned long long*>(&sched->wtot);
+  const float warm = fminf(iter_ptr[0] / warmup_iters, 1.f);
   const int row_i = tid, col_i = tid;                   // H, W <= 512 = OP_FIN_NT
   unsigned long long rp = 0ull, cp = 0ull;
   if (row_i < H) rp = ws.row_packed[n * H + row_i];
@@ -592,12 +602,34 @@ onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __rest
       cp = p > cp ? p : cp;
     }
   }
+  // chain-group numerators of this instance (warp 0; fixed order: lane-strided, then a shuffle tree at the end)
+  float num = 0.f;
+  if (wid == 0) {
+    const int ng = (chain_geom<D>(rec, H, W).nch + OP_NW - 1) / OP_NW;
+    for (int g = lane; g < ng; g += 32) num += ws.num_part[n * MAXG + g];
+  }
+  // ---- the box span of the gradient: raw pairwise gradient -> * warmup / weights (float4 read-modify-write) ----
+  const float scale = warm / fmaxf((float)wtot, 1.f);
+  const int sw4 = (sp.c_hi - sp.c_lo + 1) >> 2, srows = sp.y_hi - sp.y_lo + 1;
+  if (srows > 0) {
+    for (int i = tid; i < srows * sw4; i += OP_FIN_NT) {
+      const int ry = op_div(i, sw4), c4 = i - ry * sw4;
+      float4* p = reinterpret_cast<float4*>(ginst + (sp.y_lo + ry) * W + sp.c_lo + 4 * c4);
+      float4 q = *p;
+      q.x *= scale; q.y *= scale; q.z *= scale; q.w *= scale;
+      *p = q;
+    }
+  }
+  // ---- dice terms and their gradient coefficients ----
   const float sr = row_i < H ? sigmoid_exact(fkey_inv((unsigned)(rp >> 32))) : 0.f;
   const float sc = col_i < W ? sigmoid_exact(fkey_inv((unsigned)(cp >> 32))) : 0.f;
   const bool tr = !empty && row_i >= rec.j0 && row_i <= rec.j1, tc = !empty && col_i >= rec.i0 && col_i <= rec.i1;
   const float r0 = warp_sum(tr ? sr : 0.f), r1 = warp_sum(sr * sr), r2 = warp_sum(tc ? sc : 0.f), r3 = warp_sum(sc * sc);
   if (lane == 0) { s_f[0][wid] = r0; s_f[1][wid] = r1; s_f[2][wid] = r2; s_f[3][wid] = r3; }
-  __syncthreads();
+  const int ar = (int)(0xffffffffu - (unsigned)(rp & 0xffffffffull)), ac = (int)(0xffffffffu - (unsigned)(cp & 0xffffffffull));
+  if (row_i < H) s_arg[row_i] = ar;
+  if (col_i < W) s_arg[512 + col_i] = ac;
+  __syncthreads();               // also: every span store of this CTA is visible to its threads
   float Ir = 0.f, Xr = 0.f, Ic = 0.f, Xc = 0.f;
 #pragma unroll
   for (int i = 0; i < NWF; ++i) { Ir += s_f[0][i]; Xr += s_f[1][i]; Ic += s_f[2][i]; Xc += s_f[3][i]; }
@@ -605,26 +637,28 @@ onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __rest
   const float Ur = Xr + (empty ? 0.f : (float)(rec.j1 - rec.j0 + 1)) + kDiceEps;
   const float Uc = Xc + (empty ? 0.f : (float)(rec.i1 - rec.i0 + 1)) + kDiceEps;
   // d dice / d s = -2 t / U + 4 I s / U^2 ; through the sigmoid: * s (1 - s); mean over N
+  const float crow = inv_n * (-2.f * (tr ? 1.f : 0.f) / Ur + 4.f * Ir * sr / (Ur * Ur)) * sr * (1.f - sr);
+  const float ccol = inv_n * (-2.f * (tc ? 1.f : 0.f) / Uc + 4.f * Ic * sc / (Uc * Uc)) * sc * (1.f - sc);
+  // scaled pairwise gradient at the arg-max positions (kept for upstream gradients != 1)
+  float svr = 0.f, svc = 0.f;
+  if (row_i < H) { svr = ginst[row_i * W + ar]; s_coef[row_i] = crow; }
+  if (col_i < W) { svc = ginst[ac * W + col_i]; s_coef[512 + col_i] = ccol; }
+  __syncthreads();               // all reads of the arg-max positions precede the writes below
+  // ---- projection terms for upstream gradients (1, 1); a position that is both a row and a column arg-max is
+  //      written once, by its column ----
   if (row_i < H) {
-    ws.coef_row[n * H + row_i] = inv_n * (-2.f * (tr ? 1.f : 0.f) / Ur + 4.f * Ir * sr / (Ur * Ur)) * sr * (1.f - sr);
-    ws.arg_row[n * H + row_i] = (int)(0xffffffffu - (unsigned)(rp & 0xffffffffull));
+    if (s_arg[512 + ar] != row_i) ginst[row_i * W + ar] = svr + crow;
+    ws.coef_row[n * H + row_i] = crow; ws.arg_row[n * H + row_i] = ar; ws.sv_row[n * H + row_i] = svr;
   }
   if (col_i < W) {
-    ws.coef_col[n * W + col_i] = inv_n * (-2.f * (tc ? 1.f : 0.f) / Uc + 4.f * Ic * sc / (Uc * Uc)) * sc * (1.f - sc);
-    ws.arg_col[n * W + col_i] = (int)(0xffffffffu - (unsigned)(cp & 0xffffffffull));
+    ginst[ac * W + col_i] = s_arg[ac] == col_i ? (svc + s_coef[ac]) + ccol : svc + ccol;
+    ws.coef_col[n * W + col_i] = ccol; ws.arg_col[n * W + col_i] = ac; ws.sv_col[n * W + col_i] = svc;
   }
   if (wid == 0) {
-    // fixed-order sums of the chain-group partials of this instance (lane-strided, then a shuffle tree)
-    const int ng = (chain_geom<D>(rec, H, W).nch + OP_NW - 1) / OP_NW;
-    float num = 0.f;
-    int den = 0;
-    for (int g = lane; g < ng; g += 32) { num += ws.num_part[n * MAXG + g]; den += ws.den_part[n * MAXG + g]; }
     num = warp_sum(num);
-    den = warp_sum(den);
     if (lane == 0) {
       ws.inst_prj[n] = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
       ws.inst_num[n] = num;
-      ws.inst_den[n] = den;
       reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
       __threadfence();
       s_last = atomicAdd(&sched->ticket, 1u) == (unsigned)(N - 1);
@@ -634,43 +668,39 @@ onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __rest
   if (!s_last || tid >= 32) return;
   __threadfence();
   float prj = 0.f, pn = 0.f;
-  long long wtot = 0;
-  for (int i = lane; i < N; i += 32) { prj += __ldcg(ws.inst_prj + i); pn += __ldcg(ws.inst_num + i); wtot += __ldcg(ws.inst_den + i); }
+  for (int i = lane; i < N; i += 32) { prj += __ldcg(ws.inst_prj + i); pn += __ldcg(ws.inst_num + i); }
   prj = warp_sum(prj);
   pn = warp_sum(pn);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wtot += __shfl_xor_sync(kFull, wtot, o);
   if (lane == 0) {
-    const float warm = fminf(iter_ptr[0] / warmup_iters, 1.f);
-    const float scale = warm / fmaxf((float)wtot, 1.f);
     losses_out[0] = prj * inv_n;
     losses_out[1] = pn * scale;
     losses_out[2] = pn;
     losses_out[3] = (float)wtot;
     ws.scale[0] = scale;
-    sched->ticket = 0u;
+    sched->ticket = 0u;          // every CTA of this grid has read wtot before taking its ticket
+    sched->wtot = 0ull;
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// backward: one CTA per instance turns the raw pairwise gradient into the final gradient, in place:
-//   span pixels *= g_pair * scale;  arg-max positions += g_prj * coefficient.  A position that is both a row and
-//   a column arg-max is written once (by its column), so no two threads touch the same address in a phase.
+// backward: the gradient for upstream gradients (1, 1) is already in place (finalize); anything else converts it in
+// place, exactly: span *= g_pair, arg-max positions = g_pair * saved pairwise part + g_prj * coefficients.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(OP_FIN_NT)
 onepass_backward_kernel(int H, int W, OpWorkspace ws, const float* __restrict__ g_prj_p,
                         const float* __restrict__ g_pair_p, float* __restrict__ g_logits) {
   __shared__ int s_ar[512], s_ac[512];
   __shared__ float s_cr[512];
-  const int n = blockIdx.x, tid = threadIdx.x;
-  float* ginst = g_logits + (int64_t)n * H * W;
   asm volatile("griddepcontrol.wait;" ::: "memory");     // everything below may read the previous kernel's results
-  const float gp = g_prj_p[0], gq = g_pair_p[0] * ws.scale[0];
+  const float gp = g_prj_p[0], gq = g_pair_p[0];
+  if (gp == 1.f && gq == 1.f) return;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  float* ginst = g_logits + (unsigned)(n * H * W);
   const int4 sp = reinterpret_cast<const int4*>(ws.span)[n];
   int ar = 0, ac = 0;
-  float cr = 0.f, cc = 0.f;
-  if (tid < H) { ar = ws.arg_row[n * H + tid]; cr = ws.coef_row[n * H + tid] * gp; s_ar[tid] = ar; s_cr[tid] = cr; }
-  if (tid < W) { ac = ws.arg_col[n * W + tid]; cc = ws.coef_col[n * W + tid] * gp; s_ac[tid] = ac; }
+  float cr = 0.f, cc = 0.f, svr = 0.f, svc = 0.f;
+  if (tid < H) { ar = ws.arg_row[n * H + tid]; cr = ws.coef_row[n * H + tid] * gp; svr = ws.sv_row[n * H + tid] * gq; s_ar[tid] = ar; s_cr[tid] = cr; }
+  if (tid < W) { ac = ws.arg_col[n * W + tid]; cc = ws.coef_col[n * W + tid] * gp; svc = ws.sv_col[n * W + tid] * gq; s_ac[tid] = ac; }
   const int sw4 = (sp.w - sp.z + 1) >> 2, srows = sp.y - sp.x + 1;
   if (srows > 0) {
     for (int i = tid; i < srows * sw4; i += OP_FIN_NT) {
@@ -682,11 +712,8 @@ onepass_backward_kernel(int H, int W, OpWorkspace ws, const float* __restrict__ 
     }
   }
   __syncthreads();
-  if (tid < H && s_ac[ar] != tid) ginst[tid * W + ar] += cr;
-  if (tid < W) {
-    float* p = ginst + ac * W + tid;
-    *p = s_ar[ac] == tid ? (*p + s_cr[ac]) + cc : *p + cc;
-  }
+  if (tid < H && s_ac[ar] != tid) ginst[tid * W + ar] = svr + cr;
+  if (tid < W) ginst[ac * W + tid] = s_ar[ac] == tid ? (svc + s_cr[ac]) + cc : svc + cc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -792,7 +819,7 @@ extern "C" int bxs_boxinst_loss_fused_forward(const float* logits, const uint8_t
                                                        (int)W, ws, sched, g_logits);                                \
   if (rc == BXS_OK) {                                                                                               \
     op_launch_pdl(onepass_finalize_kernel<DD>, dim3((unsigned)N), dim3(OP_FIN_NT), 0, st, rects, inst_gt, gt_img, (int)N, \
-                  (int)H, (int)W, S, (int)op_max_groups(H, W), ws, sched, iter_ptr, warmup_iters, losses_out);      \
+                  (int)H, (int)W, S, (int)op_max_groups(H, W), ws, sched, iter_ptr, warmup_iters, losses_out, g_logits); \
     rc = check_launch();                                                                                            \
   }
 #define BXS_OP_D(NC)                                                  \

@@ -108,15 +108,16 @@ int bxs_boxinst_loss_backward(const float* logits, const uint8_t* edge_bits, con
  * gradient once.  Use when a gradient is wanted (training); the two-call API above remains for
  * forward-only use and for shapes outside bxs_boxinst_loss_fused_supported().
  *
- * forward: computes losses_out (as above) and fills g_logits [N,1,H,W] with the RAW pairwise
- *   gradient (zeros outside the box spans); g_logits is not a gradient yet.
- * backward: g_prj / g_pair are device floats (upstream gradients); converts g_logits IN PLACE to
- *   g_prj * d loss_prj/d logits + g_pair * d loss_pairwise/d logits (touches only the box spans
- *   and the H + W arg-max positions of each instance).  Call it exactly once per forward.
+ * forward: computes losses_out (as above) and writes g_logits [N,1,H,W] = d(loss_prj +
+ *   loss_pairwise)/d logits, i.e. the gradient for upstream gradients (1, 1).
+ * backward: g_prj / g_pair are device floats (upstream gradients).  When both are 1 the kernel
+ *   returns at once (g_logits already holds the answer); otherwise g_logits is converted IN
+ *   PLACE to g_prj * d loss_prj + g_pair * d loss_pairwise (exact: the pairwise part at the
+ *   arg-max positions is kept in the workspace).  Call it at most once per forward.
  * workspace: bxs_boxinst_loss_fused_workspace_bytes(N,H,W) bytes, no initial state needed.
- * sched_state: bxs_boxinst_loss_fused_sched_bytes() bytes of device memory that MUST be zero
- *   before the first call and is owned by one stream at a time (the kernels' work-item counter
- *   and finalize ticket live there; each call leaves it zeroed again).
+ * sched_state: bxs_boxinst_loss_fused_sched_bytes() (32) bytes of device memory that MUST be zero
+ *   before the first call and is owned by one stream at a time (the kernels' work-item counter,
+ *   finalize ticket and integer weight total live there; each call leaves it zeroed again).
  * Returns BXS_ERR_UNSUPPORTED outside the supported envelope (W % 4 == 0, W,H <= 512,
  * 1 <= dilation <= 4, N <= 2048, 16-byte aligned logits / g_logits).
  * --------------------------------------------------------------------------------------- */
