@@ -198,7 +198,7 @@ struct SmemBwd {
 };
 
 template <int CMAX>
-__global__ void __launch_bounds__(NT) head_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ params,
+__global__ void __launch_bounds__(NT, 2) head_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ params,
                                                       const float* __restrict__ coors, const float* __restrict__ soi,
                                                       const float* __restrict__ g_out, const int* __restrict__ order,
                                                       const int* __restrict__ start, float* __restrict__ g_feat,
@@ -231,6 +231,21 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(const float* __restrict__ 
       if (c < d.C) fin[2 + c] = __ldg(feat_img + c * plane + pix);
   }
 
+  // transpose of the aligned upsample for factor 2 (every BoxInst/CondInst config): the weights of the 6 x 6 output
+  // pixels that read this low-res pixel depend only on (y, x), not on the instance -> computed once per thread
+  const bool f2 = d.f == 2;
+  float wyv[6], wxv[6];
+  const int Y0 = max(2 * (y - 1), 0), X0 = max(2 * (x - 1), 0);
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    wyv[a] = 0.f; wxv[a] = 0.f;
+    if (f2 && live) {
+      int i0, i1; float fr;
+      const int Y = Y0 + a, X = X0 + a;
+      if (Y < min(2 * (y + 2), OH)) { up_src(Y, 2, d.h, i0, i1, fr); wyv[a] = (i0 == y ? 1.f - fr : 0.f) + (i1 == y ? fr : 0.f); }
+      if (X < min(2 * (x + 2), OW)) { up_src(X, 2, d.w, i0, i1, fr); wxv[a] = (i0 == x ? 1.f - fr : 0.f) + (i1 == x ? fr : 0.f); }
+    }
+  }
   const int grp = blockIdx.z;                      // this CTA handles instances start[b] + grp, + groups, ...
   for (int it = start[b] + grp; it < start[b + 1]; it += groups) {
     const int n = order[it];
@@ -241,19 +256,32 @@ __global__ void __launch_bounds__(NT) head_bwd_kernel(const float* __restrict__ 
     if (live) {
       // ---- d/d low-res logit: transpose of the aligned upsample (gather) ----
       const float* go = g_out + (int64_t)n * OH * OW;
-      for (int Y = max(d.f * (y - 1), 0); Y < min(d.f * (y + 2), OH); ++Y) {
-        int a0, a1; float fr;
-        up_src(Y, d.f, d.h, a0, a1, fr);
-        const float wy = (a0 == y ? 1.f - fr : 0.f) + (a1 == y ? fr : 0.f);
-        if (wy == 0.f) continue;
-        float rowacc = 0.f;
-        for (int X = max(d.f * (x - 1), 0); X < min(d.f * (x + 2), OW); ++X) {
-          int c0, c1; float fc;
-          up_src(X, d.f, d.w, c0, c1, fc);
-          const float wx = (c0 == x ? 1.f - fc : 0.f) + (c1 == x ? fc : 0.f);
-          if (wx != 0.f) rowacc = fmaf(wx, __ldg(go + (int64_t)Y * OW + X), rowacc);
+      if (f2) {                                      // same terms, same order as the general loop below
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          if (wyv[a] == 0.f) continue;
+          const float* grow = go + (int64_t)(Y0 + a) * OW + X0;
+          float rowacc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 6; ++c)
+            if (wxv[c] != 0.f) rowacc = fmaf(wxv[c], __ldg(grow + c), rowacc);
+          g3 = fmaf(wyv[a], rowacc, g3);
         }
-        g3 = fmaf(wy, rowacc, g3);
+      } else {
+        for (int Y = max(d.f * (y - 1), 0); Y < min(d.f * (y + 2), OH); ++Y) {
+          int a0, a1; float fr;
+          up_src(Y, d.f, d.h, a0, a1, fr);
+          const float wy = (a0 == y ? 1.f - fr : 0.f) + (a1 == y ? fr : 0.f);
+          if (wy == 0.f) continue;
+          float rowacc = 0.f;
+          for (int X = max(d.f * (x - 1), 0); X < min(d.f * (x + 2), OW); ++X) {
+            int c0, c1; float fc;
+            up_src(X, d.f, d.w, c0, c1, fc);
+            const float wx = (c0 == x ? 1.f - fc : 0.f) + (c1 == x ? fc : 0.f);
+            if (wx != 0.f) rowacc = fmaf(wx, __ldg(go + (int64_t)Y * OW + X), rowacc);
+          }
+          g3 = fmaf(wy, rowacc, g3);
+        }
       }
       // ---- recompute the forward, then backpropagate through the three layers ----
       if (d.rel) {
