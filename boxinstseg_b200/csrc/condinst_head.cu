@@ -116,9 +116,15 @@ __device__ __forceinline__ float mlp_forward(const SmemParams& sp, const float* 
 
 // aligned_bilinear source of output index Y (condinst_head.py:146-167): position max(Y - f/2, 0)/f
 __device__ __forceinline__ void up_src(int Y, int f, int len, int& i0, int& i1, float& fr) {
-  const int s = max(Y - f / 2, 0);
-  i0 = s / f;
-  fr = (float)(s - i0 * f) / (float)f;
+  if (f == 2) {                                    // every BoxInst/CondInst config: no integer / float division
+    const int s = max(Y - 1, 0);
+    i0 = s >> 1;
+    fr = (s & 1) ? 0.5f : 0.f;
+  } else {
+    const int s = max(Y - f / 2, 0);
+    i0 = s / f;
+    fr = (float)(s - i0 * f) / (float)f;
+  }
   i1 = min(i0 + 1, len - 1);
 }
 
@@ -149,8 +155,11 @@ __global__ void __launch_bounds__(NT) head_fwd_kernel(const float* __restrict__ 
   const int OH = d.f * d.h, OW = d.f * d.w;
   const int oy0 = ty0 * d.f, ox0 = tx0 * d.f, th = FTY * d.f, tw = FTX * d.f;
   float* o = out + (int64_t)n * OH * OW;
+  const int tw_shift = 31 - __clz(tw);             // tw = FTX * f is a power of two when f is (f = 2 -> 64)
+  const bool tw_pow2 = (tw & (tw - 1)) == 0;
   for (int i = threadIdx.x; i < th * tw; i += NT) {
-    const int Y = oy0 + i / tw, X = ox0 + i % tw;
+    const int ry = tw_pow2 ? (i >> tw_shift) : i / tw;
+    const int Y = oy0 + ry, X = ox0 + (i - ry * tw);
     if (Y >= OH || X >= OW) continue;
     int y0, y1, x0, x1i;
     float fy, fx;
