@@ -148,6 +148,73 @@ def main_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------
+# The reference's own GPU path for the same loss (baseline only): its unmodified CUDA pairwise op, compiled by
+# oracle/Makefile into oracle/_ref/, inside a restatement of CondInstMaskHead.loss (condinst_head.py:1288-1343) that
+# materialises what the reference materialises (per-instance similarity [N,8,H,W], bitmask [N,1,H,W], pairwise [N,8,H,W]).
+# ------------------------------------------------------------------------------------------
+def run_gpu_reference(case, dev, iters=10):
+    import glob
+    import importlib.util
+    hits = glob.glob(os.path.join(ROOT, 'oracle', '_ref', 'pairwise_ext_ref*.so'))
+    if not hits:
+        return None
+    from boxinstseg_b200.ops.boxinst import boxinst_targets
+    spec = importlib.util.spec_from_file_location('pairwise_ext_ref', hits[0])
+    ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ext)
+
+    class RefPairwise(torch.autograd.Function):            # mmdet/ops/pairwise/pairwise.py:6-26
+        @staticmethod
+        def forward(ctx, logits, size, dilation):
+            pw = ext.pairwise_nlog_forward(size, dilation, logits)
+            ctx.save_for_backward(logits, pw)
+            ctx.cfg = (size, dilation)
+            return pw
+
+        @staticmethod
+        def backward(ctx, g):
+            logits, pw = ctx.saved_tensors
+            return ext.pairwise_nlog_backward(ctx.cfg[0], ctx.cfg[1], logits, pw, g.contiguous()), None, None
+
+    t = boxinst_targets(case['img'].to(dev), case['metas'], [b.to(dev) for b in case['gt_bboxes']], want_similarity=True)
+    gi = case['gt_inds'].to(dev)
+    sim = t.similarity[case['img_inds'].to(dev)]                       # [N,8,H,W]: the G-fold gather of condinst_head.py:1316
+    bm = torch.cat(t.bitmasks())[gi][:, None]                          # [N,1,H,W]
+    x = case['logits'].to(dev).requires_grad_(True)
+
+    def dice(a, b):                                                    # condinst_head.py:117-131
+        a, b = a.flatten(1), b.flatten(1)
+        return 1.0 - 2.0 * (a * b).sum(1) / ((a * a).sum(1) + (b * b).sum(1) + 1e-5)
+
+    def step():
+        scores = x.sigmoid()
+        prj = (dice(scores.max(dim=2, keepdim=True)[0], bm.max(dim=2, keepdim=True)[0]) +
+               dice(scores.max(dim=3, keepdim=True)[0], bm.max(dim=3, keepdim=True)[0])).mean()     # :134-143
+        pw = RefPairwise.apply(x, 3, 2)
+        w = (sim >= 0.3).float() * bm
+        pair = (pw * w).sum() / w.sum().clamp(min=1.0)                                              # :1318-1332
+        x.grad = None
+        (prj + pair).backward()
+        return prj, pair
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        prj, pair = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {'value': ms / B_IMG, 'unit': 'ms/img', 'ms_per_step': ms, 'iters': iters,
+            'what': "restated CondInstMaskHead.loss (condinst_head.py:1288-1343) on this GPU around the reference's own "
+                    'unmodified CUDA pairwise op (oracle/_ref/pairwise_ext_ref, built by oracle/Makefile); targets precomputed, '
+                    'eager PyTorch as in the reference',
+            'loss_prj': float(prj.detach()), 'loss_pairwise': float(pair.detach())}
+
+
+# ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
 FWD_BYTES = N_INST * H * W * 4 + B_IMG * K_NEIGH * H * W * 4            # read logits + similarity      (29.5 MB)
@@ -413,6 +480,13 @@ def main_cuda(args, rank, world, local_rank):
     }
     if cpu_ms is not None:
         line['cpu_baseline'] = {'value': cpu_ms, 'unit': 'ms/img', 'cores': cores, 'kind': 'port', 'sample': sample}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ref_gpu = run_gpu_reference(case, dev)
+        except Exception as e:  # noqa: BLE001  (baseline only: never let it take the bench line down)
+            ref_gpu = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
+        if ref_gpu is not None:
+            line['gpu_reference'] = ref_gpu
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

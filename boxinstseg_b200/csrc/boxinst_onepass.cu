@@ -38,7 +38,6 @@ struct OpWorkspace {
   unsigned long long* row_packed;  // [N*H]    (key(max logit) << 32) | ~x
   unsigned long long* col_part;    // [N*S*W]  per strip (key(max logit) << 32) | ~y
   float* num_part;                 // [N*MAXG] per chain group pairwise numerator
-  int* den_part;                   // [N*MAXG] per chain group weight count
   float* coef_row;                 // [N*H]    d loss_prj / d logit at the row arg-max
   float* coef_col;                 // [N*W]
   int* arg_row;                    // [N*H]
@@ -48,7 +47,6 @@ struct OpWorkspace {
   float* inst_num;                 // [N]
   float* sv_row;                   // [N*H]    scaled pairwise gradient at the row arg-max position
   float* sv_col;                   // [N*W]
-  float* scale;                    // [1]      warmup / max(weight sum, 1)
   size_t total_bytes;
 };
 
@@ -75,7 +73,6 @@ inline OpWorkspace op_carve(void* base, int64_t N, int64_t H, int64_t W) {
   w.col_part = (unsigned long long*)take(8 * N * S * W);
   const int64_t G = op_max_groups(H, W);
   w.num_part = (float*)take(4 * N * G);
-  w.den_part = (int*)take(4 * N * G);
   w.coef_row = (float*)take(4 * N * H);
   w.coef_col = (float*)take(4 * N * W);
   w.arg_row = (int*)take(4 * N * H);
@@ -85,7 +82,6 @@ inline OpWorkspace op_carve(void* base, int64_t N, int64_t H, int64_t W) {
   w.inst_num = (float*)take(4 * N);
   w.sv_row = (float*)take(4 * N * H);
   w.sv_col = (float*)take(4 * N * W);
-  w.scale = (float*)take(4);
   w.total_bytes = off;
   return w;
 }
@@ -547,7 +543,6 @@ onepass_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict_
 #pragma unroll
       for (int i = 0; i < OP_NW; ++i) { v += s_redf[i]; w += s_redi[i]; }
       ws.num_part[n * MAXG + it.s] = v;
-      ws.den_part[n * MAXG + it.s] = w;
       if (w) atomicAdd(&sched->wtot, (unsigned long long)w);      // integer: order-independent, deterministic
     }
     stage ^= 1;
@@ -676,7 +671,6 @@ onepass_finalize_kernel(const int32_t* __restrict__ rects, const int32_t* __rest
     losses_out[1] = pn * scale;
     losses_out[2] = pn;
     losses_out[3] = (float)wtot;
-    ws.scale[0] = scale;
     sched->ticket = 0u;          // every CTA of this grid has read wtot before taking its ticket
     sched->wtot = 0ull;
   }
