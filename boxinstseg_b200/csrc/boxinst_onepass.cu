@@ -740,18 +740,20 @@ int op_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bit
                    float* g_logits) {
   const size_t smem = op_smem_bytes(N, W);
   auto kern = onepass_main_kernel<NCHUNK, D, FULLW>;
-  static thread_local size_t configured = 0;      // per instantiation
+  constexpr int kMaxDev = 64;
+  static thread_local size_t configured[kMaxDev] = {};   // per instantiation and device: opted-in dynamic shared memory
   static thread_local int occ_dev = -1, occ = 0;
   static thread_local size_t occ_smem = 0;
-  if (smem > configured) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool tracked = dev >= 0 && dev < kMaxDev;
+  if (!tracked || smem > configured[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_last_error(cudaGetLastError());
       return BXS_ERR_UNSUPPORTED;
     }
-    configured = smem;
+    if (tracked) configured[dev] = smem;
   }
-  int dev = 0;
-  cudaGetDevice(&dev);
   if (dev != occ_dev || smem != occ_smem) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OP_NT, smem) != cudaSuccess || occ < 1) {
       set_last_error(cudaGetLastError());
