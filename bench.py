@@ -225,7 +225,7 @@ ONEPASS_BYTES = 2 * N_INST * H * W * 4 + B_IMG * H * W                  # logits
 def main_cuda(args, rank, world, local_rank):
     from boxinstseg_b200 import _lib as L
     from boxinstseg_b200.models.dense_heads import CondInstMaskHead
-    from boxinstseg_b200.ops.boxinst import boxinst_mask_loss, boxinst_targets
+    from boxinstseg_b200.ops.boxinst import boxinst_loss_plan, boxinst_mask_loss, boxinst_targets
     lib = L.lib()                                # fail loudly if the CUDA extension is missing
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
@@ -254,6 +254,8 @@ def main_cuda(args, rank, world, local_rank):
     gt_inds32 = gt_inds.to(torch.int32)       # instance -> GT indices are part of the (precomputed) targets
     it = torch.tensor([10000.0], device=dev)
     targets = boxinst_targets(img, case['metas'], boxes)
+    # the work plan of the single-pass kernel is index work on the targets (item list + weight total): built with them
+    plan = None if os.environ.get('BXS_ONEPASS_CTA') == '1' else boxinst_loss_plan(targets, gt_inds32, H, W, 2)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
     logit_sets = [case['logits'].to(dev)] + [torch.randn(N_INST, 1, H, W, device=dev, generator=gen) * 2
                                              for _ in range(ROTATE - 1)]
@@ -263,7 +265,7 @@ def main_cuda(args, rank, world, local_rank):
 
     def step(i):
         x = logit_sets[i % ROTATE]
-        prj, pair = boxinst_mask_loss(x, targets, gt_inds32, it)
+        prj, pair = boxinst_mask_loss(x, targets, gt_inds32, it, plan=plan)
         torch.autograd.backward([prj, pair], [ones, ones])
         grad_ring[i % ROTATE], x.grad = x.grad, None
         return prj, pair
@@ -309,7 +311,7 @@ def main_cuda(args, rank, world, local_rank):
         with torch.cuda.graph(g):
             for i in range(ROTATE):
                 x = logit_sets[i]
-                prj, pair = boxinst_mask_loss(x, targets, gt_inds32, it)
+                prj, pair = boxinst_mask_loss(x, targets, gt_inds32, it, plan=plan)
                 torch.autograd.backward([prj, pair], [ones, ones])
                 graphs.append((prj, pair, x.grad))
         for i in range(max(warm // ROTATE, 1)):
@@ -345,6 +347,11 @@ def main_cuda(args, rank, world, local_rank):
                                               L.ptr(raw_g[i % ROTATE]), N_INST, H, W, 2, s_ or st), 'bwd')
 
     def raw_one_fwd(i, s_=None):
+        if plan is not None:
+            L.check(lib.bxs_boxinst_loss_fused_forward_planned(L.ptr(raw_x[i % ROTATE]), L.ptr(targets.edge_bits), L.ptr(plan),
+                                                               L.ptr(it), 10000.0, L.ptr(ws1), L.ptr(sched), L.ptr(out4),
+                                                               L.ptr(raw_g[i % ROTATE]), N_INST, H, W, 2, s_ or st), 'fused fwd')
+            return
         L.check(lib.bxs_boxinst_loss_fused_forward(L.ptr(raw_x[i % ROTATE]), L.ptr(targets.edge_bits), L.ptr(targets.rects),
                                                    L.ptr(inst_gt), L.ptr(targets.gt_img), L.ptr(it), 10000.0, L.ptr(ws1),
                                                    L.ptr(sched), L.ptr(out4), L.ptr(raw_g[i % ROTATE]), N_INST, H, W, 2, s_ or st),

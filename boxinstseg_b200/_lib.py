@@ -38,6 +38,9 @@ SIGNATURES = {
     'bxs_boxinst_loss_fused_sched_bytes': [],
     'bxs_boxinst_loss_fused_forward': [c_p] * 6 + [c_f] + [c_p] * 4 + [c_i64] * 3 + [c_int, c_p],
     'bxs_boxinst_loss_fused_backward': [c_p] * 4 + [c_i64] * 3 + [c_p],
+    'bxs_boxinst_loss_plan_bytes': [c_i64, c_i64, c_i64, c_int],
+    'bxs_boxinst_loss_plan': [c_p] * 5 + [c_i64] * 3 + [c_int, c_p],
+    'bxs_boxinst_loss_fused_forward_planned': [c_p] * 4 + [c_f] + [c_p] * 4 + [c_i64] * 3 + [c_int, c_p],
     'bxs_condinst_head_forward': [c_p] * 6 + [c_i64] * 6 + [c_int] * 3 + [c_p],
     'bxs_condinst_head_workspace_bytes': [c_i64] * 5,
     'bxs_condinst_head_backward': [c_p] * 9 + [c_i64] * 6 + [c_int] * 3 + [c_p],
@@ -68,7 +71,8 @@ SIGNATURES = {
     'bxs_upsampled_rowcol_max': [c_p] * 4 + [c_i64] * 5 + [c_int, c_p],
 }
 _RESTYPE = {'bxs_mst_workspace_bytes': c_i64, 'bxs_bfs_workspace_bytes': c_i64, 'bxs_refine_scratch_bytes': c_i64, 'bxs_lcm_workspace_bytes': c_i64, 'bxs_meanfield_workspace_bytes': c_i64, 'bxs_projection_workspace_bytes': c_i64, 'bxs_levelset_workspace_bytes': c_i64, 'bxs_condinst_head_workspace_bytes': c_i64, 'bxs_last_error': ctypes.c_char_p, 'bxs_boxinst_loss_workspace_bytes': c_i64,
-             'bxs_boxinst_loss_fused_workspace_bytes': c_i64, 'bxs_boxinst_loss_fused_sched_bytes': c_i64}
+             'bxs_boxinst_loss_fused_workspace_bytes': c_i64, 'bxs_boxinst_loss_fused_sched_bytes': c_i64,
+             'bxs_boxinst_loss_plan_bytes': c_i64}
 
 _STATUS = {-1: 'invalid argument', -2: 'kernel launch failed', -3: 'unsupported shape', -4: 'no CUDA device'}
 

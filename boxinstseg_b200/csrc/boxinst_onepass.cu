@@ -22,6 +22,7 @@
 //
 // Everything is summed in a fixed order: results do not depend on which CTA processed which strip.
 #include <algorithm>
+#include <cstdlib>
 
 #include "boxinst_common.cuh"
 
@@ -198,7 +199,8 @@ __device__ __forceinline__ ChainGeom chain_geom(const SRec& r, int H, int W) {
 template <int D>
 __device__ __forceinline__ void op_chain(const float* __restrict__ img, const uint8_t* __restrict__ bits, int H, int W,
                                          int y0, int nrows, int xs, int c_hi, const SRec& r, int lane,
-                                         float* __restrict__ ginst, float& acc_lg, float& acc_slow, int& acc_w) {
+                                         float* __restrict__ ginst, float gscale, float& acc_lg, float& acc_slow,
+                                         int& acc_w) {
   const int x = xs + lane;
   const bool x_ok = x >= 0 && x < W, x_box = x >= r.i0 && x <= r.i1;
   const bool owner = lane >= D && lane < 32 - D && x <= c_hi;
@@ -283,7 +285,7 @@ __device__ __forceinline__ void op_chain(const float* __restrict__ img, const ui
     const float to_right = __shfl_up_sync(kFull, gq7, D);
     if (count) {
       acc_w += __popc(cur.e);
-      ginst[y * W + x] = (ga + carry) + from_left;                // owners have lane >= D: from_left is a real lane's value
+      ginst[y * W + x] = ((ga + carry) + from_left) * gscale;     // owners have lane >= D: from_left is a real lane's value
     }
     carry = gq6 + (dn_ok ? to_left : 0.f) + (up_ok ? to_right : 0.f);
     cur = nxt;
@@ -529,8 +531,8 @@ onepass_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict_
         const int k0 = piece * OP_LEN;
         if (k0 < rows_p)
           op_chain<D>(logits + (int64_t)n * H * W, edge_bits + (int64_t)rec.img * H * W, H, W, cg.y_lo + p + D * k0,
-                      min(OP_LEN, rows_p - k0), cg.c_lo - D + seg * (32 - 2 * D), cg.c_hi, rec, lane, ginst, acc_lg, acc_slow,
-                      acc_w);
+                      min(OP_LEN, rows_p - k0), cg.c_lo - D + seg * (32 - 2 * D), cg.c_hi, rec, lane, ginst, 1.f, acc_lg,
+                      acc_slow, acc_w);
       }
       const float v = warp_sum(fmaf(acc_lg, -0.69314718055994531f, acc_slow));
       const int w = warp_sum(acc_w);
@@ -770,6 +772,15 @@ int op_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bit
   return check_launch();
 }
 
+#include "boxinst_warpq.cuh"
+
+// which schedule bxs_boxinst_loss_fused_forward runs: the warp-granular queue (default) or, with
+// BXS_ONEPASS_CTA=1 in the environment, the CTA-granular kernels above (kept for A/B measurements on one box)
+inline bool op_use_cta_schedule() {
+  static const bool v = [] { const char* e = getenv("BXS_ONEPASS_CTA"); return e && e[0] == '1'; }();
+  return v;
+}
+
 }  // namespace
 }  // namespace bxs
 
@@ -785,12 +796,46 @@ extern "C" int bxs_boxinst_loss_fused_supported(int64_t N, int64_t H, int64_t W,
   return op_supported(N, H, W, dilation) ? 1 : 0;
 }
 
+// workspace = the forward->backward tables (op_carve) followed by room for a plan (used when the caller passes none)
 extern "C" int64_t bxs_boxinst_loss_fused_workspace_bytes(int64_t N, int64_t H, int64_t W) {
   if (N <= 0 || H <= 0 || W <= 0) return 0;
-  return (int64_t)op_carve(nullptr, N, H, W).total_bytes;
+  size_t plan = 0;
+  for (int d = 1; d <= 4; ++d) plan = std::max(plan, wq_plan_bytes(N, H, W, d));
+  return (int64_t)(op_align(op_carve(nullptr, N, H, W).total_bytes) + plan);
 }
 
-extern "C" int64_t bxs_boxinst_loss_fused_sched_bytes(void) { return (int64_t)sizeof(OpSched); }
+extern "C" int64_t bxs_boxinst_loss_fused_sched_bytes(void) {
+  return (int64_t)std::max(sizeof(OpSched), sizeof(WqSched));
+}
+
+extern "C" int64_t bxs_boxinst_loss_plan_bytes(int64_t N, int64_t H, int64_t W, int dilation) {
+  if (N <= 0 || H <= 0 || W <= 0 || dilation < 1 || dilation > 4) return 0;
+  return (int64_t)wq_plan_bytes(N, H, W, dilation);
+}
+
+extern "C" int bxs_boxinst_loss_plan(const uint8_t* edge_bits, const int32_t* rects, const int32_t* inst_gt,
+                                     const int32_t* gt_img, void* plan, int64_t N, int64_t H, int64_t W, int dilation,
+                                     bxs_stream_t stream) {
+  if (!edge_bits || !rects || !inst_gt || !gt_img || !plan || N <= 0 || H <= 0 || W <= 0) return BXS_ERR_INVALID_ARG;
+  if (!op_supported(N, H, W, dilation)) return BXS_ERR_UNSUPPORTED;
+  return wq_build_plan(as_stream(stream), edge_bits, rects, inst_gt, gt_img, reinterpret_cast<unsigned char*>(plan), (int)N,
+                       (int)H, (int)W, dilation);
+}
+
+extern "C" int bxs_boxinst_loss_fused_forward_planned(const float* logits, const uint8_t* edge_bits, const void* plan,
+                                                      const float* iter_ptr, float warmup_iters, void* workspace,
+                                                      void* sched_state, float* losses_out, float* g_logits, int64_t N,
+                                                      int64_t H, int64_t W, int dilation, bxs_stream_t stream) {
+  if (!logits || !edge_bits || !plan || !iter_ptr || !workspace || !sched_state || !losses_out || !g_logits || N <= 0 ||
+      H <= 0 || W <= 0 || !(warmup_iters > 0.f))
+    return BXS_ERR_INVALID_ARG;
+  if (!op_supported(N, H, W, dilation) || (reinterpret_cast<uintptr_t>(logits) & 15) ||
+      (reinterpret_cast<uintptr_t>(g_logits) & 15) || (reinterpret_cast<uintptr_t>(plan) & 15))
+    return BXS_ERR_UNSUPPORTED;
+  return wq_forward(as_stream(stream), logits, edge_bits, reinterpret_cast<const unsigned char*>(plan), iter_ptr, warmup_iters,
+                    op_carve(workspace, N, H, W), reinterpret_cast<WqSched*>(sched_state), losses_out, g_logits, (int)N, (int)H,
+                    (int)W, dilation);
+}
 
 extern "C" int bxs_boxinst_loss_fused_forward(const float* logits, const uint8_t* edge_bits, const int32_t* rects,
                                               const int32_t* inst_gt, const int32_t* gt_img, const float* iter_ptr,
@@ -805,6 +850,13 @@ extern "C" int bxs_boxinst_loss_fused_forward(const float* logits, const uint8_t
     return BXS_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   OpWorkspace ws = op_carve(workspace, N, H, W);
+  if (!op_use_cta_schedule()) {            // plan in the tail of the workspace, then the warp-granular kernel
+    unsigned char* plan = reinterpret_cast<unsigned char*>(workspace) + op_align(ws.total_bytes);
+    const int prc = wq_build_plan(st, edge_bits, rects, inst_gt, gt_img, plan, (int)N, (int)H, (int)W, dilation);
+    if (prc != BXS_OK) return prc;
+    return wq_forward(st, logits, edge_bits, plan, iter_ptr, warmup_iters, ws, reinterpret_cast<WqSched*>(sched_state),
+                      losses_out, g_logits, (int)N, (int)H, (int)W, dilation);
+  }
   OpSched* sched = reinterpret_cast<OpSched*>(sched_state);
   const int S = (int)ceil_div(H, OP_R);
   int rc = BXS_ERR_UNSUPPORTED;

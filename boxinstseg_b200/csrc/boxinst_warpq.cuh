@@ -1,0 +1,545 @@
+// a6 + a7 + a8, single pass, second schedule: ONE persistent kernel whose unit of work is a WARP item.
+// (Included by boxinst_onepass.cu inside namespace bxs::{anonymous}; shares SRec / op_span / chain_geom / op_chain
+// and the PTX wrappers with the CTA-granular schedule there.)
+//
+// Why: the CTA-granular kernel (onepass_main_kernel) spent 31 % of its duration with SMs idle (per-CTA prologue of
+// 128 record loads + a block scan, a tail of CTA-wide pair items) and its top stall was the CTA barrier around the
+// strip buffers; a separate finalize kernel added a 7.5 us latency chain (profiles/r1_ncu_full_onepass.csv).  Here
+//   * the work list is a PLAN built once per target set (wq_count_kernel + wq_build_kernel): the instance records,
+//     every work item as a 32-byte descriptor, the logit-independent weight total, all in queue order -- the main
+//     kernel has no prologue beyond one header load;
+//   * every item is processed by ONE warp, so there is no CTA barrier anywhere:
+//       - stream item: 24 rows x W of one instance, 4 rows at a time through the warp's own 2-stage shared-memory
+//         ring, each stage filled by ONE cp.async.bulk (TMA engine) that completes on the warp's own mbarrier;
+//         row maxima (integer redux + ballot arg-max), column maxima with their rows in registers, float4 zero
+//         stores of the gradient outside the box span;
+//       - pair item: one chain (op_chain) = 8 rows of a 32-lane column segment; because the weight total is known
+//         from the plan, the chain stores the FINAL scaled pairwise gradient (no second pass over the span);
+//     pair and stream items are merged proportionally in the queue (Bresenham), so issue-bound and HBM-bound work
+//     overlap on every SM;
+//   * per-instance completion counters: the warp that completes the last item of an instance finalizes it in
+//     place (profiles -> dice terms -> coefficients -> read-modify-write of the H + W arg-max positions); the loss
+//     sums are 64-bit fixed-point atomics (order-independent => deterministic); the last finalizer writes the
+//     four scalars.  No finalize kernel, no span rescaling pass.
+// Every gradient element is written by exactly one warp and every sum is either fixed-order or integer: results
+// do not depend on which warp processed which item.
+
+constexpr int WQ_NT = 256;          // threads per CTA
+constexpr int WQ_NW = WQ_NT / 32;
+constexpr int WQ_SUB = 4;           // rows per ring stage
+constexpr int WQ_R = 24;            // rows per stream item
+constexpr int WQ_STAGES = 2;
+constexpr double WQ_NUM_FX = 16777216.0;            // 2^24: fixed-point scale of the pairwise numerator
+constexpr double WQ_PRJ_FX = 1099511627776.0;       // 2^40: fixed-point scale of the projection terms
+
+struct WqHeader {                   // first 64 bytes of the plan
+  int total, n_pair, n_stream, S;
+  int N, H, W, D;
+  unsigned long long wtot;          // sum over instances of the edge bits set inside their boxes
+  int pad[6];
+};
+static_assert(sizeof(WqHeader) == 64, "plan header is 64 bytes");
+
+// 32-byte work item.  a = {kind << 31 | n, y0 | nrows << 16, xs | c_hi << 16, items of instance n}
+//                     b = {j0 | j1 << 16, i0 | i1 << 16, pair: image / stream: ya | yb << 16, stream: c_lo}
+struct __align__(16) WqItem { int4 a, b; };
+
+struct WqSched {                    // device state: zero before the first call, left zero by every call
+  unsigned next, done, ticket, pad;
+  unsigned long long num_fx, prj_fx;
+  unsigned inst_cnt[OP_MAX_N];
+};
+
+inline int wq_strips(int64_t H) { return (int)ceil_div(H, WQ_R); }
+inline int64_t wq_max_chains(int64_t H, int64_t W, int d) {
+  const int64_t nseg = ceil_div(W + 4, 32 - 2 * d) + 1, pc = ceil_div(ceil_div(H, d), OP_LEN) + 1;
+  return d * pc * nseg;
+}
+inline size_t wq_plan_items_offset(int64_t N) { return op_align(64 + 4 * (size_t)N, 64); }
+inline size_t wq_plan_bytes(int64_t N, int64_t H, int64_t W, int d) {
+  return wq_plan_items_offset(N) + (size_t)N * (size_t)(wq_max_chains(H, W, d) + wq_strips(H)) * sizeof(WqItem);
+}
+
+__device__ __forceinline__ int wq_pack16(int lo, int hi) { return (lo & 0xffff) | (hi << 16); }
+__device__ __forceinline__ int wq_lo16(int v) { return (int)(short)(v & 0xffff); }
+__device__ __forceinline__ int wq_hi16(int v) { return v >> 16; }
+
+// ---------------------------------------------------------------------------------------
+// plan, step 1: per-instance weight count = edge bits set inside the box (one CTA per instance)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+wq_count_kernel(const uint8_t* __restrict__ edge_bits, const int32_t* __restrict__ rects,
+                const int32_t* __restrict__ inst_gt, const int32_t* __restrict__ gt_img, int H, int W,
+                unsigned* __restrict__ inst_w) {
+  __shared__ int s_red[4];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
+  int cnt = 0;
+  if (r.j0 <= r.j1) {
+    const uint8_t* bits = edge_bits + (int64_t)r.img * H * W;
+    const int bw = r.i1 - r.i0 + 1, tot = (r.j1 - r.j0 + 1) * bw;
+    for (int i = tid; i < tot; i += 128) {
+      const int ry = i / bw, rx = i - ry * bw;
+      cnt += __popc((unsigned)__ldg(bits + (r.j0 + ry) * W + r.i0 + rx));
+    }
+  }
+  cnt = warp_sum(cnt);
+  if ((tid & 31) == 0) s_red[tid >> 5] = cnt;
+  __syncthreads();
+  if (tid == 0) inst_w[n] = (unsigned)(s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+}
+
+// ---------------------------------------------------------------------------------------
+// plan, step 2: queue order and item descriptors (one CTA).  Instances are ranked by chain count (large boxes
+// first, so the queue ends with cheap items); pair items and stream items, each in rank order, are merged
+// proportionally: position q is a pair item iff floor((q+1) P / total) > floor(q P / total).
+// ---------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(1024)
+wq_build_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ inst_gt,
+                const int32_t* __restrict__ gt_img, int N, int H, int W, unsigned char* __restrict__ plan) {
+  __shared__ int s_nch[OP_MAX_N];
+  __shared__ int s_order[OP_MAX_N];
+  __shared__ int s_pre[OP_MAX_N + 1];
+  __shared__ int s_scan[32];
+  __shared__ unsigned long long s_w[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned* inst_w = reinterpret_cast<const unsigned*>(plan + 64);
+  const int S = (H + WQ_R - 1) / WQ_R;
+  unsigned long long wsum = 0ull;
+  for (int n = tid; n < N; n += 1024) {
+    s_nch[n] = chain_geom<D>(make_srec(rects, inst_gt, gt_img, n, H, W), H, W).nch;
+    wsum += inst_w[n];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(kFull, wsum, o);
+  if (lane == 0) s_w[wid] = wsum;
+  __syncthreads();
+  // rank (descending chain count, ties by instance id) -> order
+  for (int n = tid; n < N; n += 1024) {
+    const int c = s_nch[n];
+    int rank = 0;
+    for (int m = 0; m < N; ++m) {
+      const int cm = s_nch[m];
+      rank += (cm > c || (cm == c && m < n)) ? 1 : 0;
+    }
+    s_order[rank] = n;
+  }
+  __syncthreads();
+  // exclusive prefix of the chain counts in rank order (two elements per thread)
+  {
+    const int i0 = 2 * tid, i1 = 2 * tid + 1;
+    const int c0 = i0 < N ? s_nch[s_order[i0]] : 0, c1 = i1 < N ? s_nch[s_order[i1]] : 0;
+    int inc = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_scan[wid] = inc;
+    __syncthreads();
+    int wbase = 0;
+    for (int i = 0; i < wid; ++i) wbase += s_scan[i];
+    const int excl = wbase + inc - (c0 + c1);
+    if (i0 < N) s_pre[i0] = excl;
+    if (i1 < N) s_pre[i1] = excl + c0;
+    if (tid == 1023) s_pre[N] = wbase + inc;       // N <= 2048 = 2 * 1024: the last thread's inclusive sum is the total
+  }
+  __syncthreads();
+  const int P = s_pre[N], T = N * S, total = P + T;
+  if (tid == 0) {
+    WqHeader h{};
+    h.total = total; h.n_pair = P; h.n_stream = T; h.S = S; h.N = N; h.H = H; h.W = W; h.D = D;
+    unsigned long long w = 0ull;
+    for (int i = 0; i < 32; ++i) w += s_w[i];
+    h.wtot = w;
+    *reinterpret_cast<WqHeader*>(plan) = h;
+  }
+  WqItem* items = reinterpret_cast<WqItem*>(plan + ((64 + 4 * (size_t)N + 63) / 64) * 64);
+  for (int q = tid; q < total; q += 1024) {
+    const int pidx = (int)(((long long)q * P) / total), pnext = (int)(((long long)(q + 1) * P) / total);
+    WqItem it;
+    if (pnext > pidx) {                     // pair item: chain (pidx - pre[r]) of the r-th ranked instance
+      int lo = 0, hi = N;                   // largest r with s_pre[r] <= pidx
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_pre[mid] <= pidx) lo = mid; else hi = mid;
+      }
+      const int n = s_order[lo], c = pidx - s_pre[lo];
+      const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
+      const ChainGeom cg = chain_geom<D>(r, H, W);
+      const int u = c / cg.nseg, seg = c - u * cg.nseg;
+      const int p = u / cg.pc, piece = u - p * cg.pc;              // parity class, piece within the class
+      const int rows_p = (cg.rows - p + D - 1) / D;                 // rows of class p
+      const int k0 = piece * OP_LEN;
+      const int nrows = max(0, min(OP_LEN, rows_p - k0));
+      it.a = make_int4((int)(0x80000000u | (unsigned)n), wq_pack16(cg.y_lo + p + D * k0, nrows),
+                       wq_pack16(cg.c_lo - D + seg * (32 - 2 * D), cg.c_hi), s_nch[n] + S);
+      it.b = make_int4(wq_pack16(r.j0, r.j1), wq_pack16(r.i0, r.i1), r.img, 0);
+    } else {                                // stream item: strip s of the r-th ranked instance
+      const int sidx = q - pidx;
+      const int rk = sidx / S, s = sidx - rk * S;
+      const int n = s_order[rk];
+      const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
+      const OpSpan sp = op_span<D>(r, H, W);
+      const int row0 = s * WQ_R, nrows = min(WQ_R, H - row0);
+      int ya = 1, yb = 0;
+      if (sp.y_lo <= sp.y_hi) { ya = max(row0, sp.y_lo); yb = min(row0 + nrows - 1, sp.y_hi); }
+      it.a = make_int4(n, wq_pack16(row0, nrows), wq_pack16(s, sp.c_hi), s_nch[n] + S);
+      it.b = make_int4(wq_pack16(r.j0, r.j1), wq_pack16(r.i0, r.i1), wq_pack16(ya, yb), sp.c_lo);
+    }
+    items[q] = it;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize of one instance by one warp (called by the warp that completed the instance's last item)
+// ---------------------------------------------------------------------------------------
+template <int D>
+__device__ __noinline__ void wq_finalize(int n, const SRec rec, int N, int H, int W, int S, const OpWorkspace& ws,
+                                         WqSched* __restrict__ sched, float scale, unsigned long long wtot,
+                                         float* __restrict__ losses_out, float* __restrict__ g_logits, int lane) {
+  const bool empty = rec.j0 > rec.j1;
+  float* ginst = g_logits + (size_t)n * H * W;
+  // ---- pass A: profiles, their sums, arg-max tables ----
+  float Ir = 0.f, Xr = 0.f, Ic = 0.f, Xc = 0.f;
+  for (int row = lane; row < H; row += 32) {
+    const unsigned long long rp = __ldcg(ws.row_packed + n * H + row);
+    const float sr = sigmoid_exact(fkey_inv((unsigned)(rp >> 32)));
+    const bool tr = !empty && row >= rec.j0 && row <= rec.j1;
+    Ir += tr ? sr : 0.f;
+    Xr = fmaf(sr, sr, Xr);
+    ws.arg_row[n * H + row] = (int)(0xffffffffu - (unsigned)(rp & 0xffffffffull));
+  }
+  for (int col = lane; col < W; col += 32) {
+    const unsigned long long* src = ws.col_part + (int64_t)n * S * W + col;
+    unsigned long long cp = 0ull;
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) {
+      const unsigned long long p = __ldcg(src + s * W);
+      cp = p > cp ? p : cp;                 // larger key; on equal keys the smaller row (larger ~row)
+    }
+    const float xc = fkey_inv((unsigned)(cp >> 32));
+    const float sc = sigmoid_exact(xc);
+    const bool tc = !empty && col >= rec.i0 && col <= rec.i1;
+    Ic += tc ? sc : 0.f;
+    Xc = fmaf(sc, sc, Xc);
+    ws.arg_col[n * W + col] = (int)(0xffffffffu - (unsigned)(cp & 0xffffffffull));
+    ws.coef_col[n * W + col] = xc;          // the column's maximum logit, replaced by the coefficient in pass B
+  }
+  Ir = warp_sum(Ir); Xr = warp_sum(Xr); Ic = warp_sum(Ic); Xc = warp_sum(Xc);
+  const float inv_n = 1.f / (float)N;
+  const float Ur = Xr + (empty ? 0.f : (float)(rec.j1 - rec.j0 + 1)) + kDiceEps;
+  const float Uc = Xc + (empty ? 0.f : (float)(rec.i1 - rec.i0 + 1)) + kDiceEps;
+  __syncwarp();
+  // ---- pass B, rows: d dice / d s = -2 t / U + 4 I s / U^2; through the sigmoid: * s (1 - s); mean over N.
+  //      A position that is both a row and a column arg-max is written once, by its column. ----
+  for (int row = lane; row < H; row += 32) {
+    const unsigned long long rp = __ldcg(ws.row_packed + n * H + row);
+    const float sr = sigmoid_exact(fkey_inv((unsigned)(rp >> 32)));
+    const bool tr = !empty && row >= rec.j0 && row <= rec.j1;
+    const float crow = inv_n * (-2.f * (tr ? 1.f : 0.f) / Ur + 4.f * Ir * sr / (Ur * Ur)) * sr * (1.f - sr);
+    const int ar = (int)(0xffffffffu - (unsigned)(rp & 0xffffffffull));
+    const float v = __ldcg(ginst + row * W + ar);        // the scaled pairwise gradient there (0 outside the span)
+    if (__ldcg(ws.arg_col + n * W + ar) != row) ginst[row * W + ar] = v + crow;
+    ws.coef_row[n * H + row] = crow;
+    ws.sv_row[n * H + row] = v;
+  }
+  __syncwarp();
+  for (int col = lane; col < W; col += 32) {
+    const float sc = sigmoid_exact(__ldcg(ws.coef_col + n * W + col));
+    const bool tc = !empty && col >= rec.i0 && col <= rec.i1;
+    const float ccol = inv_n * (-2.f * (tc ? 1.f : 0.f) / Uc + 4.f * Ic * sc / (Uc * Uc)) * sc * (1.f - sc);
+    const int ac = __ldcg(ws.arg_col + n * W + col);
+    const float v = __ldcg(ginst + ac * W + col);
+    const bool both = __ldcg(ws.arg_row + n * H + ac) == col;
+    ginst[ac * W + col] = both ? (v + __ldcg(ws.coef_row + n * H + ac)) + ccol : v + ccol;
+    ws.coef_col[n * W + col] = ccol;
+    ws.sv_col[n * W + col] = v;
+  }
+  if (lane == 0) {
+    const OpSpan sp = op_span<D>(rec, H, W);
+    reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
+    const float prj_n = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
+    ws.inst_prj[n] = prj_n;
+    atomicAdd(&sched->prj_fx, (unsigned long long)__double2ll_rn((double)prj_n * WQ_PRJ_FX));
+    sched->inst_cnt[n] = 0u;              // nobody touches this counter again in this launch
+    __threadfence();
+    if (atomicAdd(&sched->ticket, 1u) == (unsigned)(N - 1)) {      // every instance is final: write the losses
+      __threadfence();
+      const long long prj_fx = (long long)atomicAdd(&sched->prj_fx, 0ull);
+      const long long num_fx = (long long)atomicAdd(&sched->num_fx, 0ull);
+      const float pn = (float)((double)num_fx * (1.0 / WQ_NUM_FX));
+      losses_out[0] = (float)((double)prj_fx * (1.0 / WQ_PRJ_FX)) * inv_n;
+      losses_out[1] = pn * scale;
+      losses_out[2] = pn;
+      losses_out[3] = (float)wtot;
+      sched->prj_fx = 0ull;
+      sched->num_fx = 0ull;
+      sched->ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------
+template <int NCHUNK, int D, bool FULLW>
+__global__ void __launch_bounds__(WQ_NT, NCHUNK <= 2 ? 3 : 1)
+wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edge_bits,
+               const unsigned char* __restrict__ plan, int N, int H, int W_rt, OpWorkspace ws,
+               WqSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
+               float* __restrict__ losses_out, float* __restrict__ g_logits) {
+  const int W = FULLW ? NCHUNK * 128 : W_rt;
+  extern __shared__ __align__(128) unsigned char wq_smem[];
+  __shared__ __align__(8) uint64_t s_bar[WQ_NW][WQ_STAGES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int stage_floats = WQ_SUB * W;
+  float* ring = reinterpret_cast<float*>(wq_smem) + (size_t)warp * WQ_STAGES * stage_floats;
+  uint64_t* bar = s_bar[warp];
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < WQ_STAGES; ++i) op_mbar_init(&bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // the plan, the scheduler state and the workspace may belong to the predecessor
+  const WqHeader* hdr = reinterpret_cast<const WqHeader*>(plan);
+  const int total = __ldg(&hdr->total), S = __ldg(&hdr->S);
+  const unsigned long long wtot = __ldg(&hdr->wtot);
+  const float scale = fminf(__ldg(iter_ptr) / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
+  const WqItem* __restrict__ items = reinterpret_cast<const WqItem*>(plan + ((64 + 4 * (size_t)N + 63) / 64) * 64);
+  const unsigned nwarps = gridDim.x * WQ_NW;
+
+  // queue: the first item of a warp is its global index; later ones come from the counter, fetched two items ahead
+  unsigned q_cur = blockIdx.x * WQ_NW + warp;
+  unsigned q_nxt_l0 = 0u;
+  if (lane == 0) q_nxt_l0 = nwarps + atomicAdd(&sched->next, 1u);
+  int4 ia = make_int4(0, 0, 0, 0), ib = ia;
+  if (q_cur < (unsigned)total) { ia = __ldg(&items[q_cur].a); ib = __ldg(&items[q_cur].b); }
+  unsigned phases = 0u;          // mbarrier parity per stage (bit s)
+
+  while (q_cur < (unsigned)total) {
+    const unsigned q_nxt = __shfl_sync(kFull, q_nxt_l0, 0);
+    int4 na = make_int4(0, 0, 0, 0), nb = na;
+    if (q_nxt < (unsigned)total) { na = __ldg(&items[q_nxt].a); nb = __ldg(&items[q_nxt].b); }
+    if (lane == 0) q_nxt_l0 = nwarps + atomicAdd(&sched->next, 1u);
+
+    const int n = ia.x & 0x7fffffff;
+    SRec rec;
+    rec.j0 = (short)wq_lo16(ib.x); rec.j1 = (short)wq_hi16(ib.x);
+    rec.i0 = (short)wq_lo16(ib.y); rec.i1 = (short)wq_hi16(ib.y);
+    rec.img = 0;
+    float* ginst = g_logits + (size_t)n * H * W;
+    if (ia.x >= 0) {
+      // =============================== stream item: rows [row0, row0 + nrows) of instance n ===============================
+      const int row0 = wq_lo16(ia.y), nrows = wq_hi16(ia.y);
+      const int s_idx = wq_lo16(ia.z), c_hi = wq_hi16(ia.z), c_lo = ib.w;
+      const int ya = wq_lo16(ib.z), yb = wq_hi16(ib.z);
+      const float* src = logits + ((size_t)n * H + row0) * W;
+      const int nsub = (nrows + WQ_SUB - 1) / WQ_SUB;
+      auto issue = [&](int k) {              // sub-strip k -> stage k & 1: ONE bulk copy (rows are contiguous)
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)min(WQ_SUB, nrows - k * WQ_SUB) * (uint32_t)W * 4u;
+          op_mbar_expect_tx(&bar[k & 1], bytes);
+          op_bulk_g2s(ring + (k & 1) * stage_floats, src + (size_t)k * stage_floats, bytes, &bar[k & 1]);
+        }
+      };
+      issue(0);
+      if (nsub > 1) issue(1);
+      float cbest[NCHUNK][4];
+      int crow[NCHUNK][4];
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { cbest[ch][e] = -INFINITY; crow[ch][e] = row0; }
+      for (int k = 0; k < nsub; ++k) {
+        const int st = k & 1;
+        op_mbar_wait(&bar[st], (phases >> st) & 1u);
+        phases ^= 1u << st;
+        const float* xb = ring + st * stage_floats;
+        const int rows_here = min(WQ_SUB, nrows - k * WQ_SUB);
+#pragma unroll
+        for (int r = 0; r < WQ_SUB; ++r) {
+          if (r < rows_here) {                                         // warp-uniform
+            const int y = row0 + k * WQ_SUB + r;
+            const float* row = xb + r * W;
+            float v[NCHUNK][4];
+            float cm[NCHUNK];
+#pragma unroll
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+              const int col0 = (ch * 32 + lane) * 4;
+              float4 q;
+              if (FULLW || col0 < W) q = *reinterpret_cast<const float4*>(row + col0);
+              else q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+              v[ch][0] = q.x; v[ch][1] = q.y; v[ch][2] = q.z; v[ch][3] = q.w;
+              cm[ch] = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w));
+            }
+            float m = cm[0];
+#pragma unroll
+            for (int ch = 1; ch < NCHUNK; ++ch) m = fmaxf(m, cm[ch]);
+            const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
+            const float mv = fkey_inv(kmax);
+            // first chunk (lowest columns) that holds the maximum, first lane within it, first element within the lane
+            unsigned bal = __ballot_sync(kFull, cm[0] == mv);
+            int chunk = 0;
+#pragma unroll
+            for (int ch = 1; ch < NCHUNK; ++ch) {
+              const unsigned b = __ballot_sync(kFull, cm[ch] == mv);
+              if (bal == 0u) { bal = b; chunk = ch; }
+            }
+            if (lane == (bal ? __ffs(bal) - 1 : 0)) {                  // bal == 0 only for an all-NaN row: any in-range index
+              float w0 = v[0][0], w1 = v[0][1], w2 = v[0][2];
+#pragma unroll
+              for (int ch = 1; ch < NCHUNK; ++ch)
+                if (chunk == ch) { w0 = v[ch][0]; w1 = v[ch][1]; w2 = v[ch][2]; }
+              const int e = w0 == mv ? 0 : (w1 == mv ? 1 : (w2 == mv ? 2 : 3));
+              ws.row_packed[n * H + y] = pack_key(kmax, min((chunk * 32 + lane) * 4 + e, W - 1));
+            }
+            // zero part of the gradient: everything outside the span (the chains write the span)
+            float* grow = ginst + y * W + lane * 4;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= ya && y <= yb) {                                  // warp-uniform: a span row
+#pragma unroll
+              for (int ch = 0; ch < NCHUNK; ++ch) {
+                const int col0 = (ch * 32 + lane) * 4;
+                if ((FULLW || col0 < W) && (col0 < c_lo || col0 > c_hi)) *reinterpret_cast<float4*>(grow + ch * 128) = z;
+              }
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < NCHUNK; ++ch)
+                if (FULLW || (ch * 32 + lane) * 4 < W) *reinterpret_cast<float4*>(grow + ch * 128) = z;
+            }
+            // column maxima (first row wins ties)
+#pragma unroll
+            for (int ch = 0; ch < NCHUNK; ++ch)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (v[ch][e] > cbest[ch][e]) { cbest[ch][e] = v[ch][e]; crow[ch][e] = y; }
+          }
+        }
+        __syncwarp();                        // every lane has read stage st
+        if (k + 2 < nsub) issue(k + 2);
+      }
+      unsigned long long* cdst = ws.col_part + ((int64_t)n * S + s_idx) * W;
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int col0 = (ch * 32 + lane) * 4;
+        if (FULLW || col0 < W) {
+          ulonglong2 p0, p1;
+          p0.x = pack_key(fkey(cbest[ch][0]), crow[ch][0]); p0.y = pack_key(fkey(cbest[ch][1]), crow[ch][1]);
+          p1.x = pack_key(fkey(cbest[ch][2]), crow[ch][2]); p1.y = pack_key(fkey(cbest[ch][3]), crow[ch][3]);
+          *reinterpret_cast<ulonglong2*>(cdst + col0) = p0;
+          *reinterpret_cast<ulonglong2*>(cdst + col0 + 2) = p1;
+        }
+      }
+    } else {
+      // =============================== pair item: one chain of instance n ===============================
+      const int y0 = wq_lo16(ia.y), nrows = wq_hi16(ia.y);
+      const int xs = wq_lo16(ia.z), c_hi = wq_hi16(ia.z);
+      rec.img = ib.z;
+      if (nrows > 0) {
+        float acc_lg = 0.f, acc_slow = 0.f;
+        int acc_w = 0;
+        op_chain<D>(logits + (size_t)n * H * W, edge_bits + (size_t)rec.img * H * W, H, W, y0, nrows, xs, c_hi, rec, lane,
+                    ginst, scale, acc_lg, acc_slow, acc_w);
+        const float val = warp_sum(fmaf(acc_lg, -0.69314718055994531f, acc_slow));
+        if (lane == 0 && val != 0.f)
+          atomicAdd(&sched->num_fx, (unsigned long long)__double2ll_rn((double)val * WQ_NUM_FX));
+      }
+    }
+    // ---- completion: the warp that completes the last item of instance n finalizes it ----
+    __threadfence();                        // this lane's stores (gradient, partial maxima) before the counter
+    __syncwarp();
+    unsigned old = 0u;
+    if (lane == 0) old = atomicAdd(&sched->inst_cnt[n], 1u);
+    old = __shfl_sync(kFull, old, 0);
+    if (old + 1u == (unsigned)ia.w) {
+      __threadfence();
+      wq_finalize<D>(n, rec, N, H, W, S, ws, sched, scale, wtot, losses_out, g_logits, lane);
+    }
+    q_cur = q_nxt; ia = na; ib = nb;
+  }
+  // ---- queue counter reset by the last warp (every fetch of a warp precedes its `done` increment) ----
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(&sched->done, 1u) == nwarps - 1u) {
+      sched->next = 0u;
+      sched->done = 0u;
+      __threadfence();
+    }
+  }
+}
+
+inline size_t wq_smem_bytes(int64_t W) { return (size_t)WQ_NW * WQ_STAGES * WQ_SUB * W * 4; }
+
+template <int NCHUNK, int D, bool FULLW>
+int wq_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bits, const unsigned char* plan, int N, int H,
+                   int W, OpWorkspace ws, WqSched* sched, const float* iter_ptr, float warmup_iters, float* losses_out,
+                   float* g_logits) {
+  const size_t smem = wq_smem_bytes(W);
+  auto kern = wq_main_kernel<NCHUNK, D, FULLW>;
+  constexpr int kMaxDev = 64;
+  static thread_local size_t configured[kMaxDev] = {};   // per instantiation and device: opted-in dynamic shared memory
+  static thread_local int occ_dev = -1, occ = 0;
+  static thread_local size_t occ_smem = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool tracked = dev >= 0 && dev < kMaxDev;
+  if (!tracked || smem > configured[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_last_error(cudaGetLastError());
+      return BXS_ERR_UNSUPPORTED;
+    }
+    if (tracked) configured[dev] = smem;
+  }
+  if (dev != occ_dev || smem != occ_smem) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WQ_NT, smem) != cudaSuccess || occ < 1) {
+      set_last_error(cudaGetLastError());
+      return BXS_ERR_UNSUPPORTED;
+    }
+    occ_dev = dev;
+    occ_smem = smem;
+  }
+  const int64_t min_items = (int64_t)N * wq_strips(H);                     // stream items alone
+  const int grid = (int)std::min<int64_t>(ceil_div(min_items, WQ_NW), (int64_t)sm_count() * occ);
+  op_launch_pdl(kern, dim3((unsigned)grid), dim3(WQ_NT), smem, st, logits, edge_bits, plan, N, H, W, ws, sched, iter_ptr,
+                warmup_iters, losses_out, g_logits);
+  return check_launch();
+}
+
+inline int wq_build_plan(cudaStream_t st, const uint8_t* edge_bits, const int32_t* rects, const int32_t* inst_gt,
+                         const int32_t* gt_img, unsigned char* plan, int N, int H, int W, int dilation) {
+  wq_count_kernel<<<N, 128, 0, st>>>(edge_bits, rects, inst_gt, gt_img, H, W, reinterpret_cast<unsigned*>(plan + 64));
+  switch (dilation) {
+    case 1: wq_build_kernel<1><<<1, 1024, 0, st>>>(rects, inst_gt, gt_img, N, H, W, plan); break;
+    case 2: wq_build_kernel<2><<<1, 1024, 0, st>>>(rects, inst_gt, gt_img, N, H, W, plan); break;
+    case 3: wq_build_kernel<3><<<1, 1024, 0, st>>>(rects, inst_gt, gt_img, N, H, W, plan); break;
+    default: wq_build_kernel<4><<<1, 1024, 0, st>>>(rects, inst_gt, gt_img, N, H, W, plan); break;
+  }
+  return check_launch();
+}
+
+inline int wq_forward(cudaStream_t st, const float* logits, const uint8_t* edge_bits, const unsigned char* plan,
+                      const float* iter_ptr, float warmup_iters, OpWorkspace ws, WqSched* sched, float* losses_out,
+                      float* g_logits, int N, int H, int W, int dilation) {
+  int rc = BXS_ERR_UNSUPPORTED;
+#define BXS_WQ_CASE(NC, DD)                                                                                            \
+  rc = (W == NC * 128) ? wq_launch_main<NC, DD, true>(st, logits, edge_bits, plan, N, H, W, ws, sched, iter_ptr,        \
+                                                      warmup_iters, losses_out, g_logits)                            \
+                       : wq_launch_main<NC, DD, false>(st, logits, edge_bits, plan, N, H, W, ws, sched, iter_ptr,       \
+                                                       warmup_iters, losses_out, g_logits);
+#define BXS_WQ_D(NC)                                                  \
+  switch (dilation) {                                                 \
+    case 1: { BXS_WQ_CASE(NC, 1) } break;                             \
+    case 2: { BXS_WQ_CASE(NC, 2) } break;                             \
+    case 3: { BXS_WQ_CASE(NC, 3) } break;                             \
+    default: { BXS_WQ_CASE(NC, 4) } break;                            \
+  }
+  if (W <= 128) { BXS_WQ_D(1) }
+  else if (W <= 256) { BXS_WQ_D(2) }
+  else { BXS_WQ_D(4) }
+#undef BXS_WQ_D
+#undef BXS_WQ_CASE
+  return rc;
+}

@@ -41,10 +41,17 @@ def _norm_cfg(img_metas):
     cfg = img_metas[0]['img_norm_cfg']
     mean = np.ascontiguousarray(np.asarray(cfg['mean'], dtype=np.float32).reshape(3))
     std = np.ascontiguousarray(np.asarray(cfg['std'], dtype=np.float32).reshape(3))
+    to_rgb = bool(cfg.get('to_rgb', True))
     for m in img_metas[1:]:
         c = m['img_norm_cfg']
-        if not (np.allclose(np.asarray(c['mean'], np.float32), mean) and np.allclose(np.asarray(c['std'], np.float32), std)):
+        if not (np.allclose(np.asarray(c['mean'], np.float32), mean) and np.allclose(np.asarray(c['std'], np.float32), std)
+                and bool(c.get('to_rgb', True)) == to_rgb):
             raise NotImplementedError('per-image normalisation constants are not supported')
+    if not to_rgb:
+        # get_original_image (condinst_head.py:176-186) always hands true RGB to rgb2lab: tensor2imgs(to_rgb=...) followed
+        # by the [::-1] flip.  The LAB kernel reads channel 0 as R, so a BGR-ordered tensor (caffe-style configs) would be
+        # silently mis-coloured; all shipped BoxInst configs use to_rgb=True.
+        raise NotImplementedError('img_norm_cfg.to_rgb=False (BGR input tensors) is not supported by the LAB kernel')
     return mean, std
 
 
@@ -90,12 +97,26 @@ def boxinst_targets(img, img_metas, gt_bboxes, stride=4, pairwise_size=3, pairwi
     return BoxInstTargets(bits, sim, rects, gt_img, num_gts, lab, valid)
 
 
-# Scheduler state of the single-pass kernels (work-item counter + finalize ticket): zero before first use, left
-# zero by every call, owned by ONE stream at a time.  A pool of slots is created per device outside any graph
-# capture; eager calls take the slot of their stream, every captured call site takes a slot of its own (a captured
-# graph may be replayed on any stream, concurrently with eager work).
+# Scheduler state of the single-pass kernel (work-item counter, per-instance completion counters, finalize ticket,
+# fixed-point loss sums): zero before first use, left zero by every call that runs to completion, owned by ONE stream
+# at a time.  Pools of slots are created per device outside any graph capture; eager calls take the slot of their
+# stream, every captured call site takes a slot of its own (a captured graph may be replayed on any stream,
+# concurrently with eager work).  A pool is zero-filled on the stream that creates it; other streams wait on the
+# pool's creation event before their first use.  When the pool runs dry an eager call simply adds another pool; a
+# capturing call falls back to a graph-private state that is re-zeroed by a memset node at every replay.
 _SCHED_SLOTS = 256
-_SCHED = {}     # device index -> dict(pool=tensor [slots, words], by_stream={}, next=int)
+_SCHED = {}     # device index -> dict(pools=[tensor [slots, words]], events=[Event], by_stream={}, next=int, seen=set())
+
+
+def _sched_new_pool(st, words, device):
+    st['pools'].append(torch.zeros((_SCHED_SLOTS, words), dtype=torch.int32, device=device))
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    st['events'].append(ev)
+
+
+def _sched_slot(st, slot):
+    return st['pools'][slot // _SCHED_SLOTS][slot % _SCHED_SLOTS]
 
 
 def _sched_state(device):
@@ -105,21 +126,45 @@ def _sched_state(device):
     if st is None:
         if capturing:           # first use ever is inside a capture: a graph-private, memset-initialised state
             return torch.zeros(words, dtype=torch.int32, device=device)
-        st = dict(pool=torch.zeros((_SCHED_SLOTS, words), dtype=torch.int32, device=device), by_stream={}, next=0)
+        st = dict(pools=[], events=[], by_stream={}, next=0, seen=set())
+        _sched_new_pool(st, words, device)
         _SCHED[device.index] = st
+    cur = torch.cuda.current_stream(device)
     if capturing:
-        if st['next'] >= _SCHED_SLOTS:
+        if st['next'] >= _SCHED_SLOTS * len(st['pools']):
             return torch.zeros(words, dtype=torch.int32, device=device)
         slot, st['next'] = st['next'], st['next'] + 1
-        return st['pool'][slot]
-    key = torch.cuda.current_stream(device).cuda_stream
+        return _sched_slot(st, slot)
+    key = cur.cuda_stream
     slot = st['by_stream'].get(key)
     if slot is None:
-        if st['next'] >= _SCHED_SLOTS:
-            raise RuntimeError('boxinstseg_b200: out of scheduler-state slots (too many streams / captured graphs)')
+        if st['next'] >= _SCHED_SLOTS * len(st['pools']):
+            _sched_new_pool(st, words, device)
         slot, st['next'] = st['next'], st['next'] + 1
         st['by_stream'][key] = slot
-    return st['pool'][slot]
+    pool = slot // _SCHED_SLOTS
+    if (key, pool) not in st['seen']:       # first use of this pool on this stream: its zero fill must have completed
+        cur.wait_event(st['events'][pool])
+        st['seen'].add((key, pool))
+    return _sched_slot(st, slot)
+
+
+def boxinst_loss_plan(targets, gt_inds, H, W, pairwise_dilation=2):
+    """Work plan of the single-pass loss kernel for one (targets, instance->GT assignment) pair: item descriptors in
+    queue order + the logit-independent weight total of condinst_head.py:1318-1319.  Index work on the targets only;
+    build it where the targets are built and pass it to `boxinst_mask_loss(plan=...)` (without it the loss call
+    builds one itself, two small extra launches).  Returns None outside the single-pass envelope."""
+    inst_gt = gt_inds if (gt_inds.dtype == torch.int32 and gt_inds.is_contiguous()) else gt_inds.to(torch.int32).contiguous()
+    N = int(inst_gt.numel())
+    lib = L.lib()
+    if targets.edge_bits is None or N == 0 or not lib.bxs_boxinst_loss_fused_supported(N, H, W, pairwise_dilation):
+        return None
+    dev = targets.edge_bits.device
+    plan = torch.empty(lib.bxs_boxinst_loss_plan_bytes(N, H, W, pairwise_dilation), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.bxs_boxinst_loss_plan(L.ptr(targets.edge_bits), L.ptr(targets.rects), L.ptr(inst_gt), L.ptr(targets.gt_img),
+                                          L.ptr(plan), N, H, W, pairwise_dilation, L.stream()), 'boxinst_loss_plan')
+    return plan
 
 
 class _BoxInstMaskLoss(torch.autograd.Function):
@@ -130,7 +175,7 @@ class _BoxInstMaskLoss(torch.autograd.Function):
     kernels, because the single-pass gradient buffer is converted in place."""
 
     @staticmethod
-    def forward(ctx, mask_logits, edge_bits, rects, inst_gt, gt_img, iter_buf, warmup_iters, dilation):
+    def forward(ctx, mask_logits, edge_bits, rects, inst_gt, gt_img, iter_buf, warmup_iters, dilation, plan=None):
         logits = mask_logits.contiguous()
         L.require_cuda(logits, edge_bits, rects, inst_gt, gt_img, iter_buf)
         N, _, H, W = logits.shape
@@ -145,10 +190,18 @@ class _BoxInstMaskLoss(torch.autograd.Function):
             if fused:
                 ws = torch.empty(lib.bxs_boxinst_loss_fused_workspace_bytes(N, H, W), dtype=torch.uint8, device=dev)
                 g_logits = torch.empty_like(logits)
-                L.check(lib.bxs_boxinst_loss_fused_forward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
-                                                           L.ptr(gt_img), L.ptr(iter_buf), float(warmup_iters), L.ptr(ws),
-                                                           L.ptr(_sched_state(dev)), L.ptr(out), L.ptr(g_logits), N, H, W,
-                                                           dilation, L.stream()), 'boxinst_loss_fused_forward')
+                sched = _sched_state(dev)
+                if plan is not None:
+                    rc = lib.bxs_boxinst_loss_fused_forward_planned(L.ptr(logits), L.ptr(edge_bits), L.ptr(plan), L.ptr(iter_buf),
+                                                                    float(warmup_iters), L.ptr(ws), L.ptr(sched), L.ptr(out),
+                                                                    L.ptr(g_logits), N, H, W, dilation, L.stream())
+                else:
+                    rc = lib.bxs_boxinst_loss_fused_forward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
+                                                            L.ptr(gt_img), L.ptr(iter_buf), float(warmup_iters), L.ptr(ws),
+                                                            L.ptr(sched), L.ptr(out), L.ptr(g_logits), N, H, W, dilation, L.stream())
+                if rc != 0:
+                    sched.zero_()        # a failed launch may leave the counters dirty: never reuse them as they are
+                L.check(rc, 'boxinst_loss_fused_forward')
             else:
                 g_logits = None
                 ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N, H, W), dtype=torch.uint8, device=dev)
@@ -174,7 +227,7 @@ class _BoxInstMaskLoss(torch.autograd.Function):
         lib = L.lib()
         ctx.calls += 1
         if g_prj is None and g_pair is None:
-            return (None,) * 8
+            return (None,) * 9
         zero = None
         if g_prj is None or g_pair is None:
             zero = torch.zeros((), dtype=torch.float32, device=logits.device)
@@ -186,7 +239,7 @@ class _BoxInstMaskLoss(torch.autograd.Function):
                 del saved
                 L.check(lib.bxs_boxinst_loss_fused_backward(L.ptr(ws), L.ptr(g_prj), L.ptr(g_pair), L.ptr(g_logits), N, H, W,
                                                             L.stream()), 'boxinst_loss_fused_backward')
-                return g_logits, None, None, None, None, None, None, None
+                return g_logits, None, None, None, None, None, None, None, None
             if ctx.fused:       # the in-place buffer is spent: recompute with the two-call kernels
                 ws = torch.empty(lib.bxs_boxinst_loss_workspace_bytes(N, H, W), dtype=torch.uint8, device=logits.device)
                 tmp = torch.empty(4, dtype=torch.float32, device=logits.device)
@@ -198,18 +251,19 @@ class _BoxInstMaskLoss(torch.autograd.Function):
             L.check(lib.bxs_boxinst_loss_backward(L.ptr(logits), L.ptr(edge_bits), L.ptr(rects), L.ptr(inst_gt),
                                                   L.ptr(gt_img), L.ptr(ws), L.ptr(g), L.ptr(g_logits), N, H, W,
                                                   ctx.dilation, L.stream()), 'boxinst_loss_backward')
-        return g_logits, None, None, None, None, None, None, None
+        return g_logits, None, None, None, None, None, None, None, None
 
 
 def boxinst_mask_loss(mask_logits, targets: BoxInstTargets, gt_inds, iter_buf, warmup_iters=10000,
-                      pairwise_dilation=2):
+                      pairwise_dilation=2, plan=None):
     """(loss_prj, loss_pairwise) for mask_logits [N,1,H,W] float32; gt_inds [N] indexes the
-    concatenated GT list (as in condinst_head.py:1302,1316).  Requires pairwise_size == 3."""
+    concatenated GT list (as in condinst_head.py:1302,1316).  Requires pairwise_size == 3.
+    `plan`: optional result of `boxinst_loss_plan(targets, gt_inds, H, W, dilation)` for the same arguments."""
     if targets.edge_bits is None:
         raise NotImplementedError('the fused loss is specialised to pairwise_size == 3')
     if mask_logits.dtype != torch.float32:
         mask_logits = mask_logits.float()        # @force_fp32(apply_to=('mask_logits',)), :1288
     inst_gt = gt_inds if (gt_inds.dtype == torch.int32 and gt_inds.is_contiguous()) else gt_inds.to(torch.int32).contiguous()
     prj, pair, _ = _BoxInstMaskLoss.apply(mask_logits, targets.edge_bits, targets.rects, inst_gt, targets.gt_img,
-                                          iter_buf, warmup_iters, pairwise_dilation)
+                                          iter_buf, warmup_iters, pairwise_dilation, plan)
     return prj, pair

@@ -115,9 +115,10 @@ int bxs_boxinst_loss_backward(const float* logits, const uint8_t* edge_bits, con
  *   PLACE to g_prj * d loss_prj + g_pair * d loss_pairwise (exact: the pairwise part at the
  *   arg-max positions is kept in the workspace).  Call it at most once per forward.
  * workspace: bxs_boxinst_loss_fused_workspace_bytes(N,H,W) bytes, no initial state needed.
- * sched_state: bxs_boxinst_loss_fused_sched_bytes() (32) bytes of device memory that MUST be zero
- *   before the first call and is owned by one stream at a time (the kernels' work-item counter,
- *   finalize ticket and integer weight total live there; each call leaves it zeroed again).
+ * sched_state: bxs_boxinst_loss_fused_sched_bytes() bytes of device memory that MUST be zero
+ *   before the first call and is owned by one stream at a time (the kernel's work-item counter,
+ *   per-instance completion counters, finalize ticket and fixed-point loss sums live there; each call that runs to
+ *   completion leaves it zeroed again -- after a failed launch, zero it with cudaMemsetAsync before the next call).
  * Returns BXS_ERR_UNSUPPORTED outside the supported envelope (W % 4 == 0, W,H <= 512,
  * 1 <= dilation <= 4, N <= 2048, 16-byte aligned logits / g_logits).
  * --------------------------------------------------------------------------------------- */
@@ -132,6 +133,20 @@ int bxs_boxinst_loss_fused_forward(const float* logits, const uint8_t* edge_bits
 int bxs_boxinst_loss_fused_backward(const void* workspace, const float* g_prj, const float* g_pair,
                                     float* g_logits, int64_t N, int64_t H, int64_t W,
                                     bxs_stream_t stream);
+
+/* The work plan of the single-pass kernel: instance records, every work item (32-byte descriptor, in queue
+ * order) and the logit-independent weight total of condinst_head.py:1318-1319, derived from the TARGETS only
+ * (edge_bits, rects, the instance->GT assignment).  Build it once per target set and pass it to
+ * bxs_boxinst_loss_fused_forward_planned(); bxs_boxinst_loss_fused_forward() (no plan argument) builds one in the
+ * tail of its workspace on every call.  plan: bxs_boxinst_loss_plan_bytes() bytes, 16-byte aligned. */
+int64_t bxs_boxinst_loss_plan_bytes(int64_t N, int64_t H, int64_t W, int dilation);
+int bxs_boxinst_loss_plan(const uint8_t* edge_bits, const int32_t* rects, const int32_t* inst_gt,
+                          const int32_t* gt_img, void* plan, int64_t N, int64_t H, int64_t W, int dilation,
+                          bxs_stream_t stream);
+int bxs_boxinst_loss_fused_forward_planned(const float* logits, const uint8_t* edge_bits, const void* plan,
+                                           const float* iter_ptr, float warmup_iters, void* workspace,
+                                           void* sched_state, float* losses_out, float* g_logits, int64_t N,
+                                           int64_t H, int64_t W, int dilation, bxs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * a1  CondInst dynamic mask head       replaces CondInstMaskHead.forward + parse_dynamic_params +
