@@ -38,6 +38,7 @@ struct WqHeader {                   // first 64 bytes of the plan
   unsigned long long wtot;          // sum over instances of the edge bits set inside their boxes
   int pad[6];
 };
+static_assert(WQ_R % WQ_SUB == 0, "strips start on a 4-row group");
 static_assert(sizeof(WqHeader) == 64, "plan header is 64 bytes");
 
 // 32-byte work item.  a = {kind << 31 | n, y0 | nrows << 16, xs | c_hi << 16, items of instance n}
@@ -47,7 +48,6 @@ struct __align__(16) WqItem { int4 a, b; };
 struct WqSched {                    // device state: zero before the first call, left zero by every call
   unsigned next, done, ticket, pad;
   unsigned long long num_fx, prj_fx;
-  unsigned inst_cnt[OP_MAX_N];
 };
 
 inline int wq_strips(int64_t H) { return (int)ceil_div(H, WQ_R); }
@@ -55,7 +55,9 @@ inline int64_t wq_max_chains(int64_t H, int64_t W, int d) {
   const int64_t nseg = ceil_div(W + 4, 32 - 2 * d) + 1, pc = ceil_div(ceil_div(H, d), OP_LEN) + 1;
   return d * pc * nseg;
 }
-inline size_t wq_plan_items_offset(int64_t N) { return op_align(64 + 4 * (size_t)N, 64); }
+// plan layout: header (64 B) | inst_w [N] uint32 | recs [N] int4 (j0, j1, i0, i1) | items
+__host__ __device__ inline size_t wq_plan_rec_offset(int64_t N) { return (64 + 4 * (size_t)N + 63) / 64 * 64; }
+__host__ __device__ inline size_t wq_plan_items_offset(int64_t N) { return (wq_plan_rec_offset(N) + 16 * (size_t)N + 63) / 64 * 64; }
 inline size_t wq_plan_bytes(int64_t N, int64_t H, int64_t W, int d) {
   return wq_plan_items_offset(N) + (size_t)N * (size_t)(wq_max_chains(H, W, d) + wq_strips(H)) * sizeof(WqItem);
 }
@@ -152,7 +154,12 @@ wq_build_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ i
     h.wtot = w;
     *reinterpret_cast<WqHeader*>(plan) = h;
   }
-  WqItem* items = reinterpret_cast<WqItem*>(plan + ((64 + 4 * (size_t)N + 63) / 64) * 64);
+  int4* recs = reinterpret_cast<int4*>(plan + wq_plan_rec_offset(N));
+  for (int n = tid; n < N; n += 1024) {
+    const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
+    recs[n] = make_int4(r.j0, r.j1, r.i0, r.i1);
+  }
+  WqItem* items = reinterpret_cast<WqItem*>(plan + wq_plan_items_offset(N));
   for (int q = tid; q < total; q += 1024) {
     const int pidx = (int)(((long long)q * P) / total), pnext = (int)(((long long)(q + 1) * P) / total);
     WqItem it;
@@ -189,105 +196,36 @@ wq_build_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ i
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// finalize of one instance by one warp (called by the warp that completed the instance's last item)
-// ---------------------------------------------------------------------------------------
-template <int D>
-__device__ __noinline__ void wq_finalize(int n, const SRec rec, int N, int H, int W, int S, const OpWorkspace& ws,
-                                         WqSched* __restrict__ sched, float scale, unsigned long long wtot,
-                                         float* __restrict__ losses_out, float* __restrict__ g_logits, int lane) {
-  const bool empty = rec.j0 > rec.j1;
-  float* ginst = g_logits + (size_t)n * H * W;
-  // ---- pass A: profiles, their sums, arg-max tables ----
-  float Ir = 0.f, Xr = 0.f, Ic = 0.f, Xc = 0.f;
-  for (int row = lane; row < H; row += 32) {
-    const unsigned long long rp = __ldcg(ws.row_packed + n * H + row);
-    const float sr = sigmoid_exact(fkey_inv((unsigned)(rp >> 32)));
-    const bool tr = !empty && row >= rec.j0 && row <= rec.j1;
-    Ir += tr ? sr : 0.f;
-    Xr = fmaf(sr, sr, Xr);
-    ws.arg_row[n * H + row] = (int)(0xffffffffu - (unsigned)(rp & 0xffffffffull));
+#ifdef BXS_OP_TRACE
+// diagnostic build only (tools/trace_wq.py): per-WARP event log {globaltimer, tag}; 16 slots per warp
+#define WQ_TRACE(tag)                                                                          \
+  if (lane == 0 && g_op_trace && trace_slot < 16) {                                             \
+    unsigned long long t_;                                                                     \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                     \
+    const size_t w_ = (size_t)blockIdx.x * WQ_NW + warp;                                       \
+    g_op_trace[(w_ * 16 + trace_slot) * 2] = t_;                                               \
+    g_op_trace[(w_ * 16 + trace_slot) * 2 + 1] = (unsigned long long)(tag);                    \
+    ++trace_slot;                                                                              \
   }
-  for (int col = lane; col < W; col += 32) {
-    const unsigned long long* src = ws.col_part + (int64_t)n * S * W + col;
-    unsigned long long cp = 0ull;
-#pragma unroll 4
-    for (int s = 0; s < S; ++s) {
-      const unsigned long long p = __ldcg(src + s * W);
-      cp = p > cp ? p : cp;                 // larger key; on equal keys the smaller row (larger ~row)
-    }
-    const float xc = fkey_inv((unsigned)(cp >> 32));
-    const float sc = sigmoid_exact(xc);
-    const bool tc = !empty && col >= rec.i0 && col <= rec.i1;
-    Ic += tc ? sc : 0.f;
-    Xc = fmaf(sc, sc, Xc);
-    ws.arg_col[n * W + col] = (int)(0xffffffffu - (unsigned)(cp & 0xffffffffull));
-    ws.coef_col[n * W + col] = xc;          // the column's maximum logit, replaced by the coefficient in pass B
-  }
-  Ir = warp_sum(Ir); Xr = warp_sum(Xr); Ic = warp_sum(Ic); Xc = warp_sum(Xc);
-  const float inv_n = 1.f / (float)N;
-  const float Ur = Xr + (empty ? 0.f : (float)(rec.j1 - rec.j0 + 1)) + kDiceEps;
-  const float Uc = Xc + (empty ? 0.f : (float)(rec.i1 - rec.i0 + 1)) + kDiceEps;
-  __syncwarp();
-  // ---- pass B, rows: d dice / d s = -2 t / U + 4 I s / U^2; through the sigmoid: * s (1 - s); mean over N.
-  //      A position that is both a row and a column arg-max is written once, by its column. ----
-  for (int row = lane; row < H; row += 32) {
-    const unsigned long long rp = __ldcg(ws.row_packed + n * H + row);
-    const float sr = sigmoid_exact(fkey_inv((unsigned)(rp >> 32)));
-    const bool tr = !empty && row >= rec.j0 && row <= rec.j1;
-    const float crow = inv_n * (-2.f * (tr ? 1.f : 0.f) / Ur + 4.f * Ir * sr / (Ur * Ur)) * sr * (1.f - sr);
-    const int ar = (int)(0xffffffffu - (unsigned)(rp & 0xffffffffull));
-    const float v = __ldcg(ginst + row * W + ar);        // the scaled pairwise gradient there (0 outside the span)
-    if (__ldcg(ws.arg_col + n * W + ar) != row) ginst[row * W + ar] = v + crow;
-    ws.coef_row[n * H + row] = crow;
-    ws.sv_row[n * H + row] = v;
-  }
-  __syncwarp();
-  for (int col = lane; col < W; col += 32) {
-    const float sc = sigmoid_exact(__ldcg(ws.coef_col + n * W + col));
-    const bool tc = !empty && col >= rec.i0 && col <= rec.i1;
-    const float ccol = inv_n * (-2.f * (tc ? 1.f : 0.f) / Uc + 4.f * Ic * sc / (Uc * Uc)) * sc * (1.f - sc);
-    const int ac = __ldcg(ws.arg_col + n * W + col);
-    const float v = __ldcg(ginst + ac * W + col);
-    const bool both = __ldcg(ws.arg_row + n * H + ac) == col;
-    ginst[ac * W + col] = both ? (v + __ldcg(ws.coef_row + n * H + ac)) + ccol : v + ccol;
-    ws.coef_col[n * W + col] = ccol;
-    ws.sv_col[n * W + col] = v;
-  }
-  if (lane == 0) {
-    const OpSpan sp = op_span<D>(rec, H, W);
-    reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
-    const float prj_n = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
-    ws.inst_prj[n] = prj_n;
-    atomicAdd(&sched->prj_fx, (unsigned long long)__double2ll_rn((double)prj_n * WQ_PRJ_FX));
-    sched->inst_cnt[n] = 0u;              // nobody touches this counter again in this launch
-    __threadfence();
-    if (atomicAdd(&sched->ticket, 1u) == (unsigned)(N - 1)) {      // every instance is final: write the losses
-      __threadfence();
-      const long long prj_fx = (long long)atomicAdd(&sched->prj_fx, 0ull);
-      const long long num_fx = (long long)atomicAdd(&sched->num_fx, 0ull);
-      const float pn = (float)((double)num_fx * (1.0 / WQ_NUM_FX));
-      losses_out[0] = (float)((double)prj_fx * (1.0 / WQ_PRJ_FX)) * inv_n;
-      losses_out[1] = pn * scale;
-      losses_out[2] = pn;
-      losses_out[3] = (float)wtot;
-      sched->prj_fx = 0ull;
-      sched->num_fx = 0ull;
-      sched->ticket = 0u;
-      __threadfence();
-    }
-  }
-}
+#else
+#define WQ_TRACE(tag)
+#endif
 
 // ---------------------------------------------------------------------------------------
-// main kernel
+// main kernel: the work queue.  Items are independent (no completion protocol): the kernel boundary orders them
+// before wq_finalize_kernel.
+//   row results    row_packed[n*H + y]       = key(max logit of the row) << 32 | ~(first float4 group holding it)
+//   column results col_part[(n*S + s)*W + x] = key(max logit of the column within strip s) << 32 | ~(first 4-row
+//                                               group of the strip holding it)
+// (the exact element / row inside the group is resolved by the finalize kernel, one thread per row / column)
 // ---------------------------------------------------------------------------------------
 template <int NCHUNK, int D, bool FULLW>
 __global__ void __launch_bounds__(WQ_NT, NCHUNK <= 2 ? 3 : 1)
 wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edge_bits,
-               const unsigned char* __restrict__ plan, int N, int H, int W_rt, OpWorkspace ws,
+               const unsigned char* __restrict__ plan, int N, int H, int W_rt,
+               unsigned long long* __restrict__ row_packed, unsigned long long* __restrict__ col_part,
                WqSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
-               float* __restrict__ losses_out, float* __restrict__ g_logits) {
+               float* __restrict__ g_logits) {
   const int W = FULLW ? NCHUNK * 128 : W_rt;
   extern __shared__ __align__(128) unsigned char wq_smem[];
   __shared__ __align__(8) uint64_t s_bar[WQ_NW][WQ_STAGES];
@@ -295,6 +233,10 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
   const int stage_floats = WQ_SUB * W;
   float* ring = reinterpret_cast<float*>(wq_smem) + (size_t)warp * WQ_STAGES * stage_floats;
   uint64_t* bar = s_bar[warp];
+#ifdef BXS_OP_TRACE
+  int trace_slot = 0;
+#endif
+  WQ_TRACE(1);
   asm volatile("griddepcontrol.launch_dependents;");
   if (lane == 0) {
 #pragma unroll
@@ -308,7 +250,7 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
   const int total = __ldg(&hdr->total), S = __ldg(&hdr->S);
   const unsigned long long wtot = __ldg(&hdr->wtot);
   const float scale = fminf(__ldg(iter_ptr) / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
-  const WqItem* __restrict__ items = reinterpret_cast<const WqItem*>(plan + ((64 + 4 * (size_t)N + 63) / 64) * 64);
+  const WqItem* __restrict__ items = reinterpret_cast<const WqItem*>(plan + wq_plan_items_offset(N));
   const unsigned nwarps = gridDim.x * WQ_NW;
 
   // queue: the first item of a warp is its global index; later ones come from the counter, fetched two items ahead
@@ -326,11 +268,8 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
     if (lane == 0) q_nxt_l0 = nwarps + atomicAdd(&sched->next, 1u);
 
     const int n = ia.x & 0x7fffffff;
-    SRec rec;
-    rec.j0 = (short)wq_lo16(ib.x); rec.j1 = (short)wq_hi16(ib.x);
-    rec.i0 = (short)wq_lo16(ib.y); rec.i1 = (short)wq_hi16(ib.y);
-    rec.img = 0;
     float* ginst = g_logits + (size_t)n * H * W;
+    WQ_TRACE(2 + (ia.x < 0 ? 1 : 0) + ((unsigned long long)n << 8));
     if (ia.x >= 0) {
       // =============================== stream item: rows [row0, row0 + nrows) of instance n ===============================
       const int row0 = wq_lo16(ia.y), nrows = wq_hi16(ia.y);
@@ -348,56 +287,55 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
       issue(0);
       if (nsub > 1) issue(1);
       float cbest[NCHUNK][4];
-      int crow[NCHUNK][4];
+      int csub[NCHUNK][4];
 #pragma unroll
       for (int ch = 0; ch < NCHUNK; ++ch)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { cbest[ch][e] = -INFINITY; crow[ch][e] = row0; }
+        for (int e = 0; e < 4; ++e) { cbest[ch][e] = -INFINITY; csub[ch][e] = 0; }
+      unsigned long long* rdst = row_packed + (size_t)n * H + row0;
+      float* grow = ginst + (size_t)row0 * W + lane * 4;
+      const int sub0 = row0 / WQ_SUB;        // WQ_R % WQ_SUB == 0: strips start on a 4-row group
+      int y = row0;
       for (int k = 0; k < nsub; ++k) {
         const int st = k & 1;
         op_mbar_wait(&bar[st], (phases >> st) & 1u);
         phases ^= 1u << st;
-        const float* xb = ring + st * stage_floats;
+        const float* xb = ring + st * stage_floats + lane * 4;
         const int rows_here = min(WQ_SUB, nrows - k * WQ_SUB);
+        float gm[NCHUNK][4];                 // column maxima of this 4-row group
+#pragma unroll
+        for (int ch = 0; ch < NCHUNK; ++ch)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) gm[ch][e] = -INFINITY;
 #pragma unroll
         for (int r = 0; r < WQ_SUB; ++r) {
           if (r < rows_here) {                                         // warp-uniform
-            const int y = row0 + k * WQ_SUB + r;
-            const float* row = xb + r * W;
-            float v[NCHUNK][4];
             float cm[NCHUNK];
 #pragma unroll
             for (int ch = 0; ch < NCHUNK; ++ch) {
-              const int col0 = (ch * 32 + lane) * 4;
               float4 q;
-              if (FULLW || col0 < W) q = *reinterpret_cast<const float4*>(row + col0);
+              if (FULLW || (ch * 32 + lane) * 4 < W) q = *reinterpret_cast<const float4*>(xb + r * W + ch * 128);
               else q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-              v[ch][0] = q.x; v[ch][1] = q.y; v[ch][2] = q.z; v[ch][3] = q.w;
               cm[ch] = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w));
+              gm[ch][0] = fmaxf(gm[ch][0], q.x); gm[ch][1] = fmaxf(gm[ch][1], q.y);
+              gm[ch][2] = fmaxf(gm[ch][2], q.z); gm[ch][3] = fmaxf(gm[ch][3], q.w);
             }
             float m = cm[0];
 #pragma unroll
             for (int ch = 1; ch < NCHUNK; ++ch) m = fmaxf(m, cm[ch]);
             const unsigned kmax = __reduce_max_sync(kFull, fkey(m));
             const float mv = fkey_inv(kmax);
-            // first chunk (lowest columns) that holds the maximum, first lane within it, first element within the lane
+            // first float4 group (lowest columns) that holds the row maximum: chunk-major, then lane
             unsigned bal = __ballot_sync(kFull, cm[0] == mv);
-            int chunk = 0;
+            int grp = 0;
 #pragma unroll
             for (int ch = 1; ch < NCHUNK; ++ch) {
               const unsigned b = __ballot_sync(kFull, cm[ch] == mv);
-              if (bal == 0u) { bal = b; chunk = ch; }
+              if (bal == 0u) { bal = b; grp = ch * 32; }
             }
-            if (lane == (bal ? __ffs(bal) - 1 : 0)) {                  // bal == 0 only for an all-NaN row: any in-range index
-              float w0 = v[0][0], w1 = v[0][1], w2 = v[0][2];
-#pragma unroll
-              for (int ch = 1; ch < NCHUNK; ++ch)
-                if (chunk == ch) { w0 = v[ch][0]; w1 = v[ch][1]; w2 = v[ch][2]; }
-              const int e = w0 == mv ? 0 : (w1 == mv ? 1 : (w2 == mv ? 2 : 3));
-              ws.row_packed[n * H + y] = pack_key(kmax, min((chunk * 32 + lane) * 4 + e, W - 1));
-            }
+            grp += bal ? __ffs(bal) - 1 : 0;                          // bal == 0 only for an all-NaN row: any in-range group
+            if (lane == 0) rdst[y - row0] = pack_key(kmax, grp);
             // zero part of the gradient: everything outside the span (the chains write the span)
-            float* grow = ginst + y * W + lane * 4;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             if (y >= ya && y <= yb) {                                  // warp-uniform: a span row
 #pragma unroll
@@ -410,25 +348,27 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
               for (int ch = 0; ch < NCHUNK; ++ch)
                 if (FULLW || (ch * 32 + lane) * 4 < W) *reinterpret_cast<float4*>(grow + ch * 128) = z;
             }
-            // column maxima (first row wins ties)
-#pragma unroll
-            for (int ch = 0; ch < NCHUNK; ++ch)
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (v[ch][e] > cbest[ch][e]) { cbest[ch][e] = v[ch][e]; crow[ch][e] = y; }
+            grow += W;
+            ++y;
           }
         }
+        // column maxima: the first 4-row group wins ties
+#pragma unroll
+        for (int ch = 0; ch < NCHUNK; ++ch)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (gm[ch][e] > cbest[ch][e]) { cbest[ch][e] = gm[ch][e]; csub[ch][e] = sub0 + k; }
         __syncwarp();                        // every lane has read stage st
         if (k + 2 < nsub) issue(k + 2);
       }
-      unsigned long long* cdst = ws.col_part + ((int64_t)n * S + s_idx) * W;
+      unsigned long long* cdst = col_part + ((size_t)n * S + s_idx) * W;
 #pragma unroll
       for (int ch = 0; ch < NCHUNK; ++ch) {
         const int col0 = (ch * 32 + lane) * 4;
         if (FULLW || col0 < W) {
           ulonglong2 p0, p1;
-          p0.x = pack_key(fkey(cbest[ch][0]), crow[ch][0]); p0.y = pack_key(fkey(cbest[ch][1]), crow[ch][1]);
-          p1.x = pack_key(fkey(cbest[ch][2]), crow[ch][2]); p1.y = pack_key(fkey(cbest[ch][3]), crow[ch][3]);
+          p0.x = pack_key(fkey(cbest[ch][0]), csub[ch][0]); p0.y = pack_key(fkey(cbest[ch][1]), csub[ch][1]);
+          p1.x = pack_key(fkey(cbest[ch][2]), csub[ch][2]); p1.y = pack_key(fkey(cbest[ch][3]), csub[ch][3]);
           *reinterpret_cast<ulonglong2*>(cdst + col0) = p0;
           *reinterpret_cast<ulonglong2*>(cdst + col0 + 2) = p1;
         }
@@ -437,6 +377,9 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
       // =============================== pair item: one chain of instance n ===============================
       const int y0 = wq_lo16(ia.y), nrows = wq_hi16(ia.y);
       const int xs = wq_lo16(ia.z), c_hi = wq_hi16(ia.z);
+      SRec rec;
+      rec.j0 = (short)wq_lo16(ib.x); rec.j1 = (short)wq_hi16(ib.x);
+      rec.i0 = (short)wq_lo16(ib.y); rec.i1 = (short)wq_hi16(ib.y);
       rec.img = ib.z;
       if (nrows > 0) {
         float acc_lg = 0.f, acc_slow = 0.f;
@@ -444,22 +387,14 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
         op_chain<D>(logits + (size_t)n * H * W, edge_bits + (size_t)rec.img * H * W, H, W, y0, nrows, xs, c_hi, rec, lane,
                     ginst, scale, acc_lg, acc_slow, acc_w);
         const float val = warp_sum(fmaf(acc_lg, -0.69314718055994531f, acc_slow));
-        if (lane == 0 && val != 0.f)
+        if (lane == 0 && val != 0.f)           // fixed-point sum: order-independent, hence deterministic
           atomicAdd(&sched->num_fx, (unsigned long long)__double2ll_rn((double)val * WQ_NUM_FX));
       }
     }
-    // ---- completion: the warp that completes the last item of instance n finalizes it ----
-    __threadfence();                        // this lane's stores (gradient, partial maxima) before the counter
-    __syncwarp();
-    unsigned old = 0u;
-    if (lane == 0) old = atomicAdd(&sched->inst_cnt[n], 1u);
-    old = __shfl_sync(kFull, old, 0);
-    if (old + 1u == (unsigned)ia.w) {
-      __threadfence();
-      wq_finalize<D>(n, rec, N, H, W, S, ws, sched, scale, wtot, losses_out, g_logits, lane);
-    }
+    WQ_TRACE(4);
     q_cur = q_nxt; ia = na; ib = nb;
   }
+  WQ_TRACE(7);
   // ---- queue counter reset by the last warp (every fetch of a warp precedes its `done` increment) ----
   if (lane == 0) {
     __threadfence();
@@ -468,6 +403,121 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
       sched->done = 0u;
       __threadfence();
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize: one CTA per instance, one thread per row and per column.  Resolves the arg-max positions, dice terms,
+// gradient coefficients, adds the projection terms at the H + W arg-max positions for upstream gradients (1, 1)
+// (a position that is both a row and a column arg-max is written once, by its column); the loss sums are 64-bit
+// fixed-point atomics (order-independent); the last CTA (ticket) writes the four scalars.
+// ---------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(OP_FIN_NT)
+wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ plan, int N, int H, int W,
+                   OpWorkspace ws, WqSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
+                   float* __restrict__ losses_out, float* __restrict__ g_logits) {
+  constexpr int NWF = OP_FIN_NT / 32;
+  __shared__ float s_f[4][NWF];
+  __shared__ float s_coef[512];       // row coefficients
+  __shared__ int s_arow[512], s_acol[512];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const WqHeader* hdr = reinterpret_cast<const WqHeader*>(plan);
+  const int S = __ldg(&hdr->S);
+  const unsigned long long wtot = __ldg(&hdr->wtot);
+  const float* xin = logits + (size_t)n * H * W;
+  float* ginst = g_logits + (size_t)n * H * W;
+  const int4 recv = __ldg(reinterpret_cast<const int4*>(plan + wq_plan_rec_offset(N)) + n);
+  SRec rec;
+  rec.j0 = (short)recv.x; rec.j1 = (short)recv.y; rec.i0 = (short)recv.z; rec.i1 = (short)recv.w; rec.img = 0;
+  const bool empty = rec.j0 > rec.j1;
+  // ---- independent loads: this thread's row result and its column's strip results ----
+  const int row_i = tid, col_i = tid;                   // H, W <= 512 = OP_FIN_NT
+  unsigned long long rp = 0ull, cp = 0ull;
+  if (row_i < H) rp = ws.row_packed[(size_t)n * H + row_i];
+  if (col_i < W) {
+    const unsigned long long* src = ws.col_part + (size_t)n * S * W + col_i;
+#pragma unroll 4
+    for (int s = 0; s < S; ++s) {
+      const unsigned long long p = src[(size_t)s * W];
+      cp = p > cp ? p : cp;             // larger key; on equal keys the earlier group (larger ~group)
+    }
+  }
+  // ---- exact positions: first element of the float4 group / first row of the 4-row group equal to the maximum ----
+  const float xr = fkey_inv((unsigned)(rp >> 32)), xc = fkey_inv((unsigned)(cp >> 32));
+  int ar = 0, ac = 0;
+  if (row_i < H) {
+    const int grp = min((int)(0xffffffffu - (unsigned)(rp & 0xffffffffull)), (W - 4) >> 2);
+    const float4 q = *reinterpret_cast<const float4*>(xin + (size_t)row_i * W + 4 * grp);
+    ar = 4 * grp + (q.x == xr ? 0 : (q.y == xr ? 1 : (q.z == xr ? 2 : 3)));
+    ar = min(ar, W - 1);
+  }
+  if (col_i < W) {
+    const int y4 = min(4 * (int)(0xffffffffu - (unsigned)(cp & 0xffffffffull)), H - 1);
+    const float v0 = xin[(size_t)y4 * W + col_i];
+    const float v1 = y4 + 1 < H ? xin[(size_t)(y4 + 1) * W + col_i] : 0.f;
+    const float v2 = y4 + 2 < H ? xin[(size_t)(y4 + 2) * W + col_i] : 0.f;
+    ac = y4 + (v0 == xc ? 0 : (v1 == xc ? 1 : (v2 == xc ? 2 : 3)));
+    ac = min(ac, H - 1);
+  }
+  // ---- dice terms ----
+  const float sr = row_i < H ? sigmoid_exact(xr) : 0.f;
+  const float sc = col_i < W ? sigmoid_exact(xc) : 0.f;
+  const bool tr = !empty && row_i >= rec.j0 && row_i <= rec.j1, tc = !empty && col_i >= rec.i0 && col_i <= rec.i1;
+  const float r0 = warp_sum(tr ? sr : 0.f), r1 = warp_sum(sr * sr), r2 = warp_sum(tc ? sc : 0.f), r3 = warp_sum(sc * sc);
+  if (lane == 0) { s_f[0][wid] = r0; s_f[1][wid] = r1; s_f[2][wid] = r2; s_f[3][wid] = r3; }
+  if (row_i < H) s_arow[row_i] = ar;
+  if (col_i < W) s_acol[col_i] = ac;
+  // the (scaled) pairwise gradient at the arg-max positions, loaded before the barrier
+  float svr = 0.f, svc = 0.f;
+  if (row_i < H) svr = ginst[(size_t)row_i * W + ar];
+  if (col_i < W) svc = ginst[(size_t)ac * W + col_i];
+  __syncthreads();
+  float Ir = 0.f, Xr = 0.f, Ic = 0.f, Xc = 0.f;
+#pragma unroll
+  for (int i = 0; i < NWF; ++i) { Ir += s_f[0][i]; Xr += s_f[1][i]; Ic += s_f[2][i]; Xc += s_f[3][i]; }
+  const float inv_n = 1.f / (float)N;
+  const float Ur = Xr + (empty ? 0.f : (float)(rec.j1 - rec.j0 + 1)) + kDiceEps;
+  const float Uc = Xc + (empty ? 0.f : (float)(rec.i1 - rec.i0 + 1)) + kDiceEps;
+  // d dice / d s = -2 t / U + 4 I s / U^2 ; through the sigmoid: * s (1 - s); mean over N
+  const float crow = inv_n * (-2.f * (tr ? 1.f : 0.f) / Ur + 4.f * Ir * sr / (Ur * Ur)) * sr * (1.f - sr);
+  const float ccol = inv_n * (-2.f * (tc ? 1.f : 0.f) / Uc + 4.f * Ic * sc / (Uc * Uc)) * sc * (1.f - sc);
+  if (row_i < H) s_coef[row_i] = crow;
+  __syncthreads();               // all reads of the arg-max positions precede the writes below
+  if (row_i < H) {
+    if (s_acol[ar] != row_i) ginst[(size_t)row_i * W + ar] = svr + crow;
+    ws.coef_row[(size_t)n * H + row_i] = crow; ws.arg_row[(size_t)n * H + row_i] = ar; ws.sv_row[(size_t)n * H + row_i] = svr;
+  }
+  if (col_i < W) {
+    ginst[(size_t)ac * W + col_i] = s_arow[ac] == col_i ? (svc + s_coef[ac]) + ccol : svc + ccol;
+    ws.coef_col[(size_t)n * W + col_i] = ccol; ws.arg_col[(size_t)n * W + col_i] = ac; ws.sv_col[(size_t)n * W + col_i] = svc;
+  }
+  if (tid == 0) {
+    const OpSpan sp = op_span<D>(rec, H, W);
+    reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
+    const float prj_n = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
+    ws.inst_prj[n] = prj_n;
+    const unsigned long long mine = (unsigned long long)__double2ll_rn((double)prj_n * WQ_PRJ_FX);
+    const unsigned long long before = atomicAdd(&sched->prj_fx, mine);
+    __threadfence();
+    if (atomicAdd(&sched->ticket, 1u) == (unsigned)(N - 1)) {      // every instance has added its term
+      __threadfence();
+      const long long prj_fx = (long long)atomicAdd(&sched->prj_fx, 0ull);
+      const long long num_fx = (long long)atomicAdd(&sched->num_fx, 0ull);
+      const float scale = fminf(iter_ptr[0] / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
+      const float pn = (float)((double)num_fx * (1.0 / WQ_NUM_FX));
+      losses_out[0] = (float)((double)prj_fx * (1.0 / WQ_PRJ_FX)) * inv_n;
+      losses_out[1] = pn * scale;
+      losses_out[2] = pn;
+      losses_out[3] = (float)wtot;
+      sched->prj_fx = 0ull;
+      sched->num_fx = 0ull;
+      sched->ticket = 0u;
+      __threadfence();
+    }
+    (void)before;
   }
 }
 
@@ -501,9 +551,15 @@ int wq_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bit
     occ_dev = dev;
     occ_smem = smem;
   }
-  const int64_t min_items = (int64_t)N * wq_strips(H);                     // stream items alone
-  const int grid = (int)std::min<int64_t>(ceil_div(min_items, WQ_NW), (int64_t)sm_count() * occ);
-  op_launch_pdl(kern, dim3((unsigned)grid), dim3(WQ_NT), smem, st, logits, edge_bits, plan, N, H, W, ws, sched, iter_ptr,
+  // the item count lives in the plan (device memory): size the grid for the machine, bounded by the largest possible
+  // queue; warps beyond the queue leave at once
+  const int64_t max_items = (int64_t)N * (wq_strips(H) + wq_max_chains(H, W, D));
+  const int grid = (int)std::min<int64_t>(ceil_div(max_items, WQ_NW), (int64_t)sm_count() * occ);
+  op_launch_pdl(kern, dim3((unsigned)grid), dim3(WQ_NT), smem, st, logits, edge_bits, plan, N, H, W, ws.row_packed,
+                ws.col_part, sched, iter_ptr, warmup_iters, g_logits);
+  int rc = check_launch();
+  if (rc != BXS_OK) return rc;
+  op_launch_pdl(wq_finalize_kernel<D>, dim3((unsigned)N), dim3(OP_FIN_NT), 0, st, logits, plan, N, H, W, ws, sched, iter_ptr,
                 warmup_iters, losses_out, g_logits);
   return check_launch();
 }

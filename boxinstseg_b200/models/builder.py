@@ -55,9 +55,28 @@ except Exception:                               # noqa: BLE001
     MATCH_COST = Registry('Match Cost')
 
 
-def register(registry, **kw):
-    """register_module that overrides a same-named reference class when mmdet is present."""
-    return registry.register_module(force=True, **kw)
+def register(registry, partial=False, **kw):
+    """register_module under the reference's own name.
+
+    Complete replacements (losses, match costs) simply override a same-named reference class.  ``partial=True``
+    marks classes that implement only the mask-loss hot path of a reference head: when the reference's class is
+    already registered under that name (mmdet importable) the registered class becomes a subclass of BOTH -- this
+    package's methods first in the MRO, the reference's own ``__init__`` and every method this package does not
+    provide (``training_sample``, ``simple_test``, ``get_masks``, target builders, ...) inherited unchanged -- so
+    ``detectors/condinst.py:54-90`` keeps working after ``import boxinstseg_b200.models``."""
+    def _do(cls):
+        key = kw.get('name') or cls.__name__
+        ref = registry.get(key) if partial else None
+        if ref is not None and ref is not cls and not issubclass(ref, cls):
+            def _init(self, *a, **k):
+                ref.__init__(self, *a, **k)                    # every attribute the inherited reference methods use
+                post = getattr(cls, '_bxs_post_init', None)
+                if post is not None:
+                    post(self)
+            cls = type(cls.__name__, (cls, ref), {'__init__': _init, '__module__': cls.__module__,
+                                                   '__doc__': cls.__doc__, '_bxs_reference_class': ref})
+        return registry.register_module(force=True, module=cls, **kw)
+    return _do
 
 
 def build_head(cfg):

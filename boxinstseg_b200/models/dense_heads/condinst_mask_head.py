@@ -16,7 +16,7 @@ from ...ops import boxinst as boxinst_ops
 from ..builder import HEADS, register
 
 
-@register(HEADS)
+@register(HEADS, partial=True)
 class CondInstMaskHead(nn.Module):
     def __init__(self,
                  in_channels=8,

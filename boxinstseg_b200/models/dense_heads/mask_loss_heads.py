@@ -36,7 +36,7 @@ def _phi_and_pixels(mask_pred, box_mask):
     return phi, pix
 
 
-@register(HEADS)
+@register(HEADS, partial=True)
 class BoxSOLOv2Head(nn.Module):
     """BoxLevelset head: mask-loss path only."""
 
@@ -100,7 +100,7 @@ class BoxSOLOv2Head(nn.Module):
         return self.mst(uniq)[group]
 
 
-@register(HEADS)
+@register(HEADS, partial=True)
 class DiscoBoxSOLOv2Head(nn.Module):
     """DiscoBox head: mask-loss path only (corr_loss / object bank out of scope)."""
 
@@ -163,7 +163,7 @@ def _disco_dice(x, t):
     return 1 - 2 * (x * t).sum(1) / ((x * x).sum(1) + 0.001 + (t * t).sum(1) + 0.001)
 
 
-@register(HEADS)
+@register(HEADS, partial=True)
 class Box2MaskHead(nn.Module):
     """Box2Mask head: mask-loss path only."""
 

@@ -218,6 +218,40 @@ def tree_filter(feature_in, embed_in, tree, low_tree=True, sigma=0.02):
     return out.reshape(shape)
 
 
+def tree_filter_f64(feature_in, embed_in, idx, par, low_tree=True, sigma=0.02):
+    """Float64 arbiter of the same recursion (refine.cu:19-199 semantics) on a GIVEN
+    parent-before-child order, differentiable by torch autograd wrt feature and embed (whatever low_tree is: callers
+    compare d/d embed only where the reference propagates it).  Level by level, vectorised: any size the tests use.
+        up   U[p] = x[p] + sum_children w[c] U[c]        down  A[0] = U[0]; A[p] = (1 - w^2) U[p] + w A[par]
+        out = A / Z with Z the same for x == 1."""
+    shape = feature_in.shape
+    B, C = shape[0], shape[1]
+    V = shape[2] * shape[3]
+    idx_l, par_l = idx.long(), par.long()
+    w_all = build_edge_weight(embed_in.double(), idx, par, low_tree, sigma)          # [B,V], entry 0 unused
+    outs = []
+    for b in range(B):
+        ib, pb = idx_l[b], par_l[b]
+        depth = torch.zeros(V, dtype=torch.long)
+        for p in range(1, V):                                                         # parents precede children
+            depth[p] = depth[pb[p]] + 1
+        order = torch.argsort(depth, stable=True)
+        bounds = torch.searchsorted(depth[order].contiguous(), torch.arange(int(depth.max()) + 2))
+        levels = [order[bounds[l]:bounds[l + 1]] for l in range(int(depth.max()) + 1)]
+        w = torch.cat([w_all[b, :1].detach() * 0, w_all[b, 1:]])
+        x = torch.cat([feature_in[b].reshape(C, V).double()[:, ib], torch.ones(1, V, dtype=torch.float64)])   # + normaliser
+        U = x
+        for nodes in reversed(levels[1:]):                                            # deepest level first
+            U = U.index_add(1, pb[nodes], U[:, nodes] * w[nodes])
+        A = U
+        for nodes in levels[1:]:
+            wn = w[nodes]
+            A = A.index_copy(1, nodes, (1 - wn * wn) * U[:, nodes] + wn * A[:, pb[nodes]])
+        res = (A[:C] / A[C:]).new_zeros(C, V).index_copy(1, ib, A[:C] / A[C:])
+        outs.append(res)
+    return torch.stack(outs).reshape(shape)
+
+
 def tree_filter_dense(feature, embed, tree, low_tree=True, sigma=0.02):
     """Closed form for tiny cases (pure python/numpy, float64):
     out[i] = sum_j prod_{edges on path i..j} w * x[j] / sum_j prod w.   SURVEY appendix A15."""

@@ -105,23 +105,32 @@ def test_refine_matches_reference_cuda(ref_tree, B, C, h, w):
 
 
 def test_reference_bfs_order_is_accepted(ref_tree):
-    """The reference's own (racy, but valid) BFS order drives our refine to the same result as our order does."""
+    """The reference's own (racy, any parent-before-child) BFS order, fed to OUR refine entry points, gives the
+    reference's results: the shim adopts foreign orders (tree_filter_cuda._adopt) instead of assuming its own."""
     from boxinstseg_b200.ops.tree_filter import tree_filter_cuda as ours
     B, C, h, w = 2, 2, 20, 28
     _, index, weight = _grid_problem(B, 3, h, w, seed=11)
     V = h * w
     tree = ours.mst_forward(index, weight, V)
     ridx, rpar, rchd = ref_tree.bfs_forward(tree.clone(), 4)
-    p = rpar.cpu().numpy()
-    if not (np.all(np.diff(p[:, 1:], axis=1) >= 0)):
-        pytest.skip('the reference BFS order of this run is not level-contiguous')
     gen = torch.Generator().manual_seed(2)
     feat = torch.rand(B, C, V, generator=gen).to(DEV)
+    gout = torch.randn(B, C, V, generator=gen).to(DEV)
+    ew = torch.rand(B, V, generator=gen).to(DEV) * 0.9 + 0.05          # per position of the REFERENCE order
+    r = ref_tree.refine_forward(feat, ew.clone(), ridx.clone(), rpar.clone(), rchd.clone())
+    o = ours.refine_forward(feat, ew, ridx, rpar, rchd)
+    for a, b in zip(o, r):
+        assert rel_err(a, b) <= 1e-5
+    ew0 = ew.clone(); ew0[:, 0] = 0
+    par0 = rpar.clone(); par0[:, 0] = 0
+    gf_ref = ref_tree.refine_backward_feature(feat, ew0, ridx, par0, rchd, r[0], r[1], r[2], r[3], r[4], gout)
+    gf = ours.refine_backward_feature(feat, ew, ridx, rpar, rchd, o[0], o[1], o[2], o[3], o[4], gout)
+    assert rel_err(gf, gf_ref) <= 1e-5
+    gw_ref = ref_tree.refine_backward_weight(feat, ew0, ridx, par0, rchd, r[0], r[1], r[2], r[3], r[4], gout)
+    gw = ours.refine_backward_weight(feat, ew, ridx, rpar, rchd, o[0], o[1], o[2], o[3], o[4], gout)
+    assert rel_err(gw[:, 1:], gw_ref[:, 1:]) <= 1e-4
+    # and the same tree through our own deterministic order gives the same filter output
     idx, par, chd = ours.bfs_forward(tree, 4)
-    # edge weight per VERTEX pair: take it from the vertex ids so that both orders see the same tree weights
-    wv = torch.rand(B, V, generator=gen).to(DEV) * 0.9 + 0.05      # weight of the edge (vertex -> its parent), by vertex id
-    ew_ours = torch.gather(wv, 1, idx.long())
-    ew_ref = torch.gather(wv, 1, ridx.long())
-    o = ours.refine_forward(feat, ew_ours, idx, par, chd)[0]
-    o2 = ours.refine_forward(feat, ew_ref, ridx, rpar, rchd)[0]
-    assert rel_err(o2, o) <= 1e-4
+    wv = torch.zeros(B, V, device=DEV).scatter_(1, ridx.long(), ew)   # weight of the edge (vertex -> parent), by vertex id
+    o2 = ours.refine_forward(feat, torch.gather(wv, 1, idx.long()), idx, par, chd)[0]
+    assert rel_err(o2, o[0]) <= 1e-5

@@ -35,3 +35,38 @@ def test_tree_filter_graph_construction_matches_oracle():
     mst = MinimumSpanningTree(TreeFilter2D.norm2_distance)
     assert (mst._build_matrix_index(fm)[0].numpy() == ot.grid_edges(5, 7)).all()
     assert torch.equal(mst._build_feature_weight(fm), ot.grid_edge_weights(fm))
+
+
+def test_partial_heads_inherit_the_reference_methods():
+    """with mmdet importable the hot-path heads must not shadow the reference's other methods
+    (detectors/condinst.py:69,90 call training_sample / simple_test).  Simulated with a stand-in reference class."""
+    from boxinstseg_b200.models import builder as b
+    reg = b.Registry('sim') if not b.HAVE_MMDET else None
+    if reg is None:
+        return
+
+    class FakeHead(torch.nn.Module):                   # plays mmdet's complete class, registered first
+        def __init__(self, width=3):
+            super().__init__()
+            self.width = width
+
+        def training_sample(self):
+            return 'ref training_sample'
+
+        def simple_test(self):
+            return 'ref simple_test'
+
+        def loss(self):
+            return 'ref loss'
+    reg.register_module(module=FakeHead)
+
+    @b.register(reg, partial=True, name='FakeHead')
+    class HotPath(torch.nn.Module):
+        def loss(self):
+            return 'b200 loss'
+    head = reg.build(dict(type='FakeHead', width=7))
+    assert head.width == 7                              # the reference constructor ran
+    assert head.loss() == 'b200 loss'                   # hot path overridden
+    assert head.training_sample() == 'ref training_sample' and head.simple_test() == 'ref simple_test'
+    for m in ('forward', 'training_sample', 'loss', 'simple_test'):     # detectors/condinst.py:54-90
+        assert hasattr(head, m)
