@@ -28,9 +28,8 @@ constexpr int WQ_NT = 256;          // threads per CTA
 constexpr int WQ_NW = WQ_NT / 32;
 constexpr int WQ_SUB = 4;           // rows per ring stage
 constexpr int WQ_R = 24;            // rows per stream item
-constexpr int WQ_STAGES = 2;
 constexpr double WQ_NUM_FX = 16777216.0;            // 2^24: fixed-point scale of the pairwise numerator
-constexpr double WQ_PRJ_FX = 1099511627776.0;       // 2^40: fixed-point scale of the projection terms
+constexpr double WQ_PRJ_FX = 4294967296.0;          // 2^32: fixed-point scale of the projection terms (N <= 2048 terms <= 2 fit 48 bits)
 
 struct WqHeader {                   // first 64 bytes of the plan
   int total, n_pair, n_stream, S;
@@ -46,9 +45,10 @@ static_assert(sizeof(WqHeader) == 64, "plan header is 64 bytes");
 struct __align__(16) WqItem { int4 a, b; };
 
 struct WqSched {                    // device state: zero before the first call, left zero by every call
-  unsigned next, done, ticket, pad;
-  unsigned long long num_fx, prj_fx;
+  unsigned next_s, next_p, done, ticket;      // stream / pair queue positions, warps done, finalize ticket
+  unsigned long long num_fx, prj_fx;          // fixed-point loss sums
 };
+constexpr int WQ_STREAMERS = 2;     // warps per CTA that take stream items first (the others take pair items first)
 
 inline int wq_strips(int64_t H) { return (int)ceil_div(H, WQ_R); }
 inline int64_t wq_max_chains(int64_t H, int64_t W, int d) {
@@ -92,9 +92,8 @@ wq_count_kernel(const uint8_t* __restrict__ edge_bits, const int32_t* __restrict
 }
 
 // ---------------------------------------------------------------------------------------
-// plan, step 2: queue order and item descriptors (one CTA).  Instances are ranked by chain count (large boxes
-// first, so the queue ends with cheap items); pair items and stream items, each in rank order, are merged
-// proportionally: position q is a pair item iff floor((q+1) P / total) > floor(q P / total).
+// plan, step 2: the two queues and their item descriptors (one CTA).  Instances are ranked by chain count (large
+// boxes first, so both queues end with cheap items); items [0, T) are the stream items, [T, T + P) the pair items.
 // ---------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(1024)
@@ -160,10 +159,10 @@ wq_build_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ i
     recs[n] = make_int4(r.j0, r.j1, r.i0, r.i1);
   }
   WqItem* items = reinterpret_cast<WqItem*>(plan + wq_plan_items_offset(N));
-  for (int q = tid; q < total; q += 1024) {
-    const int pidx = (int)(((long long)q * P) / total), pnext = (int)(((long long)(q + 1) * P) / total);
+  for (int q = tid; q < total; q += 1024) {          // [0, T): stream items, [T, T + P): pair items, both in rank order
     WqItem it;
-    if (pnext > pidx) {                     // pair item: chain (pidx - pre[r]) of the r-th ranked instance
+    if (q >= T) {                           // pair item: chain (pidx - pre[r]) of the r-th ranked instance
+      const int pidx = q - T;
       int lo = 0, hi = N;                   // largest r with s_pre[r] <= pidx
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -181,7 +180,7 @@ wq_build_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ i
                        wq_pack16(cg.c_lo - D + seg * (32 - 2 * D), cg.c_hi), s_nch[n] + S);
       it.b = make_int4(wq_pack16(r.j0, r.j1), wq_pack16(r.i0, r.i1), r.img, 0);
     } else {                                // stream item: strip s of the r-th ranked instance
-      const int sidx = q - pidx;
+      const int sidx = q;
       const int rk = sidx / S, s = sidx - rk * S;
       const int n = s_order[rk];
       const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
@@ -212,80 +211,85 @@ wq_build_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ i
 #endif
 
 // ---------------------------------------------------------------------------------------
-// main kernel: the work queue.  Items are independent (no completion protocol): the kernel boundary orders them
-// before wq_finalize_kernel.
+// main kernel.  Items are independent (no completion protocol): the kernel boundary orders them before
+// wq_finalize_kernel.  Two roles:
+//   streamers   the first `NS` of the grid's WQ_STREAMERS-per-CTA "streamer slots" take the stream items, statically
+//               (slot i owns items i, i + NS, ...; NS is chosen by the host so that every streamer owns the same
+//               number of items): the logits flow through the warp's own 4-stage shared-memory ring, one
+//               cp.async.bulk (TMA engine) per 4-row group, up to 3 groups in flight ACROSS item boundaries.  A few
+//               hundred such warps keep HBM saturated for the whole kernel; their own instruction stream is light.
+//   pair warps  every other warp (and every streamer once it is done) pulls chains from the pair queue (one atomic
+//               per item, fetched two items ahead): issue-bound work that fills the SMs while the copies fly.
 //   row results    row_packed[n*H + y]       = key(max logit of the row) << 32 | ~(first float4 group holding it)
 //   column results col_part[(n*S + s)*W + x] = key(max logit of the column within strip s) << 32 | ~(first 4-row
 //                                               group of the strip holding it)
 // (the exact element / row inside the group is resolved by the finalize kernel, one thread per row / column)
 // ---------------------------------------------------------------------------------------
+constexpr int WQ_RING = 4;          // ring stages of a streamer warp
+
 template <int NCHUNK, int D, bool FULLW>
-__global__ void __launch_bounds__(WQ_NT, NCHUNK <= 2 ? 3 : 1)
+__global__ void __launch_bounds__(WQ_NT, NCHUNK <= 2 ? 4 : 1)
 wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edge_bits,
-               const unsigned char* __restrict__ plan, int N, int H, int W_rt,
+               const unsigned char* __restrict__ plan, int N, int H, int W_rt, int NS,
                unsigned long long* __restrict__ row_packed, unsigned long long* __restrict__ col_part,
                WqSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
                float* __restrict__ g_logits) {
   const int W = FULLW ? NCHUNK * 128 : W_rt;
   extern __shared__ __align__(128) unsigned char wq_smem[];
-  __shared__ __align__(8) uint64_t s_bar[WQ_NW][WQ_STAGES];
+  __shared__ __align__(8) uint64_t s_bar[WQ_STREAMERS][WQ_RING];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stage_floats = WQ_SUB * W;
-  float* ring = reinterpret_cast<float*>(wq_smem) + (size_t)warp * WQ_STAGES * stage_floats;
-  uint64_t* bar = s_bar[warp];
 #ifdef BXS_OP_TRACE
   int trace_slot = 0;
 #endif
   WQ_TRACE(1);
   asm volatile("griddepcontrol.launch_dependents;");
-  if (lane == 0) {
+  if (warp < WQ_STREAMERS && lane == 0) {
 #pragma unroll
-    for (int i = 0; i < WQ_STAGES; ++i) op_mbar_init(&bar[i], 1);
+    for (int i = 0; i < WQ_RING; ++i) op_mbar_init(&s_bar[warp][i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
   asm volatile("griddepcontrol.wait;" ::: "memory");     // the plan, the scheduler state and the workspace may belong to the predecessor
   const WqHeader* hdr = reinterpret_cast<const WqHeader*>(plan);
-  const int total = __ldg(&hdr->total), S = __ldg(&hdr->S);
-  const unsigned long long wtot = __ldg(&hdr->wtot);
-  const float scale = fminf(__ldg(iter_ptr) / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
   const WqItem* __restrict__ items = reinterpret_cast<const WqItem*>(plan + wq_plan_items_offset(N));
-  const unsigned nwarps = gridDim.x * WQ_NW;
+  const int S = (H + WQ_R - 1) / WQ_R, T = N * S;
+  const int slot = blockIdx.x * WQ_STREAMERS + warp;      // streamer slot of this warp (warp < WQ_STREAMERS)
 
-  // queue: the first item of a warp is its global index; later ones come from the counter, fetched two items ahead
-  unsigned q_cur = blockIdx.x * WQ_NW + warp;
-  unsigned q_nxt_l0 = 0u;
-  if (lane == 0) q_nxt_l0 = nwarps + atomicAdd(&sched->next, 1u);
-  int4 ia = make_int4(0, 0, 0, 0), ib = ia;
-  if (q_cur < (unsigned)total) { ia = __ldg(&items[q_cur].a); ib = __ldg(&items[q_cur].b); }
-  unsigned phases = 0u;          // mbarrier parity per stage (bit s)
-
-  while (q_cur < (unsigned)total) {
-    const unsigned q_nxt = __shfl_sync(kFull, q_nxt_l0, 0);
-    int4 na = make_int4(0, 0, 0, 0), nb = na;
-    if (q_nxt < (unsigned)total) { na = __ldg(&items[q_nxt].a); nb = __ldg(&items[q_nxt].b); }
-    if (lane == 0) q_nxt_l0 = nwarps + atomicAdd(&sched->next, 1u);
-
-    const int n = ia.x & 0x7fffffff;
-    float* ginst = g_logits + (size_t)n * H * W;
-    WQ_TRACE(2 + (ia.x < 0 ? 1 : 0) + ((unsigned long long)n << 8));
-    if (ia.x >= 0) {
-      // =============================== stream item: rows [row0, row0 + nrows) of instance n ===============================
-      const int row0 = wq_lo16(ia.y), nrows = wq_hi16(ia.y);
-      const int s_idx = wq_lo16(ia.z), c_hi = wq_hi16(ia.z), c_lo = ib.w;
-      const int ya = wq_lo16(ib.z), yb = wq_hi16(ib.z);
-      const float* src = logits + ((size_t)n * H + row0) * W;
+  if (warp < WQ_STREAMERS && slot < NS) {
+    // ======================================= streamer =======================================
+    float* ring = reinterpret_cast<float*>(wq_smem) + (size_t)warp * WQ_RING * stage_floats;
+    uint64_t* bar = s_bar[warp];
+    int4 a0 = __ldg(&items[slot].a), b0 = __ldg(&items[slot].b), a1 = a0, b1 = b0;
+    bool have1 = slot + NS < T;
+    if (have1) { a1 = __ldg(&items[slot + NS].a); b1 = __ldg(&items[slot + NS].b); }
+    int jp = 0;                      // this streamer's item sequence position being processed (item slot + jp * NS)
+    int gi = 0, gp = 0;              // 4-row groups issued / processed so far (ring stage = g & 3, parity = (g >> 2) & 1)
+    int iq = 0, ik = 0;              // issue cursor: item (0 = the one being processed, 1 = the next), group within it
+    auto issue_one = [&]() {
+      if (iq > 1 || (iq == 1 && !have1)) return;
+      const int4 da = iq == 0 ? a0 : a1;
+      const int row0 = wq_lo16(da.y), nrows = wq_hi16(da.y);
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)min(WQ_SUB, nrows - ik * WQ_SUB) * (uint32_t)W * 4u;
+        uint64_t* bb = &bar[gi & (WQ_RING - 1)];
+        op_mbar_expect_tx(bb, bytes);
+        op_bulk_g2s(ring + (gi & (WQ_RING - 1)) * stage_floats,
+                    logits + ((size_t)da.x * H + row0) * W + (size_t)ik * stage_floats, bytes, bb);
+      }
+      ++gi;
+      if (++ik == (nrows + WQ_SUB - 1) / WQ_SUB) { ik = 0; ++iq; }
+    };
+#pragma unroll
+    for (int i = 0; i < WQ_RING - 1; ++i) issue_one();
+    for (;;) {
+      const int n = a0.x;
+      const int row0 = wq_lo16(a0.y), nrows = wq_hi16(a0.y);
+      const int s_idx = wq_lo16(a0.z), c_hi = wq_hi16(a0.z), c_lo = b0.w;
+      const int ya = wq_lo16(b0.z), yb = wq_hi16(b0.z);
+      WQ_TRACE(2 + ((unsigned long long)n << 8));
       const int nsub = (nrows + WQ_SUB - 1) / WQ_SUB;
-      auto issue = [&](int k) {              // sub-strip k -> stage k & 1: ONE bulk copy (rows are contiguous)
-        if (lane == 0) {
-          const uint32_t bytes = (uint32_t)min(WQ_SUB, nrows - k * WQ_SUB) * (uint32_t)W * 4u;
-          op_mbar_expect_tx(&bar[k & 1], bytes);
-          op_bulk_g2s(ring + (k & 1) * stage_floats, src + (size_t)k * stage_floats, bytes, &bar[k & 1]);
-        }
-      };
-      issue(0);
-      if (nsub > 1) issue(1);
       float cbest[NCHUNK][4];
       int csub[NCHUNK][4];
 #pragma unroll
@@ -293,13 +297,12 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
 #pragma unroll
         for (int e = 0; e < 4; ++e) { cbest[ch][e] = -INFINITY; csub[ch][e] = 0; }
       unsigned long long* rdst = row_packed + (size_t)n * H + row0;
-      float* grow = ginst + (size_t)row0 * W + lane * 4;
+      float* grow = g_logits + ((size_t)n * H + row0) * W + lane * 4;
       const int sub0 = row0 / WQ_SUB;        // WQ_R % WQ_SUB == 0: strips start on a 4-row group
       int y = row0;
       for (int k = 0; k < nsub; ++k) {
-        const int st = k & 1;
-        op_mbar_wait(&bar[st], (phases >> st) & 1u);
-        phases ^= 1u << st;
+        const int st = gp & (WQ_RING - 1);
+        op_mbar_wait(&bar[st], (unsigned)(gp >> 2) & 1u);
         const float* xb = ring + st * stage_floats + lane * 4;
         const int rows_here = min(WQ_SUB, nrows - k * WQ_SUB);
         float gm[NCHUNK][4];                 // column maxima of this 4-row group
@@ -359,7 +362,8 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
           for (int e = 0; e < 4; ++e)
             if (gm[ch][e] > cbest[ch][e]) { cbest[ch][e] = gm[ch][e]; csub[ch][e] = sub0 + k; }
         __syncwarp();                        // every lane has read stage st
-        if (k + 2 < nsub) issue(k + 2);
+        ++gp;
+        issue_one();                         // refill the ring: the stage read one group ago is free
       }
       unsigned long long* cdst = col_part + ((size_t)n * S + s_idx) * W;
 #pragma unroll
@@ -373,23 +377,56 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
           *reinterpret_cast<ulonglong2*>(cdst + col0 + 2) = p1;
         }
       }
-    } else {
-      // =============================== pair item: one chain of instance n ===============================
-      const int y0 = wq_lo16(ia.y), nrows = wq_hi16(ia.y);
-      const int xs = wq_lo16(ia.z), c_hi = wq_hi16(ia.z);
-      SRec rec;
-      rec.j0 = (short)wq_lo16(ib.x); rec.j1 = (short)wq_hi16(ib.x);
-      rec.i0 = (short)wq_lo16(ib.y); rec.i1 = (short)wq_hi16(ib.y);
-      rec.img = ib.z;
-      if (nrows > 0) {
-        float acc_lg = 0.f, acc_slow = 0.f;
-        int acc_w = 0;
-        op_chain<D>(logits + (size_t)n * H * W, edge_bits + (size_t)rec.img * H * W, H, W, y0, nrows, xs, c_hi, rec, lane,
-                    ginst, scale, acc_lg, acc_slow, acc_w);
-        const float val = warp_sum(fmaf(acc_lg, -0.69314718055994531f, acc_slow));
-        if (lane == 0 && val != 0.f)           // fixed-point sum: order-independent, hence deterministic
-          atomicAdd(&sched->num_fx, (unsigned long long)__double2ll_rn((double)val * WQ_NUM_FX));
-      }
+      WQ_TRACE(4);
+      if (!have1) break;
+      a0 = a1; b0 = b1;
+      ++jp; --iq;
+      const int nx = slot + (jp + 1) * NS;
+      have1 = nx < T;
+      if (have1) { a1 = __ldg(&items[nx].a); b1 = __ldg(&items[nx].b); }
+    }
+  }
+
+  // ======================================= pair queue =======================================
+  const unsigned long long wtot = __ldg(&hdr->wtot);
+  const float scale = fminf(__ldg(iter_ptr) / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
+  const int n_pair = __ldg(&hdr->n_pair);
+  const unsigned nwarps = gridDim.x * WQ_NW;
+  const unsigned n_pair_static = gridDim.x * (WQ_NW - WQ_STREAMERS) + (gridDim.x * WQ_STREAMERS - (unsigned)NS);
+  // the first pair item of a warp is static (warps that streamed have none); later ones come from the queue counter,
+  // fetched two items ahead of their use
+  unsigned raw_l0 = 0xffffffffu;
+  bool streamed = warp < WQ_STREAMERS && slot < NS;
+  if (!streamed) raw_l0 = warp >= WQ_STREAMERS ? blockIdx.x * (WQ_NW - WQ_STREAMERS) + (warp - WQ_STREAMERS)
+                                               : gridDim.x * (WQ_NW - WQ_STREAMERS) + (unsigned)(slot - NS);
+  else if (lane == 0) raw_l0 = n_pair_static + atomicAdd(&sched->next_p, 1u);
+  unsigned raw = __shfl_sync(kFull, raw_l0, 0);
+  int q_cur = raw < (unsigned)n_pair ? (int)raw : -1;
+  int4 ia = make_int4(0, 0, 0, 0), ib = ia;
+  if (q_cur >= 0) { ia = __ldg(&items[T + q_cur].a); ib = __ldg(&items[T + q_cur].b); }
+  if (lane == 0 && q_cur >= 0) raw_l0 = n_pair_static + atomicAdd(&sched->next_p, 1u);
+  while (q_cur >= 0) {
+    raw = __shfl_sync(kFull, raw_l0, 0);
+    const int q_nxt = raw < (unsigned)n_pair ? (int)raw : -1;
+    int4 na = make_int4(0, 0, 0, 0), nb = na;
+    if (q_nxt >= 0) { na = __ldg(&items[T + q_nxt].a); nb = __ldg(&items[T + q_nxt].b); }
+    if (lane == 0 && q_nxt >= 0) raw_l0 = n_pair_static + atomicAdd(&sched->next_p, 1u);
+    const int n = ia.x & 0x7fffffff;
+    WQ_TRACE(3 + ((unsigned long long)n << 8));
+    const int y0 = wq_lo16(ia.y), nrows = wq_hi16(ia.y);
+    const int xs = wq_lo16(ia.z), c_hi = wq_hi16(ia.z);
+    SRec rec;
+    rec.j0 = (short)wq_lo16(ib.x); rec.j1 = (short)wq_hi16(ib.x);
+    rec.i0 = (short)wq_lo16(ib.y); rec.i1 = (short)wq_hi16(ib.y);
+    rec.img = ib.z;
+    if (nrows > 0) {
+      float acc_lg = 0.f, acc_slow = 0.f;
+      int acc_w = 0;
+      op_chain<D>(logits + (size_t)n * H * W, edge_bits + (size_t)rec.img * H * W, H, W, y0, nrows, xs, c_hi, rec, lane,
+                  g_logits + (size_t)n * H * W, scale, acc_lg, acc_slow, acc_w);
+      const float val = warp_sum(fmaf(acc_lg, -0.69314718055994531f, acc_slow));
+      if (lane == 0 && val != 0.f)           // fixed-point sum: order-independent, hence deterministic
+        atomicAdd(&sched->num_fx, (unsigned long long)__double2ll_rn((double)val * WQ_NUM_FX));
     }
     WQ_TRACE(4);
     q_cur = q_nxt; ia = na; ib = nb;
@@ -399,7 +436,8 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
   if (lane == 0) {
     __threadfence();
     if (atomicAdd(&sched->done, 1u) == nwarps - 1u) {
-      sched->next = 0u;
+      sched->next_s = 0u;
+      sched->next_p = 0u;
       sched->done = 0u;
       __threadfence();
     }
@@ -423,7 +461,22 @@ wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __rest
   __shared__ int s_arow[512], s_acol[512];
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   asm volatile("griddepcontrol.launch_dependents;");
+#ifdef BXS_OP_TRACE
+  constexpr size_t kFinTrace = (size_t)148 * 4 * 8 * 16;          // after the main kernel's per-warp slots
+  if (tid == 0 && g_op_trace) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    g_op_trace[(kFinTrace + blockIdx.x * 4 + 0) * 2] = t_;
+  }
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef BXS_OP_TRACE
+  if (tid == 0 && g_op_trace) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    g_op_trace[(kFinTrace + blockIdx.x * 4 + 1) * 2] = t_;
+  }
+#endif
   const WqHeader* hdr = reinterpret_cast<const WqHeader*>(plan);
   const int S = __ldg(&hdr->S);
   const unsigned long long wtot = __ldg(&hdr->wtot);
@@ -499,13 +552,13 @@ wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __rest
     reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
     const float prj_n = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
     ws.inst_prj[n] = prj_n;
-    const unsigned long long mine = (unsigned long long)__double2ll_rn((double)prj_n * WQ_PRJ_FX);
+    // ONE atomic carries this instance's term (low 48 bits, fixed point) and the arrival count (top 16 bits): the CTA
+    // that sees count == N - 1 in the returned value knows the complete sum without another round trip
+    const unsigned long long mine = (unsigned long long)__double2ll_rn((double)fmaxf(prj_n, 0.f) * WQ_PRJ_FX) + (1ull << 48);
     const unsigned long long before = atomicAdd(&sched->prj_fx, mine);
-    __threadfence();
-    if (atomicAdd(&sched->ticket, 1u) == (unsigned)(N - 1)) {      // every instance has added its term
-      __threadfence();
-      const long long prj_fx = (long long)atomicAdd(&sched->prj_fx, 0ull);
-      const long long num_fx = (long long)atomicAdd(&sched->num_fx, 0ull);
+    if ((before >> 48) == (unsigned long long)(N - 1)) {           // every instance has added its term
+      const long long prj_fx = (long long)((before + mine) & ((1ull << 48) - 1));
+      const long long num_fx = (long long)*reinterpret_cast<volatile unsigned long long*>(&sched->num_fx);   // main kernel: complete
       const float scale = fminf(iter_ptr[0] / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
       const float pn = (float)((double)num_fx * (1.0 / WQ_NUM_FX));
       losses_out[0] = (float)((double)prj_fx * (1.0 / WQ_PRJ_FX)) * inv_n;
@@ -514,14 +567,19 @@ wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __rest
       losses_out[3] = (float)wtot;
       sched->prj_fx = 0ull;
       sched->num_fx = 0ull;
-      sched->ticket = 0u;
-      __threadfence();
     }
-    (void)before;
   }
+#ifdef BXS_OP_TRACE
+  __syncthreads();
+  if (tid == 0 && g_op_trace) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    g_op_trace[(kFinTrace + blockIdx.x * 4 + 2) * 2] = t_;
+  }
+#endif
 }
 
-inline size_t wq_smem_bytes(int64_t W) { return (size_t)WQ_NW * WQ_STAGES * WQ_SUB * W * 4; }
+inline size_t wq_smem_bytes(int64_t W) { return (size_t)WQ_STREAMERS * WQ_RING * WQ_SUB * W * 4; }
 
 template <int NCHUNK, int D, bool FULLW>
 int wq_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bits, const unsigned char* plan, int N, int H,
@@ -555,7 +613,11 @@ int wq_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bit
   // queue; warps beyond the queue leave at once
   const int64_t max_items = (int64_t)N * (wq_strips(H) + wq_max_chains(H, W, D));
   const int grid = (int)std::min<int64_t>(ceil_div(max_items, WQ_NW), (int64_t)sm_count() * occ);
-  op_launch_pdl(kern, dim3((unsigned)grid), dim3(WQ_NT), smem, st, logits, edge_bits, plan, N, H, W, ws.row_packed,
+  // streamers: as many as give every one the same number of stream items (k each), at most WQ_STREAMERS per CTA
+  const int64_t T = (int64_t)N * wq_strips(H), slots = (int64_t)grid * WQ_STREAMERS;
+  const int64_t per = ceil_div(T, slots);
+  const int NS = (int)ceil_div(T, per);
+  op_launch_pdl(kern, dim3((unsigned)grid), dim3(WQ_NT), smem, st, logits, edge_bits, plan, N, H, W, NS, ws.row_packed,
                 ws.col_part, sched, iter_ptr, warmup_iters, g_logits);
   int rc = check_launch();
   if (rc != BXS_OK) return rc;

@@ -46,6 +46,54 @@ class _LevelsetLoss(torch.autograd.Function):
         return gs, gt, None, None
 
 
+class _LevelsetFused(torch.autograd.Function):
+    """One launch forward (a cluster of 8 CTAs per instance, the means -> energy dependency through distributed shared
+    memory), one launch backward.  mode 1 = the whole assembly of box_solov2_head.py:341-360 / box2mask_head.py:305-327
+    from (logits, box mask, raw targets); mode 0 = LevelsetLoss.forward on dense (scores2, targets, pixel_num)."""
+
+    @staticmethod
+    def forward(ctx, x, y, targets, pixel_num, loss_weight, mode):
+        xs = x.contiguous().float()
+        ys = y.contiguous().float() if y is not None else None
+        t = targets.contiguous().float()
+        p = pixel_num.contiguous().float() if pixel_num is not None else None
+        L.require_cuda(xs, ys, t, p)
+        n, C, h, w = t.shape
+        lib = L.lib()
+        loss = torch.empty(n, dtype=torch.float32, device=t.device)
+        ws = torch.empty(max(lib.bxs_levelset_fused_workspace_bytes(n), 1), dtype=torch.uint8, device=t.device)
+        if n:
+            with torch.cuda.device(t.device):
+                L.check(lib.bxs_levelset_fused_forward(L.ptr(xs), L.ptr(ys), L.ptr(t), L.ptr(p), L.ptr(loss), L.ptr(ws), n, C, h,
+                                                       w, float(loss_weight), mode, L.stream()), 'levelset_fused_forward')
+        ctx.save_for_backward(xs, ys, t, ws)
+        ctx.cfg = (float(loss_weight), mode)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        xs, ys, t, ws = ctx.saved_tensors
+        loss_weight, mode = ctx.cfg
+        n, C, h, w = t.shape
+        need_x, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+        gx = torch.empty_like(xs) if need_x else None
+        gt = torch.empty_like(t) if need_t else None
+        if n and (need_x or need_t):
+            with torch.cuda.device(t.device):
+                L.check(L.lib().bxs_levelset_fused_backward(L.ptr(xs), L.ptr(ys), L.ptr(t), L.ptr(ws),
+                                                            L.ptr(g_loss.contiguous().float()), L.ptr(gx), L.ptr(gt), n, C, h, w,
+                                                            loss_weight, mode, L.stream()), 'levelset_fused_backward')
+        return gx, None, gt, None, None, None
+
+
+def levelset_assembly(mask_logits, box_mask, targets, loss_weight=1.0):
+    """loss [n] = LevelsetLoss(cat(s, 1 - s) * box, targets * box, clamp(sum box, 1)) with s = sigmoid(mask_logits):
+    mask_logits, box_mask [n,h,w] (or [n,1,h,w]), targets [n,C,h,w] raw (NOT yet multiplied by the box mask).
+    box_solov2_head.py:341-351,357-360; box2mask_head.py:305-312,322-327."""
+    n, C, h, w = targets.shape
+    return _LevelsetFused.apply(mask_logits.reshape(n, h, w), box_mask.reshape(n, h, w), targets, None, loss_weight, 1)
+
+
 class _LengthReg(torch.autograd.Function):
     @staticmethod
     def forward(ctx, scores):
@@ -95,6 +143,8 @@ class LevelsetLoss(nn.Module):
         self.loss_weight = loss_weight
 
     def forward(self, mask_logits, targets, pixel_num):
+        if targets.shape[1] <= 8:
+            return _LevelsetFused.apply(mask_logits, None, targets, pixel_num, self.loss_weight, 0)
         return _LevelsetLoss.apply(mask_logits, targets, pixel_num, self.loss_weight)
 
 

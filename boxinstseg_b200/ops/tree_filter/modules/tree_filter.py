@@ -1,12 +1,14 @@
 """``MinimumSpanningTree`` and ``TreeFilter2D`` -- drop-ins for
 mmdet/ops/tree_filter/modules/tree_filter.py:9-150 (same constructor arguments and forward signatures).
 
-The grid-graph construction and the edge-weight arithmetic stay in torch, written so that the float32
-results are bit-identical to the reference's (near-ties decide the tree); only the
-tree selection / ordering / aggregation run in libboxseg_b200.
+The grid-graph construction and the MST edge weights stay in torch, written so that the float32 results are
+bit-identical to the reference's (near-ties decide the tree); the tree selection, ordering,
+the FILTER's edge weights (build_edge_weight, forward and autograd) and the aggregation run in libboxseg_b200.
 """
 import torch
 from torch import nn
+
+from .... import _lib as L
 
 from ..functions.bfs import bfs
 from ..functions.mst import mst
@@ -16,6 +18,43 @@ from ..functions.refine import refine
 def _squared_distance(a, b):
     d = a - b
     return (d * d).sum(dim=1)
+
+
+class _EdgeWeight(torch.autograd.Function):
+    """w[p] = exp(-|E(v_p) - E(v_par(p))|^2 / sigma) for the default norm2 distance (tree_filter.py:72-108): one gather
+    kernel forward, one gather kernel backward (the reference: two [n,C,V] torch.gather + elementwise ops + their
+    autograd scatters)."""
+
+    @staticmethod
+    def forward(ctx, embed, sorted_index, sorted_parent, sorted_child, groups, sigma):
+        e = embed.contiguous().float()
+        L.require_cuda(e, sorted_index, sorted_parent, sorted_child)
+        B, Ctot = e.shape[0], e.shape[1]
+        V = e.shape[2] * e.shape[3]
+        C = Ctot // groups
+        w = torch.empty((B * groups, V), dtype=torch.float32, device=e.device)
+        with torch.cuda.device(e.device):
+            L.check(L.lib().bxs_tree_edge_weight_forward(L.ptr(e), L.ptr(sorted_index), L.ptr(sorted_parent), L.ptr(w), B,
+                                                         groups, C, V, float(sigma), L.stream()), 'tree_edge_weight_forward')
+        ctx.save_for_backward(e, sorted_index, sorted_parent, sorted_child, w)
+        ctx.cfg = (groups, float(sigma))
+        ctx.set_materialize_grads(False)        # refine returns no d/d weight when low_tree (refine.py:36-37): embed gets None
+        return w
+
+    @staticmethod
+    def backward(ctx, g_w):
+        if g_w is None:
+            return None, None, None, None, None, None
+        e, idx, par, chd, w = ctx.saved_tensors
+        groups, sigma = ctx.cfg
+        B, Ctot = e.shape[0], e.shape[1]
+        V = e.shape[2] * e.shape[3]
+        g = torch.empty_like(e)
+        with torch.cuda.device(e.device):
+            L.check(L.lib().bxs_tree_edge_weight_backward(L.ptr(e), L.ptr(idx), L.ptr(par), L.ptr(chd), L.ptr(w),
+                                                          L.ptr(g_w.contiguous().float()), L.ptr(g), B, groups,
+                                                          Ctot // groups, V, sigma, L.stream()), 'tree_edge_weight_backward')
+        return g, None, None, None, None, None
 
 
 class MinimumSpanningTree(nn.Module):
@@ -76,8 +115,15 @@ class TreeFilter2D(nn.Module):
             index = index.long().unsqueeze(1).expand(-1, data.shape[1], -1)
         return torch.gather(data, 2, index)
 
-    def build_edge_weight(self, fm, sorted_index, sorted_parent, low_tree):
-        """w[pos] = exp(-dist(E(v_pos), E(v_par)) / (sigma if low_tree else 1)); tree_filter.py:91-108."""
+    def build_edge_weight(self, fm, sorted_index, sorted_parent, low_tree, sorted_child=None):
+        """w[pos] = exp(-dist(E(v_pos), E(v_par)) / (sigma if low_tree else 1)); tree_filter.py:91-108.
+        With the default distance and the BFS child table at hand this is one kernel (and one for its autograd);
+        a custom ``distance_func`` keeps the reference's torch formulation."""
+        if self.distance_func is TreeFilter2D.norm2_distance and sorted_child is not None and fm.is_cuda and \
+                sorted_index.dtype == torch.int32 and sorted_index.is_contiguous() and sorted_parent.is_contiguous() and \
+                sorted_child.is_contiguous():
+            return _EdgeWeight.apply(fm, sorted_index, sorted_parent, sorted_child, self.groups,
+                                     self.sigma if low_tree else 1.0)
         b, c = fm.shape[0], fm.shape[1]
         v = fm.shape[2] * fm.shape[3]
         flat = fm.reshape(b, c, -1)
@@ -91,7 +137,7 @@ class TreeFilter2D(nn.Module):
     def forward(self, feature_in, embed_in, tree, low_tree=True):
         shape = feature_in.shape
         sorted_index, sorted_parent, sorted_child = bfs(tree, 4)
-        edge_weight = self.build_edge_weight(embed_in, sorted_index, sorted_parent, low_tree)
+        edge_weight = self.build_edge_weight(embed_in, sorted_index, sorted_parent, low_tree, sorted_child)
         feat = feature_in.reshape(shape[0] * self.groups, shape[1] // self.groups, -1).contiguous()
         if self.groups > 1:                                  # tree_filter.py:110-120 (split_group)
             from .. import tree_filter_cuda as _C

@@ -301,6 +301,54 @@ int bxs_dynconv1x1_forward(const float* feat, const float* kernels, float* out, 
 int bxs_upsampled_rowcol_max(const float* x, float* row_prof, float* col_prof, void* workspace, int64_t n,
                              int64_t h, int64_t w, int64_t H, int64_t W, int sigmoid_act, bxs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * a18  bilinear resize      replaces F.interpolate(mode='bilinear') as the heads call it:
+ *     _scale_target (mmdet/models/utils/misc.py:75-86), box2mask_head.py:232-233,300,315-317,323-324,329,
+ *     box_solov2_head.py:213,412-415 (align_corners=False); discobox_head.py:1201 (align_corners=True).
+ * in [NC,h,w] -> out [NC,H,W] with ATen's upsample_bilinear2d arithmetic; backward g_out [NC,H,W] -> g_in [NC,h,w]
+ * fully overwritten, deterministic gather (ATen scatters with atomicAdd).
+ * --------------------------------------------------------------------------------------- */
+int bxs_bilinear_resize_forward(const float* in, float* out, int64_t NC, int64_t h, int64_t w, int64_t H,
+                                int64_t W, int align_corners, bxs_stream_t stream);
+int bxs_bilinear_resize_backward(const float* g_out, float* g_in, int64_t NC, int64_t h, int64_t w, int64_t H,
+                                 int64_t W, int align_corners, bxs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a14  tree edge weights     replaces TreeFilter2D.build_edge_weight with the default norm2 distance
+ *     (mmdet/ops/tree_filter/modules/tree_filter.py:72-108) and its autograd.
+ * embed [B*groups, C, V] (vertex order; a [B, groups*C, V] tensor viewed per group), sorted_index / sorted_parent
+ * [B,V], sorted_child [B,V,4] (bfs_forward) -> edge_weight [B*groups, V], w[p] = exp(-|E(v_p)-E(v_par(p))|^2 / sigma)
+ * (sigma = 1 gives exp(-dist), the low_tree=False form).  backward: g_weight -> g_embed, fully overwritten,
+ * deterministic (each vertex gathers its own edge and its children's edges).
+ * --------------------------------------------------------------------------------------- */
+int bxs_tree_edge_weight_forward(const float* embed, const int32_t* sorted_index, const int32_t* sorted_parent,
+                                 float* edge_weight, int64_t B, int64_t groups, int64_t C, int64_t V, float sigma,
+                                 bxs_stream_t stream);
+int bxs_tree_edge_weight_backward(const float* embed, const int32_t* sorted_index, const int32_t* sorted_parent,
+                                  const int32_t* sorted_child, const float* edge_weight, const float* g_weight,
+                                  float* g_embed, int64_t B, int64_t groups, int64_t C, int64_t V, float sigma,
+                                  bxs_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a17 + a9  level-set assembly in one launch    replaces the eager chain around LevelsetLoss in
+ *     box_solov2_head.py:341-360 and box2mask_head.py:305-327 (sigmoid, cat(s, 1-s) * box, T * box,
+ *     clamp(sum box, 1)) together with LevelsetLoss.forward / region_levelset (levelset_loss.py:13-44).
+ * mode 1: x = mask logits [n,h,w], y = box mask [n,h,w], T = raw targets [n,C,h,w]; pixel_num ignored.
+ * mode 0: x = scores2 [n,2,h,w], T [n,C,h,w], pixel_num [n] (the dense LevelsetLoss signature), y ignored.
+ * One thread-block cluster of 8 CTAs per instance; the means -> energy dependency goes through distributed
+ * shared memory.  loss [n] = loss_weight * E / pixel_num.  workspace: bxs_levelset_fused_workspace_bytes(n),
+ * carries the statistics to the backward.  backward: g_loss [n] -> g_x (mode 1: d/d logits [n,h,w]; mode 0:
+ * d/d scores2 [n,2,h,w]) and/or g_T [n,C,h,w] (mode 1: d/d raw T, i.e. already multiplied by the box mask).
+ * C <= 8.
+ * --------------------------------------------------------------------------------------- */
+int64_t bxs_levelset_fused_workspace_bytes(int64_t n);
+int bxs_levelset_fused_forward(const float* x, const float* y, const float* T, const float* pixel_num, float* loss,
+                               void* workspace, int64_t n, int64_t C, int64_t h, int64_t w, float loss_weight,
+                               int mode, bxs_stream_t stream);
+int bxs_levelset_fused_backward(const float* x, const float* y, const float* T, const void* workspace,
+                                const float* g_loss, float* g_x, float* g_T, int64_t n, int64_t C, int64_t h,
+                                int64_t w, float loss_weight, int mode, bxs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

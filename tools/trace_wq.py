@@ -35,7 +35,7 @@ ws = torch.empty(lib.bxs_boxinst_loss_fused_workspace_bytes(N_INST, H, W), dtype
 sched = torch.zeros(int(lib.bxs_boxinst_loss_fused_sched_bytes()), dtype=torch.uint8, device=dev)
 out = torch.empty(4, device=dev)
 NWMAX = 148 * 4 * 8
-trace = torch.zeros(NWMAX * 16 * 2, dtype=torch.int64, device=dev)
+trace = torch.zeros((NWMAX * 16 + 2048 * 4) * 2, dtype=torch.int64, device=dev)
 h = ctypes.CDLL(TRACE_LIB)
 h.bxs_debug_set_trace.argtypes = [ctypes.c_void_p]
 def run(i):
@@ -46,7 +46,8 @@ torch.cuda.synchronize()
 assert h.bxs_debug_set_trace(ctypes.c_void_p(trace.data_ptr())) == 0
 run(5)
 torch.cuda.synchronize()
-tr = trace.cpu().numpy().reshape(NWMAX, 16, 2)
+fin = trace.cpu().numpy()[NWMAX * 16 * 2:].reshape(2048, 4, 2)[:N_INST, :, 0]
+tr = trace.cpu().numpy()[:NWMAX * 16 * 2].reshape(NWMAX, 16, 2)
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 np.save(os.path.join(ROOT, 'gpurun_out', 'wq_trace.npy'), tr)
 warps = [w for w in range(NWMAX) if tr[w, 0, 0] != 0]
@@ -73,4 +74,9 @@ print('busy warps per us [stream/pair/fin]:')
 T = int(max(exits) // 1000) + 1
 for u in range(0, T, max(T // 40, 1)):
     print(f'  t={u:3d}us  {int(busy[2][u]):5d} {int(busy[3][u]):5d} {int(busy["fin"][u]):4d}')
+f = (fin - t0) / 1e3
+print('finalize CTAs: launch   ', st((fin[:, 0] - t0).tolist()))
+print('finalize CTAs: released ', st((fin[:, 1] - t0).tolist()))
+print('finalize CTAs: done     ', st((fin[:, 2] - t0).tolist()))
+print('finalize CTAs: duration ', st((fin[:, 2] - fin[:, 1]).tolist()))
 print('losses', out.tolist())
