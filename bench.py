@@ -499,6 +499,136 @@ def main_cuda(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------
+# configs C / D / E (BASELINE.json configs[2..4]): the mask-loss steps of DiscoBox, BoxLevelset, Box2Mask
+# ------------------------------------------------------------------------------------------
+def main_config(args, rank, world, local_rank):
+    import bench_configs as bc
+    from boxinstseg_b200 import _lib as L
+    L.lib()                                      # fail loudly if the CUDA extension is missing
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    cfg = args.config
+    # rotate over R independent input sets so that a step never finds its inputs in the 126 MB L2
+    set_mb = dict(C=110, D=30, E=75)[cfg]
+    R = max(2, -(-140 // set_mb))
+    built = [bc.BUILDERS[cfg](dev, 1234 + rank + 100 * r) for r in range(R)]
+    steps_fn = [b[0] for b in built]
+    info = built[0][1]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / steps
+
+    warm = max(args.warmup, 3)
+    for i in range(max(warm, R)):
+        steps_fn[i % R]()
+    steps = max(args.steps, 1)
+    ms_eager = timed(lambda i: steps_fn[i % R](), steps)
+    mode, ms_step, steps_timed = 'eager', ms_eager, steps
+    try:                                          # the same steps as ONE CUDA graph of R consecutive steps
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for r in range(R):
+                steps_fn[r]()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        keep = []
+        with torch.cuda.graph(g):
+            for r in range(R):
+                keep.append(steps_fn[r]())
+        g.replay()
+        reps = max(steps // R, 1)
+        ms_step = timed(lambda i: g.replay(), reps) / R
+        steps_timed = reps * R
+        mode = f'cuda_graph ({R} steps per graph)'
+    except Exception as e:  # noqa: BLE001
+        mode = f'eager (graph capture failed: {type(e).__name__}: {str(e)[:80]})'
+    clocks = sampler.stop()
+    ms_step, ms_eager = reduce_max_over_ranks([ms_step, ms_eager], dist, dev)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak_gbs()
+    achieved = info['algo_bytes'] / (ms_step * 1e-3) / 1e9
+    imgs = info['images']
+    line = {
+        'metric': METRIC, 'value': ms_step / (imgs * world), 'unit': 'ms/img', 'n_gpus': world, 'steps': steps_timed,
+        'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': info['workload'], 'gradients': info['grads'],
+                   'l2': f'inputs rotate over {R} independent sets (> 126 MB L2 in total)',
+                   'launch': mode, 'eager_ms_per_step': ms_eager,
+                   'parallelism': f'replicas x{world} (loss is per image; no data-path collective)'},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_step': info['algo_bytes'],
+                     'algorithmic_bytes': info['algo'],
+                     'note': 'whole step against the HBM lower bound of SURVEY 8d; the tree-filter / mean-field / LCM kernels are '
+                             'dependency-latency bound (levels / iterations), see profiles/r2_notes.md for the per-kernel ncu summaries'},
+        'e2e': {'value': ms_eager / (imgs * world), 'unit': 'ms/img', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                'note': 'eager launch through the public head API (Python + autograd overhead included); inputs are feature maps '
+                        'produced on the device by the network, so there is no host copy on this path'},
+        'gpu_launches': None,
+        'clocks': clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ref = bc.REFERENCE[cfg](info)
+            if ref is not None:
+                for _ in range(2):
+                    ref()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                iters = 3
+                for _ in range(iters):
+                    rl = ref()
+                e1.record()
+                torch.cuda.synchronize()
+                ours = steps_fn[0]()
+                ours_loss = ours[0] if torch.is_tensor(ours[0]) else sum(ours[0].values())
+                line['gpu_reference'] = {
+                    'value': e0.elapsed_time(e1) / iters / imgs, 'unit': 'ms/img', 'iters': iters,
+                    'what': "the reference's eager PyTorch path on this GPU around its own compiled tree_filter_cuda (oracle/_ref, "
+                            'built by oracle/Makefile from mmdet/ops/tree_filter/src unmodified), restated in bench_configs.py',
+                    'loss_reference': float(rl[0]), 'loss_b200': float(ours_loss)}
+        except Exception as e:  # noqa: BLE001
+            line['gpu_reference'] = {'unavailable': f'{type(e).__name__}: {e}'[:300]}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -506,12 +636,16 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--config', default='A', choices=['A', 'C', 'D', 'E'],
+                    help='A (default, the headline): BoxInst; C: DiscoBox; D: BoxLevelset; E: Box2Mask (BASELINE.json configs)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
         main_reference(args, rank, world)
+    elif args.config != 'A':
+        main_config(args, rank, world, local_rank)
     else:
         main_cuda(args, rank, world, local_rank)
 

@@ -67,6 +67,9 @@ SIGNATURES = {
     'bxs_refine_forward': [c_p] * 13 + [c_i64] * 3 + [c_p],
     'bxs_refine_backward_feature': [c_p] * 10 + [c_i64] * 3 + [c_p],
     'bxs_refine_backward_weight': [c_p] * 14 + [c_i64] * 3 + [c_p],
+    'bxs_refine_forward_grouped': [c_p] * 14 + [c_i64] * 4 + [c_p],
+    'bxs_refine_backward_feature_grouped': [c_p] * 11 + [c_i64] * 4 + [c_p],
+    'bxs_refine_backward_weight_grouped': [c_p] * 15 + [c_i64] * 4 + [c_p],
     'bxs_dynconv1x1_forward': [c_p] * 3 + [c_i64] * 4 + [c_p],
     'bxs_upsampled_rowcol_max': [c_p] * 4 + [c_i64] * 5 + [c_int, c_p],
     'bxs_bilinear_resize_forward': [c_p, c_p] + [c_i64] * 5 + [c_int, c_p],

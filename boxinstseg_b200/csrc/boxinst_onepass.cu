@@ -218,6 +218,15 @@ __device__ __forceinline__ void op_chain(const float* __restrict__ img, const ui
     op_sigmoid_pair(w.x, v.s, v.n);
     return v;
   };
+  {  // every row this chain will read, requested from HBM into L2 NOW (one prefetch per lane: row = lane & 15, 64-byte half
+     // = lane >> 4): the step-ahead loads below then hit L2 even while the stream items keep HBM saturated
+    const int pr = y0 + ((lane & 15) - 1) * D, px = xs + (lane >> 4) * 16;
+    if ((lane & 15) < nrows + 2 && pr >= 0 && pr < H) {
+      const int pxc = min(max(px, 0), W - 1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(img + (size_t)pr * W + pxc));
+      if (lane < 16 && pr >= r.j0 && pr <= r.j1) asm volatile("prefetch.global.L2 [%0];" ::"l"(bits + (size_t)pr * W + pxc));
+    }
+  }
   PSeg cur = finish(load(y0 - D));
   PRaw ahead = load(y0);
   float carry = 0.f;
@@ -822,7 +831,7 @@ extern "C" int bxs_boxinst_loss_plan(const uint8_t* edge_bits, const int32_t* re
                        (int)H, (int)W, dilation);
 }
 
-extern "C" int bxs_boxinst_loss_fused_forward_planned(const float* logits, const uint8_t* edge_bits, const void* plan,
+extern "C" int bxs_boxinst_loss_fused_forward_planned(const float* logits, const uint8_t* edge_bits, void* plan,
                                                       const float* iter_ptr, float warmup_iters, void* workspace,
                                                       void* sched_state, float* losses_out, float* g_logits, int64_t N,
                                                       int64_t H, int64_t W, int dilation, bxs_stream_t stream) {
@@ -832,7 +841,7 @@ extern "C" int bxs_boxinst_loss_fused_forward_planned(const float* logits, const
   if (!op_supported(N, H, W, dilation) || (reinterpret_cast<uintptr_t>(logits) & 15) ||
       (reinterpret_cast<uintptr_t>(g_logits) & 15) || (reinterpret_cast<uintptr_t>(plan) & 15))
     return BXS_ERR_UNSUPPORTED;
-  return wq_forward(as_stream(stream), logits, edge_bits, reinterpret_cast<const unsigned char*>(plan), iter_ptr, warmup_iters,
+  return wq_forward(as_stream(stream), logits, edge_bits, reinterpret_cast<unsigned char*>(plan), iter_ptr, warmup_iters,
                     op_carve(workspace, N, H, W), reinterpret_cast<WqSched*>(sched_state), losses_out, g_logits, (int)N, (int)H,
                     (int)W, dilation);
 }

@@ -1,35 +1,39 @@
-// a6 + a7 + a8, single pass, second schedule: ONE persistent kernel whose unit of work is a WARP item.
-// (Included by boxinst_onepass.cu inside namespace bxs::{anonymous}; shares SRec / op_span / chain_geom / op_chain
-// and the PTX wrappers with the CTA-granular schedule there.)
+// a6 + a7 + a8, single pass, second schedule: ONE persistent kernel whose unit of work is a WARP item, plus a small
+// finalize kernel.  (Included by boxinst_onepass.cu inside namespace bxs::{anonymous}; shares SRec / op_span /
+// chain_geom / op_chain and the PTX wrappers with the CTA-granular schedule there.)
 //
 // Why: the CTA-granular kernel (onepass_main_kernel) spent 31 % of its duration with SMs idle (per-CTA prologue of
-// 128 record loads + a block scan, a tail of CTA-wide pair items) and its top stall was the CTA barrier around the
-// strip buffers; a separate finalize kernel added a 7.5 us latency chain (profiles/r1_ncu_full_onepass.csv).  Here
-//   * the work list is a PLAN built once per target set (wq_count_kernel + wq_build_kernel): the instance records,
-//     every work item as a 32-byte descriptor, the logit-independent weight total, all in queue order -- the main
-//     kernel has no prologue beyond one header load;
-//   * every item is processed by ONE warp, so there is no CTA barrier anywhere:
-//       - stream item: 24 rows x W of one instance, 4 rows at a time through the warp's own 2-stage shared-memory
-//         ring, each stage filled by ONE cp.async.bulk (TMA engine) that completes on the warp's own mbarrier;
-//         row maxima (integer redux + ballot arg-max), column maxima with their rows in registers, float4 zero
-//         stores of the gradient outside the box span;
-//       - pair item: one chain (op_chain) = 8 rows of a 32-lane column segment; because the weight total is known
-//         from the plan, the chain stores the FINAL scaled pairwise gradient (no second pass over the span);
-//     pair and stream items are merged proportionally in the queue (Bresenham), so issue-bound and HBM-bound work
-//     overlap on every SM;
-//   * per-instance completion counters: the warp that completes the last item of an instance finalizes it in
-//     place (profiles -> dice terms -> coefficients -> read-modify-write of the H + W arg-max positions); the loss
-//     sums are 64-bit fixed-point atomics (order-independent => deterministic); the last finalizer writes the
-//     four scalars.  No finalize kernel, no span rescaling pass.
-// Every gradient element is written by exactly one warp and every sum is either fixed-order or integer: results
-// do not depend on which warp processed which item.
+// 128 record loads + a block scan, a tail of CTA-wide pair items), its top stall was the CTA barrier around the strip
+// buffers, and its finalize kernel re-scaled the whole box span (profiles/r1_ncu_full_onepass.csv).  Here
+//   * the work list is a PLAN built once per target set (wq_count_kernel + wq_build_kernel): instance records, every
+//     pair item as a 32-byte descriptor (long chains first) and the logit-independent weight total -- the main kernel
+//     has no prologue beyond one header load;
+//   * every item is processed by ONE warp, there is no CTA barrier anywhere:
+//       - stream item = 24 rows x W of one instance, owned STATICALLY by one of the WQ_STREAMERS streamer warps of a
+//         CTA (a queue atomic costs microseconds under load; the streamers are the long pole).  The logits flow
+//         through the warp's own 4-stage shared-memory ring, one cp.async.bulk (TMA engine) per 4-row group
+//         completing on the warp's own mbarrier, 3 groups in flight ACROSS item boundaries.  Row maxima by integer
+//         redux + ballot; per-item column maxima with the 4-row group that holds them; float4 zero stores of the
+//         gradient outside the box span;
+//       - pair item = one chain (op_chain) = 8 rows of a 32-lane column segment; the weight total is known from the
+//         plan, so the chain stores the FINAL scaled pairwise gradient (no second pass over the span).  The other
+//         warps (and the streamers once the stream queue is empty) pull them from the pair queue;
+//   * the loss sums are 64-bit fixed-point atomics (order-independent => deterministic);
+//   * wq_finalize_kernel (one CTA per instance) resolves the exact arg-max positions, the dice terms and their
+//     gradient coefficients and adds them at the H + W arg-max positions.  It is released by a flag the main kernel's
+//     last warp publishes, not by the main grid's retirement.
+// Every gradient element is written by exactly one warp and every sum is either fixed-order or integer: results do not
+// depend on which warp processed which item.
 
 constexpr int WQ_NT = 256;          // threads per CTA
 constexpr int WQ_NW = WQ_NT / 32;
-constexpr int WQ_SUB = 4;           // rows per ring stage
+constexpr int WQ_SUB = 4;           // rows per ring stage (one bulk copy)
 constexpr int WQ_R = 24;            // rows per stream item
+constexpr int WQ_RING = 4;          // ring stages of a streamer warp
+constexpr int WQ_STREAMERS = 2;     // warps per CTA that take stream items first (the others take pair items)
 constexpr double WQ_NUM_FX = 16777216.0;            // 2^24: fixed-point scale of the pairwise numerator
 constexpr double WQ_PRJ_FX = 4294967296.0;          // 2^32: fixed-point scale of the projection terms (N <= 2048 terms <= 2 fit 48 bits)
+static_assert(WQ_R % WQ_SUB == 0 && WQ_R / WQ_SUB <= 16, "stream items start on a 4-row group; <= 16 groups per item (4-bit fields)");
 
 struct WqHeader {                   // first 64 bytes of the plan
   int total, n_pair, n_stream, S;
@@ -37,29 +41,28 @@ struct WqHeader {                   // first 64 bytes of the plan
   unsigned long long wtot;          // sum over instances of the edge bits set inside their boxes
   int pad[6];
 };
-static_assert(WQ_R % WQ_SUB == 0, "strips start on a 4-row group");
 static_assert(sizeof(WqHeader) == 64, "plan header is 64 bytes");
 
-// 32-byte work item.  a = {kind << 31 | n, y0 | nrows << 16, xs | c_hi << 16, items of instance n}
-//                     b = {j0 | j1 << 16, i0 | i1 << 16, pair: image / stream: ya | yb << 16, stream: c_lo}
+// 32-byte pair item.  a = {n, y0 | nrows << 16, xs | c_hi << 16, 0}   b = {j0 | j1 << 16, i0 | i1 << 16, image, 0}
 struct __align__(16) WqItem { int4 a, b; };
 
 struct WqSched {                    // device state: zero before the first call, left zero by every call
-  unsigned next_s, next_p, done, ticket;      // stream / pair queue positions, warps done, finalize ticket
+  unsigned next_s, next_p, done, ticket;      // stream / pair queue positions, warps done, "results are published" flag
   unsigned long long num_fx, prj_fx;          // fixed-point loss sums
 };
-constexpr int WQ_STREAMERS = 2;     // warps per CTA that take stream items first (the others take pair items first)
 
 inline int wq_strips(int64_t H) { return (int)ceil_div(H, WQ_R); }
 inline int64_t wq_max_chains(int64_t H, int64_t W, int d) {
   const int64_t nseg = ceil_div(W + 4, 32 - 2 * d) + 1, pc = ceil_div(ceil_div(H, d), OP_LEN) + 1;
   return d * pc * nseg;
 }
-// plan layout: header (64 B) | inst_w [N] uint32 | recs [N] int4 (j0, j1, i0, i1) | items
+// plan layout: header (64 B) | inst_w [N] uint32 | recs [N] int4 (j0, j1, i0, i1) | pair items
 __host__ __device__ inline size_t wq_plan_rec_offset(int64_t N) { return (64 + 4 * (size_t)N + 63) / 64 * 64; }
-__host__ __device__ inline size_t wq_plan_items_offset(int64_t N) { return (wq_plan_rec_offset(N) + 16 * (size_t)N + 63) / 64 * 64; }
+__host__ __device__ inline size_t wq_plan_items_offset(int64_t N, int64_t /*W*/) {
+  return (wq_plan_rec_offset(N) + 16 * (size_t)N + 63) / 64 * 64;
+}
 inline size_t wq_plan_bytes(int64_t N, int64_t H, int64_t W, int d) {
-  return wq_plan_items_offset(N) + (size_t)N * (size_t)(wq_max_chains(H, W, d) + wq_strips(H)) * sizeof(WqItem);
+  return wq_plan_items_offset(N, W) + (size_t)N * (size_t)wq_max_chains(H, W, d) * sizeof(WqItem);
 }
 
 __device__ __forceinline__ int wq_pack16(int lo, int hi) { return (lo & 0xffff) | (hi << 16); }
@@ -91,25 +94,45 @@ wq_count_kernel(const uint8_t* __restrict__ edge_bits, const int32_t* __restrict
   if (tid == 0) inst_w[n] = (unsigned)(s_red[0] + s_red[1] + s_red[2] + s_red[3]);
 }
 
+// chains of one instance by length: `full` = pieces of OP_LEN rows, `part` = the shorter last piece of a parity class
+template <int D>
+__device__ __forceinline__ void wq_chain_counts(const ChainGeom& cg, int& full, int& part) {
+  full = 0; part = 0;
+  if (cg.rows <= 0) return;
+#pragma unroll
+  for (int p = 0; p < D; ++p) {
+    const int rows_p = (cg.rows - p + D - 1) / D;
+    if (rows_p <= 0) continue;
+    full += (rows_p / OP_LEN) * cg.nseg;
+    part += (rows_p % OP_LEN) ? cg.nseg : 0;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
-// plan, step 2: the two queues and their item descriptors (one CTA).  Instances are ranked by chain count (large
-// boxes first, so both queues end with cheap items); items [0, T) are the stream items, [T, T + P) the pair items.
+// plan, step 2: the pair queue (one CTA).  Instances are ranked by chain count (large boxes first); the queue holds
+// all full-length chains in rank order, then the shorter ones: longest-processing-time-first, so the dynamic queue
+// ends with its cheapest items.  Stream items need no descriptors: item q = rows [8 s, 8 s + 8) of instance q / S.
 // ---------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(1024)
 wq_build_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ inst_gt,
                 const int32_t* __restrict__ gt_img, int N, int H, int W, unsigned char* __restrict__ plan) {
-  __shared__ int s_nch[OP_MAX_N];
+  __shared__ int s_full[OP_MAX_N], s_part[OP_MAX_N];
   __shared__ int s_order[OP_MAX_N];
-  __shared__ int s_pre[OP_MAX_N + 1];
-  __shared__ int s_scan[32];
+  __shared__ int s_pre_f[OP_MAX_N + 1], s_pre_p[OP_MAX_N + 1];
+  __shared__ int s_scan[2][32];
   __shared__ unsigned long long s_w[32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned* inst_w = reinterpret_cast<const unsigned*>(plan + 64);
+  int4* recs = reinterpret_cast<int4*>(plan + wq_plan_rec_offset(N));
   const int S = (H + WQ_R - 1) / WQ_R;
   unsigned long long wsum = 0ull;
   for (int n = tid; n < N; n += 1024) {
-    s_nch[n] = chain_geom<D>(make_srec(rects, inst_gt, gt_img, n, H, W), H, W).nch;
+    const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
+    recs[n] = make_int4(r.j0, r.j1, r.i0, r.i1);
+    int f, p;
+    wq_chain_counts<D>(chain_geom<D>(r, H, W), f, p);
+    s_full[n] = f; s_part[n] = p;
     wsum += inst_w[n];
   }
 #pragma unroll
@@ -118,79 +141,79 @@ wq_build_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ i
   __syncthreads();
   // rank (descending chain count, ties by instance id) -> order
   for (int n = tid; n < N; n += 1024) {
-    const int c = s_nch[n];
+    const int c = s_full[n] + s_part[n];
     int rank = 0;
     for (int m = 0; m < N; ++m) {
-      const int cm = s_nch[m];
+      const int cm = s_full[m] + s_part[m];
       rank += (cm > c || (cm == c && m < n)) ? 1 : 0;
     }
     s_order[rank] = n;
   }
   __syncthreads();
-  // exclusive prefix of the chain counts in rank order (two elements per thread)
+  // exclusive prefixes of the full / partial chain counts in rank order (two elements per thread)
   {
     const int i0 = 2 * tid, i1 = 2 * tid + 1;
-    const int c0 = i0 < N ? s_nch[s_order[i0]] : 0, c1 = i1 < N ? s_nch[s_order[i1]] : 0;
-    int inc = c0 + c1;
+    const int f0 = i0 < N ? s_full[s_order[i0]] : 0, f1 = i1 < N ? s_full[s_order[i1]] : 0;
+    const int p0 = i0 < N ? s_part[s_order[i0]] : 0, p1 = i1 < N ? s_part[s_order[i1]] : 0;
+    int incf = f0 + f1, incp = p0 + p1;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) s_scan[wid] = inc;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tf = __shfl_up_sync(kFull, incf, o), tp = __shfl_up_sync(kFull, incp, o);
+      if (lane >= o) { incf += tf; incp += tp; }
+    }
+    if (lane == 31) { s_scan[0][wid] = incf; s_scan[1][wid] = incp; }
     __syncthreads();
-    int wbase = 0;
-    for (int i = 0; i < wid; ++i) wbase += s_scan[i];
-    const int excl = wbase + inc - (c0 + c1);
-    if (i0 < N) s_pre[i0] = excl;
-    if (i1 < N) s_pre[i1] = excl + c0;
-    if (tid == 1023) s_pre[N] = wbase + inc;       // N <= 2048 = 2 * 1024: the last thread's inclusive sum is the total
+    int bf = 0, bp = 0;
+    for (int i = 0; i < wid; ++i) { bf += s_scan[0][i]; bp += s_scan[1][i]; }
+    const int ef = bf + incf - (f0 + f1), ep = bp + incp - (p0 + p1);
+    if (i0 < N) { s_pre_f[i0] = ef; s_pre_p[i0] = ep; }
+    if (i1 < N) { s_pre_f[i1] = ef + f0; s_pre_p[i1] = ep + p0; }
+    if (tid == 1023) { s_pre_f[N] = bf + incf; s_pre_p[N] = bp + incp; }   // N <= 2048 = 2 * 1024
   }
   __syncthreads();
-  const int P = s_pre[N], T = N * S, total = P + T;
+  const int Pf = s_pre_f[N], Pp = s_pre_p[N], P = Pf + Pp, T = N * S;
   if (tid == 0) {
     WqHeader h{};
-    h.total = total; h.n_pair = P; h.n_stream = T; h.S = S; h.N = N; h.H = H; h.W = W; h.D = D;
+    h.total = P + T; h.n_pair = P; h.n_stream = T; h.S = S; h.N = N; h.H = H; h.W = W; h.D = D;
     unsigned long long w = 0ull;
     for (int i = 0; i < 32; ++i) w += s_w[i];
     h.wtot = w;
     *reinterpret_cast<WqHeader*>(plan) = h;
   }
-  int4* recs = reinterpret_cast<int4*>(plan + wq_plan_rec_offset(N));
-  for (int n = tid; n < N; n += 1024) {
-    const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
-    recs[n] = make_int4(r.j0, r.j1, r.i0, r.i1);
-  }
-  WqItem* items = reinterpret_cast<WqItem*>(plan + wq_plan_items_offset(N));
-  for (int q = tid; q < total; q += 1024) {          // [0, T): stream items, [T, T + P): pair items, both in rank order
-    WqItem it;
-    if (q >= T) {                           // pair item: chain (pidx - pre[r]) of the r-th ranked instance
-      const int pidx = q - T;
-      int lo = 0, hi = N;                   // largest r with s_pre[r] <= pidx
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (s_pre[mid] <= pidx) lo = mid; else hi = mid;
-      }
-      const int n = s_order[lo], c = pidx - s_pre[lo];
-      const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
-      const ChainGeom cg = chain_geom<D>(r, H, W);
-      const int u = c / cg.nseg, seg = c - u * cg.nseg;
-      const int p = u / cg.pc, piece = u - p * cg.pc;              // parity class, piece within the class
-      const int rows_p = (cg.rows - p + D - 1) / D;                 // rows of class p
-      const int k0 = piece * OP_LEN;
-      const int nrows = max(0, min(OP_LEN, rows_p - k0));
-      it.a = make_int4((int)(0x80000000u | (unsigned)n), wq_pack16(cg.y_lo + p + D * k0, nrows),
-                       wq_pack16(cg.c_lo - D + seg * (32 - 2 * D), cg.c_hi), s_nch[n] + S);
-      it.b = make_int4(wq_pack16(r.j0, r.j1), wq_pack16(r.i0, r.i1), r.img, 0);
-    } else {                                // stream item: strip s of the r-th ranked instance
-      const int sidx = q;
-      const int rk = sidx / S, s = sidx - rk * S;
-      const int n = s_order[rk];
-      const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
-      const OpSpan sp = op_span<D>(r, H, W);
-      const int row0 = s * WQ_R, nrows = min(WQ_R, H - row0);
-      int ya = 1, yb = 0;
-      if (sp.y_lo <= sp.y_hi) { ya = max(row0, sp.y_lo); yb = min(row0 + nrows - 1, sp.y_hi); }
-      it.a = make_int4(n, wq_pack16(row0, nrows), wq_pack16(s, sp.c_hi), s_nch[n] + S);
-      it.b = make_int4(wq_pack16(r.j0, r.j1), wq_pack16(r.i0, r.i1), wq_pack16(ya, yb), sp.c_lo);
+  WqItem* items = reinterpret_cast<WqItem*>(plan + wq_plan_items_offset(N, W));
+  for (int q = tid; q < P; q += 1024) {
+    const bool is_full = q < Pf;
+    const int* pre = is_full ? s_pre_f : s_pre_p;
+    const int idx = is_full ? q : q - Pf;
+    int lo = 0, hi = N;                     // largest r with pre[r] <= idx
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (pre[mid] <= idx) lo = mid; else hi = mid;
     }
+    const int n = s_order[lo];
+    int c = idx - pre[lo];
+    const SRec r = make_srec(rects, inst_gt, gt_img, n, H, W);
+    const ChainGeom cg = chain_geom<D>(r, H, W);
+    int p = 0, piece = 0, seg = 0, nrows = 0;
+#pragma unroll
+    for (int pp = 0; pp < D; ++pp) {
+      const int rows_p = (cg.rows - pp + D - 1) / D;
+      if (rows_p <= 0 || c < 0) continue;
+      const int cnt = is_full ? (rows_p / OP_LEN) * cg.nseg : ((rows_p % OP_LEN) ? cg.nseg : 0);
+      if (c < cnt) {
+        p = pp;
+        piece = is_full ? c / cg.nseg : rows_p / OP_LEN;
+        seg = is_full ? c - piece * cg.nseg : c;
+        nrows = is_full ? OP_LEN : rows_p % OP_LEN;
+        c = -1;                               // found
+      } else {
+        c -= cnt;
+      }
+    }
+    WqItem it;
+    it.a = make_int4(n, wq_pack16(cg.y_lo + p + D * piece * OP_LEN, nrows),
+                     wq_pack16(cg.c_lo - D + seg * (32 - 2 * D), cg.c_hi), 0);
+    it.b = make_int4(wq_pack16(r.j0, r.j1), wq_pack16(r.i0, r.i1), r.img, 0);
     items[q] = it;
   }
 }
@@ -211,26 +234,17 @@ wq_build_kernel(const int32_t* __restrict__ rects, const int32_t* __restrict__ i
 #endif
 
 // ---------------------------------------------------------------------------------------
-// main kernel.  Items are independent (no completion protocol): the kernel boundary orders them before
-// wq_finalize_kernel.  Two roles:
-//   streamers   the first `NS` of the grid's WQ_STREAMERS-per-CTA "streamer slots" take the stream items, statically
-//               (slot i owns items i, i + NS, ...; NS is chosen by the host so that every streamer owns the same
-//               number of items): the logits flow through the warp's own 4-stage shared-memory ring, one
-//               cp.async.bulk (TMA engine) per 4-row group, up to 3 groups in flight ACROSS item boundaries.  A few
-//               hundred such warps keep HBM saturated for the whole kernel; their own instruction stream is light.
-//   pair warps  every other warp (and every streamer once it is done) pulls chains from the pair queue (one atomic
-//               per item, fetched two items ahead): issue-bound work that fills the SMs while the copies fly.
-//   row results    row_packed[n*H + y]       = key(max logit of the row) << 32 | ~(first float4 group holding it)
-//   column results col_part[(n*S + s)*W + x] = key(max logit of the column within strip s) << 32 | ~(first 4-row
-//                                               group of the strip holding it)
-// (the exact element / row inside the group is resolved by the finalize kernel, one thread per row / column)
+// main kernel.  Items are independent (no completion protocol).
+//   row results    row_packed[n*H + y] = key(max logit of the row) << 32 | ~(first float4 group holding it)
+//   column results col_part[(n*S + s)*W + x] = key(max logit of column x within stream item s) << 32 | ~(first 4-row
+//                                               group of the item holding it)
+// (the exact element / row inside the group is resolved by the finalize kernel, one thread per row / column: the
+//  first one that equals the maximum, like torch.max(dim))
 // ---------------------------------------------------------------------------------------
-constexpr int WQ_RING = 4;          // ring stages of a streamer warp
-
 template <int NCHUNK, int D, bool FULLW>
 __global__ void __launch_bounds__(WQ_NT, NCHUNK <= 2 ? 4 : 1)
 wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edge_bits,
-               const unsigned char* __restrict__ plan, int N, int H, int W_rt, int NS,
+               unsigned char* __restrict__ plan, int N, int H, int W_rt, int NS,
                unsigned long long* __restrict__ row_packed, unsigned long long* __restrict__ col_part,
                WqSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
                float* __restrict__ g_logits) {
@@ -253,52 +267,62 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
   __syncwarp();
   asm volatile("griddepcontrol.wait;" ::: "memory");     // the plan, the scheduler state and the workspace may belong to the predecessor
   const WqHeader* hdr = reinterpret_cast<const WqHeader*>(plan);
-  const WqItem* __restrict__ items = reinterpret_cast<const WqItem*>(plan + wq_plan_items_offset(N));
   const int S = (H + WQ_R - 1) / WQ_R, T = N * S;
-  const int slot = blockIdx.x * WQ_STREAMERS + warp;      // streamer slot of this warp (warp < WQ_STREAMERS)
 
-  if (warp < WQ_STREAMERS && slot < NS) {
+  if (warp < WQ_STREAMERS) {
     // ======================================= streamer =======================================
     float* ring = reinterpret_cast<float*>(wq_smem) + (size_t)warp * WQ_RING * stage_floats;
     uint64_t* bar = s_bar[warp];
-    int4 a0 = __ldg(&items[slot].a), b0 = __ldg(&items[slot].b), a1 = a0, b1 = b0;
-    bool have1 = slot + NS < T;
-    if (have1) { a1 = __ldg(&items[slot + NS].a); b1 = __ldg(&items[slot + NS].b); }
-    int jp = 0;                      // this streamer's item sequence position being processed (item slot + jp * NS)
+    const int4* __restrict__ recs = reinterpret_cast<const int4*>(plan + wq_plan_rec_offset(N));
+    // Stream items are STATIC: streamer slot i < NS owns items i, i + NS, ... (NS is chosen by the host so that every
+    // streamer owns the same number of items).  A queue atomic costs microseconds under load and a stream item is the
+    // long pole of the kernel, so nothing on this path waits for one.  q0 is being processed, q1 is next (its groups
+    // may already be in flight).
+    const int slot = (int)(blockIdx.x * WQ_STREAMERS + warp);
+    int q0 = slot < NS && slot < T ? slot : -1;
+    int q1 = q0 >= 0 && q0 + NS < T ? q0 + NS : -1;
+    int4 rec0 = make_int4(1, 0, 1, 0), rec1 = rec0;
+    if (q0 >= 0) rec0 = __ldg(recs + q0 / S);
+    if (q1 >= 0) rec1 = __ldg(recs + q1 / S);
     int gi = 0, gp = 0;              // 4-row groups issued / processed so far (ring stage = g & 3, parity = (g >> 2) & 1)
-    int iq = 0, ik = 0;              // issue cursor: item (0 = the one being processed, 1 = the next), group within it
+    int iq = 0, ik = 0;              // issue cursor: item (0 = q0, 1 = q1), group within it
     auto issue_one = [&]() {
-      if (iq > 1 || (iq == 1 && !have1)) return;
-      const int4 da = iq == 0 ? a0 : a1;
-      const int row0 = wq_lo16(da.y), nrows = wq_hi16(da.y);
+      const int q = iq == 0 ? q0 : (iq == 1 ? q1 : -1);
+      if (q < 0) return;
+      const int n = q / S, row0 = (q - n * S) * WQ_R, nrows = min(WQ_R, H - row0);
       if (lane == 0) {
         const uint32_t bytes = (uint32_t)min(WQ_SUB, nrows - ik * WQ_SUB) * (uint32_t)W * 4u;
         uint64_t* bb = &bar[gi & (WQ_RING - 1)];
         op_mbar_expect_tx(bb, bytes);
-        op_bulk_g2s(ring + (gi & (WQ_RING - 1)) * stage_floats,
-                    logits + ((size_t)da.x * H + row0) * W + (size_t)ik * stage_floats, bytes, bb);
+        op_bulk_g2s(ring + (gi & (WQ_RING - 1)) * stage_floats, logits + ((size_t)n * H + row0) * W + (size_t)ik * stage_floats,
+                    bytes, bb);
       }
       ++gi;
       if (++ik == (nrows + WQ_SUB - 1) / WQ_SUB) { ik = 0; ++iq; }
     };
 #pragma unroll
     for (int i = 0; i < WQ_RING - 1; ++i) issue_one();
-    for (;;) {
-      const int n = a0.x;
-      const int row0 = wq_lo16(a0.y), nrows = wq_hi16(a0.y);
-      const int s_idx = wq_lo16(a0.z), c_hi = wq_hi16(a0.z), c_lo = b0.w;
-      const int ya = wq_lo16(b0.z), yb = wq_hi16(b0.z);
+    while (q0 >= 0) {
+      const int n = q0 / S, s_idx = q0 - n * S;
+      const int row0 = s_idx * WQ_R, nrows = min(WQ_R, H - row0);
+      SRec rec;
+      rec.j0 = (short)rec0.x; rec.j1 = (short)rec0.y; rec.i0 = (short)rec0.z; rec.i1 = (short)rec0.w; rec.img = 0;
+      const OpSpan sp = op_span<D>(rec, H, W);
+      const int ya = max(row0, sp.y_lo), yb = min(row0 + nrows - 1, sp.y_hi);    // ya > yb: no span row in this item
+      const int c_lo = sp.c_lo, c_hi = sp.c_hi;
       WQ_TRACE(2 + ((unsigned long long)n << 8));
       const int nsub = (nrows + WQ_SUB - 1) / WQ_SUB;
-      float cbest[NCHUNK][4];
-      int csub[NCHUNK][4];
+      float cbest[NCHUNK][4];            // column maxima of this item ...
+      unsigned cpk[(NCHUNK + 1) / 2];    // ... and the 4-row group (0..5 within the item) that holds each: 4-bit fields
 #pragma unroll
       for (int ch = 0; ch < NCHUNK; ++ch)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { cbest[ch][e] = -INFINITY; csub[ch][e] = 0; }
+        for (int e = 0; e < 4; ++e) cbest[ch][e] = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < (NCHUNK + 1) / 2; ++i) cpk[i] = 0u;
       unsigned long long* rdst = row_packed + (size_t)n * H + row0;
       float* grow = g_logits + ((size_t)n * H + row0) * W + lane * 4;
-      const int sub0 = row0 / WQ_SUB;        // WQ_R % WQ_SUB == 0: strips start on a 4-row group
+      const int sub0 = row0 / WQ_SUB;
       int y = row0;
       for (int k = 0; k < nsub; ++k) {
         const int st = gp & (WQ_RING - 1);
@@ -360,7 +384,12 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
         for (int ch = 0; ch < NCHUNK; ++ch)
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if (gm[ch][e] > cbest[ch][e]) { cbest[ch][e] = gm[ch][e]; csub[ch][e] = sub0 + k; }
+            if (gm[ch][e] > cbest[ch][e]) {
+              cbest[ch][e] = gm[ch][e];
+              constexpr unsigned kDummy = 0u; (void)kDummy;
+              const int f = ch * 4 + e;
+              asm("bfi.b32 %0, %1, %0, %2, 4;" : "+r"(cpk[f >> 3]) : "r"(k), "r"((f & 7) * 4));
+            }
         __syncwarp();                        // every lane has read stage st
         ++gp;
         issue_one();                         // refill the ring: the stage read one group ago is free
@@ -371,47 +400,56 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
         const int col0 = (ch * 32 + lane) * 4;
         if (FULLW || col0 < W) {
           ulonglong2 p0, p1;
-          p0.x = pack_key(fkey(cbest[ch][0]), csub[ch][0]); p0.y = pack_key(fkey(cbest[ch][1]), csub[ch][1]);
-          p1.x = pack_key(fkey(cbest[ch][2]), csub[ch][2]); p1.y = pack_key(fkey(cbest[ch][3]), csub[ch][3]);
+          const unsigned f4 = cpk[ch >> 1] >> ((ch & 1) * 16);       // this chunk's four 4-bit group fields
+          p0.x = pack_key(fkey(cbest[ch][0]), sub0 + (int)(f4 & 15u)); p0.y = pack_key(fkey(cbest[ch][1]), sub0 + (int)((f4 >> 4) & 15u));
+          p1.x = pack_key(fkey(cbest[ch][2]), sub0 + (int)((f4 >> 8) & 15u)); p1.y = pack_key(fkey(cbest[ch][3]), sub0 + (int)((f4 >> 12) & 15u));
           *reinterpret_cast<ulonglong2*>(cdst + col0) = p0;
           *reinterpret_cast<ulonglong2*>(cdst + col0 + 2) = p1;
         }
       }
       WQ_TRACE(4);
-      if (!have1) break;
-      a0 = a1; b0 = b1;
-      ++jp; --iq;
-      const int nx = slot + (jp + 1) * NS;
-      have1 = nx < T;
-      if (have1) { a1 = __ldg(&items[nx].a); b1 = __ldg(&items[nx].b); }
+      // advance to this streamer's next item
+      q0 = q1; rec0 = rec1; --iq;
+      q1 = q0 >= 0 && q0 + NS < T ? q0 + NS : -1;
+      if (q0 >= 0) {
+        if (q1 >= 0) rec1 = __ldg(recs + q1 / S);
+        if (iq < 0) iq = 0;
+        while (gi - gp < WQ_RING - 1) {      // top the ring up (the item after next just became known)
+          const int before = gi;
+          issue_one();
+          if (gi == before) break;
+        }
+      }
     }
   }
 
   // ======================================= pair queue =======================================
+  const WqItem* __restrict__ items = reinterpret_cast<const WqItem*>(plan + wq_plan_items_offset(N, W));
   const unsigned long long wtot = __ldg(&hdr->wtot);
   const float scale = fminf(__ldg(iter_ptr) / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
   const int n_pair = __ldg(&hdr->n_pair);
   const unsigned nwarps = gridDim.x * WQ_NW;
-  const unsigned n_pair_static = gridDim.x * (WQ_NW - WQ_STREAMERS) + (gridDim.x * WQ_STREAMERS - (unsigned)NS);
-  // the first pair item of a warp is static (warps that streamed have none); later ones come from the queue counter,
-  // fetched two items ahead of their use
+  const unsigned n_idle_slots = gridDim.x * WQ_STREAMERS > (unsigned)NS ? gridDim.x * WQ_STREAMERS - (unsigned)NS : 0u;
+  const unsigned n_pair_static = gridDim.x * (WQ_NW - WQ_STREAMERS) + n_idle_slots;
+  // the first pair item of a warp that did not stream is static; later ones (and a finished streamer's first) come from
+  // the queue counter, fetched two items ahead of their use
   unsigned raw_l0 = 0xffffffffu;
-  bool streamed = warp < WQ_STREAMERS && slot < NS;
-  if (!streamed) raw_l0 = warp >= WQ_STREAMERS ? blockIdx.x * (WQ_NW - WQ_STREAMERS) + (warp - WQ_STREAMERS)
-                                               : gridDim.x * (WQ_NW - WQ_STREAMERS) + (unsigned)(slot - NS);
+  const int sslot = (int)(blockIdx.x * WQ_STREAMERS + warp);
+  if (warp >= WQ_STREAMERS) raw_l0 = blockIdx.x * (WQ_NW - WQ_STREAMERS) + (warp - WQ_STREAMERS);
+  else if (sslot >= NS) raw_l0 = gridDim.x * (WQ_NW - WQ_STREAMERS) + (unsigned)(sslot - NS);
   else if (lane == 0) raw_l0 = n_pair_static + atomicAdd(&sched->next_p, 1u);
   unsigned raw = __shfl_sync(kFull, raw_l0, 0);
   int q_cur = raw < (unsigned)n_pair ? (int)raw : -1;
   int4 ia = make_int4(0, 0, 0, 0), ib = ia;
-  if (q_cur >= 0) { ia = __ldg(&items[T + q_cur].a); ib = __ldg(&items[T + q_cur].b); }
+  if (q_cur >= 0) { ia = __ldg(&items[q_cur].a); ib = __ldg(&items[q_cur].b); }
   if (lane == 0 && q_cur >= 0) raw_l0 = n_pair_static + atomicAdd(&sched->next_p, 1u);
   while (q_cur >= 0) {
     raw = __shfl_sync(kFull, raw_l0, 0);
     const int q_nxt = raw < (unsigned)n_pair ? (int)raw : -1;
     int4 na = make_int4(0, 0, 0, 0), nb = na;
-    if (q_nxt >= 0) { na = __ldg(&items[T + q_nxt].a); nb = __ldg(&items[T + q_nxt].b); }
+    if (q_nxt >= 0) { na = __ldg(&items[q_nxt].a); nb = __ldg(&items[q_nxt].b); }
     if (lane == 0 && q_nxt >= 0) raw_l0 = n_pair_static + atomicAdd(&sched->next_p, 1u);
-    const int n = ia.x & 0x7fffffff;
+    const int n = ia.x;
     WQ_TRACE(3 + ((unsigned long long)n << 8));
     const int y0 = wq_lo16(ia.y), nrows = wq_hi16(ia.y);
     const int xs = wq_lo16(ia.z), c_hi = wq_hi16(ia.z);
@@ -432,7 +470,7 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
     q_cur = q_nxt; ia = na; ib = nb;
   }
   WQ_TRACE(7);
-  // ---- queue counter reset by the last warp (every fetch of a warp precedes its `done` increment) ----
+  // ---- queue counters reset and results published by the last warp (every fetch of a warp precedes its `done` increment) ----
   if (lane == 0) {
     __threadfence();
     if (atomicAdd(&sched->done, 1u) == nwarps - 1u) {
@@ -440,6 +478,8 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
       sched->next_p = 0u;
       sched->done = 0u;
       __threadfence();
+      // every warp fenced its stores before its `done` increment: the finalize CTAs (already resident, polling) may go
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&sched->ticket), "r"(1u) : "memory");
     }
   }
 }
@@ -452,7 +492,7 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
 // ---------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(OP_FIN_NT)
-wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ plan, int N, int H, int W,
+wq_finalize_kernel(const float* __restrict__ logits, unsigned char* __restrict__ plan, int N, int H, int W,
                    OpWorkspace ws, WqSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
                    float* __restrict__ losses_out, float* __restrict__ g_logits) {
   constexpr int NWF = OP_FIN_NT / 32;
@@ -469,7 +509,19 @@ wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __rest
     g_op_trace[(kFinTrace + blockIdx.x * 4 + 0) * 2] = t_;
   }
 #endif
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // Launched with programmatic stream serialization and NOT waiting for the main grid to retire (griddepcontrol.wait
+  // costs ~2.5 us after the last warp's exit: grid completion + flush): the CTAs become resident as main CTAs leave
+  // and poll the flag the main kernel's last warp publishes after every warp has fenced its results.  The main kernel
+  // never waits for this one, so there is nothing to deadlock on.
+  if (tid == 0) {
+    unsigned ready = 0u;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ready) : "l"(&sched->ticket) : "memory");
+      if (ready) break;
+      __nanosleep(40);
+    }
+  }
+  __syncthreads();
 #ifdef BXS_OP_TRACE
   if (tid == 0 && g_op_trace) {
     unsigned long long t_;
@@ -478,7 +530,6 @@ wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __rest
   }
 #endif
   const WqHeader* hdr = reinterpret_cast<const WqHeader*>(plan);
-  const int S = __ldg(&hdr->S);
   const unsigned long long wtot = __ldg(&hdr->wtot);
   const float* xin = logits + (size_t)n * H * W;
   float* ginst = g_logits + (size_t)n * H * W;
@@ -486,16 +537,20 @@ wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __rest
   SRec rec;
   rec.j0 = (short)recv.x; rec.j1 = (short)recv.y; rec.i0 = (short)recv.z; rec.i1 = (short)recv.w; rec.img = 0;
   const bool empty = rec.j0 > rec.j1;
-  // ---- independent loads: this thread's row result and its column's strip results ----
+  // ---- independent loads: this thread's row result and its column's key (re-zeroed for the next call) ----
   const int row_i = tid, col_i = tid;                   // H, W <= 512 = OP_FIN_NT
-  unsigned long long rp = 0ull, cp = 0ull;
+  unsigned long long rp = 0ull;
   if (row_i < H) rp = ws.row_packed[(size_t)n * H + row_i];
+  const int S = (H + WQ_R - 1) / WQ_R;
+  unsigned long long cp = 0ull;
   if (col_i < W) {
     const unsigned long long* src = ws.col_part + (size_t)n * S * W + col_i;
-#pragma unroll 4
-    for (int s = 0; s < S; ++s) {
-      const unsigned long long p = src[(size_t)s * W];
-      cp = p > cp ? p : cp;             // larger key; on equal keys the earlier group (larger ~group)
+    for (int s0 = 0; s0 < S; s0 += 8) {                  // all loads of a batch first: one round trip for S <= 8
+      unsigned long long v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = s0 + j < S ? src[(size_t)(s0 + j) * W] : 0ull;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cp = v[j] > cp ? v[j] : cp;  // larger key; on equal keys the earlier group (larger ~group)
     }
   }
   // ---- exact positions: first element of the float4 group / first row of the 4-row group equal to the maximum ----
@@ -528,6 +583,13 @@ wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __rest
   if (row_i < H) svr = ginst[(size_t)row_i * W + ar];
   if (col_i < W) svc = ginst[(size_t)ac * W + col_i];
   __syncthreads();
+#ifdef BXS_OP_TRACE
+  if (tid == 0 && g_op_trace) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    g_op_trace[(kFinTrace + blockIdx.x * 4 + 3) * 2] = t_;
+  }
+#endif
   float Ir = 0.f, Xr = 0.f, Ic = 0.f, Xc = 0.f;
 #pragma unroll
   for (int i = 0; i < NWF; ++i) { Ir += s_f[0][i]; Xr += s_f[1][i]; Ic += s_f[2][i]; Xc += s_f[3][i]; }
@@ -567,6 +629,7 @@ wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __rest
       losses_out[3] = (float)wtot;
       sched->prj_fx = 0ull;
       sched->num_fx = 0ull;
+      sched->ticket = 0u;          // every CTA passed its poll before it added its term
     }
   }
 #ifdef BXS_OP_TRACE
@@ -582,8 +645,8 @@ wq_finalize_kernel(const float* __restrict__ logits, const unsigned char* __rest
 inline size_t wq_smem_bytes(int64_t W) { return (size_t)WQ_STREAMERS * WQ_RING * WQ_SUB * W * 4; }
 
 template <int NCHUNK, int D, bool FULLW>
-int wq_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bits, const unsigned char* plan, int N, int H,
-                   int W, OpWorkspace ws, WqSched* sched, const float* iter_ptr, float warmup_iters, float* losses_out,
+int wq_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bits, unsigned char* plan, int N, int H, int W,
+                   OpWorkspace ws, WqSched* sched, const float* iter_ptr, float warmup_iters, float* losses_out,
                    float* g_logits) {
   const size_t smem = wq_smem_bytes(W);
   auto kern = wq_main_kernel<NCHUNK, D, FULLW>;
@@ -609,14 +672,13 @@ int wq_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bit
     occ_dev = dev;
     occ_smem = smem;
   }
-  // the item count lives in the plan (device memory): size the grid for the machine, bounded by the largest possible
-  // queue; warps beyond the queue leave at once
+  // the pair-item count lives in the plan (device memory): size the grid for the machine, bounded by the largest
+  // possible queue; warps beyond the queues leave at once
   const int64_t max_items = (int64_t)N * (wq_strips(H) + wq_max_chains(H, W, D));
   const int grid = (int)std::min<int64_t>(ceil_div(max_items, WQ_NW), (int64_t)sm_count() * occ);
   // streamers: as many as give every one the same number of stream items (k each), at most WQ_STREAMERS per CTA
   const int64_t T = (int64_t)N * wq_strips(H), slots = (int64_t)grid * WQ_STREAMERS;
-  const int64_t per = ceil_div(T, slots);
-  const int NS = (int)ceil_div(T, per);
+  const int NS = (int)ceil_div(T, ceil_div(T, slots));
   op_launch_pdl(kern, dim3((unsigned)grid), dim3(WQ_NT), smem, st, logits, edge_bits, plan, N, H, W, NS, ws.row_packed,
                 ws.col_part, sched, iter_ptr, warmup_iters, g_logits);
   int rc = check_launch();
@@ -638,7 +700,7 @@ inline int wq_build_plan(cudaStream_t st, const uint8_t* edge_bits, const int32_
   return check_launch();
 }
 
-inline int wq_forward(cudaStream_t st, const float* logits, const uint8_t* edge_bits, const unsigned char* plan,
+inline int wq_forward(cudaStream_t st, const float* logits, const uint8_t* edge_bits, unsigned char* plan,
                       const float* iter_ptr, float warmup_iters, OpWorkspace ws, WqSched* sched, float* losses_out,
                       float* g_logits, int N, int H, int W, int dilation) {
   int rc = BXS_ERR_UNSUPPORTED;

@@ -144,6 +144,7 @@ struct BfsWs {
   int* deg;        // [B*V]
   int* adj;        // [B*V*4]
   int* counts;     // [B*V] scratch of the level scan
+  int* flags;      // [B]   1: ordered by the grid fast path
   size_t total_bytes;
 };
 inline BfsWs carve_bfs(void* base, int64_t B, int64_t V) {
@@ -154,12 +155,15 @@ inline BfsWs carve_bfs(void* base, int64_t B, int64_t V) {
   w.deg = (int*)take(4 * B * V);
   w.adj = (int*)take(16 * B * V);
   w.counts = (int*)take(4 * B * V);
+  w.flags = (int*)take(4 * B);
   w.total_bytes = off;
   return w;
 }
 
-__global__ void bfs_adj_kernel(const int32_t* __restrict__ tree, BfsWs ws, int V, int* __restrict__ err) {
+__global__ void bfs_adj_kernel(const int32_t* __restrict__ tree, BfsWs ws, int V, int* __restrict__ err,
+                               const int* __restrict__ flags) {
   const int b = blockIdx.y;
+  if (flags && flags[b]) return;
   const int32_t* te = tree + (int64_t)b * (V - 1) * 2;
   int* deg = ws.deg + (int64_t)b * V;
   int* adj = ws.adj + (int64_t)b * V * 4;
@@ -220,10 +224,11 @@ __global__ void __launch_bounds__(NT) bfs_block_kernel(BfsWs ws, int V, int32_t*
                                                        int32_t* __restrict__ sorted_parent,
                                                        int32_t* __restrict__ sorted_child,
                                                        int32_t* __restrict__ level_start,
-                                                       int32_t* __restrict__ num_levels) {
+                                                       int32_t* __restrict__ num_levels, const int* __restrict__ flags) {
   __shared__ int s_warp[33];
   __shared__ int s_v[2][NT], s_pv[2][NT];
   const int b = blockIdx.x;
+  if (flags && flags[b]) return;                     // bfs_grid_kernel already ordered this tree
   const int4* adj = reinterpret_cast<const int4*>(ws.adj + (int64_t)b * V * 4);
   int* pvert = ws.counts + (int64_t)b * V;           // parent VERTEX of each position (frontiers wider than NT)
   int32_t* idx = sorted_index + (int64_t)b * V;
@@ -276,6 +281,103 @@ __global__ void __launch_bounds__(NT) bfs_block_kernel(BfsWs ws, int V, int32_t*
   if (threadIdx.x == 0) num_levels[b] = level;      // lvl[level] == number of reached vertices
 }
 
+// ---------------------------------------------------------------------------------------
+// BFS, fast path for trees of a 4-connected GRID graph (every tree the heads build: tree_filter.py:15-25 lists the
+// vertical edges (v, v + W) and the horizontal edges (v, v + 1)).  The adjacency of such a tree is 4 bits per vertex
+// (up, left, right, down), i.e. V bytes: it lives in SHARED memory, so a level costs a shared-memory read + a warp
+// scan instead of a dependent L2 round trip per level (bfs_block_kernel: ~0.9 us per level, 1667 levels at 200x256).
+// One warp per tree: no CTA barrier.  Children are emitted in ascending vertex order (up, left, right, down minus the
+// parent), exactly the order bfs_block_kernel produces, so both paths give the same result.
+// `flags[b]`: 0 = not a grid tree (or too large for shared memory): bfs_block_kernel must run; 1 = done here.
+// ---------------------------------------------------------------------------------------
+constexpr int BFS_FRONT = 2048;         // frontier entries kept in shared memory (wider frontiers re-read sorted_index)
+
+__global__ void __launch_bounds__(32) bfs_grid_kernel(const int32_t* __restrict__ tree, int V, int32_t* __restrict__ sorted_index,
+                                                      int32_t* __restrict__ sorted_parent, int32_t* __restrict__ sorted_child,
+                                                      int32_t* __restrict__ level_start, int32_t* __restrict__ num_levels,
+                                                      int* __restrict__ flags) {
+  extern __shared__ unsigned bfs_smem[];
+  unsigned* s_adj = bfs_smem;                                   // V bytes, packed 4 per word
+  int* s_v = reinterpret_cast<int*>(bfs_smem + (V + 3) / 4);   // [2][BFS_FRONT] frontier vertex ids
+  int* s_pv = s_v + 2 * BFS_FRONT;                              // [2][BFS_FRONT] their parents' vertex ids
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int32_t* te = tree + (int64_t)b * (V - 1) * 2;
+  // row pitch of the grid = the (single) non-unit difference of an edge's end points
+  int Wd = 0;
+  bool ok = true;
+  for (int i = lane; i < V - 1; i += 32) {
+    const int d = abs(te[2 * i + 1] - te[2 * i]);
+    if (d == 0) ok = false;
+    else if (d != 1) Wd = max(Wd, d);
+  }
+  Wd = __reduce_max_sync(kFull, Wd);
+  if (Wd == 0) Wd = V;                                          // a single row: no vertical edge
+  for (int i = lane; i < (V + 3) / 4; i += 32) s_adj[i] = 0u;
+  __syncwarp();
+  for (int i = lane; i < V - 1; i += 32) {
+    const int ea = te[2 * i], eb = te[2 * i + 1];
+    const int u = min(ea, eb), v = max(ea, eb), d = v - u;
+    if (u < 0 || v >= V || (d != 1 && d != Wd) || (d == 1 && Wd < V && (v % Wd) == 0)) { ok = false; continue; }
+    // bit 0 = up (v - Wd), 1 = left (v - 1), 2 = right (v + 1), 3 = down (v + Wd)
+    atomicOr(&s_adj[u >> 2], (d == 1 ? 4u : 8u) << ((u & 3) * 8));
+    atomicOr(&s_adj[v >> 2], (d == 1 ? 2u : 1u) << ((v & 3) * 8));
+  }
+  ok = __all_sync(kFull, ok);
+  if (!ok) { if (lane == 0) flags[b] = 0; return; }
+  __syncwarp();
+  int32_t* idx = sorted_index + (int64_t)b * V;
+  int32_t* par = sorted_parent + (int64_t)b * V;
+  int4* chd = reinterpret_cast<int4*>(sorted_child + (int64_t)b * V * 4);
+  int32_t* lvl = level_start + (int64_t)b * (V + 1);
+  if (lane == 0) { idx[0] = 0; par[0] = 0; lvl[0] = 0; s_v[0] = 0; s_pv[0] = -1; }
+  __syncwarp();
+  int ls = 0, le = 1, level = 0, cur = 0;
+  while (ls < le) {
+    int next = le;
+    for (int base = ls; base < le; base += 32) {
+      const int p = base + lane;
+      int v = -1, pv = -1, cnt = 0;
+      unsigned bits = 0u;
+      if (p < le) {
+        if (p - ls < BFS_FRONT) { v = s_v[cur * BFS_FRONT + p - ls]; pv = s_pv[cur * BFS_FRONT + p - ls]; }
+        else { v = idx[p]; pv = idx[par[p]]; }                  // very wide frontier: the global copies (written by this warp)
+        bits = (s_adj[v >> 2] >> ((v & 3) * 8)) & 15u;
+        // drop the parent: it is one of the four neighbours
+        if (pv >= 0) bits &= ~(pv == v - Wd ? 1u : (pv == v - 1 ? 2u : (pv == v + 1 ? 4u : 8u)));
+        cnt = __popc(bits);
+      }
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
+      const int total = __shfl_sync(kFull, inc, 31);
+      if (p < le) {
+        int q = next + inc - cnt;
+        int c4[4] = {0, 0, 0, 0};
+        int k2 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (!((bits >> k) & 1u)) continue;
+          const int u = k == 0 ? v - Wd : (k == 1 ? v - 1 : (k == 2 ? v + 1 : v + Wd));
+          idx[q] = u;
+          par[q] = p;
+          if (q - le < BFS_FRONT) { s_v[(cur ^ 1) * BFS_FRONT + q - le] = u; s_pv[(cur ^ 1) * BFS_FRONT + q - le] = v; }
+          c4[k2++] = q;
+          ++q;
+        }
+        chd[p] = make_int4(c4[0], c4[1], c4[2], c4[3]);
+      }
+      next += total;
+    }
+    __syncwarp();
+    ls = le;
+    le = next;
+    cur ^= 1;
+    ++level;
+    if (lane == 0) lvl[level] = ls;
+  }
+  if (lane == 0) { num_levels[b] = level; flags[b] = ls == V ? 1 : 0; }       // every vertex reached <=> a spanning tree
+}
+
 // level boundaries from (level-contiguous) sorted_parent when they were not produced by bfs_block_kernel:
 // depth by pointer doubling, one CTA per tree, scratch in global memory
 __global__ void __launch_bounds__(NT) levels_from_parent_kernel(const int32_t* __restrict__ sorted_parent, int V,
@@ -315,6 +417,8 @@ __global__ void __launch_bounds__(NT) levels_from_parent_kernel(const int32_t* _
 // (values gathered into position order; child weights packed next to the child range) and (b) prefetched into
 // registers PF levels ahead, so that the per-level critical path is shared-memory read -> FMA -> write -> barrier.
 constexpr int PF = 4;                    // software-pipeline depth (levels in flight)
+constexpr int RNT = 256;                 // threads of a refine CTA: a level up to RNT nodes wide is served by the prefetch ring; 64 was
+                                         // measured SLOWER (wide levels fall back to un-prefetched loads: +8 % forward, +30 % backward)
 
 struct TreeView {
   const int32_t* idx;     // [V] position -> vertex
@@ -405,7 +509,7 @@ __device__ __forceinline__ void up_pass(const TreeView& t, float* buf, float* __
         buf[p] = v;
         if (save_up) save_up[p] = v;
       }
-      for (p += NT; p < nd.e; p += NT) {                    // wide levels: plenty of parallelism, plain loads
+      for (p += RNT; p < nd.e; p += RNT) {                    // wide levels: plenty of parallelism, plain loads
         const float v = up_node(buf[p], __ldg(t.cinfo + p), __ldg(t.cw + p), buf);
         buf[p] = v;
         if (save_up) save_up[p] = v;
@@ -439,7 +543,7 @@ __device__ __forceinline__ void down_pass(const TreeView& t, float* buf, float* 
         buf[p] = a;
         if (out_vertex) out_vertex[nd.idx] = a;
       }
-      for (p += NT; p < nd.e; p += NT) {
+      for (p += RNT; p < nd.e; p += RNT) {
         const float ew = __ldg(t.w + p);
         const float a = fmaf(buf[__ldg(t.par + p)], ew, buf[p] * (1.f - ew * ew));
         buf[p] = a;
@@ -461,25 +565,30 @@ __device__ __forceinline__ TreeView make_view(const float* w, const int32_t* idx
 // MODE 0: forward (channel c < C: feature; c == C: normaliser with input 1)
 // MODE 1: backward wrt feature: input = g / Z
 template <int MODE, bool SMEM>
-__global__ void __launch_bounds__(NT) refine_updown_kernel(const float* __restrict__ feature, const float* __restrict__ w,
+__global__ void __launch_bounds__(RNT) refine_updown_kernel(const float* __restrict__ feature, const float* __restrict__ w,
                                                            const int32_t* __restrict__ idx, const int32_t* __restrict__ par,
                                                            const int32_t* __restrict__ cinfo, const float4* __restrict__ cw,
                                                            const int32_t* __restrict__ lvl, const int32_t* __restrict__ nlv,
                                                            const float* __restrict__ wsum, float* __restrict__ aggr,
                                                            float* __restrict__ aggr_up, float* __restrict__ wsum_out,
                                                            float* __restrict__ wsum_up, float* __restrict__ scratch, int C,
-                                                           int V) {
+                                                           int V, const int32_t* __restrict__ tree_of, int norm_only) {
+  // tree_of (may be null): the tree / edge weights / normaliser of batch entry b are those of group tree_of[b] -- the
+  // instances of one image share one tree (box_solov2_head.py:300-305,353; box2mask_head.py:271-276), so the order,
+  // the packed child weights and the normaliser Z exist once per image instead of once per instance.
+  // norm_only: this launch computes only the normaliser channel (blockIdx.x indexes trees).
   extern __shared__ float s_buf[];
-  const int b = blockIdx.x, c = blockIdx.y;
-  const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, b, V);
+  const int b = blockIdx.x, c = norm_only ? C : blockIdx.y;
+  const int tb = tree_of ? __ldg(tree_of + b) : b;
+  const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, tb, V);
   float* buf = SMEM ? s_buf : scratch + ((int64_t)b * (C + 1) + c) * V;
   const bool norm = MODE == 0 && c == C;
   const float* x = norm ? nullptr : feature + ((int64_t)b * C + c) * V;
-  const float* z = MODE == 1 ? wsum + (int64_t)b * V : nullptr;
+  const float* z = MODE == 1 ? wsum + (int64_t)tb * V : nullptr;
   float* save_up = MODE == 0 ? (norm ? wsum_up + (int64_t)b * V : aggr_up + ((int64_t)b * C + c) * V) : nullptr;
   float* out_v = MODE == 0 ? (norm ? wsum_out + (int64_t)b * V : aggr + ((int64_t)b * C + c) * V)
                            : aggr + ((int64_t)b * C + c) * V;     // MODE 1: aggr == grad_feature
-  for (int p = threadIdx.x; p < V; p += NT) {               // parallel gather of the inputs into position order
+  for (int p = threadIdx.x; p < V; p += RNT) {               // parallel gather of the inputs into position order
     const int v = __ldg(t.idx + p);
     buf[p] = norm ? 1.f : (MODE == 1 ? x[v] / z[v] : x[v]);
   }
@@ -489,11 +598,12 @@ __global__ void __launch_bounds__(NT) refine_updown_kernel(const float* __restri
 }
 
 __global__ void refine_div_kernel(const float* __restrict__ aggr, const float* __restrict__ wsum, float* __restrict__ out,
-                                  int C, int V, int64_t total) {
+                                  int C, int V, int64_t total, const int32_t* __restrict__ tree_of) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int v = i % V;
     const int64_t b = i / ((int64_t)C * V);
-    out[i] = aggr[i] / wsum[b * V + v];
+    const int64_t tb = tree_of ? __ldg(tree_of + b) : b;
+    out[i] = aggr[i] / wsum[tb * V + v];
   }
 }
 
@@ -505,22 +615,23 @@ __global__ void refine_div_kernel(const float* __restrict__ aggr, const float* _
 struct SweepNode { int s, e, par; float w, ind, outp; };
 
 template <bool SMEM>
-__global__ void __launch_bounds__(NT) refine_bwd_weight_kernel(
+__global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
     const float* __restrict__ w, const int32_t* __restrict__ idx, const int32_t* __restrict__ par,
     const int32_t* __restrict__ cinfo, const float4* __restrict__ cw, const int32_t* __restrict__ lvl,
     const int32_t* __restrict__ nlv, const float* __restrict__ out, const float* __restrict__ aggr,
     const float* __restrict__ aggr_up, const float* __restrict__ wsum, const float* __restrict__ wsum_up,
     const float* __restrict__ g_out, float* __restrict__ grad_w, float* __restrict__ scratch, float* __restrict__ outd_par,
-    int C, int V) {
+    int C, int V, const int32_t* __restrict__ tree_of) {
   extern __shared__ float s_buf[];
   const int b = blockIdx.x;
-  const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, b, V);
+  const int tb = tree_of ? __ldg(tree_of + b) : b;          // tree / weights / normaliser of the instance's image
+  const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, tb, V);
   float* buf = SMEM ? s_buf : scratch + (int64_t)b * V;
   float* gw = grad_w + (int64_t)b * V;
   float* op = outd_par + (int64_t)b * V;
-  const float* z = wsum + (int64_t)b * V;
-  const float* zu = wsum_up + (int64_t)b * V;
-  for (int p = threadIdx.x; p < V; p += NT) gw[p] = 0.f;
+  const float* z = wsum + (int64_t)tb * V;
+  const float* zu = wsum_up + (int64_t)tb * V;
+  for (int p = threadIdx.x; p < V; p += RNT) gw[p] = 0.f;
   for (int c = 0; c < C; ++c) {
     const float* g = g_out + ((int64_t)b * C + c) * V;
     const float* o = out + ((int64_t)b * C + c) * V;
@@ -532,7 +643,7 @@ __global__ void __launch_bounds__(NT) refine_bwd_weight_kernel(
       const float* outd = phase ? z : ag;
       const float sign = phase ? -1.f : 1.f;
       __syncthreads();
-      for (int p = threadIdx.x; p < V; p += NT) {           // parallel pre-pass: inputs and parent data, position order
+      for (int p = threadIdx.x; p < V; p += RNT) {           // parallel pre-pass: inputs and parent data, position order
         const int v = __ldg(t.idx + p);
         const float gn = g[v] / z[v];
         buf[p] = phase ? gn * o[v] : gn;
@@ -568,7 +679,7 @@ __global__ void __launch_bounds__(NT) refine_bwd_weight_kernel(
             gw[p] += sign * (gup * (nd.outp - nd.w * nd.ind) + nd.ind * (Gp - nd.w * gup));
             buf[p] = fmaf(Gp, nd.w, gup * (1.f - nd.w * nd.w));
           }
-          for (p += NT; p < nd.e; p += NT) {
+          for (p += RNT; p < nd.e; p += RNT) {
             const float ew = __ldg(t.w + p), in_p = ind[p], gup = buf[p], Gp = buf[__ldg(t.par + p)];
             gw[p] += sign * (gup * (op[p] - ew * in_p) + in_p * (Gp - ew * gup));
             buf[p] = fmaf(Gp, ew, gup * (1.f - ew * ew));
@@ -632,13 +743,25 @@ extern "C" int bxs_bfs_forward(const int32_t* tree_edges, int32_t* sorted_index,
   cudaStream_t st = as_stream(stream);
   BfsWs ws = carve_bfs(workspace, B, V);
   int* err = (int*)((char*)workspace + ws.total_bytes);
+  int* flags = ws.flags;
   cudaMemsetAsync(ws.deg, 0, sizeof(int) * B * V, st);
   cudaMemsetAsync(err, 0, sizeof(int), st);
+  // fast path: 4-connected grid trees with the adjacency bits in shared memory (one warp per tree)
+  const size_t grid_smem = ((size_t)(V + 3) / 4) * 4 + (size_t)4 * BFS_FRONT * sizeof(int);
+  const bool try_grid = grid_smem <= kMaxTreeSmem;
+  if (try_grid) {
+    cudaFuncSetAttribute(bfs_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+    bfs_grid_kernel<<<(unsigned)B, 32, grid_smem, st>>>(tree_edges, (int)V, sorted_index, sorted_parent, sorted_child,
+                                                        level_start, num_levels, flags);
+  } else {
+    cudaMemsetAsync(flags, 0, sizeof(int) * B, st);
+  }
+  // generic path for whatever the fast path declined (its CTAs return at once otherwise)
   bfs_adj_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div(V, 256), 1024), (unsigned)B), 256, 0, st>>>(tree_edges, ws,
-                                                                                                         (int)V, err);
+                                                                                                         (int)V, err, flags);
   bfs_sort_adj_kernel<<<grid_for(B * V, 256), 256, 0, st>>>(ws, B * V);
   bfs_block_kernel<<<(unsigned)B, NT, 0, st>>>(ws, (int)V, sorted_index, sorted_parent, sorted_child, level_start,
-                                               num_levels);
+                                               num_levels, flags);
   return check_launch();
 }
 
@@ -697,15 +820,15 @@ extern "C" int bxs_refine_forward(const float* feature, const float* edge_weight
   const dim3 grid((unsigned)B, (unsigned)(C + 1));
   if (sm <= kMaxTreeSmem) {
     cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
-    refine_updown_kernel<0, true><<<grid, NT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+    refine_updown_kernel<0, true><<<grid, RNT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, nullptr, aggr, aggr_up, wsum, wsum_up,
-                                                        nullptr, (int)C, (int)V);
+                                                        nullptr, (int)C, (int)V, nullptr, 0);
   } else {
-    refine_updown_kernel<0, false><<<grid, NT, 0, st>>>(feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+    refine_updown_kernel<0, false><<<grid, RNT, 0, st>>>(feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, nullptr, aggr, aggr_up, wsum, wsum_up,
-                                                        rs.bufs, (int)C, (int)V);
+                                                        rs.bufs, (int)C, (int)V, nullptr, 0);
   }
-  refine_div_kernel<<<grid_for(B * C * V, 256), 256, 0, st>>>(aggr, wsum, feature_out, (int)C, (int)V, B * C * V);
+  refine_div_kernel<<<grid_for(B * C * V, 256), 256, 0, st>>>(aggr, wsum, feature_out, (int)C, (int)V, B * C * V, nullptr);
   return check_launch();
 }
 
@@ -725,13 +848,13 @@ extern "C" int bxs_refine_backward_feature(const float* edge_weight, const int32
   const dim3 grid((unsigned)B, (unsigned)C);
   if (sm <= kMaxTreeSmem) {
     cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
-    refine_updown_kernel<1, true><<<grid, NT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+    refine_updown_kernel<1, true><<<grid, RNT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
-                                                        nullptr, nullptr, (int)C, (int)V);
+                                                        nullptr, nullptr, (int)C, (int)V, nullptr, 0);
   } else {
-    refine_updown_kernel<1, false><<<grid, NT, 0, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+    refine_updown_kernel<1, false><<<grid, RNT, 0, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
-                                                        nullptr, rs.bufs, (int)C, (int)V);
+                                                        nullptr, rs.bufs, (int)C, (int)V, nullptr, 0);
   }
   return check_launch();
 }
@@ -752,15 +875,113 @@ extern "C" int bxs_refine_backward_weight(const float* edge_weight, const int32_
   const size_t sm = V * sizeof(float);
   if (sm <= kMaxTreeSmem) {
     cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
-    refine_bwd_weight_kernel<true><<<(unsigned)B, NT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+    refine_bwd_weight_kernel<true><<<(unsigned)B, RNT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                                 level_start, num_levels, feature_out, aggr, aggr_up, wsum,
                                                                 wsum_up, grad_out, grad_weight, nullptr, rs.outd_par,
-                                                                (int)C, (int)V);
+                                                                (int)C, (int)V, nullptr);
   } else {
-    refine_bwd_weight_kernel<false><<<(unsigned)B, NT, 0, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+    refine_bwd_weight_kernel<false><<<(unsigned)B, RNT, 0, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                                  level_start, num_levels, feature_out, aggr, aggr_up, wsum,
                                                                  wsum_up, grad_out, grad_weight, rs.bufs, rs.outd_par,
-                                                                 (int)C, (int)V);
+                                                                 (int)C, (int)V, nullptr);
+  }
+  return check_launch();
+}
+
+// ---------------------------------------------------------------------------------------
+// Grouped forms: n instances share G trees (tree_of [n] -> group).  Order, packed child weights, edge weights and the
+// normaliser exist once per group; per-instance work is one CTA per (instance, channel).
+// ---------------------------------------------------------------------------------------
+extern "C" int bxs_refine_forward_grouped(const float* feature, const float* edge_weight, const int32_t* sorted_index,
+                                          const int32_t* sorted_parent, const int32_t* sorted_child,
+                                          const int32_t* level_start, const int32_t* num_levels, const int32_t* tree_of,
+                                          float* feature_out, float* aggr, float* aggr_up, float* wsum, float* wsum_up,
+                                          void* scratch, int64_t n, int64_t G, int64_t C, int64_t V, bxs_stream_t stream) {
+  if (!feature || !edge_weight || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels ||
+      !tree_of || !feature_out || !aggr || !aggr_up || !wsum || !wsum_up || !scratch || n <= 0 || n >= 65536 || G <= 0 ||
+      G >= 65536 || C <= 0 || C >= 65535 || V <= 0 || V >= (int64_t(1) << 28))
+    return BXS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  RefineScratch rs = carve_refine(scratch, std::max(n, G), C, V);
+  pack_tree(edge_weight, sorted_child, rs, G, V, st);
+  const size_t sm = V * sizeof(float);
+  if (sm <= kMaxTreeSmem) {
+    cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+    refine_updown_kernel<0, true><<<dim3((unsigned)G, 1), RNT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent,
+                                                                        rs.cinfo, rs.cw, level_start, num_levels, nullptr, aggr,
+                                                                        aggr_up, wsum, wsum_up, nullptr, (int)C, (int)V,
+                                                                        nullptr, 1);
+    refine_updown_kernel<0, true><<<dim3((unsigned)n, (unsigned)C), RNT, sm, st>>>(
+        feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw, level_start, num_levels, nullptr, aggr, aggr_up,
+        wsum, wsum_up, nullptr, (int)C, (int)V, tree_of, 0);
+  } else {
+    refine_updown_kernel<0, false><<<dim3((unsigned)G, 1), RNT, 0, st>>>(feature, edge_weight, sorted_index, sorted_parent,
+                                                                        rs.cinfo, rs.cw, level_start, num_levels, nullptr, aggr,
+                                                                        aggr_up, wsum, wsum_up, rs.bufs, (int)C, (int)V,
+                                                                        nullptr, 1);
+    refine_updown_kernel<0, false><<<dim3((unsigned)n, (unsigned)C), RNT, 0, st>>>(
+        feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw, level_start, num_levels, nullptr, aggr, aggr_up,
+        wsum, wsum_up, rs.bufs, (int)C, (int)V, tree_of, 0);
+  }
+  refine_div_kernel<<<grid_for(n * C * V, 256), 256, 0, st>>>(aggr, wsum, feature_out, (int)C, (int)V, n * C * V, tree_of);
+  return check_launch();
+}
+
+extern "C" int bxs_refine_backward_feature_grouped(const float* edge_weight, const int32_t* sorted_index,
+                                                   const int32_t* sorted_parent, const int32_t* sorted_child,
+                                                   const int32_t* level_start, const int32_t* num_levels,
+                                                   const int32_t* tree_of, const float* wsum, const float* grad_out,
+                                                   float* grad_feature, void* scratch, int64_t n, int64_t G, int64_t C,
+                                                   int64_t V, bxs_stream_t stream) {
+  if (!edge_weight || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels || !tree_of || !wsum ||
+      !grad_out || !grad_feature || !scratch || n <= 0 || n >= 65536 || G <= 0 || G >= 65536 || C <= 0 || C >= 65535 ||
+      V <= 0 || V >= (int64_t(1) << 28))
+    return BXS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  RefineScratch rs = carve_refine(scratch, std::max(n, G), C, V);
+  pack_tree(edge_weight, sorted_child, rs, G, V, st);
+  const size_t sm = V * sizeof(float);
+  const dim3 grid((unsigned)n, (unsigned)C);
+  if (sm <= kMaxTreeSmem) {
+    cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+    refine_updown_kernel<1, true><<<grid, RNT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+                                                        level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
+                                                        nullptr, nullptr, (int)C, (int)V, tree_of, 0);
+  } else {
+    refine_updown_kernel<1, false><<<grid, RNT, 0, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+                                                        level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
+                                                        nullptr, rs.bufs, (int)C, (int)V, tree_of, 0);
+  }
+  return check_launch();
+}
+
+// grad_weight [n,V]: per INSTANCE (the caller sums the rows of a group: d/d w of a shared tree)
+extern "C" int bxs_refine_backward_weight_grouped(const float* edge_weight, const int32_t* sorted_index,
+                                                  const int32_t* sorted_parent, const int32_t* sorted_child,
+                                                  const int32_t* level_start, const int32_t* num_levels,
+                                                  const int32_t* tree_of, const float* feature_out, const float* aggr,
+                                                  const float* aggr_up, const float* wsum, const float* wsum_up,
+                                                  const float* grad_out, float* grad_weight, void* scratch, int64_t n,
+                                                  int64_t G, int64_t C, int64_t V, bxs_stream_t stream) {
+  if (!edge_weight || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels || !tree_of ||
+      !feature_out || !aggr || !aggr_up || !wsum || !wsum_up || !grad_out || !grad_weight || !scratch || n <= 0 ||
+      n >= 65536 || G <= 0 || G >= 65536 || C <= 0 || V <= 0 || V >= (int64_t(1) << 28))
+    return BXS_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  RefineScratch rs = carve_refine(scratch, std::max(n, G), C, V);
+  pack_tree(edge_weight, sorted_child, rs, G, V, st);
+  const size_t sm = V * sizeof(float);
+  if (sm <= kMaxTreeSmem) {
+    cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+    refine_bwd_weight_kernel<true><<<(unsigned)n, RNT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+                                                                level_start, num_levels, feature_out, aggr, aggr_up, wsum,
+                                                                wsum_up, grad_out, grad_weight, nullptr, rs.outd_par, (int)C,
+                                                                (int)V, tree_of);
+  } else {
+    refine_bwd_weight_kernel<false><<<(unsigned)n, RNT, 0, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
+                                                                 level_start, num_levels, feature_out, aggr, aggr_up, wsum,
+                                                                 wsum_up, grad_out, grad_weight, rs.bufs, rs.outd_par, (int)C,
+                                                                 (int)V, tree_of);
   }
   return check_launch();
 }

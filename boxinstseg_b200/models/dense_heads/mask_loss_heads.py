@@ -16,17 +16,11 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ...ops.dynconv import box2mask_mask_pred, dynconv1x1, solo_dynamic_conv
+from ...ops.resize import bilinear_resize, scale_target as _scale_target   # a18: F.interpolate / _scale_target as kernels
 from ...ops.tree_filter import MinimumSpanningTree, TreeFilter2D
 from ..builder import HEADS, build_loss, register
-from ..losses import LCM, mil_loss
+from ..losses import LCM, levelset_assembly, mil_loss
 from .meanfield import MeanField
-
-
-def _scale_target(t, size=(96, 96)):
-    """mmdet/models/utils/misc.py:75-86."""
-    if t.dim() == 3:
-        t = t.unsqueeze(1)
-    return F.interpolate(t, size=size, mode='bilinear', align_corners=False)
 
 
 def _phi_and_pixels(mask_pred, box_mask):
@@ -62,29 +56,40 @@ class BoxSOLOv2Head(nn.Module):
             flat = kernel_pred.permute(0, 2, 3, 1).reshape(B, S * S, C)
             ins = [dynconv1x1(feature_pred[b:b + 1], flat[b:b + 1, cells[b]])[0] for b in range(B)]
         if out_size is not None:
-            up = lambda t: F.interpolate(t, size=out_size, mode='bilinear')   # noqa: E731  (:213)
+            up = lambda t: bilinear_resize(t, out_size)   # noqa: E731  (:213, align_corners=False)
             ins = up(ins) if cells is None else [up(t[None])[0] for t in ins]
         return ins
 
     # a17 -- box_solov2_head.py:334-367
-    def mask_loss(self, ins_preds, ins_labels, img_targets, lst_targets, shared_trees=True):
-        """Per level lists: ins_pred [n,h,w] logits, ins_label [n,h,w] box masks, img_target [n,3,h,w],
-        lst_target [n,5,h,w].  ``shared_trees``: instances of one image share their MSTs -- the reference
-        rebuilds identical trees per instance (:300-305,353); here identical rows are detected and deduplicated,
-        which does not change the result."""
+    def mask_loss(self, ins_preds, ins_labels, img_targets, lst_targets, shared_trees=True, inst_imgs=None):
+        """Per level lists: ins_pred [n,h,w] logits, ins_label [n,h,w] box masks, and either
+          * img_target [n,3,h,w], lst_target [n,5,h,w] per INSTANCE (the reference's tensors, :296-305), or
+          * with ``inst_imgs`` (list of int tensors [n], image of each instance): img_target [B,3,h,w],
+            lst_target [B,5,h,w] per IMAGE -- the trees, their BFS orders, edge weights and normalisers are then
+            built once per image and shared by its instances (``tree_of``), with no host synchronisation at all.
+        ``shared_trees`` (per-instance inputs only): identical rows are detected and their MSTs shared; the reference
+        rebuilds identical trees per instance (:300-305,353).  Same losses either way.
+        Per level: one sigmoid, BoxProjectionLoss, ONE launch per level-set term (sigmoid / cat / * box / clamp inside,
+        ``levelset_assembly``), two tree filters."""
         loss_project, loss_levelset = [], []
-        for ins_pred, box_mask, img_t, lst_t in zip(ins_preds, ins_labels, img_targets, lst_targets):
+        w_ls = self.loss_levelset.loss_weight
+        for lvl, (ins_pred, box_mask, img_t, lst_t) in enumerate(zip(ins_preds, ins_labels, img_targets, lst_targets)):
             if ins_pred.size(0) == 0:
                 continue
             mask_pred = torch.sigmoid(ins_pred.unsqueeze(1))
             box = box_mask.unsqueeze(1).to(mask_pred.dtype)
             loss_project.append(self.loss_boxpro(mask_pred, box))
-            phi, pix = _phi_and_pixels(mask_pred, box)
-            loss_img = self.loss_levelset(phi, img_t * box, pix) * 0.05
-            f_img = self.tree_filter(mask_pred, img_t, self._mst(img_t, shared_trees))
-            f_lst = self.tree_filter(f_img, lst_t, self._mst(lst_t, shared_trees), low_tree=False)
-            high = torch.cat((f_img, f_lst), dim=1) * box
-            loss_feat = self.loss_levelset(phi, high, pix) * 5.0
+            if inst_imgs is not None:
+                ii = inst_imgs[lvl]
+                img_inst = img_t.index_select(0, ii.long())
+                f_img = self.tree_filter(mask_pred, img_t, self.mst(img_t), tree_of=ii)
+                f_lst = self.tree_filter(f_img, lst_t, self.mst(lst_t), low_tree=False, tree_of=ii)
+            else:
+                img_inst = img_t
+                f_img = self.tree_filter(mask_pred, img_t, self._mst(img_t, shared_trees))
+                f_lst = self.tree_filter(f_img, lst_t, self._mst(lst_t, shared_trees), low_tree=False)
+            loss_img = levelset_assembly(ins_pred, box, img_inst, w_ls) * 0.05             # :341-351
+            loss_feat = levelset_assembly(ins_pred, box, torch.cat((f_img, f_lst), dim=1), w_ls) * 5.0   # :357-360
             loss_levelset.append(loss_img + loss_feat)
         return dict(loss_boxpro=torch.cat(loss_project).mean(), loss_levelset=torch.cat(loss_levelset).mean())
 
@@ -127,33 +132,33 @@ class DiscoBoxSOLOv2Head(nn.Module):
     # a17 -- discobox_head.py:1266-1300, 1302-1339 (without corr_loss)
     def mask_loss(self, s_ins_pred_list, ins_labels, img_ind_list, color_feats, t_ins_pred_list=None, use_loss_ts=True):
         """Per level: s_ins_pred [n,h,w] logits, ins_label [n,h,w] box masks, img_inds [n];
-        color_feats [B,3,h,w] = image resized with align_corners=True (:1201)."""
-        mean_fields = [MeanField(cf.unsqueeze(0), alpha0=self.alpha0, theta0=self.theta0, theta1=self.theta1,
-                                 theta2=self.theta2, iter=self.crf_max_iter, kernel_size=self.mkernel,
-                                 base=self.crf_base) for cf in color_feats] if use_loss_ts else []
+        color_feats [B,3,h,w] = image resized with align_corners=True (:1201).
+        No host synchronisation and no boolean indexing: instances with an all-zero target (removed by the reference,
+        :1283-1287) stay in the batch with weight 0 -- the mean over the kept instances is a weighted mean -- and ONE
+        mean-field module holds the bilateral kernels of all images (``obj_img`` picks the image of each object)."""
+        mf = MeanField(color_feats, alpha0=self.alpha0, theta0=self.theta0, theta1=self.theta1, theta2=self.theta2,
+                       iter=self.crf_max_iter, kernel_size=self.mkernel, base=self.crf_base) if use_loss_ts else None
         t_list = t_ins_pred_list if t_ins_pred_list is not None else s_ins_pred_list
-        loss_ins, loss_ts = [], []
+        num_ins, num_ts, den = [], [], []
         for s_in, t_in, img_inds, target in zip(s_ins_pred_list, t_list, img_ind_list, ins_labels):
-            if s_in is None:
+            if s_in is None or s_in.shape[0] == 0:
                 continue
-            keep = target.flatten(1).sum(1) > 0                      # remove all-zero targets (:1283-1287)
-            if not bool(keep.any()):
-                continue
-            s = torch.sigmoid(s_in)[keep]
-            t = s if t_ins_pred_list is None else torch.sigmoid(t_in)[keep]
-            img_inds, target = img_inds[keep], target[keep].float()
-            loss_ins.append(mil_loss(None, s, s, target))
+            target = target.float()
+            keep = (target.flatten(1).sum(1) > 0).float()            # all-zero targets carry weight 0 (:1283-1287)
+            s = torch.sigmoid(s_in)
+            t = s if t_ins_pred_list is None else torch.sigmoid(t_in)
+            num_ins.append((mil_loss(None, s, s, target) * keep).sum())
+            den.append(keep.sum())
             if use_loss_ts:
                 enlarged = F.max_pool2d(target.unsqueeze(1), kernel_size=3, stride=1, padding=1).squeeze(1)
-                for img_idx, mf in enumerate(mean_fields):
-                    sel = img_inds == img_idx
-                    if not bool(sel.any()):
-                        continue
-                    pseudo, _ = mf(((t[sel] + s[sel]) / 2).unsqueeze(1), target[sel].unsqueeze(1))
-                    loss_ts.append(_disco_dice(s[sel] * enlarged[sel], pseudo))
+                pseudo, _ = mf(((t + s) / 2).unsqueeze(1), target.unsqueeze(1), obj_img=img_inds)
+                num_ts.append((_disco_dice(s * enlarged, pseudo) * keep).sum())
         zero = color_feats.new_zeros(())
-        l_ins = torch.cat(loss_ins).mean() * self.ins_loss_weight if loss_ins else zero
-        l_ts = torch.cat(loss_ts).mean() * self.ts_loss_weight if (use_loss_ts and loss_ts) else zero
+        if not num_ins:
+            return dict(loss_ins=zero, loss_ts=zero)
+        count = torch.stack(den).sum().clamp(min=1.0)
+        l_ins = torch.stack(num_ins).sum() / count * self.ins_loss_weight
+        l_ts = torch.stack(num_ts).sum() / count * self.ts_loss_weight if (use_loss_ts and num_ts) else zero
         return dict(loss_ins=l_ins, loss_ts=l_ts)
 
 
@@ -183,29 +188,38 @@ class Box2MaskHead(nn.Module):
         return box2mask_mask_pred(mask_embed, mask_feature)
 
     # a17 -- box2mask_head.py:229-233, 269-335
-    def mask_loss_single(self, mask_preds, mask_targets, num_per_img, norm_img, lst_feat):
+    def mask_loss_single(self, mask_preds, mask_targets, num_per_img, norm_img, lst_feat, trees=None):
         """mask_preds [n,h,w] matched logits (images concatenated), mask_targets [n,H,W] box masks,
-        num_per_img: list of matched queries per image; norm_img [B,3,*,*], lst_feat [B,1,*,*]."""
+        num_per_img: list of matched queries per image; norm_img [B,3,*,*], lst_feat [B,1,*,*].
+        ``trees`` (optional): the ``image_trees`` of this batch -- the image MST at 96x96 does not depend on the decoder
+        layer, the reference rebuilds it in each of its 10 loss_single calls (:269-272).
+        Every resize is the bilinear kernel of ops.resize (a18), the two level-set terms are one launch each (a17), the
+        trees / orders / edge weights / normalisers exist once per image (``tree_of``); no host synchronisation."""
         pred_shape = mask_preds.shape[-2:]
-        norm_img = F.interpolate(norm_img, pred_shape, mode='bilinear', align_corners=False)
-        lst_feat = F.interpolate(lst_feat, pred_shape, mode='bilinear', align_corners=False)
+        norm_img = bilinear_resize(norm_img, pred_shape)              # :232-233
+        lst_feat = bilinear_resize(lst_feat, pred_shape)
         if mask_preds.shape[0] == 0:                                  # zero match (:264-268)
             return mask_preds.sum(), mask_preds.sum()
-        img_tree = self.mst(_scale_target(norm_img))                  # one tree per IMAGE (:269-272)
-        lst_tree = self.mst(_scale_target(lst_feat))
-        rep = torch.as_tensor(num_per_img, device=mask_preds.device)
-        img_targets = norm_img.repeat_interleave(rep, 0)
-        lst_targets = lst_feat.repeat_interleave(rep, 0)
-        box = F.interpolate(mask_targets.unsqueeze(1).to(mask_preds.dtype), pred_shape, mode='bilinear', align_corners=False)
+        dev = mask_preds.device
+        img96_b, lst96_b = _scale_target(norm_img), _scale_target(lst_feat)       # per IMAGE, :269-272
+        img_tree = trees if trees is not None else self.mst(img96_b)
+        lst_tree = self.mst(lst96_b)
+        # instance -> image, built from device-side fills only (host ints in, no copy: CUDA-graph capturable)
+        tree_of = torch.cat([torch.full((int(c),), i, device=dev, dtype=torch.int32) for i, c in enumerate(num_per_img)])
+        box = bilinear_resize(mask_targets.unsqueeze(1).to(mask_preds.dtype), pred_shape)   # :300
         s = torch.sigmoid(mask_preds.unsqueeze(1))
         loss_project = self.loss_box(s, box).mean()
-        phi, pix = _phi_and_pixels(s, box)
-        loss_img = self.loss_mask(phi, img_targets * box, pix).mean() * 0.05
-        img96, lst96, s96 = _scale_target(img_targets), _scale_target(lst_targets), _scale_target(s)
-        f_img = self.tree_filter(s96, img96, img_tree.repeat_interleave(rep, 0))
-        f_lst = self.tree_filter(f_img, lst96, lst_tree.repeat_interleave(rep, 0), low_tree=False)
-        up = lambda t: F.interpolate(t, pred_shape, mode='bilinear', align_corners=False)   # noqa: E731
-        deep = torch.cat((up(f_img), up(f_lst)), dim=1) * box
-        loss_feat = self.loss_mask(phi, deep, pix).mean() * 5.0
-        loss_lcm = 0.2 * LCM(img96, s96, _scale_target(box))
+        w_ls = self.loss_mask.loss_weight
+        loss_img = levelset_assembly(mask_preds, box, norm_img.index_select(0, tree_of.long()), w_ls).mean() * 0.05   # :305-312
+        s96 = _scale_target(s)
+        f_img = self.tree_filter(s96, img96_b, img_tree, tree_of=tree_of)                  # :315-322
+        f_lst = self.tree_filter(f_img, lst96_b, lst_tree, low_tree=False, tree_of=tree_of)
+        deep = torch.cat((bilinear_resize(f_img, pred_shape), bilinear_resize(f_lst, pred_shape)), dim=1)   # :323-324
+        loss_feat = levelset_assembly(mask_preds, box, deep, w_ls).mean() * 5.0            # :325-327
+        loss_lcm = 0.2 * LCM(img96_b.index_select(0, tree_of.long()), s96, _scale_target(box))   # :329-331
         return loss_project, loss_img + loss_feat + loss_lcm
+
+    def image_trees(self, norm_img, pred_shape):
+        """MST of every image at 96x96 (box2mask_head.py:232,269-272): identical for all decoder layers of a step."""
+        with torch.no_grad():
+            return self.mst(_scale_target(bilinear_resize(norm_img, pred_shape)))

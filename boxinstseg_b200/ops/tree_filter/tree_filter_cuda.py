@@ -158,3 +158,57 @@ def refine_backward_weight(feature_in, edge_weight, sorted_index, sorted_parent,
                                                    L.ptr(_scratch(B, C, V, g.device)), B, C, V, L.stream()),
                 'refine_backward_weight')
     return _to_theirs(gw, perm)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# grouped forms (not part of the reference's pybind surface): n instances share G trees, tree_of [n] -> group
+# ----------------------------------------------------------------------------------------------------------------
+def refine_forward_grouped(feature_in, edge_weight, sorted_index, sorted_parent, sorted_child, levels, tree_of):
+    f, w = _f32(feature_in), _f32(edge_weight)
+    idx, par, chd = _i32(sorted_index), _i32(sorted_parent), _i32(sorted_child)
+    L.require_cuda(f, w, idx, par, chd, tree_of)
+    lvl, nlv = levels
+    n, C, V = f.shape
+    G = w.shape[0]
+    out, aggr, aggr_up = torch.empty_like(f), torch.empty_like(f), torch.empty_like(f)
+    wsum = torch.empty((G, V), dtype=torch.float32, device=f.device)
+    wsum_up = torch.empty_like(wsum)
+    with torch.cuda.device(f.device):
+        L.check(L.lib().bxs_refine_forward_grouped(L.ptr(f), L.ptr(w), L.ptr(idx), L.ptr(par), L.ptr(chd), L.ptr(lvl), L.ptr(nlv),
+                                                   L.ptr(tree_of), L.ptr(out), L.ptr(aggr), L.ptr(aggr_up), L.ptr(wsum),
+                                                   L.ptr(wsum_up), L.ptr(_scratch(max(n, G), C, V, f.device)), n, G, C, V,
+                                                   L.stream()), 'refine_forward_grouped')
+    return out, aggr, aggr_up, wsum, wsum_up
+
+
+def refine_backward_feature_grouped(edge_weight, sorted_index, sorted_parent, sorted_child, levels, tree_of, weight_sum,
+                                    grad_out):
+    w, g = _f32(edge_weight), _f32(grad_out)
+    lvl, nlv = levels
+    n, C, V = g.shape
+    G = w.shape[0]
+    gf = torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        L.check(L.lib().bxs_refine_backward_feature_grouped(L.ptr(w), L.ptr(sorted_index), L.ptr(sorted_parent),
+                                                            L.ptr(sorted_child), L.ptr(lvl), L.ptr(nlv), L.ptr(tree_of),
+                                                            L.ptr(weight_sum), L.ptr(g), L.ptr(gf),
+                                                            L.ptr(_scratch(max(n, G), C, V, g.device)), n, G, C, V, L.stream()),
+                'refine_backward_feature_grouped')
+    return gf
+
+
+def refine_backward_weight_grouped(edge_weight, sorted_index, sorted_parent, sorted_child, levels, tree_of, feature_out,
+                                   feature_aggr, feature_aggr_up, weight_sum, weight_sum_up, grad_out):
+    w, g = _f32(edge_weight), _f32(grad_out)
+    lvl, nlv = levels
+    n, C, V = g.shape
+    G = w.shape[0]
+    gw = torch.empty((n, V), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        L.check(L.lib().bxs_refine_backward_weight_grouped(L.ptr(w), L.ptr(sorted_index), L.ptr(sorted_parent),
+                                                           L.ptr(sorted_child), L.ptr(lvl), L.ptr(nlv), L.ptr(tree_of),
+                                                           L.ptr(feature_out), L.ptr(feature_aggr), L.ptr(feature_aggr_up),
+                                                           L.ptr(weight_sum), L.ptr(weight_sum_up), L.ptr(g), L.ptr(gw),
+                                                           L.ptr(_scratch(max(n, G), C, V, g.device)), n, G, C, V, L.stream()),
+                'refine_backward_weight_grouped')
+    return gw

@@ -138,12 +138,13 @@ int bxs_boxinst_loss_fused_backward(const void* workspace, const float* g_prj, c
  * order) and the logit-independent weight total of condinst_head.py:1318-1319, derived from the TARGETS only
  * (edge_bits, rects, the instance->GT assignment).  Build it once per target set and pass it to
  * bxs_boxinst_loss_fused_forward_planned(); bxs_boxinst_loss_fused_forward() (no plan argument) builds one in the
- * tail of its workspace on every call.  plan: bxs_boxinst_loss_plan_bytes() bytes, 16-byte aligned. */
+ * tail of its workspace on every call.  plan: bxs_boxinst_loss_plan_bytes() bytes, 16-byte aligned, read-only for
+ * the loss kernels. */
 int64_t bxs_boxinst_loss_plan_bytes(int64_t N, int64_t H, int64_t W, int dilation);
 int bxs_boxinst_loss_plan(const uint8_t* edge_bits, const int32_t* rects, const int32_t* inst_gt,
                           const int32_t* gt_img, void* plan, int64_t N, int64_t H, int64_t W, int dilation,
                           bxs_stream_t stream);
-int bxs_boxinst_loss_fused_forward_planned(const float* logits, const uint8_t* edge_bits, const void* plan,
+int bxs_boxinst_loss_fused_forward_planned(const float* logits, const uint8_t* edge_bits, void* plan,
                                            const float* iter_ptr, float warmup_iters, void* workspace,
                                            void* sched_state, float* losses_out, float* g_logits, int64_t N,
                                            int64_t H, int64_t W, int dilation, bxs_stream_t stream);
@@ -300,6 +301,31 @@ int bxs_dynconv1x1_forward(const float* feat, const float* kernels, float* out, 
  * --------------------------------------------------------------------------------------- */
 int bxs_upsampled_rowcol_max(const float* x, float* row_prof, float* col_prof, void* workspace, int64_t n,
                              int64_t h, int64_t w, int64_t H, int64_t W, int sigmoid_act, bxs_stream_t stream);
+
+/* Grouped forms of the three refine entry points: n instances share G trees (tree_of [n] int32 -> group), as the
+ * heads use them -- the instances of one image share the image's tree (box_solov2_head.py:300-305,353;
+ * box2mask_head.py:271-276).  edge_weight / sorted_* / level_start / num_levels / wsum / wsum_up are per GROUP
+ * ([G,...]); feature, feature_out, aggr, aggr_up, grad_* are per INSTANCE ([n,...]).  The normaliser is computed once
+ * per group.  bxs_refine_backward_weight_grouped returns d/d edge_weight per instance [n,V]; the caller sums the
+ * rows of a group.  scratch: bxs_refine_scratch_bytes(max(n, G), C, V). */
+int bxs_refine_forward_grouped(const float* feature, const float* edge_weight, const int32_t* sorted_index,
+                               const int32_t* sorted_parent, const int32_t* sorted_child,
+                               const int32_t* level_start, const int32_t* num_levels, const int32_t* tree_of,
+                               float* feature_out, float* aggr, float* aggr_up, float* wsum, float* wsum_up,
+                               void* scratch, int64_t n, int64_t G, int64_t C, int64_t V, bxs_stream_t stream);
+int bxs_refine_backward_feature_grouped(const float* edge_weight, const int32_t* sorted_index,
+                                        const int32_t* sorted_parent, const int32_t* sorted_child,
+                                        const int32_t* level_start, const int32_t* num_levels,
+                                        const int32_t* tree_of, const float* wsum, const float* grad_out,
+                                        float* grad_feature, void* scratch, int64_t n, int64_t G, int64_t C,
+                                        int64_t V, bxs_stream_t stream);
+int bxs_refine_backward_weight_grouped(const float* edge_weight, const int32_t* sorted_index,
+                                       const int32_t* sorted_parent, const int32_t* sorted_child,
+                                       const int32_t* level_start, const int32_t* num_levels,
+                                       const int32_t* tree_of, const float* feature_out, const float* aggr,
+                                       const float* aggr_up, const float* wsum, const float* wsum_up,
+                                       const float* grad_out, float* grad_weight, void* scratch, int64_t n,
+                                       int64_t G, int64_t C, int64_t V, bxs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * a18  bilinear resize      replaces F.interpolate(mode='bilinear') as the heads call it:

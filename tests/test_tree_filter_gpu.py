@@ -54,6 +54,29 @@ def _check_bfs(idx, par, chd, tree, V):
     for pos in range(V):
         kids = [k for k in c[pos] if k > 0]
         assert all(p[k] == pos for k in kids) and len(kids) == int(np.sum(p[1:] == pos))
+        # the deterministic order both BFS paths promise: children adjacent in position, ascending in vertex id
+        assert kids == list(range(kids[0], kids[0] + len(kids))) if kids else True
+        assert [int(i[k]) for k in kids] == sorted(int(i[k]) for k in kids)
+
+
+def test_bfs_generic_path_on_a_non_grid_tree():
+    """A random (non-grid) tree takes the generic adjacency-list BFS; a grid tree takes the shared-memory bit-adjacency
+    fast path.  Both must satisfy the same contract."""
+    from boxinstseg_b200.ops.tree_filter import bfs
+    gen = torch.Generator().manual_seed(3)
+    V = 700
+    par = (torch.rand(V - 1, generator=gen) * torch.arange(1, V)).long().clamp(max=V - 2)      # parent of vertex k+1 in [0, k]
+    deg = torch.zeros(V, dtype=torch.long)
+    edges = []
+    for k in range(1, V):                       # keep every degree <= 4 (bfs_forward's max_adj)
+        cand = int(par[k - 1])
+        while deg[cand] >= 3:
+            cand = (cand + 1) % k
+        deg[cand] += 1; deg[k] += 1
+        edges.append((cand, k))
+    tree = torch.tensor(edges, dtype=torch.int32).unsqueeze(0).to(DEV)
+    idx, p, c = bfs(tree, 4)
+    _check_bfs(idx[0], p[0], c[0], tree[0], V)
 
 
 def test_bfs_valid_and_deterministic():
@@ -144,3 +167,31 @@ def test_box2mask_call_pattern():
     (s1.sum() + s2.sum()).backward()
     assert torch.isfinite(preds.grad).all() and torch.isfinite(lst.grad).all()
     assert 0.0 <= float(s2.min()) and float(s2.max()) <= 1.0 + 1e-5       # a normalised filter of values in [0,1]
+
+
+@pytest.mark.parametrize('G,per,C,h,w,low', [(2, [3, 2], 1, 24, 30, True), (2, [1, 4], 1, 24, 30, False), (3, [2, 2, 1], 2, 96, 96, False)])
+def test_grouped_tree_filter_equals_repeated_trees(G, per, C, h, w, low):
+    """tree_of: n instances sharing G trees == the reference's repeat-per-instance call pattern (box2mask_head.py:271-276)."""
+    from boxinstseg_b200.ops.tree_filter import MinimumSpanningTree, TreeFilter2D
+    gen = torch.Generator().manual_seed(G * h)
+    guide = torch.randn(G, 3, h, w, generator=gen).to(DEV)
+    embed = (torch.randn(G, 5, h, w, generator=gen) * (0.05 if low else 0.4)).to(DEV)
+    rep = torch.tensor(per, device=DEV)
+    n = int(rep.sum())
+    tree_of = torch.repeat_interleave(torch.arange(G, device=DEV), rep).to(torch.int32)
+    feat = torch.rand(n, C, h, w, generator=gen).to(DEV)
+    gout = torch.randn(n, C, h, w, generator=gen).to(DEV)
+    tree = MinimumSpanningTree(TreeFilter2D.norm2_distance)(guide)
+    tf = TreeFilter2D()
+    f1, e1 = feat.clone().requires_grad_(True), embed.clone().requires_grad_(True)
+    o1 = tf(f1, e1, tree, low_tree=low, tree_of=tree_of)
+    f2, e2 = feat.clone().requires_grad_(True), embed.clone().requires_grad_(True)
+    o2 = tf(f2, e2.repeat_interleave(rep, 0), tree.repeat_interleave(rep, 0), low_tree=low)
+    assert rel_err(o1, o2) <= 1e-6
+    g1 = torch.autograd.grad((o1 * gout).sum(), [f1, e1], allow_unused=True)
+    g2 = torch.autograd.grad((o2 * gout).sum(), [f2, e2], allow_unused=True)
+    assert rel_err(g1[0], g2[0]) <= 1e-6
+    if low:
+        assert g1[1] is None and g2[1] is None
+    else:
+        assert rel_err(g1[1], g2[1]) <= 1e-5

@@ -11,7 +11,7 @@ if len(sys.argv) > 1 and sys.argv[1] == 'build':
     os.makedirs(os.path.join(B.LIBDIR, 'obj_trace'), exist_ok=True)
     for src in B.sources():
         obj = os.path.join(B.LIBDIR, 'obj_trace', os.path.basename(src)[:-3] + '.o')
-        if 'onepass' in src or not os.path.exists(obj):
+        if 'onepass' in src or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), B._headers_mtime()):
             subprocess.run([B._nvcc()] + B.NVCC_FLAGS + ['-DBXS_OP_TRACE', '-c', src, '-o', obj], check=True)
         objs.append(obj)
     subprocess.run([B._nvcc(), '-shared', '-o', TRACE_LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'], check=True)
@@ -79,4 +79,5 @@ print('finalize CTAs: launch   ', st((fin[:, 0] - t0).tolist()))
 print('finalize CTAs: released ', st((fin[:, 1] - t0).tolist()))
 print('finalize CTAs: done     ', st((fin[:, 2] - t0).tolist()))
 print('finalize CTAs: duration ', st((fin[:, 2] - fin[:, 1]).tolist()))
+print('finalize CTAs: released -> first barrier ', st((fin[:, 3] - fin[:, 1]).tolist()))
 print('losses', out.tolist())
