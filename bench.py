@@ -91,6 +91,72 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
 
 
+def pin_to_numa_node(local_rank, world=1):
+    """Keep this rank's host threads (launch loop, pinned-memory staging) on the CPU socket its GPU hangs off: the e2e
+    path moves 72 MB / step / rank over PCIe, and round 1's 8-rank e2e lost ~35 % to cross-socket traffic and launch
+    contention.  Topology of the 8 x B200 boxes of this pool (SCALE_r01.json): GPUs 0-3 <-> CPUs 0-31,64-95; GPUs 4-7 <->
+    CPUs 32-63,96-127.  Best effort: any failure leaves the affinity alone."""
+    try:
+        ncpu = os.cpu_count() or 0
+        if ncpu < 128 or not hasattr(os, 'sched_setaffinity'):
+            return None
+        half = ncpu // 4
+        node = 0 if local_rank < 4 else 1
+        cpus = set(range(node * half, (node + 1) * half)) | set(range(2 * half + node * half, 2 * half + (node + 1) * half))
+        # one slice of the node per rank so that the ranks of a socket do not fight for the same cores
+        per = min(4, max(1, (world + 1) // 2))          # ranks sharing this socket
+        mine = sorted(cpus)[(local_rank % 4 % per) * (len(cpus) // per):(local_rank % 4 % per + 1) * (len(cpus) // per)]
+        os.sched_setaffinity(0, mine)
+        if world > 1:
+            torch.set_num_threads(max(1, min(8, len(mine))))
+        return f'{mine[0]}-{mine[-1]} ({len(mine)} cpus, numa node {node})'
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def ddp_allreduce_leg(dist, dev, world, loss_step, steps):
+    """The one exchange step of a data-parallel iteration: the DDP gradient all-reduce of BoxInst R-50,
+    ~136 MB fp32 in 25 MB buckets (mmdet/apis/train.py:153-161 wraps the model in MMDistributedDataParallel), NCCL over
+    NVLink, issued asynchronously so that it overlaps the mask-loss step.  Returns busbw and the exposed time."""
+    total_bytes, bucket_bytes = 136 * 2 ** 20, 25 * 2 ** 20
+    sizes = [bucket_bytes] * (total_bytes // bucket_bytes) + ([total_bytes % bucket_bytes] if total_bytes % bucket_bytes else [])
+    buckets = [torch.randn(b // 4, device=dev) for b in sizes]
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    def comm_only(i):
+        for w_ in [dist.all_reduce(b, async_op=True) for b in buckets]:
+            w_.wait()
+
+    def loss_and_comm(i):
+        works = [dist.all_reduce(b, async_op=True) for b in buckets]     # NCCL's stream: overlaps the loss kernels
+        loss_step(i)
+        for w_ in works:
+            w_.wait()
+
+    for i in range(3):
+        loss_and_comm(i)
+    k = max(10, min(steps, 50))
+    ms_comm, ms_loss, ms_both = timed(comm_only, k), timed(loss_step, k), timed(loss_and_comm, k)
+    t = torch.tensor([ms_comm, ms_loss, ms_both], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_comm, ms_loss, ms_both = t.tolist()
+    busbw = 2.0 * (world - 1) / world * total_bytes / (ms_comm * 1e-3) / 1e9
+    return {'bytes': total_bytes, 'buckets': len(sizes), 'allreduce_ms': ms_comm, 'allreduce_busbw_gbs': busbw,
+            'loss_step_eager_ms': ms_loss, 'loss_step_plus_allreduce_ms': ms_both,
+            'exposed_comm_us': max(ms_both - ms_loss, 0.0) * 1e3,
+            'what': 'fp32 gradient all-reduce of BoxInst R-50 (136 MB, 25 MB buckets, NCCL, async) overlapped with the eager '
+                    'mask-loss step; reported next to the replica metric, not folded into it (the loss itself has no collective)'}
+
+
 def reduce_max_over_ranks(values, dist, device):
     """Per-rank timings -> MAX over ranks (the N>1 contract); identity without a process group."""
     t = torch.tensor(values, device=device, dtype=torch.float64)
@@ -229,6 +295,7 @@ def main_cuda(args, rank, world, local_rank):
     lib = L.lib()                                # fail loudly if the CUDA extension is missing
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
+    pinned_cpus = pin_to_numa_node(local_rank, world)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -430,6 +497,7 @@ def main_cuda(args, rank, world, local_rank):
     for i in range(4):
         e2e_step(i)
     ms_e2e = timed_streams(e2e_step, args.steps)
+    ddp = ddp_allreduce_leg(dist, dev, world, step, args.steps) if dist is not None else None
     clocks = sampler.stop()
 
     ms_step, ms_e2e, ms_eager, us_fwd, us_bwd, us_one_fwd, us_one_bwd, us_one_step = reduce_max_over_ranks(
@@ -485,6 +553,10 @@ def main_cuda(args, rank, world, local_rank):
         'gpu_launches': 3 * steps_timed,        # onepass_main + onepass_finalize + onepass_backward kernels per step
         'clocks': clocks,
     }
+    if ddp is not None:
+        line['ddp_allreduce'] = ddp
+    if pinned_cpus:
+        line['config']['cpu_affinity_rank0'] = pinned_cpus
     if cpu_ms is not None:
         line['cpu_baseline'] = {'value': cpu_ms, 'unit': 'ms/img', 'cores': cores, 'kind': 'port', 'sample': sample}
     if world == 1 and not args.no_cpu_baseline:

@@ -494,7 +494,7 @@ template <int D>
 __global__ void __launch_bounds__(OP_FIN_NT)
 wq_finalize_kernel(const float* __restrict__ logits, unsigned char* __restrict__ plan, int N, int H, int W,
                    OpWorkspace ws, WqSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
-                   float* __restrict__ losses_out, float* __restrict__ g_logits) {
+                   float* __restrict__ losses_out, float* __restrict__ g_logits, int first_pass) {
   constexpr int NWF = OP_FIN_NT / 32;
   __shared__ float s_f[4][NWF];
   __shared__ float s_coef[512];       // row coefficients
@@ -506,138 +506,163 @@ wq_finalize_kernel(const float* __restrict__ logits, unsigned char* __restrict__
   if (tid == 0 && g_op_trace) {
     unsigned long long t_;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
-    g_op_trace[(kFinTrace + blockIdx.x * 4 + 0) * 2] = t_;
+    g_op_trace[(kFinTrace + blockIdx.x * 8 + 0) * 2] = t_;
   }
 #endif
   // Launched with programmatic stream serialization and NOT waiting for the main grid to retire (griddepcontrol.wait
   // costs ~2.5 us after the last warp's exit: grid completion + flush): the CTAs become resident as main CTAs leave
   // and poll the flag the main kernel's last warp publishes after every warp has fenced its results.  The main kernel
   // never waits for this one, so there is nothing to deadlock on.
-  if (tid == 0) {
-    unsigned ready = 0u;
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ready) : "l"(&sched->ticket) : "memory");
-      if (ready) break;
-      __nanosleep(40);
-    }
-  }
-  __syncthreads();
-#ifdef BXS_OP_TRACE
-  if (tid == 0 && g_op_trace) {
-    unsigned long long t_;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
-    g_op_trace[(kFinTrace + blockIdx.x * 4 + 1) * 2] = t_;
-  }
-#endif
+  //
+  // While it waits, a CTA runs the whole body ONCE AS A REHEARSAL (pass 0: every load in range by construction, every
+  // global store / atomic switched off): this kernel runs once per SM per step, right after a 60 KB kernel, so its
+  // instructions are never in the instruction caches when the flag arrives -- the trace (tools/trace_wq.py) showed
+  // 2.9 us from release to the first loaded value on cold code, i.e. instruction fetch, not data.
   const WqHeader* hdr = reinterpret_cast<const WqHeader*>(plan);
-  const unsigned long long wtot = __ldg(&hdr->wtot);
   const float* xin = logits + (size_t)n * H * W;
   float* ginst = g_logits + (size_t)n * H * W;
-  const int4 recv = __ldg(reinterpret_cast<const int4*>(plan + wq_plan_rec_offset(N)) + n);
-  SRec rec;
-  rec.j0 = (short)recv.x; rec.j1 = (short)recv.y; rec.i0 = (short)recv.z; rec.i1 = (short)recv.w; rec.img = 0;
-  const bool empty = rec.j0 > rec.j1;
-  // ---- independent loads: this thread's row result and its column's key (re-zeroed for the next call) ----
   const int row_i = tid, col_i = tid;                   // H, W <= 512 = OP_FIN_NT
-  unsigned long long rp = 0ull;
-  if (row_i < H) rp = ws.row_packed[(size_t)n * H + row_i];
   const int S = (H + WQ_R - 1) / WQ_R;
-  unsigned long long cp = 0ull;
-  if (col_i < W) {
-    const unsigned long long* src = ws.col_part + (size_t)n * S * W + col_i;
-    for (int s0 = 0; s0 < S; s0 += 8) {                  // all loads of a batch first: one round trip for S <= 8
-      unsigned long long v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = s0 + j < S ? src[(size_t)(s0 + j) * W] : 0ull;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cp = v[j] > cp ? v[j] : cp;  // larger key; on equal keys the earlier group (larger ~group)
-    }
-  }
-  // ---- exact positions: first element of the float4 group / first row of the 4-row group equal to the maximum ----
-  const float xr = fkey_inv((unsigned)(rp >> 32)), xc = fkey_inv((unsigned)(cp >> 32));
-  int ar = 0, ac = 0;
-  if (row_i < H) {
-    const int grp = min((int)(0xffffffffu - (unsigned)(rp & 0xffffffffull)), (W - 4) >> 2);
-    const float4 q = *reinterpret_cast<const float4*>(xin + (size_t)row_i * W + 4 * grp);
-    ar = 4 * grp + (q.x == xr ? 0 : (q.y == xr ? 1 : (q.z == xr ? 2 : 3)));
-    ar = min(ar, W - 1);
-  }
-  if (col_i < W) {
-    const int y4 = min(4 * (int)(0xffffffffu - (unsigned)(cp & 0xffffffffull)), H - 1);
-    const float v0 = xin[(size_t)y4 * W + col_i];
-    const float v1 = y4 + 1 < H ? xin[(size_t)(y4 + 1) * W + col_i] : 0.f;
-    const float v2 = y4 + 2 < H ? xin[(size_t)(y4 + 2) * W + col_i] : 0.f;
-    ac = y4 + (v0 == xc ? 0 : (v1 == xc ? 1 : (v2 == xc ? 2 : 3)));
-    ac = min(ac, H - 1);
-  }
-  // ---- dice terms ----
-  const float sr = row_i < H ? sigmoid_exact(xr) : 0.f;
-  const float sc = col_i < W ? sigmoid_exact(xc) : 0.f;
-  const bool tr = !empty && row_i >= rec.j0 && row_i <= rec.j1, tc = !empty && col_i >= rec.i0 && col_i <= rec.i1;
-  const float r0 = warp_sum(tr ? sr : 0.f), r1 = warp_sum(sr * sr), r2 = warp_sum(tc ? sc : 0.f), r3 = warp_sum(sc * sc);
-  if (lane == 0) { s_f[0][wid] = r0; s_f[1][wid] = r1; s_f[2][wid] = r2; s_f[3][wid] = r3; }
-  if (row_i < H) s_arow[row_i] = ar;
-  if (col_i < W) s_acol[col_i] = ac;
-  // the (scaled) pairwise gradient at the arg-max positions, loaded before the barrier
-  float svr = 0.f, svc = 0.f;
-  if (row_i < H) svr = ginst[(size_t)row_i * W + ar];
-  if (col_i < W) svc = ginst[(size_t)ac * W + col_i];
-  __syncthreads();
+  for (int pass = first_pass; pass < 2; ++pass) {
+    const bool real = pass >= 1;
+    if (real) {
+      if (tid == 0) {
+        unsigned ready = 0u;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ready) : "l"(&sched->ticket) : "memory");
+          if (ready) break;
+          __nanosleep(32);
+        }
+      }
+      __syncthreads();
 #ifdef BXS_OP_TRACE
-  if (tid == 0 && g_op_trace) {
-    unsigned long long t_;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
-    g_op_trace[(kFinTrace + blockIdx.x * 4 + 3) * 2] = t_;
-  }
+      if (tid == 0 && g_op_trace) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        g_op_trace[(kFinTrace + blockIdx.x * 8 + 1) * 2] = t_;
+      }
 #endif
-  float Ir = 0.f, Xr = 0.f, Ic = 0.f, Xc = 0.f;
-#pragma unroll
-  for (int i = 0; i < NWF; ++i) { Ir += s_f[0][i]; Xr += s_f[1][i]; Ic += s_f[2][i]; Xc += s_f[3][i]; }
-  const float inv_n = 1.f / (float)N;
-  const float Ur = Xr + (empty ? 0.f : (float)(rec.j1 - rec.j0 + 1)) + kDiceEps;
-  const float Uc = Xc + (empty ? 0.f : (float)(rec.i1 - rec.i0 + 1)) + kDiceEps;
-  // d dice / d s = -2 t / U + 4 I s / U^2 ; through the sigmoid: * s (1 - s); mean over N
-  const float crow = inv_n * (-2.f * (tr ? 1.f : 0.f) / Ur + 4.f * Ir * sr / (Ur * Ur)) * sr * (1.f - sr);
-  const float ccol = inv_n * (-2.f * (tc ? 1.f : 0.f) / Uc + 4.f * Ic * sc / (Uc * Uc)) * sc * (1.f - sc);
-  if (row_i < H) s_coef[row_i] = crow;
-  __syncthreads();               // all reads of the arg-max positions precede the writes below
-  if (row_i < H) {
-    if (s_acol[ar] != row_i) ginst[(size_t)row_i * W + ar] = svr + crow;
-    ws.coef_row[(size_t)n * H + row_i] = crow; ws.arg_row[(size_t)n * H + row_i] = ar; ws.sv_row[(size_t)n * H + row_i] = svr;
-  }
-  if (col_i < W) {
-    ginst[(size_t)ac * W + col_i] = s_arow[ac] == col_i ? (svc + s_coef[ac]) + ccol : svc + ccol;
-    ws.coef_col[(size_t)n * W + col_i] = ccol; ws.arg_col[(size_t)n * W + col_i] = ac; ws.sv_col[(size_t)n * W + col_i] = svc;
-  }
-  if (tid == 0) {
-    const OpSpan sp = op_span<D>(rec, H, W);
-    reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
-    const float prj_n = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
-    ws.inst_prj[n] = prj_n;
-    // ONE atomic carries this instance's term (low 48 bits, fixed point) and the arrival count (top 16 bits): the CTA
-    // that sees count == N - 1 in the returned value knows the complete sum without another round trip
-    const unsigned long long mine = (unsigned long long)__double2ll_rn((double)fmaxf(prj_n, 0.f) * WQ_PRJ_FX) + (1ull << 48);
-    const unsigned long long before = atomicAdd(&sched->prj_fx, mine);
-    if ((before >> 48) == (unsigned long long)(N - 1)) {           // every instance has added its term
-      const long long prj_fx = (long long)((before + mine) & ((1ull << 48) - 1));
-      const long long num_fx = (long long)*reinterpret_cast<volatile unsigned long long*>(&sched->num_fx);   // main kernel: complete
-      const float scale = fminf(iter_ptr[0] / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
-      const float pn = (float)((double)num_fx * (1.0 / WQ_NUM_FX));
-      losses_out[0] = (float)((double)prj_fx * (1.0 / WQ_PRJ_FX)) * inv_n;
-      losses_out[1] = pn * scale;
-      losses_out[2] = pn;
-      losses_out[3] = (float)wtot;
-      sched->prj_fx = 0ull;
-      sched->num_fx = 0ull;
-      sched->ticket = 0u;          // every CTA passed its poll before it added its term
     }
+    const unsigned long long wtot = __ldg(&hdr->wtot);
+    const int4 recv = __ldg(reinterpret_cast<const int4*>(plan + wq_plan_rec_offset(N)) + n);
+    SRec rec;
+    rec.j0 = (short)recv.x; rec.j1 = (short)recv.y; rec.i0 = (short)recv.z; rec.i1 = (short)recv.w; rec.img = 0;
+    const bool empty = rec.j0 > rec.j1;
+    // ---- independent loads: this thread's row result and its column's per-item keys ----
+    unsigned long long rp = 0ull;
+    if (row_i < H) rp = __ldcg(ws.row_packed + (size_t)n * H + row_i);
+    unsigned long long cp = 0ull;
+    if (col_i < W) {
+      const unsigned long long* src = ws.col_part + (size_t)n * S * W + col_i;
+      for (int s0 = 0; s0 < S; s0 += 12) {               // all loads of a batch first: one round trip for S <= 12
+        unsigned long long v[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) v[j] = s0 + j < S ? __ldcg(src + (size_t)(s0 + j) * W) : 0ull;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) cp = v[j] > cp ? v[j] : cp;  // larger key; on equal keys the earlier group (larger ~group)
+      }
+    }
+#ifdef BXS_OP_TRACE
+    if (real && tid == 32 && g_op_trace) {          // a column thread: its partial keys have arrived
+      unsigned long long t_;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) : "r"((unsigned)cp));
+      g_op_trace[(kFinTrace + blockIdx.x * 8 + 4) * 2] = t_;
+    }
+#endif
+    // ---- exact positions: first element of the float4 group / first row of the 4-row group equal to the maximum
+    //      (indices are clamped into the map: the rehearsal reads whatever the buffers hold) ----
+    const float xr = fkey_inv((unsigned)(rp >> 32)), xc = fkey_inv((unsigned)(cp >> 32));
+    int ar = 0, ac = 0;
+    if (row_i < H) {
+      const int grp = max(min((int)(0xffffffffu - (unsigned)(rp & 0xffffffffull)), (W - 4) >> 2), 0);
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(xin + (size_t)row_i * W + 4 * grp));
+      ar = 4 * grp + (q.x == xr ? 0 : (q.y == xr ? 1 : (q.z == xr ? 2 : 3)));
+      ar = min(ar, W - 1);
+    }
+    if (col_i < W) {
+      const int y4 = max(min(4 * (int)(0xffffffffu - (unsigned)(cp & 0xffffffffull)), H - 1), 0);
+      const float v0 = __ldcg(xin + (size_t)y4 * W + col_i);
+      const float v1 = y4 + 1 < H ? __ldcg(xin + (size_t)(y4 + 1) * W + col_i) : 0.f;
+      const float v2 = y4 + 2 < H ? __ldcg(xin + (size_t)(y4 + 2) * W + col_i) : 0.f;
+      ac = y4 + (v0 == xc ? 0 : (v1 == xc ? 1 : (v2 == xc ? 2 : 3)));
+      ac = min(ac, H - 1);
+    }
+#ifdef BXS_OP_TRACE
+    if (real && tid == 32 && g_op_trace) {          // its arg-max row is resolved (second dependent load phase)
+      unsigned long long t_;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) : "r"(ac));
+      g_op_trace[(kFinTrace + blockIdx.x * 8 + 5) * 2] = t_;
+    }
+#endif
+    // ---- dice terms ----
+    const float sr = row_i < H ? sigmoid_exact(xr) : 0.f;
+    const float sc = col_i < W ? sigmoid_exact(xc) : 0.f;
+    const bool tr = !empty && row_i >= rec.j0 && row_i <= rec.j1, tc = !empty && col_i >= rec.i0 && col_i <= rec.i1;
+    const float r0 = warp_sum(tr ? sr : 0.f), r1 = warp_sum(sr * sr), r2 = warp_sum(tc ? sc : 0.f), r3 = warp_sum(sc * sc);
+    if (lane == 0) { s_f[0][wid] = r0; s_f[1][wid] = r1; s_f[2][wid] = r2; s_f[3][wid] = r3; }
+    if (row_i < H) s_arow[row_i] = ar;
+    if (col_i < W) s_acol[col_i] = ac;
+    // the (scaled) pairwise gradient at the arg-max positions, loaded before the barrier
+    float svr = 0.f, svc = 0.f;
+    if (row_i < H) svr = __ldcg(ginst + (size_t)row_i * W + ar);
+    if (col_i < W) svc = __ldcg(ginst + (size_t)ac * W + col_i);
+    __syncthreads();
+#ifdef BXS_OP_TRACE
+    if (real && tid == 0 && g_op_trace) {
+      unsigned long long t_;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+      g_op_trace[(kFinTrace + blockIdx.x * 8 + 3) * 2] = t_;
+    }
+#endif
+    float Ir = 0.f, Xr = 0.f, Ic = 0.f, Xc = 0.f;
+#pragma unroll
+    for (int i = 0; i < NWF; ++i) { Ir += s_f[0][i]; Xr += s_f[1][i]; Ic += s_f[2][i]; Xc += s_f[3][i]; }
+    const float inv_n = 1.f / (float)N;
+    const float Ur = Xr + (empty ? 0.f : (float)(rec.j1 - rec.j0 + 1)) + kDiceEps;
+    const float Uc = Xc + (empty ? 0.f : (float)(rec.i1 - rec.i0 + 1)) + kDiceEps;
+    // d dice / d s = -2 t / U + 4 I s / U^2 ; through the sigmoid: * s (1 - s); mean over N
+    const float crow = inv_n * (-2.f * (tr ? 1.f : 0.f) / Ur + 4.f * Ir * sr / (Ur * Ur)) * sr * (1.f - sr);
+    const float ccol = inv_n * (-2.f * (tc ? 1.f : 0.f) / Uc + 4.f * Ic * sc / (Uc * Uc)) * sc * (1.f - sc);
+    if (row_i < H) s_coef[row_i] = crow;
+    __syncthreads();               // all reads of the arg-max positions precede the writes below
+    if (real && row_i < H) {
+      if (s_acol[ar] != row_i) ginst[(size_t)row_i * W + ar] = svr + crow;
+      ws.coef_row[(size_t)n * H + row_i] = crow; ws.arg_row[(size_t)n * H + row_i] = ar; ws.sv_row[(size_t)n * H + row_i] = svr;
+    }
+    if (real && col_i < W) {
+      ginst[(size_t)ac * W + col_i] = s_arow[ac] == col_i ? (svc + s_coef[ac]) + ccol : svc + ccol;
+      ws.coef_col[(size_t)n * W + col_i] = ccol; ws.arg_col[(size_t)n * W + col_i] = ac; ws.sv_col[(size_t)n * W + col_i] = svc;
+    }
+    if (real && tid == 0) {
+      const OpSpan sp = op_span<D>(rec, H, W);
+      reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
+      const float prj_n = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
+      ws.inst_prj[n] = prj_n;
+      // ONE atomic carries this instance's term (low 48 bits, fixed point) and the arrival count (top 16 bits): the CTA
+      // that sees count == N - 1 in the returned value knows the complete sum without another round trip
+      const unsigned long long mine = (unsigned long long)__double2ll_rn((double)fmaxf(prj_n, 0.f) * WQ_PRJ_FX) + (1ull << 48);
+      const unsigned long long before = atomicAdd(&sched->prj_fx, mine);
+      if ((before >> 48) == (unsigned long long)(N - 1)) {           // every instance has added its term
+        const long long prj_fx = (long long)((before + mine) & ((1ull << 48) - 1));
+        const long long num_fx = (long long)*reinterpret_cast<volatile unsigned long long*>(&sched->num_fx);   // main kernel: complete
+        const float scale = fminf(iter_ptr[0] / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
+        const float pn = (float)((double)num_fx * (1.0 / WQ_NUM_FX));
+        losses_out[0] = (float)((double)prj_fx * (1.0 / WQ_PRJ_FX)) * inv_n;
+        losses_out[1] = pn * scale;
+        losses_out[2] = pn;
+        losses_out[3] = (float)wtot;
+        sched->prj_fx = 0ull;
+        sched->num_fx = 0ull;
+        sched->ticket = 0u;          // every CTA passed its poll before it added its term
+      }
+    }
+    __syncthreads();               // the shared tables are rewritten by the next pass
   }
 #ifdef BXS_OP_TRACE
-  __syncthreads();
   if (tid == 0 && g_op_trace) {
     unsigned long long t_;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
-    g_op_trace[(kFinTrace + blockIdx.x * 4 + 2) * 2] = t_;
+    g_op_trace[(kFinTrace + blockIdx.x * 8 + 2) * 2] = t_;
   }
 #endif
 }
@@ -684,7 +709,7 @@ int wq_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bit
   int rc = check_launch();
   if (rc != BXS_OK) return rc;
   op_launch_pdl(wq_finalize_kernel<D>, dim3((unsigned)N), dim3(OP_FIN_NT), 0, st, logits, plan, N, H, W, ws, sched, iter_ptr,
-                warmup_iters, losses_out, g_logits);
+                warmup_iters, losses_out, g_logits, 0 /* first_pass: 0 = rehearse once while waiting for the flag */);
   return check_launch();
 }
 

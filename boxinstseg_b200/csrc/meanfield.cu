@@ -179,7 +179,12 @@ extern "C" int bxs_meanfield_forward(const float* K, const int32_t* obj_img, con
   mc.e_bg[0] = neglog4_host[2]; mc.e_bg[1] = neglog4_host[3];
   const int64_t hw = h * w;
   const size_t sm = 2 * ((hw + 15) / 16) * 16;
-  if (sm <= kMaxFusedSmem) {
+  // One CTA per object keeps both bit maps in shared memory for all rounds, but it is ONE SM per object: a round of a
+  // 200x256 map is ~4500 instructions per thread, 1.6 ms for 10 rounds whatever the number of objects (r1: 16 objects on
+  // 16 of 148 SMs).  Unless there are enough objects to fill the machine that way, run the rounds as grid-wide
+  // kernels over all objects' pixels (bit maps ping-pong through L2; the launches are graph-captured by the callers).
+  const bool per_object = sm <= kMaxFusedSmem && (n >= 2 * (int64_t)sm_count() || !workspace);
+  if (per_object) {
     cudaFuncSetAttribute(mf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxFusedSmem);
     mf_fused_kernel<<<(unsigned)n, NT, sm, st>>>(K, obj_img, x, targets, mc, ret, valid, (int)h, (int)w, kernel_size,
                                                  num_iter);

@@ -11,9 +11,13 @@
 //                wavefront polling shared flags (>= V/64 barriers, each behind a global-memory round trip).
 //                Here the order is level-contiguous, one CTA owns a (tree, channel), the running values
 //                live in SHARED memory (V floats) and each level is one barrier.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace bxs {
 namespace {
@@ -34,6 +38,7 @@ struct MstWs {
   int* P;                     // [B*V] component label (always a root id)
   int* Q;                     // [B*V] hook parents
   uint8_t* in_tree;           // [B*E]
+  int* round_flags;           // [B*64] "this round hooked something"
   size_t total_bytes;
 };
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
@@ -46,6 +51,7 @@ inline MstWs carve_mst(void* base, int64_t B, int64_t E, int64_t V) {
   w.P = (int*)take(4 * B * V);
   w.Q = (int*)take(4 * B * V);
   w.in_tree = (uint8_t*)take(B * E);
+  w.round_flags = (int*)take(4 * B * 64);
   w.total_bytes = off;
   return w;
 }
@@ -110,6 +116,76 @@ __global__ void mst_compress_kernel(MstWs ws, int V) {
     while (Q[r] != r) r = Q[r];
     P[v] = r;
     best[v] = kInf;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// The whole Boruvka iteration in ONE launch: a thread-block cluster of 8 CTAs per tree runs the three phases of a round
+// (min edge per component, hook, compress) back to back with cluster barriers in between and stops as soon as a round
+// hooks nothing (one component left).  The per-round kernels above needed 3 launches x ceil(log2 V) rounds (48
+// launches at 200x256, most of them doing nothing: components shrink ~3-4x per round) and were launch-bound:
+// ~0.67 ms whether for 16 trees or for 2.  Same keys, same integer atomicMin, same edge set.
+// ---------------------------------------------------------------------------------------
+constexpr int MST_CL = 8;
+constexpr int MST_NT = 1024;
+
+__global__ void __cluster_dims__(MST_CL, 1, 1) __launch_bounds__(MST_NT)
+mst_cluster_kernel(const int32_t* __restrict__ edge_index, const float* __restrict__ edge_weight, MstWs ws, int E, int V,
+                   int max_rounds, int* __restrict__ round_flags) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int b = blockIdx.x / MST_CL;
+  const int t0 = (int)cluster.block_rank() * MST_NT + threadIdx.x, stride = MST_CL * MST_NT;
+  const int32_t* ei = edge_index + (int64_t)b * E * 2;
+  const float* ew = edge_weight + (int64_t)b * E;
+  int* P = ws.P + (int64_t)b * V;
+  int* Q = ws.Q + (int64_t)b * V;
+  unsigned long long* best = ws.best + (int64_t)b * V;
+  uint8_t* in_tree = ws.in_tree + (int64_t)b * E;
+  int* flags = round_flags + (int64_t)b * max_rounds;
+  for (int v = t0; v < V; v += stride) { P[v] = v; best[v] = kInf; }
+  for (int e = t0; e < E; e += stride) in_tree[e] = 0;
+  for (int r = t0; r < max_rounds; r += stride) flags[r] = 0;
+  cluster.sync();
+  for (int round = 0; round < max_rounds; ++round) {
+    // every edge offers itself to the two components it connects
+    for (int e = t0; e < E; e += stride) {
+      const int2 uv = *reinterpret_cast<const int2*>(ei + 2 * e);
+      const int cu = P[uv.x], cv = P[uv.y];
+      if (cu == cv) continue;
+      const unsigned long long key = ((unsigned long long)fkey(ew[e]) << 32) | (unsigned)e;
+      atomicMin(best + cu, key);
+      atomicMin(best + cv, key);
+    }
+    cluster.sync();
+    // roots with an outgoing edge hook onto the component at its other end (2-cycles broken by id)
+    bool hooked = false;
+    for (int v = t0; v < V; v += stride) {
+      int q = P[v];
+      if (q == v) {
+        const unsigned long long bv = best[v];
+        if (bv != kInf) {
+          const int e = (int)(bv & 0xffffffffull);
+          const int cu = P[ei[2 * e]], cv = P[ei[2 * e + 1]];
+          const int other = cu == v ? cv : cu;
+          if (!(best[other] == bv && v < other)) {
+            q = other;
+            in_tree[e] = 1;
+          }
+          hooked = true;                      // an outgoing edge exists: more than one component
+        }
+      }
+      Q[v] = q;
+    }
+    if (hooked) flags[round] = 1;
+    cluster.sync();
+    if (flags[round] == 0) break;             // uniform over the cluster: nothing left to merge
+    for (int v = t0; v < V; v += stride) {
+      int r = P[v];
+      while (Q[r] != r) r = Q[r];
+      P[v] = r;
+      best[v] = kInf;
+    }
+    cluster.sync();
   }
 }
 
@@ -292,39 +368,48 @@ __global__ void __launch_bounds__(NT) bfs_block_kernel(BfsWs ws, int V, int32_t*
 // ---------------------------------------------------------------------------------------
 constexpr int BFS_FRONT = 2048;         // frontier entries kept in shared memory (wider frontiers re-read sorted_index)
 
-__global__ void __launch_bounds__(32) bfs_grid_kernel(const int32_t* __restrict__ tree, int V, int32_t* __restrict__ sorted_index,
+__global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict__ tree, int V, int32_t* __restrict__ sorted_index,
                                                       int32_t* __restrict__ sorted_parent, int32_t* __restrict__ sorted_child,
                                                       int32_t* __restrict__ level_start, int32_t* __restrict__ num_levels,
                                                       int* __restrict__ flags) {
   extern __shared__ unsigned bfs_smem[];
+  __shared__ int s_wd[NT / 32];
+  __shared__ int s_ok;
   unsigned* s_adj = bfs_smem;                                   // V bytes, packed 4 per word
   int* s_v = reinterpret_cast<int*>(bfs_smem + (V + 3) / 4);   // [2][BFS_FRONT] frontier vertex ids
   int* s_pv = s_v + 2 * BFS_FRONT;                              // [2][BFS_FRONT] their parents' vertex ids
-  const int b = blockIdx.x, lane = threadIdx.x;
-  const int32_t* te = tree + (int64_t)b * (V - 1) * 2;
-  // row pitch of the grid = the (single) non-unit difference of an edge's end points
+  const int b = blockIdx.x, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int2* te = reinterpret_cast<const int2*>(tree + (int64_t)b * (V - 1) * 2);
+  // ---- prologue, whole CTA: row pitch of the grid (the single non-unit difference of an edge's end points), then the
+  //      adjacency bits.  (One warp alone spends ~1 ms here on 51 200 dependent-latency loads.) ----
   int Wd = 0;
   bool ok = true;
-  for (int i = lane; i < V - 1; i += 32) {
-    const int d = abs(te[2 * i + 1] - te[2 * i]);
+  for (int i = tid; i < V - 1; i += NT) {
+    const int2 e = __ldg(te + i);
+    const int d = abs(e.y - e.x);
     if (d == 0) ok = false;
     else if (d != 1) Wd = max(Wd, d);
   }
   Wd = __reduce_max_sync(kFull, Wd);
+  if (lane == 0) s_wd[tid >> 5] = Wd;
+  if (tid == 0) s_ok = 1;
+  for (int i = tid; i < (V + 3) / 4; i += NT) s_adj[i] = 0u;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NT / 32; ++i) Wd = max(Wd, s_wd[i]);
   if (Wd == 0) Wd = V;                                          // a single row: no vertical edge
-  for (int i = lane; i < (V + 3) / 4; i += 32) s_adj[i] = 0u;
-  __syncwarp();
-  for (int i = lane; i < V - 1; i += 32) {
-    const int ea = te[2 * i], eb = te[2 * i + 1];
-    const int u = min(ea, eb), v = max(ea, eb), d = v - u;
+  for (int i = tid; i < V - 1; i += NT) {
+    const int2 e = __ldg(te + i);
+    const int u = min(e.x, e.y), v = max(e.x, e.y), d = v - u;
     if (u < 0 || v >= V || (d != 1 && d != Wd) || (d == 1 && Wd < V && (v % Wd) == 0)) { ok = false; continue; }
     // bit 0 = up (v - Wd), 1 = left (v - 1), 2 = right (v + 1), 3 = down (v + Wd)
     atomicOr(&s_adj[u >> 2], (d == 1 ? 4u : 8u) << ((u & 3) * 8));
     atomicOr(&s_adj[v >> 2], (d == 1 ? 2u : 1u) << ((v & 3) * 8));
   }
-  ok = __all_sync(kFull, ok);
-  if (!ok) { if (lane == 0) flags[b] = 0; return; }
-  __syncwarp();
+  if (!ok) s_ok = 0;
+  __syncthreads();
+  if (tid >= 32) return;                                        // the level loop is ONE warp: no CTA barrier from here on
+  if (!s_ok) { if (lane == 0) flags[b] = 0; return; }
   int32_t* idx = sorted_index + (int64_t)b * V;
   int32_t* par = sorted_parent + (int64_t)b * V;
   int4* chd = reinterpret_cast<int4*>(sorted_child + (int64_t)b * V * 4);
@@ -351,20 +436,17 @@ __global__ void __launch_bounds__(32) bfs_grid_kernel(const int32_t* __restrict_
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
       const int total = __shfl_sync(kFull, inc, 31);
       if (p < le) {
-        int q = next + inc - cnt;
-        int c4[4] = {0, 0, 0, 0};
-        int k2 = 0;
+        const int q0 = next + inc - cnt;            // this node's children occupy positions [q0, q0 + cnt)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (!((bits >> k) & 1u)) continue;
+          const int q = q0 + __popc(bits & ((1u << k) - 1u));
           const int u = k == 0 ? v - Wd : (k == 1 ? v - 1 : (k == 2 ? v + 1 : v + Wd));
           idx[q] = u;
           par[q] = p;
           if (q - le < BFS_FRONT) { s_v[(cur ^ 1) * BFS_FRONT + q - le] = u; s_pv[(cur ^ 1) * BFS_FRONT + q - le] = v; }
-          c4[k2++] = q;
-          ++q;
         }
-        chd[p] = make_int4(c4[0], c4[1], c4[2], c4[3]);
+        chd[p] = make_int4(cnt > 0 ? q0 : 0, cnt > 1 ? q0 + 1 : 0, cnt > 2 ? q0 + 2 : 0, cnt > 3 ? q0 + 3 : 0);
       }
       next += total;
     }
@@ -450,7 +532,7 @@ __global__ void tree_pack_kernel(const float* __restrict__ w, const int32_t* __r
 }
 
 struct UpNode { int s, e, ci; float4 cw; };
-struct DownNode { int s, e, par, idx; float w; };
+struct DownNode { int s, e, par; float w; };
 
 // Level bounds travel through their own register ring, PF levels AHEAD of the node ring: the node loads of a level
 // depend on its bounds, and a dependent pair inside one fetch would put an L2 round trip on every level's critical
@@ -471,9 +553,9 @@ __device__ __forceinline__ UpNode fetch_up(const TreeView& t, const Bnd b) {
 }
 __device__ __forceinline__ DownNode fetch_down(const TreeView& t, const Bnd b) {
   DownNode n;
-  n.s = b.s; n.e = b.e; n.par = 0; n.idx = 0; n.w = 0.f;
+  n.s = b.s; n.e = b.e; n.par = 0; n.w = 0.f;
   const int p = b.s + threadIdx.x;
-  if (p < b.e) { n.par = __ldg(t.par + p); n.idx = __ldg(t.idx + p); n.w = __ldg(t.w + p); }
+  if (p < b.e) { n.par = __ldg(t.par + p); n.w = __ldg(t.w + p); }
   return n;
 }
 
@@ -504,24 +586,19 @@ __device__ __forceinline__ void up_pass(const TreeView& t, float* buf, float* __
       ring[j] = fetch_up(t, bring[j]);                      // level l - PF: its bounds were loaded PF levels ago
       bring[j] = fetch_bnd(t, l - 2 * PF, 0);
       int p = nd.s + threadIdx.x;
-      if (p < nd.e) {
-        const float v = up_node(buf[p], nd.ci, nd.cw, buf);
-        buf[p] = v;
-        if (save_up) save_up[p] = v;
-      }
-      for (p += RNT; p < nd.e; p += RNT) {                    // wide levels: plenty of parallelism, plain loads
-        const float v = up_node(buf[p], __ldg(t.cinfo + p), __ldg(t.cw + p), buf);
-        buf[p] = v;
-        if (save_up) save_up[p] = v;
-      }
+      if (p < nd.e) buf[p] = up_node(buf[p], nd.ci, nd.cw, buf);
+      for (p += RNT; p < nd.e; p += RNT)                    // wide levels: plenty of parallelism, plain loads
+        buf[p] = up_node(buf[p], __ldg(t.cinfo + p), __ldg(t.cw + p), buf);
       __syncthreads();
     }
   }
+  // U of every position is in `buf`: one coalesced sweep instead of a global store on every level's critical path
+  if (save_up)
+    for (int p = threadIdx.x; p < t.V; p += RNT) save_up[p] = buf[p];
 }
 
 // in place: A[0] = U[0]; A[p] = (1 - w^2) U[p] + w A[par]; writes the vertex-ordered result
 __device__ __forceinline__ void down_pass(const TreeView& t, float* buf, float* __restrict__ out_vertex) {
-  if (threadIdx.x == 0 && out_vertex) out_vertex[t.idx[0]] = buf[0];
   DownNode ring[PF];
   Bnd bring[PF];
 #pragma unroll
@@ -538,20 +615,17 @@ __device__ __forceinline__ void down_pass(const TreeView& t, float* buf, float* 
       ring[j] = fetch_down(t, bring[j]);
       bring[j] = fetch_bnd(t, l + 2 * PF, 1);
       int p = nd.s + threadIdx.x;
-      if (p < nd.e) {
-        const float a = fmaf(buf[nd.par], nd.w, buf[p] * (1.f - nd.w * nd.w));
-        buf[p] = a;
-        if (out_vertex) out_vertex[nd.idx] = a;
-      }
+      if (p < nd.e) buf[p] = fmaf(buf[nd.par], nd.w, buf[p] * (1.f - nd.w * nd.w));
       for (p += RNT; p < nd.e; p += RNT) {
         const float ew = __ldg(t.w + p);
-        const float a = fmaf(buf[__ldg(t.par + p)], ew, buf[p] * (1.f - ew * ew));
-        buf[p] = a;
-        if (out_vertex) out_vertex[__ldg(t.idx + p)] = a;
+        buf[p] = fmaf(buf[__ldg(t.par + p)], ew, buf[p] * (1.f - ew * ew));
       }
       __syncthreads();
     }
   }
+  // A of every position is in `buf`: scatter to vertex order in one parallel sweep (not level by level)
+  if (out_vertex)
+    for (int p = threadIdx.x; p < t.V; p += RNT) out_vertex[__ldg(t.idx + p)] = buf[p];
 }
 
 __device__ __forceinline__ TreeView make_view(const float* w, const int32_t* idx, const int32_t* par, const int32_t* cinfo,
@@ -612,7 +686,7 @@ __global__ void refine_div_kernel(const float* __restrict__ aggr, const float* _
 //   grad[p] += sweep(aggr_up_c, gnU, aggr_c)[p] - sweep(wsum_up, fgU, wsum)[p]
 // sweep: G[0] = gup[0]; for p > 0: grad = gup (outd[v_par] - w ind) + ind (G[par] - w gup); G = gup (1 - w^2) + G[par] w
 // `outd_par` [2][V] is the position-ordered gather outd[idx[par[p]]] for the two data sets (parallel pre-pass).
-struct SweepNode { int s, e, par; float w, ind, outp; };
+struct SweepNode { int s, e, par; float w, ind, outp, gw; };
 
 template <bool SMEM>
 __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
@@ -622,13 +696,16 @@ __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
     const float* __restrict__ aggr_up, const float* __restrict__ wsum, const float* __restrict__ wsum_up,
     const float* __restrict__ g_out, float* __restrict__ grad_w, float* __restrict__ scratch, float* __restrict__ outd_par,
     int C, int V, const int32_t* __restrict__ tree_of) {
+  // The two terms of d/d w (refine.cu:302-370) are independent passes over the tree: blockIdx.y selects the term, the two
+  // CTAs of an instance run concurrently on different SMs and write separate buffers (grad_w and its twin B*V further),
+  // summed by refine_add_kernel -- the dependent-level chain of this backward is 2 passes long instead of 4.
   extern __shared__ float s_buf[];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, nb = gridDim.x, phase = blockIdx.y;
   const int tb = tree_of ? __ldg(tree_of + b) : b;          // tree / weights / normaliser of the instance's image
   const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, tb, V);
-  float* buf = SMEM ? s_buf : scratch + (int64_t)b * V;
-  float* gw = grad_w + (int64_t)b * V;
-  float* op = outd_par + (int64_t)b * V;
+  float* buf = SMEM ? s_buf : scratch + ((int64_t)phase * nb + b) * V;
+  float* gw = grad_w + ((int64_t)phase * nb + b) * V;
+  float* op = outd_par + ((int64_t)phase * nb + b) * V;
   const float* z = wsum + (int64_t)tb * V;
   const float* zu = wsum_up + (int64_t)tb * V;
   for (int p = threadIdx.x; p < V; p += RNT) gw[p] = 0.f;
@@ -637,7 +714,7 @@ __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
     const float* o = out + ((int64_t)b * C + c) * V;
     const float* ag = aggr + ((int64_t)b * C + c) * V;
     const float* au = aggr_up + ((int64_t)b * C + c) * V;
-    for (int phase = 0; phase < 2; ++phase) {
+    {
       // phase 0: gup = up(g/Z), data = (aggr_up, aggr), sign +   phase 1: gup = up(g/Z * out), data = (wsum_up, wsum), sign -
       const float* ind = phase ? zu : au;
       const float* outd = phase ? z : ag;
@@ -655,9 +732,11 @@ __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
       SweepNode ring[PF];
       auto fetch = [&](const Bnd b) {
         SweepNode n;
-        n.s = b.s; n.e = b.e; n.par = 0; n.w = n.ind = n.outp = 0.f;
+        n.s = b.s; n.e = b.e; n.par = 0; n.w = n.ind = n.outp = n.gw = 0.f;
         const int p = b.s + threadIdx.x;
-        if (p < b.e) { n.par = __ldg(t.par + p); n.w = __ldg(t.w + p); n.ind = ind[p]; n.outp = op[p]; }
+        // gw[p] is updated once per (channel, phase) and the phases are separated by barriers: its old value can
+        // travel with the prefetched node instead of being a dependent global load inside the level
+        if (p < b.e) { n.par = __ldg(t.par + p); n.w = __ldg(t.w + p); n.ind = ind[p]; n.outp = op[p]; n.gw = gw[p]; }
         return n;
       };
       Bnd bring[PF];
@@ -676,7 +755,7 @@ __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
           int p = nd.s + threadIdx.x;
           if (p < nd.e) {
             const float gup = buf[p], Gp = buf[nd.par];
-            gw[p] += sign * (gup * (nd.outp - nd.w * nd.ind) + nd.ind * (Gp - nd.w * gup));
+            gw[p] = nd.gw + sign * (gup * (nd.outp - nd.w * nd.ind) + nd.ind * (Gp - nd.w * gup));
             buf[p] = fmaf(Gp, nd.w, gup * (1.f - nd.w * nd.w));
           }
           for (p += RNT; p < nd.e; p += RNT) {
@@ -689,6 +768,10 @@ __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
       }
     }
   }
+}
+
+__global__ void refine_add_kernel(float* __restrict__ a, const float* __restrict__ b2, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) a[i] += b2[i];
 }
 
 inline int grid_for(int64_t total, int block) {
@@ -713,15 +796,20 @@ extern "C" int bxs_mst_forward(const int32_t* edge_index, const float* edge_weig
     return BXS_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   MstWs ws = carve_mst(workspace, B, E, V);
-  mst_init_kernel<<<grid_for(B * std::max(E, V), 256), 256, 0, st>>>(ws, B * V, B * E, (int)V);
   int rounds = 0;
   while ((int64_t(1) << rounds) < V) ++rounds;             // components at least halve per round
-  const dim3 ge((unsigned)std::min<int64_t>(ceil_div(E, 256), 1024), (unsigned)B);
-  const dim3 gv((unsigned)std::min<int64_t>(ceil_div(V, 256), 1024), (unsigned)B);
-  for (int r = 0; r < rounds; ++r) {
-    mst_min_edge_kernel<<<ge, 256, 0, st>>>(edge_index, edge_weight, ws, (int)E, (int)V);
-    mst_hook_kernel<<<gv, 256, 0, st>>>(edge_index, ws, (int)E, (int)V);
-    mst_compress_kernel<<<gv, 256, 0, st>>>(ws, (int)V);
+  if (rounds <= 64 && B * MST_CL < 65536 * 8) {
+    mst_cluster_kernel<<<(unsigned)(B * MST_CL), MST_NT, 0, st>>>(edge_index, edge_weight, ws, (int)E, (int)V, rounds,
+                                                                  ws.round_flags);
+  } else {
+    mst_init_kernel<<<grid_for(B * std::max(E, V), 256), 256, 0, st>>>(ws, B * V, B * E, (int)V);
+    const dim3 ge((unsigned)std::min<int64_t>(ceil_div(E, 256), 1024), (unsigned)B);
+    const dim3 gv((unsigned)std::min<int64_t>(ceil_div(V, 256), 1024), (unsigned)B);
+    for (int r = 0; r < rounds; ++r) {
+      mst_min_edge_kernel<<<ge, 256, 0, st>>>(edge_index, edge_weight, ws, (int)E, (int)V);
+      mst_hook_kernel<<<gv, 256, 0, st>>>(edge_index, ws, (int)E, (int)V);
+      mst_compress_kernel<<<gv, 256, 0, st>>>(ws, (int)V);
+    }
   }
   mst_compact_kernel<<<(unsigned)B, NT, 0, st>>>(edge_index, ws, edge_out, (int)E, (int)V);
   return check_launch();
@@ -751,7 +839,7 @@ extern "C" int bxs_bfs_forward(const int32_t* tree_edges, int32_t* sorted_index,
   const bool try_grid = grid_smem <= kMaxTreeSmem;
   if (try_grid) {
     cudaFuncSetAttribute(bfs_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
-    bfs_grid_kernel<<<(unsigned)B, 32, grid_smem, st>>>(tree_edges, (int)V, sorted_index, sorted_parent, sorted_child,
+    bfs_grid_kernel<<<(unsigned)B, NT, grid_smem, st>>>(tree_edges, (int)V, sorted_index, sorted_parent, sorted_child,
                                                         level_start, num_levels, flags);
   } else {
     cudaMemsetAsync(flags, 0, sizeof(int) * B, st);
@@ -780,6 +868,7 @@ struct RefineScratch {
   int32_t* cinfo;
   float4* cw;
   float* outd_par;
+  float* gw2;
   float* bufs;
   size_t total_bytes;
 };
@@ -790,8 +879,9 @@ inline RefineScratch carve_refine(void* base, int64_t B, int64_t C, int64_t V) {
   auto take = [&](size_t bytes) { char* q = p + off; off = align_up(off + bytes); return q; };
   r.cw = (float4*)take(16 * B * V);
   r.cinfo = (int32_t*)take(4 * B * V);
-  r.outd_par = (float*)take(4 * B * V);
-  r.bufs = (float*)take(4 * B * (C + 1) * V);
+  r.outd_par = (float*)take(2 * 4 * B * V);               // per d/d w term
+  r.gw2 = (float*)take(2 * 4 * B * V);                    // the two d/d w terms before they are summed
+  r.bufs = (float*)take(4 * B * (C + 2) * V);
   r.total_bytes = off;
   return r;
 }
@@ -875,16 +965,18 @@ extern "C" int bxs_refine_backward_weight(const float* edge_weight, const int32_
   const size_t sm = V * sizeof(float);
   if (sm <= kMaxTreeSmem) {
     cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
-    refine_bwd_weight_kernel<true><<<(unsigned)B, RNT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
-                                                                level_start, num_levels, feature_out, aggr, aggr_up, wsum,
-                                                                wsum_up, grad_out, grad_weight, nullptr, rs.outd_par,
-                                                                (int)C, (int)V, nullptr);
+    refine_bwd_weight_kernel<true><<<dim3((unsigned)B, 2), RNT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo,
+                                                                         rs.cw, level_start, num_levels, feature_out, aggr,
+                                                                         aggr_up, wsum, wsum_up, grad_out, rs.gw2, nullptr,
+                                                                         rs.outd_par, (int)C, (int)V, nullptr);
   } else {
-    refine_bwd_weight_kernel<false><<<(unsigned)B, RNT, 0, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
-                                                                 level_start, num_levels, feature_out, aggr, aggr_up, wsum,
-                                                                 wsum_up, grad_out, grad_weight, rs.bufs, rs.outd_par,
-                                                                 (int)C, (int)V, nullptr);
+    refine_bwd_weight_kernel<false><<<dim3((unsigned)B, 2), RNT, 0, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo,
+                                                                          rs.cw, level_start, num_levels, feature_out, aggr,
+                                                                          aggr_up, wsum, wsum_up, grad_out, rs.gw2, rs.bufs,
+                                                                          rs.outd_par, (int)C, (int)V, nullptr);
   }
+  cudaMemcpyAsync(grad_weight, rs.gw2, sizeof(float) * B * V, cudaMemcpyDeviceToDevice, st);
+  refine_add_kernel<<<grid_for(B * V, 256), 256, 0, st>>>(grad_weight, rs.gw2 + B * V, B * V);
   return check_launch();
 }
 
@@ -973,15 +1065,17 @@ extern "C" int bxs_refine_backward_weight_grouped(const float* edge_weight, cons
   const size_t sm = V * sizeof(float);
   if (sm <= kMaxTreeSmem) {
     cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
-    refine_bwd_weight_kernel<true><<<(unsigned)n, RNT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
-                                                                level_start, num_levels, feature_out, aggr, aggr_up, wsum,
-                                                                wsum_up, grad_out, grad_weight, nullptr, rs.outd_par, (int)C,
-                                                                (int)V, tree_of);
+    refine_bwd_weight_kernel<true><<<dim3((unsigned)n, 2), RNT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo,
+                                                                         rs.cw, level_start, num_levels, feature_out, aggr,
+                                                                         aggr_up, wsum, wsum_up, grad_out, rs.gw2, nullptr,
+                                                                         rs.outd_par, (int)C, (int)V, tree_of);
   } else {
-    refine_bwd_weight_kernel<false><<<(unsigned)n, RNT, 0, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
-                                                                 level_start, num_levels, feature_out, aggr, aggr_up, wsum,
-                                                                 wsum_up, grad_out, grad_weight, rs.bufs, rs.outd_par, (int)C,
-                                                                 (int)V, tree_of);
+    refine_bwd_weight_kernel<false><<<dim3((unsigned)n, 2), RNT, 0, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo,
+                                                                          rs.cw, level_start, num_levels, feature_out, aggr,
+                                                                          aggr_up, wsum, wsum_up, grad_out, rs.gw2, rs.bufs,
+                                                                          rs.outd_par, (int)C, (int)V, tree_of);
   }
+  cudaMemcpyAsync(grad_weight, rs.gw2, sizeof(float) * n * V, cudaMemcpyDeviceToDevice, st);
+  refine_add_kernel<<<grid_for(n * V, 256), 256, 0, st>>>(grad_weight, rs.gw2 + n * V, n * V);
   return check_launch();
 }

@@ -31,14 +31,17 @@ for (n, h, w) in [(2, 200, 256), (16, 200, 256), (2, 96, 96), (2, 50, 64)]:
     al = lambda v: (v + 255) // 256 * 256
     off = al(4 * B * V); off = al(off + 16 * B * V); off = al(off + 4 * B * V)
     flags = ws[off:off + 4 * B].view(torch.int32)
-    print(f'{n}x{h}x{w}: rc={rc} flags={flags.tolist()} levels={nlv.tolist()[:4]}',
+    print(f'{n}x{h}x{w}: rc={rc} flags={flags.tolist()} levels={nlv.tolist()[:4]}', flush=True)
+    print('  ',
           f'bfs {timeit(lambda: bfs(tree, 4)):.0f} us  mst {timeit(lambda: mst(guide)):.0f} us')
     tf = TreeFilter2D()
     feat = torch.rand(n, 1, h, w, device=dev, generator=g).requires_grad_(True)
     emb = guide.clone().requires_grad_(True)
     idx, par, chd = bfs(tree, 4)
-    ew = tf.build_edge_weight(emb, idx, par, False, chd)
     from boxinstseg_b200.ops.tree_filter.functions.refine import refine
     f3 = feat.reshape(n, 1, -1)
-    print('   refine fwd', f'{timeit(lambda: refine(f3, ew, idx, par, chd, False)):.0f} us',
-          'fwd+bwd', f'{timeit(lambda: torch.autograd.grad(refine(f3, ew, idx, par, chd, False).sum(), [feat, emb])):.0f} us')
+    ew0 = tf.build_edge_weight(emb, idx, par, False, chd).detach()
+    def fb():
+        ew = tf.build_edge_weight(emb, idx, par, False, chd)
+        return torch.autograd.grad(refine(f3, ew, idx, par, chd, False).sum(), [feat, emb])
+    print('   refine fwd', f'{timeit(lambda: refine(f3.detach(), ew0, idx, par, chd, False)):.0f} us', 'fwd+bwd', f'{timeit(fb):.0f} us', flush=True)

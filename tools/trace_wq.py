@@ -35,7 +35,7 @@ ws = torch.empty(lib.bxs_boxinst_loss_fused_workspace_bytes(N_INST, H, W), dtype
 sched = torch.zeros(int(lib.bxs_boxinst_loss_fused_sched_bytes()), dtype=torch.uint8, device=dev)
 out = torch.empty(4, device=dev)
 NWMAX = 148 * 4 * 8
-trace = torch.zeros((NWMAX * 16 + 2048 * 4) * 2, dtype=torch.int64, device=dev)
+trace = torch.zeros((NWMAX * 16 + 2048 * 8) * 2, dtype=torch.int64, device=dev)
 h = ctypes.CDLL(TRACE_LIB)
 h.bxs_debug_set_trace.argtypes = [ctypes.c_void_p]
 def run(i):
@@ -46,7 +46,7 @@ torch.cuda.synchronize()
 assert h.bxs_debug_set_trace(ctypes.c_void_p(trace.data_ptr())) == 0
 run(5)
 torch.cuda.synchronize()
-fin = trace.cpu().numpy()[NWMAX * 16 * 2:].reshape(2048, 4, 2)[:N_INST, :, 0]
+fin = trace.cpu().numpy()[NWMAX * 16 * 2:].reshape(2048, 8, 2)[:N_INST, :, 0]
 tr = trace.cpu().numpy()[:NWMAX * 16 * 2].reshape(NWMAX, 16, 2)
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 np.save(os.path.join(ROOT, 'gpurun_out', 'wq_trace.npy'), tr)
@@ -80,4 +80,6 @@ print('finalize CTAs: released ', st((fin[:, 1] - t0).tolist()))
 print('finalize CTAs: done     ', st((fin[:, 2] - t0).tolist()))
 print('finalize CTAs: duration ', st((fin[:, 2] - fin[:, 1]).tolist()))
 print('finalize CTAs: released -> first barrier ', st((fin[:, 3] - fin[:, 1]).tolist()))
+print('finalize CTAs: released -> partial keys   ', st((fin[:, 4] - fin[:, 1]).tolist()))
+print('finalize CTAs: released -> arg-max row    ', st((fin[:, 5] - fin[:, 1]).tolist()))
 print('losses', out.tolist())
