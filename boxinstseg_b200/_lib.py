@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libboxseg_b200.so')
+LIB_PATH = os.environ.get('BXS_LIB_PATH') or os.path.join(_HERE, 'lib', 'libboxseg_b200.so')   # BXS_LIB_PATH: A/B builds (tools/)
 
 _lib = None
 
@@ -62,6 +62,7 @@ SIGNATURES = {
     'bxs_mst_forward': [c_p] * 4 + [c_i64] * 3 + [c_p],
     'bxs_bfs_workspace_bytes': [c_i64] * 2,
     'bxs_bfs_forward': [c_p] * 7 + [c_i64] * 2 + [c_int, c_p],
+    'bxs_bfs_forward_rooted': [c_p] * 7 + [c_i64] * 2 + [c_int, c_i64, c_p],
     'bxs_tree_levels': [c_p] * 4 + [c_i64] * 2 + [c_p],
     'bxs_refine_scratch_bytes': [c_i64] * 3,
     'bxs_refine_forward': [c_p] * 13 + [c_i64] * 3 + [c_p],

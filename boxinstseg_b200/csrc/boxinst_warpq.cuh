@@ -28,9 +28,15 @@
 constexpr int WQ_NT = 256;          // threads per CTA
 constexpr int WQ_NW = WQ_NT / 32;
 constexpr int WQ_SUB = 4;           // rows per ring stage (one bulk copy)
-constexpr int WQ_R = 24;            // rows per stream item
+#ifndef BXS_WQ_R
+#define BXS_WQ_R 24
+#endif
+#ifndef BXS_WQ_STREAMERS
+#define BXS_WQ_STREAMERS 2
+#endif
+constexpr int WQ_R = BXS_WQ_R;      // rows per stream item (tunable at build time for A/B runs: tools/ab_variants.sh)
 constexpr int WQ_RING = 4;          // ring stages of a streamer warp
-constexpr int WQ_STREAMERS = 2;     // warps per CTA that take stream items first (the others take pair items)
+constexpr int WQ_STREAMERS = BXS_WQ_STREAMERS;     // warps per CTA that take stream items first (the others take pair items)
 constexpr double WQ_NUM_FX = 16777216.0;            // 2^24: fixed-point scale of the pairwise numerator
 constexpr double WQ_PRJ_FX = 4294967296.0;          // 2^32: fixed-point scale of the projection terms (N <= 2048 terms <= 2 fit 48 bits)
 static_assert(WQ_R % WQ_SUB == 0 && WQ_R / WQ_SUB <= 16, "stream items start on a 4-row group; <= 16 groups per item (4-bit fields)");
@@ -47,7 +53,7 @@ static_assert(sizeof(WqHeader) == 64, "plan header is 64 bytes");
 struct __align__(16) WqItem { int4 a, b; };
 
 struct WqSched {                    // device state: zero before the first call, left zero by every call
-  unsigned next_s, next_p, done, ticket;      // stream / pair queue positions, warps done, "results are published" flag
+  unsigned next_s, next_p, done, ticket;      // stream / pair queue positions, main-kernel warps arrived, (unused)
   unsigned long long num_fx, prj_fx;          // fixed-point loss sums
 };
 
@@ -470,17 +476,12 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
     q_cur = q_nxt; ia = na; ib = nb;
   }
   WQ_TRACE(7);
-  // ---- queue counters reset and results published by the last warp (every fetch of a warp precedes its `done` increment) ----
+  // ---- arrival: this warp's results are fenced, then counted (nobody waits for the count here: the finalize CTAs
+  //      poll it, and the last of them resets the queue counters) ----
+  __syncwarp();
   if (lane == 0) {
     __threadfence();
-    if (atomicAdd(&sched->done, 1u) == nwarps - 1u) {
-      sched->next_s = 0u;
-      sched->next_p = 0u;
-      sched->done = 0u;
-      __threadfence();
-      // every warp fenced its stores before its `done` increment: the finalize CTAs (already resident, polling) may go
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&sched->ticket), "r"(1u) : "memory");
-    }
+    atomicAdd(&sched->done, 1u);
   }
 }
 
@@ -494,7 +495,7 @@ template <int D>
 __global__ void __launch_bounds__(OP_FIN_NT)
 wq_finalize_kernel(const float* __restrict__ logits, unsigned char* __restrict__ plan, int N, int H, int W,
                    OpWorkspace ws, WqSched* __restrict__ sched, const float* __restrict__ iter_ptr, float warmup_iters,
-                   float* __restrict__ losses_out, float* __restrict__ g_logits, int first_pass) {
+                   float* __restrict__ losses_out, float* __restrict__ g_logits, int first_pass, unsigned main_warps) {
   constexpr int NWF = OP_FIN_NT / 32;
   __shared__ float s_f[4][NWF];
   __shared__ float s_coef[512];       // row coefficients
@@ -511,8 +512,8 @@ wq_finalize_kernel(const float* __restrict__ logits, unsigned char* __restrict__
 #endif
   // Launched with programmatic stream serialization and NOT waiting for the main grid to retire (griddepcontrol.wait
   // costs ~2.5 us after the last warp's exit: grid completion + flush): the CTAs become resident as main CTAs leave
-  // and poll the flag the main kernel's last warp publishes after every warp has fenced its results.  The main kernel
-  // never waits for this one, so there is nothing to deadlock on.
+  // and poll the main kernel's arrival counter (every warp fences its results, then counts itself in).  The main
+  // kernel never waits for this one, so there is nothing to deadlock on.
   //
   // While it waits, a CTA runs the whole body ONCE AS A REHEARSAL (pass 0: every load in range by construction, every
   // global store / atomic switched off): this kernel runs once per SM per step, right after a 60 KB kernel, so its
@@ -527,10 +528,10 @@ wq_finalize_kernel(const float* __restrict__ logits, unsigned char* __restrict__
     const bool real = pass >= 1;
     if (real) {
       if (tid == 0) {
-        unsigned ready = 0u;
+        unsigned arrived = 0u;                    // every main-kernel warp fences its results, then counts itself in
         for (;;) {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ready) : "l"(&sched->ticket) : "memory");
-          if (ready) break;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(arrived) : "l"(&sched->done) : "memory");
+          if (arrived >= main_warps) break;
           __nanosleep(32);
         }
       }
@@ -620,6 +621,21 @@ wq_finalize_kernel(const float* __restrict__ logits, unsigned char* __restrict__
     const float inv_n = 1.f / (float)N;
     const float Ur = Xr + (empty ? 0.f : (float)(rec.j1 - rec.j0 + 1)) + kDiceEps;
     const float Uc = Xc + (empty ? 0.f : (float)(rec.i1 - rec.i0 + 1)) + kDiceEps;
+    // This instance's loss term goes out NOW (one thread): the atomic's round trip overlaps the coefficient math and the
+    // gradient stores below.  ONE atomic carries the term (low 48 bits, fixed point) and the arrival count (top 16 bits):
+    // the CTA that sees count == N - 1 in the returned value knows the complete sum without another round trip.
+    bool last_cta = false;
+    long long prj_total_fx = 0;
+    if (real && tid == 0) {
+      const OpSpan sp = op_span<D>(rec, H, W);
+      reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
+      const float prj_n = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
+      ws.inst_prj[n] = prj_n;
+      const unsigned long long mine = (unsigned long long)__double2ll_rn((double)fmaxf(prj_n, 0.f) * WQ_PRJ_FX) + (1ull << 48);
+      const unsigned long long before = atomicAdd(&sched->prj_fx, mine);
+      last_cta = (before >> 48) == (unsigned long long)(N - 1);
+      prj_total_fx = (long long)((before + mine) & ((1ull << 48) - 1));
+    }
     // d dice / d s = -2 t / U + 4 I s / U^2 ; through the sigmoid: * s (1 - s); mean over N
     const float crow = inv_n * (-2.f * (tr ? 1.f : 0.f) / Ur + 4.f * Ir * sr / (Ur * Ur)) * sr * (1.f - sr);
     const float ccol = inv_n * (-2.f * (tc ? 1.f : 0.f) / Uc + 4.f * Ic * sc / (Uc * Uc)) * sc * (1.f - sc);
@@ -633,28 +649,19 @@ wq_finalize_kernel(const float* __restrict__ logits, unsigned char* __restrict__
       ginst[(size_t)ac * W + col_i] = s_arow[ac] == col_i ? (svc + s_coef[ac]) + ccol : svc + ccol;
       ws.coef_col[(size_t)n * W + col_i] = ccol; ws.arg_col[(size_t)n * W + col_i] = ac; ws.sv_col[(size_t)n * W + col_i] = svc;
     }
-    if (real && tid == 0) {
-      const OpSpan sp = op_span<D>(rec, H, W);
-      reinterpret_cast<int4*>(ws.span)[n] = make_int4(sp.y_lo, sp.y_hi, sp.c_lo, sp.c_hi);
-      const float prj_n = (1.f - 2.f * Ir / Ur) + (1.f - 2.f * Ic / Uc);
-      ws.inst_prj[n] = prj_n;
-      // ONE atomic carries this instance's term (low 48 bits, fixed point) and the arrival count (top 16 bits): the CTA
-      // that sees count == N - 1 in the returned value knows the complete sum without another round trip
-      const unsigned long long mine = (unsigned long long)__double2ll_rn((double)fmaxf(prj_n, 0.f) * WQ_PRJ_FX) + (1ull << 48);
-      const unsigned long long before = atomicAdd(&sched->prj_fx, mine);
-      if ((before >> 48) == (unsigned long long)(N - 1)) {           // every instance has added its term
-        const long long prj_fx = (long long)((before + mine) & ((1ull << 48) - 1));
-        const long long num_fx = (long long)*reinterpret_cast<volatile unsigned long long*>(&sched->num_fx);   // main kernel: complete
-        const float scale = fminf(iter_ptr[0] / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
-        const float pn = (float)((double)num_fx * (1.0 / WQ_NUM_FX));
-        losses_out[0] = (float)((double)prj_fx * (1.0 / WQ_PRJ_FX)) * inv_n;
-        losses_out[1] = pn * scale;
-        losses_out[2] = pn;
-        losses_out[3] = (float)wtot;
-        sched->prj_fx = 0ull;
-        sched->num_fx = 0ull;
-        sched->ticket = 0u;          // every CTA passed its poll before it added its term
-      }
+    if (real && tid == 0 && last_cta) {                              // every instance has added its term: the four scalars
+      const float scale = fminf(iter_ptr[0] / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
+      const long long num_fx = (long long)*reinterpret_cast<volatile unsigned long long*>(&sched->num_fx);   // main kernel: complete
+      const float pn = (float)((double)num_fx * (1.0 / WQ_NUM_FX));
+      losses_out[0] = (float)((double)prj_total_fx * (1.0 / WQ_PRJ_FX)) * inv_n;
+      losses_out[1] = pn * scale;
+      losses_out[2] = pn;
+      losses_out[3] = (float)wtot;
+      sched->prj_fx = 0ull;
+      sched->num_fx = 0ull;
+      sched->next_s = 0u;          // every CTA passed its poll before it added its term: nobody reads these any more
+      sched->next_p = 0u;
+      sched->done = 0u;
     }
     __syncthreads();               // the shared tables are rewritten by the next pass
   }
@@ -709,7 +716,7 @@ int wq_launch_main(cudaStream_t st, const float* logits, const uint8_t* edge_bit
   int rc = check_launch();
   if (rc != BXS_OK) return rc;
   op_launch_pdl(wq_finalize_kernel<D>, dim3((unsigned)N), dim3(OP_FIN_NT), 0, st, logits, plan, N, H, W, ws, sched, iter_ptr,
-                warmup_iters, losses_out, g_logits, 0 /* first_pass: 0 = rehearse once while waiting for the flag */);
+                warmup_iters, losses_out, g_logits, 0 /* first_pass: 0 = rehearse once while waiting */, (unsigned)(grid * WQ_NW));
   return check_launch();
 }
 

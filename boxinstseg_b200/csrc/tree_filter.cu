@@ -252,8 +252,9 @@ __global__ void bfs_adj_kernel(const int32_t* __restrict__ tree, BfsWs ws, int V
 }
 
 // ascending neighbour ids, unused slots = INT_MAX, so one 16-byte load per vertex describes its adjacency
-__global__ void bfs_sort_adj_kernel(BfsWs ws, int64_t BV) {
+__global__ void bfs_sort_adj_kernel(BfsWs ws, int64_t BV, int V, const int* __restrict__ flags) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < BV; i += (int64_t)gridDim.x * blockDim.x) {
+    if (flags && flags[i / V]) continue;              // ordered by the grid fast path
     int* a = ws.adj + i * 4;
     const int d = min(ws.deg[i], 4);
     int v[4];
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(NT) bfs_block_kernel(BfsWs ws, int V, int32_t*
                                                        int32_t* __restrict__ sorted_parent,
                                                        int32_t* __restrict__ sorted_child,
                                                        int32_t* __restrict__ level_start,
-                                                       int32_t* __restrict__ num_levels, const int* __restrict__ flags) {
+                                                       int32_t* __restrict__ num_levels, const int* __restrict__ flags,
+                                                       int root) {
   __shared__ int s_warp[33];
   __shared__ int s_v[2][NT], s_pv[2][NT];
   const int b = blockIdx.x;
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(NT) bfs_block_kernel(BfsWs ws, int V, int32_t*
   int32_t* chd = sorted_child + (int64_t)b * V * 4;
   int32_t* lvl = level_start + (int64_t)b * (V + 1);
   for (int i = threadIdx.x; i < V; i += NT) reinterpret_cast<int4*>(chd)[i] = make_int4(0, 0, 0, 0);
-  if (threadIdx.x == 0) { idx[0] = 0; par[0] = 0; lvl[0] = 0; pvert[0] = -1; s_v[0][0] = 0; s_pv[0][0] = -1; }
+  if (threadIdx.x == 0) { idx[0] = root; par[0] = 0; lvl[0] = 0; pvert[0] = -1; s_v[0][0] = root; s_pv[0][0] = -1; }
   __syncthreads();
   int ls = 0, le = 1, level = 0, cur = 0;
   while (ls < le) {
@@ -371,7 +373,7 @@ constexpr int BFS_FRONT = 2048;         // frontier entries kept in shared memor
 __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict__ tree, int V, int32_t* __restrict__ sorted_index,
                                                       int32_t* __restrict__ sorted_parent, int32_t* __restrict__ sorted_child,
                                                       int32_t* __restrict__ level_start, int32_t* __restrict__ num_levels,
-                                                      int* __restrict__ flags) {
+                                                      int* __restrict__ flags, int root) {
   extern __shared__ unsigned bfs_smem[];
   __shared__ int s_wd[NT / 32];
   __shared__ int s_ok;
@@ -414,8 +416,9 @@ __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict_
   int32_t* par = sorted_parent + (int64_t)b * V;
   int4* chd = reinterpret_cast<int4*>(sorted_child + (int64_t)b * V * 4);
   int32_t* lvl = level_start + (int64_t)b * (V + 1);
-  if (lane == 0) { idx[0] = 0; par[0] = 0; lvl[0] = 0; s_v[0] = 0; s_pv[0] = -1; }
+  if (lane == 0) { idx[0] = root; par[0] = 0; lvl[0] = 0; s_v[0] = root; s_pv[0] = -1; }
   __syncwarp();
+  const unsigned lt_mask = (1u << lane) - 1u;
   int ls = 0, le = 1, level = 0, cur = 0;
   while (ls < le) {
     int next = le;
@@ -431,20 +434,22 @@ __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict_
         if (pv >= 0) bits &= ~(pv == v - Wd ? 1u : (pv == v - 1 ? 2u : (pv == v + 1 ? 4u : 8u)));
         cnt = __popc(bits);
       }
-      int inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += t; }
-      const int total = __shfl_sync(kFull, inc, 31);
+      // exclusive prefix of the child counts (0..3 per lane; the root may have 4): three ballots instead of a shuffle scan
+      const unsigned b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2), b2 = __ballot_sync(kFull, cnt & 4);
+      const int excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+      const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
       if (p < le) {
-        const int q0 = next + inc - cnt;            // this node's children occupy positions [q0, q0 + cnt)
+        const int q0 = next + excl;                 // this node's children occupy positions [q0, q0 + cnt)
+        const int rel = q0 - le;
+        int* nv = s_v + (cur ^ 1) * BFS_FRONT;
+        int* npv = s_pv + (cur ^ 1) * BFS_FRONT;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (!((bits >> k) & 1u)) continue;
-          const int q = q0 + __popc(bits & ((1u << k) - 1u));
+        for (int k = 0; k < 4; ++k) {               // predicated, no divergent branches: the level's latency is the whole cost
+          const bool on = (bits >> k) & 1u;
+          const int j = __popc(bits & ((1u << k) - 1u));
           const int u = k == 0 ? v - Wd : (k == 1 ? v - 1 : (k == 2 ? v + 1 : v + Wd));
-          idx[q] = u;
-          par[q] = p;
-          if (q - le < BFS_FRONT) { s_v[(cur ^ 1) * BFS_FRONT + q - le] = u; s_pv[(cur ^ 1) * BFS_FRONT + q - le] = v; }
+          if (on) { idx[q0 + j] = u; par[q0 + j] = p; }
+          if (on && rel + j < BFS_FRONT) { nv[rel + j] = u; npv[rel + j] = v; }
         }
         chd[p] = make_int4(cnt > 0 ? q0 : 0, cnt > 1 ? q0 + 1 : 0, cnt > 2 ? q0 + 2 : 0, cnt > 3 ? q0 + 3 : 0);
       }
@@ -821,11 +826,32 @@ extern "C" int64_t bxs_bfs_workspace_bytes(int64_t B, int64_t V) {
 
 // level_start [B, V+1] and num_levels [B] are extra outputs (may be NULL -> scratch inside the workspace is NOT
 // provided: pass real buffers whenever the result feeds bxs_refine_*).
+// bxs_bfs_forward roots every tree at vertex 0 like bfs.cu:100-135; bxs_bfs_forward_rooted takes the root vertex: the
+// tree filter's result does not depend on the root, but the number of dependent levels of every pass does (a 200x256
+// image MST is ~1900 levels deep from the corner, about half of that from the centre).
+static int bfs_forward_impl(const int32_t* tree_edges, int32_t* sorted_index, int32_t* sorted_parent, int32_t* sorted_child,
+                            int32_t* level_start, int32_t* num_levels, void* workspace, int64_t B, int64_t V, int max_adj,
+                            int64_t root, bxs_stream_t stream);
+
 extern "C" int bxs_bfs_forward(const int32_t* tree_edges, int32_t* sorted_index, int32_t* sorted_parent,
                                int32_t* sorted_child, int32_t* level_start, int32_t* num_levels, void* workspace,
                                int64_t B, int64_t V, int max_adj, bxs_stream_t stream) {
+  return bfs_forward_impl(tree_edges, sorted_index, sorted_parent, sorted_child, level_start, num_levels, workspace, B, V,
+                          max_adj, 0, stream);
+}
+
+extern "C" int bxs_bfs_forward_rooted(const int32_t* tree_edges, int32_t* sorted_index, int32_t* sorted_parent,
+                                      int32_t* sorted_child, int32_t* level_start, int32_t* num_levels, void* workspace,
+                                      int64_t B, int64_t V, int max_adj, int64_t root, bxs_stream_t stream) {
+  return bfs_forward_impl(tree_edges, sorted_index, sorted_parent, sorted_child, level_start, num_levels, workspace, B, V,
+                          max_adj, root, stream);
+}
+
+static int bfs_forward_impl(const int32_t* tree_edges, int32_t* sorted_index, int32_t* sorted_parent, int32_t* sorted_child,
+                            int32_t* level_start, int32_t* num_levels, void* workspace, int64_t B, int64_t V, int max_adj,
+                            int64_t root, bxs_stream_t stream) {
   if (!tree_edges || !sorted_index || !sorted_parent || !sorted_child || !level_start || !num_levels || !workspace ||
-      B <= 0 || B >= 65536 || V <= 1)
+      B <= 0 || B >= 65536 || V <= 1 || root < 0 || root >= V)
     return BXS_ERR_INVALID_ARG;
   if (max_adj != 4) return BXS_ERR_UNSUPPORTED;             // the reference only ever passes 4 (tree_filter.py:137)
   cudaStream_t st = as_stream(stream);
@@ -840,16 +866,16 @@ extern "C" int bxs_bfs_forward(const int32_t* tree_edges, int32_t* sorted_index,
   if (try_grid) {
     cudaFuncSetAttribute(bfs_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
     bfs_grid_kernel<<<(unsigned)B, NT, grid_smem, st>>>(tree_edges, (int)V, sorted_index, sorted_parent, sorted_child,
-                                                        level_start, num_levels, flags);
+                                                        level_start, num_levels, flags, (int)root);
   } else {
     cudaMemsetAsync(flags, 0, sizeof(int) * B, st);
   }
   // generic path for whatever the fast path declined (its CTAs return at once otherwise)
   bfs_adj_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div(V, 256), 1024), (unsigned)B), 256, 0, st>>>(tree_edges, ws,
                                                                                                          (int)V, err, flags);
-  bfs_sort_adj_kernel<<<grid_for(B * V, 256), 256, 0, st>>>(ws, B * V);
+  bfs_sort_adj_kernel<<<grid_for(B * V, 256), 256, 0, st>>>(ws, B * V, (int)V, flags);
   bfs_block_kernel<<<(unsigned)B, NT, 0, st>>>(ws, (int)V, sorted_index, sorted_parent, sorted_child, level_start,
-                                               num_levels, flags);
+                                               num_levels, flags, (int)root);
   return check_launch();
 }
 

@@ -83,6 +83,43 @@ class CondInstMaskHead(nn.Module):
                                  out_stride=self.out_stride, channels=self.dynamic_channels,
                                  num_layers=self.dynamic_convs, rel_coors=not self.disable_rel_coors)
 
+    # ------------------------------------------------------------------ f2
+    def training_sample(self, cls_scores, centernesses, param_preds, coors, level_inds, img_inds, gt_inds):
+        """Instance sampling of condinst_head.py:1166-1232, index-exact, without the reference's Python loop over images and
+        ground truths (one ``.any()`` / ``.unique()`` / boolean-index host sync per image and per GT there; here: one sort, one
+        size read).  ``topk_per_img``: per image every GT that has positives keeps its ``inst_per_gt = max(int(topk /
+        #GTs of the image), 1)`` best positives by ``sigmoid(max class score) * sigmoid(centerness)`` (all of them, in their
+        original order, when it has no more than that); output order = image, GT index, then top-k order, as the reference.
+        ``max_proposals``: the reference's random permutation of the first ``min(max_proposals, P)`` positives (:1186-1189)."""
+        params = torch.cat([p.permute(0, 2, 3, 1).flatten(end_dim=2) for p in param_preds], dim=0)
+        pos = torch.nonzero(gt_inds != -1, as_tuple=False).squeeze(1)
+        params, coors, level_inds, img_inds, gt_inds = params[pos], coors[pos], level_inds[pos], img_inds[pos], gt_inds[pos]
+        P = params.size(0)
+        if self.max_proposals != -1:
+            sel = torch.randperm(min(self.max_proposals, P), device=params.device).long()
+        elif self.topk_per_img != -1 and P > 0:
+            cls = torch.cat([c.permute(0, 2, 3, 1).flatten(end_dim=2) for c in cls_scores], dim=0)[pos]
+            ctr = torch.cat([c.permute(0, 2, 3, 1).reshape(-1) for c in centernesses], dim=0)[pos]
+            score = cls.sigmoid().max(dim=1)[0] * ctr.sigmoid()
+            big = int(gt_inds.max().item()) + 1 if P else 1                     # the one size read of this function
+            key = img_inds.long() * big + gt_inds.long()                       # (image, GT) group, ascending like the reference's loops
+            uniq, inv, counts = torch.unique(key, return_inverse=True, return_counts=True)
+            gts_per_img = torch.zeros(int(img_inds.max().item()) + 1, dtype=torch.long, device=key.device)
+            gts_per_img.scatter_add_(0, torch.div(uniq, big, rounding_mode='floor'), torch.ones_like(uniq))
+            per_gt = torch.clamp(torch.div(self.topk_per_img, gts_per_img.clamp(min=1), rounding_mode='floor'), min=1)
+            limit_g = per_gt[torch.div(uniq, big, rounding_mode='floor')]       # inst_per_gt of each group's image
+            topk_g = counts > limit_g                                          # groups that are cut down by score
+            # order inside a group: descending score where the group is cut (torch.topk's order), original order otherwise
+            arange = torch.arange(P, device=key.device)
+            first = torch.argsort(torch.where(topk_g[inv], -score, score.new_zeros(()).expand(P)), stable=True)
+            order = first[torch.argsort(inv[first], stable=True)]              # stable: by group, then by the key above
+            start = torch.cumsum(counts, 0) - counts
+            rank = arange - start[inv[order]]
+            sel = order[rank < torch.minimum(counts, limit_g)[inv[order]]]
+        else:
+            sel = torch.arange(P, device=params.device)
+        return params[sel], coors[sel], level_inds[sel], img_inds[sel], gt_inds[sel]
+
     # ------------------------------------------------------------------ a5
     def get_targets(self, gt_bboxes, gt_masks, img, img_metas):
         """BoxInst: returns a BoxInstTargets (per-image similarity bits + per-GT rectangles) instead of

@@ -2,6 +2,7 @@
 from .. import tree_filter_cuda as _C
 
 
-def bfs(edge_index, max_adj_per_vertex):
-    """-> (sorted_index, sorted_parent, sorted_child); pure index work, no autograd node."""
-    return _C.bfs_forward(edge_index, max_adj_per_vertex)
+def bfs(edge_index, max_adj_per_vertex, root=0):
+    """-> (sorted_index, sorted_parent, sorted_child); pure index work, no autograd node.
+    ``root`` (extension; the reference always roots at vertex 0): the vertex at position 0."""
+    return _C.bfs_forward(edge_index, max_adj_per_vertex, root)

@@ -115,6 +115,14 @@ class TreeFilter2D(nn.Module):
             index = index.long().unsqueeze(1).expand(-1, data.shape[1], -1)
         return torch.gather(data, 2, index)
 
+    @staticmethod
+    def _root(shape):
+        """The filter A x / A 1 does not depend on where the tree is rooted, the DEPTH of the recursion does: every pass
+        is one dependent step per BFS level.  The reference roots at vertex 0, a corner (bfs.cu:100-135); the centre
+        pixel roughly halves the number of levels (1898 -> ~1000 at 200x256)."""
+        h, w = shape[-2], shape[-1]
+        return (h // 2) * w + w // 2
+
     def build_edge_weight(self, fm, sorted_index, sorted_parent, low_tree, sorted_child=None):
         """w[pos] = exp(-dist(E(v_pos), E(v_par)) / (sigma if low_tree else 1)); tree_filter.py:91-108.
         With the default distance and the BFS child table at hand this is one kernel (and one for its autograd);
@@ -141,14 +149,14 @@ class TreeFilter2D(nn.Module):
         if tree_of is not None:
             assert self.groups == 1
             shape = feature_in.shape
-            sorted_index, sorted_parent, sorted_child = bfs(tree, 4)
+            sorted_index, sorted_parent, sorted_child = bfs(tree, 4, self._root(shape))
             edge_weight = self.build_edge_weight(embed_in, sorted_index, sorted_parent, low_tree, sorted_child)
             feat = feature_in.reshape(shape[0], shape[1], -1).contiguous()
             t_of = tree_of if tree_of.dtype == torch.int32 else tree_of.to(torch.int32)
             return refine_grouped(feat, edge_weight, sorted_index, sorted_parent, sorted_child, t_of.contiguous(),
                                   low_tree).reshape(shape)
         shape = feature_in.shape
-        sorted_index, sorted_parent, sorted_child = bfs(tree, 4)
+        sorted_index, sorted_parent, sorted_child = bfs(tree, 4, self._root(shape))
         edge_weight = self.build_edge_weight(embed_in, sorted_index, sorted_parent, low_tree, sorted_child)
         feat = feature_in.reshape(shape[0] * self.groups, shape[1] // self.groups, -1).contiguous()
         if self.groups > 1:                                  # tree_filter.py:110-120 (split_group)

@@ -29,7 +29,7 @@ def mst_forward(edge_index, edge_weight, vertex_count):
     return out
 
 
-def bfs_forward(edge_index, max_adj_per_node):
+def bfs_forward(edge_index, max_adj_per_node, root=0):
     te = _i32(edge_index)
     L.require_cuda(te)
     B, V = te.shape[0], te.shape[1] + 1
@@ -42,8 +42,8 @@ def bfs_forward(edge_index, max_adj_per_node):
     lib = L.lib()
     ws = torch.empty(lib.bxs_bfs_workspace_bytes(B, V), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        L.check(lib.bxs_bfs_forward(L.ptr(te), L.ptr(idx), L.ptr(par), L.ptr(chd), L.ptr(lvl), L.ptr(nlv), L.ptr(ws), B, V,
-                                    int(max_adj_per_node), L.stream()), 'bfs_forward')
+        L.check(lib.bxs_bfs_forward_rooted(L.ptr(te), L.ptr(idx), L.ptr(par), L.ptr(chd), L.ptr(lvl), L.ptr(nlv), L.ptr(ws), B, V,
+                                           int(max_adj_per_node), int(root), L.stream()), 'bfs_forward')
     setattr(idx, _LEVELS, (lvl, nlv, idx._version))
     return idx, par, chd
 

@@ -261,6 +261,11 @@ int64_t bxs_bfs_workspace_bytes(int64_t B, int64_t V);
 int bxs_bfs_forward(const int32_t* tree_edges, int32_t* sorted_index, int32_t* sorted_parent,
                     int32_t* sorted_child, int32_t* level_start, int32_t* num_levels, void* workspace,
                     int64_t B, int64_t V, int max_adj, bxs_stream_t stream);
+/* same, rooted at vertex `root` instead of vertex 0 (the filter's result does not depend on the root; the number of
+ * dependent levels of every pass does: about half from the centre of the map) */
+int bxs_bfs_forward_rooted(const int32_t* tree_edges, int32_t* sorted_index, int32_t* sorted_parent,
+                    int32_t* sorted_child, int32_t* level_start, int32_t* num_levels, void* workspace,
+                    int64_t B, int64_t V, int max_adj, int64_t root, bxs_stream_t stream);
 int bxs_tree_levels(const int32_t* sorted_parent, int32_t* level_start, int32_t* num_levels, void* scratch,
                     int64_t B, int64_t V, bxs_stream_t stream);
 int64_t bxs_refine_scratch_bytes(int64_t B, int64_t C, int64_t V);

@@ -268,3 +268,30 @@ def condinst_mask_head(feat, params, coors, level_inds, img_inds, in_stride=8, o
     x = torch.relu(torch.bmm(w2.reshape(n, channels, channels), x) + b2[:, :, None])
     x = torch.bmm(w3.reshape(n, 1, channels), x) + b3[:, :, None]
     return aligned_bilinear(x.view(n, 1, h, w), in_stride // out_stride)
+
+
+# ----------------------------------------------------------------------------------------
+# f2: CondInstMaskHead.training_sample, topk_per_img branch (condinst_head.py:1166-1232), restated with the same loops
+# ----------------------------------------------------------------------------------------
+def training_sample_topk(cls_scores, centerness, img_inds, gt_inds, topk_per_img):
+    """cls_scores [P,C], centerness [P] (positives only, logits), img_inds / gt_inds [P] -> sampled indices into the
+    positives, in the reference's order: images ascending, unique GT indices ascending, torch.topk order inside a GT that
+    has more than inst_per_gt = max(int(topk / #GTs), 1) positives, original order otherwise."""
+    out = []
+    inst = torch.arange(cls_scores.shape[0])
+    for img_id in range(int(img_inds.max()) + 1 if img_inds.numel() else 0):
+        m = img_inds == img_id
+        if not m.any():
+            continue
+        g = gt_inds[m]
+        ids = inst[m]
+        uniq = g.unique()
+        per_gt = max(int(topk_per_img / uniq.numel()), 1)
+        for gi in uniq:
+            gm = g == gi
+            sel = ids[gm]
+            if sel.numel() > per_gt:
+                sc = cls_scores[m][gm].sigmoid().max(dim=1)[0] * centerness[m][gm].sigmoid()
+                sel = sel[sc.topk(per_gt, dim=0)[1]]
+            out.append(sel)
+    return torch.cat(out) if out else inst[:0]
