@@ -41,7 +41,7 @@ ROTATE = 8
 
 def ncu_traffic_bytes():
     """DRAM bytes per step from the committed ncu --set full capture (None when the summary is absent)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_traffic.json')
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r2_traffic.json')
     try:
         with open(path) as f:
             return float(json.load(f)['step_dram_bytes'])
@@ -208,7 +208,9 @@ def main_reference(args, rank, world):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_img, 'higher_is_better': False,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'BoxInst R-50 mask loss fwd+bwd, 800x1024, 8 GT/img, 64 inst/img (config A)'},
-            'cpu_baseline': {'value': ms_img, 'unit': 'ms/img', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': ms_img, 'unit': 'ms/img', 'cores': cores, 'cores_available': os.cpu_count(),
+                             'cores_note': 'torch intra-op threads capped at 32: the oracle port (elementwise torch ops on '
+                                           '[64,8,200,256] tensors) does not scale beyond that', 'kind': 'port', 'sample': sample},
             'e2e': {'value': ms_img, 'unit': 'ms/img', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 
@@ -218,7 +220,7 @@ def main_reference(args, rank, world):
 # oracle/Makefile into oracle/_ref/, inside a restatement of CondInstMaskHead.loss (condinst_head.py:1288-1343) that
 # materialises what the reference materialises (per-instance similarity [N,8,H,W], bitmask [N,1,H,W], pairwise [N,8,H,W]).
 # ------------------------------------------------------------------------------------------
-def run_gpu_reference(case, dev, iters=10):
+def run_gpu_reference(case, dev, iters=10, ours_grad=None):
     import glob
     import importlib.util
     hits = glob.glob(os.path.join(ROOT, 'oracle', '_ref', 'pairwise_ext_ref*.so'))
@@ -273,7 +275,10 @@ def run_gpu_reference(case, dev, iters=10):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    return {'value': ms / B_IMG, 'unit': 'ms/img', 'ms_per_step': ms, 'iters': iters,
+    grad_err = None
+    if ours_grad is not None:
+        grad_err = float((ours_grad.double() - x.grad.double()).norm() / x.grad.double().norm())
+    return {'value': ms / B_IMG, 'unit': 'ms/img', 'ms_per_step': ms, 'iters': iters, '_grad_rel_err': grad_err,
             'what': "restated CondInstMaskHead.loss (condinst_head.py:1288-1343) on this GPU around the reference's own "
                     'unmodified CUDA pairwise op (oracle/_ref/pairwise_ext_ref, built by oracle/Makefile); targets precomputed, '
                     'eager PyTorch as in the reference',
@@ -359,7 +364,7 @@ def main_cuda(args, rank, world, local_rank):
 
     # ---- the same step (public autograd op, forward + backward) captured once per rotating input set
     #      into CUDA graphs: removes the ~0.2 ms/step of Python/autograd launch overhead ----
-    graphs, mode, steps_timed = [], 'cuda_graph', args.steps
+    graphs, mode, steps_timed, ms_step_spread = [], 'cuda_graph', args.steps, None
     try:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -372,21 +377,38 @@ def main_cuda(args, rank, world, local_rank):
         torch.cuda.synchronize()
         # one graph = ROTATE consecutive steps over the rotating input sets (a training loop captures whole
         # iterations the same way); the graph launch latency is amortised over its steps
-        g = torch.cuda.CUDAGraph()
-        for x in logit_sets:
-            x.grad = None
-        with torch.cuda.graph(g):
-            for i in range(ROTATE):
-                x = logit_sets[i]
-                prj, pair = boxinst_mask_loss(x, targets, gt_inds32, it, plan=plan)
-                torch.autograd.backward([prj, pair], [ones, ones])
-                graphs.append((prj, pair, x.grad))
+        def capture(n_steps, first):
+            gr = torch.cuda.CUDAGraph()
+            for x in logit_sets:
+                x.grad = None
+            with torch.cuda.graph(gr):
+                for i in range(first, first + n_steps):
+                    x = logit_sets[i % ROTATE]
+                    prj, pair = boxinst_mask_loss(x, targets, gt_inds32, it, plan=plan)
+                    torch.autograd.backward([prj, pair], [ones, ones])
+                    graphs.append((prj, pair, x.grad))
+            return gr
+        # EXACTLY args.steps steps per timed region: full graphs of ROTATE steps + one tail graph of steps % ROTATE
+        full, tail = args.steps // ROTATE, args.steps % ROTATE
+        g = capture(ROTATE, 0)
+        g_tail = capture(tail, 0) if tail else None
         for i in range(max(warm // ROTATE, 1)):
             g.replay()
-        reps = max(args.steps // ROTATE, 1)
-        ms_step = timed(lambda i: g.replay(), reps) / ROTATE
-        steps_timed = reps * ROTATE
-        mode = f'cuda_graph ({ROTATE} steps per graph)'
+
+        def region(_i):
+            for _ in range(full):
+                g.replay()
+            if g_tail is not None:
+                g_tail.replay()
+        # a region of K steps is ~25 us x K: one hiccup would move the headline, so the region is timed REGIONS times
+        # (each bracketed by barrier + synchronize, device events) and the median region is reported
+        REGIONS = 15
+        samples = sorted(timed(region, 1) for _ in range(REGIONS))
+        ms_step = samples[REGIONS // 2] / args.steps
+        ms_step_spread = (samples[0] / args.steps, samples[-1] / args.steps)
+        steps_timed = args.steps
+        mode = f'cuda_graph ({ROTATE} steps per graph' + (f' + one tail graph of {tail}' if tail else '') + \
+            f'); median of {REGIONS} timed regions of {args.steps} steps'
     except Exception as e:  # noqa: BLE001
         mode = f'eager (graph capture failed: {type(e).__name__})'
         ms_step = ms_eager
@@ -527,15 +549,15 @@ def main_cuda(args, rank, world, local_rank):
                    'aggregate_img_per_s': world * B_IMG / (ms_step * 1e-3)},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': ncu_traffic_bytes(),
-                     'traffic_source': 'profiles/r1_traffic.json (ncu --set full, dram read+write per launch, summed over the '
+                     'traffic_source': 'profiles/r2_traffic.json (ncu --set full, dram read+write per launch, summed over the '
                                        'kernels of one step)',
                      'peak_source': peak_src,
-                     'note': 'headline = the WHOLE step (onepass_main + onepass_finalize + onepass_backward kernels, CUDA-graph '
-                             'replay through the public autograd op) against the 85.2 MB/step ALGORITHMIC figure of SURVEY 8d '
+                     'note': 'headline = the WHOLE step (wq_main + wq_finalize + onepass_backward kernels, CUDA-graph replay '
+                             'through the public autograd op) against the 85.2 MB/step ALGORITHMIC figure of SURVEY 8d '
                              '(logits read in fwd and in bwd + gradient written + similarity read twice).  The single-pass '
                              'schedule moves 52.5 MB (logits once, gradient once, edge bytes): see kernels.*; the dominant '
-                             'kernel is onepass_main_kernel (its share of the step: profiles/r1_launches_bench.csv)',
-                     'kernels': {'single_pass_forward(onepass_main+onepass_finalize)': {
+                             'kernel is wq_main_kernel (its share of the step: profiles/r2_launches_bench.csv)',
+                     'kernels': {'single_pass_forward(wq_main+wq_finalize)': {
                                      'us': us_one_fwd, 'moved_mb': ONEPASS_BYTES / 1e6,
                                      'achieved_moved': ONEPASS_BYTES / (us_one_fwd * 1e-6) / 1e9,
                                      'frac_moved': ONEPASS_BYTES / (us_one_fwd * 1e-6) / 1e9 / peak,
@@ -550,22 +572,38 @@ def main_cuda(args, rank, world, local_rank):
                                                                  'frac': ach_b / peak}},
                      'timing': 'per-call numbers: 8 rotating calls captured in one CUDA graph, CUDA events around replays'},
         'e2e': {'value': ms_e2e / (B_IMG * world), 'unit': 'ms/img', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-        'gpu_launches': 3 * steps_timed,        # onepass_main + onepass_finalize + onepass_backward kernels per step
+        'gpu_launches': 3 * steps_timed,        # wq_main + wq_finalize + onepass_backward kernels per step
         'clocks': clocks,
     }
     if ddp is not None:
         line['ddp_allreduce'] = ddp
     if pinned_cpus:
         line['config']['cpu_affinity_rank0'] = pinned_cpus
+    # the B200 arm's own results on logit set 0 (the set the gpu_reference leg uses)
+    x0 = logit_sets[0].detach().clone().requires_grad_(True)
+    p0, q0 = boxinst_mask_loss(x0, targets, gt_inds32, it, plan=plan)
+    (g0,) = torch.autograd.grad(p0 + q0, x0)
+    line['losses'] = {'loss_prj': float(p0), 'loss_pairwise': float(q0), 'logit_set': 0}
+    if ms_step_spread is not None:
+        line['config']['region_ms_per_step_min_max'] = list(ms_step_spread)
     if cpu_ms is not None:
-        line['cpu_baseline'] = {'value': cpu_ms, 'unit': 'ms/img', 'cores': cores, 'kind': 'port', 'sample': sample}
+        line['cpu_baseline'] = {'value': cpu_ms, 'unit': 'ms/img', 'cores': f'{cores} of {os.cpu_count()}', 'kind': 'port',
+                                'sample': sample}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            ref_gpu = run_gpu_reference(case, dev)
+            ref_gpu = run_gpu_reference(case, dev, ours_grad=g0)
         except Exception as e:  # noqa: BLE001  (baseline only: never let it take the bench line down)
             ref_gpu = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
         if ref_gpu is not None:
             line['gpu_reference'] = ref_gpu
+            if 'loss_prj' in ref_gpu and 'losses' in line:
+                rp, rq = ref_gpu['loss_prj'], ref_gpu['loss_pairwise']
+                line['parity_vs_gpu_reference'] = {
+                    'rel_err_loss_prj': abs(line['losses']['loss_prj'] - rp) / abs(rp),
+                    'rel_err_loss_pairwise': abs(line['losses']['loss_pairwise'] - rq) / abs(rq),
+                    'rel_err_grad': ref_gpu.pop('_grad_rel_err', None),
+                    'what': 'B200 arm vs the restated reference loss around the reference CUDA pairwise op, same logits (set 0), '
+                            'same targets; bar: 1e-3 (BASELINE.json north_star)'}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

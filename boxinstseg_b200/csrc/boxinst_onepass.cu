@@ -53,7 +53,10 @@ struct OpWorkspace {
 
 inline size_t op_align(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
-constexpr int OP_LEN = 8;          // rows per pair-chain piece
+#ifndef BXS_OP_LEN
+#define BXS_OP_LEN 12
+#endif
+constexpr int OP_LEN = BXS_OP_LEN;  // rows per pair-chain piece (build-time tunable for A/B runs)
 
 inline int64_t op_max_groups(int64_t H, int64_t W) {      // upper bound of ceil(chains / 8) for any box and dilation 1..4
   int64_t best = 1;

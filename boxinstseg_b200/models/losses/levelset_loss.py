@@ -181,8 +181,10 @@ class _LCM(torch.autograd.Function):
 
 
 class LocalConsistencyModule(nn.Module):
-    """levelset_loss.py:74-126: returns the refined phi (forward only helper kept for API parity;
-    the differentiable loss is ``LCM``)."""
+    """levelset_loss.py:74-126: ``forward(imgs, masks)`` returns the masks after ``num_iter`` rounds of affinity-weighted
+    neighbour averaging (dilation 2, 8 neighbours, alpha 0.3) -- the refined phi the ``LCM`` loss compares with its input.
+    Runs the same kernels as ``LCM`` (bxs_lcm_forward) and reads the refined map out of their workspace; no autograd
+    node (the differentiable entry point is ``LCM``, which is what Box2MaskHead.loss_single calls, box2mask_head.py:331)."""
 
     def __init__(self, dilations, num_iter):
         super().__init__()
@@ -190,6 +192,24 @@ class LocalConsistencyModule(nn.Module):
         self.dilations = dilations
         self.num_iter = num_iter
         self.alpha = 0.3
+
+    @torch.no_grad()
+    def forward(self, imgs, masks):
+        im = imgs.contiguous().float()
+        ph = masks.contiguous().float()
+        L.require_cuda(im, ph)
+        n, C, h, w = im.shape
+        assert ph.shape == (n, 1, h, w)
+        lib = L.lib()
+        out = torch.zeros(1, dtype=torch.float32, device=im.device)
+        ws = torch.empty(max(lib.bxs_lcm_workspace_bytes(n, h, w), 4), dtype=torch.uint8, device=im.device)
+        if n == 0:
+            return ph
+        with torch.cuda.device(im.device):
+            L.check(lib.bxs_lcm_forward(L.ptr(im), L.ptr(ph), L.ptr(torch.ones_like(ph)), L.ptr(out), L.ptr(ws), n, C, h, w,
+                                        self.dilations[0], self.num_iter, L.stream()), 'lcm_forward')
+        hw = h * w
+        return ws.view(torch.float32)[n * 8 * hw: n * 9 * hw].view(n, 1, h, w).clone()     # phi_T of the workspace layout
 
 
 def LCM(imgs, pred_phis, box_targets):

@@ -1,8 +1,10 @@
 """a2/a3/a4: dense dynamic 1x1 convolution ``out[b,i] = sum_c kernel[b,i,c] * feat[b,c]`` on tcgen05.
 
 Forward is the hand-written TMA + tcgen05 (TF32, FP32 accumulate in TMEM) kernel of libboxseg_b200.
-Backward is two plain GEMMs (d/d kernel = g_out . feat^T, d/d feat = kernel^T . g_out) issued through
-cuBLAS (torch.bmm) -- plain library GEMMs with no fusion opportunity.
+Backward is the same machinery (bxs_dynconv1x1_backward): d/d feat = kernel^T . g_out re-uses the forward kernel with
+the operand roles swapped, d/d kernel = g_out . feat^T is a split-K tcgen05 kernel over the pixels with an ordered
+(deterministic) reduction of the partials.  Only d/d feat with more than 256 kernels per image (outside every reference
+call site: the heads convolve the POSITIVE kernels of an image) goes through cuBLAS (torch.bmm).
 """
 import torch
 
@@ -30,9 +32,24 @@ class _DynConv1x1(torch.autograd.Function):
     def backward(ctx, g_out):
         f, k = ctx.saved_tensors
         B, C, h, w = f.shape
-        g = g_out.contiguous().float().flatten(2)                    # [B,I,P]
-        gk = torch.bmm(g, f.flatten(2).transpose(1, 2)) if ctx.needs_input_grad[1] else None     # [B,I,C]
-        gf = torch.bmm(k.transpose(1, 2), g).view(B, C, h, w) if ctx.needs_input_grad[0] else None
+        I = k.shape[1]
+        need_f, need_k = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (B and I) or not (need_f or need_k):
+            return (torch.zeros_like(f) if need_f else None), (torch.zeros_like(k) if need_k else None)
+        g = g_out.contiguous().float()
+        gf = gk = None
+        native_f = need_f and I <= 256
+        if need_f and not native_f:
+            gf = torch.bmm(k.transpose(1, 2), g.flatten(2)).view(B, C, h, w)
+        if native_f or need_k:
+            gf = torch.empty_like(f) if native_f else gf
+            gk = torch.empty_like(k) if need_k else None
+            with torch.cuda.device(f.device):
+                ws = torch.empty(L.lib().bxs_dynconv1x1_backward_workspace_bytes(B, C, h * w, I), dtype=torch.uint8,
+                                 device=f.device)
+                L.check(L.lib().bxs_dynconv1x1_backward(L.ptr(f), L.ptr(k), L.ptr(g), L.ptr(gf) if native_f else None,
+                                                        L.ptr(gk), L.ptr(ws), B, C, h * w, I, L.stream()),
+                        'dynconv1x1_backward')
         return gf, gk
 
 

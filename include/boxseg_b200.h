@@ -297,6 +297,16 @@ int bxs_refine_backward_weight(const float* edge_weight, const int32_t* sorted_i
 int bxs_dynconv1x1_forward(const float* feat, const float* kernels, float* out, int64_t B, int64_t C, int64_t P,
                            int64_t I, bxs_stream_t stream);
 
+/* Backward of the dynamic 1x1 convolution (autograd of the same call sites; the reference gets it from cuDNN / cuBLAS):
+ *   g_feat    [B,C,P] = kernels^T . g_out   (tcgen05: the forward kernel with the operand roles swapped; I <= 256)
+ *   g_kernels [B,I,C] = g_out . feat^T      (tcgen05 split-K over the pixels + an ordered reduction: deterministic)
+ * Either output may be NULL (not needed).  TF32 inputs, FP32 accumulation.  workspace:
+ * bxs_dynconv1x1_backward_workspace_bytes(B, C, P, I) bytes.  BXS_ERR_UNSUPPORTED: the forward's shape rules, or g_feat with
+ * I > 256. */
+int64_t bxs_dynconv1x1_backward_workspace_bytes(int64_t B, int64_t C, int64_t P, int64_t I);
+int bxs_dynconv1x1_backward(const float* feat, const float* kernels, const float* g_out, float* g_feat, float* g_kernels,
+                            void* workspace, int64_t B, int64_t C, int64_t P, int64_t I, bxs_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  *   projection profiles of a bilinearly resized map, never materialised.
  *     replaces, for BoxMatchingCost (mmdet/core/bbox/match_costs/match_cost.py:400-425), the F.interpolate of

@@ -142,6 +142,18 @@ def test_lcm_vs_oracle(n, h, w):
     assert torch.equal(gp, gp2)
 
 
+def test_local_consistency_module_forward():
+    """LocalConsistencyModule.forward (levelset_loss.py:121-126): the refined masks themselves."""
+    from boxinstseg_b200.models.losses import LocalConsistencyModule
+    from oracle.levelset import lcm_refine
+    gen = torch.Generator().manual_seed(8)
+    imgs = torch.rand(3, 3, 96, 96, generator=gen)
+    phis = torch.rand(3, 1, 96, 96, generator=gen)
+    out = LocalConsistencyModule(dilations=[2], num_iter=10)(imgs.to(DEV), phis.to(DEV))
+    ref = lcm_refine(imgs.double(), phis.double(), 10, 2)
+    assert out.shape == phis.shape and rel_err(out.cpu(), ref) <= 1e-5
+
+
 # ------------------------------------------------------------------ a16 mean field
 def test_meanfield_golden(golden):
     from boxinstseg_b200.models.dense_heads import MeanField
