@@ -30,6 +30,8 @@ SIGNATURES = {
     'bxs_boxinst_similarity': [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_int, c_f, c_p],
     'bxs_boxinst_rects': [c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p],
     'bxs_boxinst_bitmasks': [c_p, c_p, c_i64, c_i64, c_i64, c_p],
+    'bxs_boxinst_targets_forward': [c_p] * 13 + [c_i64] * 3 + [c_int] * 3 + [c_f, c_p],
+    'bxs_rgb_u8_to_lab': [c_p, c_p, c_i64, c_p],
     'bxs_boxinst_loss_workspace_bytes': [c_i64, c_i64, c_i64],
     'bxs_boxinst_loss_forward': [c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p],
     'bxs_boxinst_loss_backward': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p],

@@ -18,7 +18,8 @@
 // memory for the whole CTA lifetime), so one CTA per SM streams pixel tiles:
 //   warp 0   : TMA producer (B once, then a 4-stage ring of 16 KB A stages)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (4 MMAs of K = 8 per stage)
-//   warps 2-5: epilogue -- tcgen05.ld 32x32b (one pixel per thread) and coalesced stores
+//   warps 2-9: epilogue -- tcgen05.ld 32x32b (one pixel per thread; the two warps of a lane quarter split the
+//              columns) and coalesced stores
 // synchronised with mbarriers only (full/empty per stage, tmem_full/tmem_empty per accumulator).
 #include <cuda.h>
 
@@ -34,10 +35,11 @@ constexpr int BLOCK_N = 128;        // kernels per CTA (TMEM columns per accumul
 constexpr int BLOCK_K = 32;         // channels per stage = one 128-byte swizzle row of tf32
 constexpr int UMMA_K = 8;           // tf32: 32 bytes per instruction
 constexpr int MAX_KBLOCKS = 8;      // C <= 256
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;            // 96 KB of feat in flight per SM (4 stages measured 0.54 of HBM peak: latency bound)
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;      // 16 KB
 constexpr int B_KBLOCK_BYTES = BLOCK_N * BLOCK_K * 4;     // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;     // forward: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int WG_THREADS = 192;      // d/d kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int TMEM_COLS = 2 * BLOCK_N;                    // 256 (power of two)
 
 struct SmemLayout {
@@ -136,6 +138,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // grid: (ctas_per_group, B * n_chunks).  CTA (x, g): image b = g / n_chunks, kernel chunk g % n_chunks,
 // pixel tiles x, x + gridDim.x, ...
@@ -153,7 +163,7 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
     mbar_init(&S.b_full, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {                      // TMEM allocation by one full warp; the same warp frees it
@@ -219,6 +229,8 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int quarter = warp & 3;                  // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
+    const int half = (warp - 2) >> 2;              // warps 2-5: columns [0, 64), warps 6-9: columns [64, 128)
+    const int c_lo = half * (BLOCK_N / 2), c_hi = min(n_here, c_lo + BLOCK_N / 2);
     int t = 0;
     for (int mt = blockIdx.x; mt < tiles_m; mt += gridDim.x, ++t) {
       const int acc = t & 1;
@@ -227,13 +239,16 @@ dynconv_tf32_kernel(const __grid_constant__ CUtensorMap tm_feat, const __grid_co
       const int pixel = mt * BLOCK_M + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       float* dst = out + ((int64_t)b * I + chunk * BLOCK_N) * P + pixel;
-      for (int c0 = 0; c0 < n_here; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+        uint32_t r[32];
+        const bool two = c0 + 16 < c_hi;
+        tmem_ld16_async(taddr + c0, r);
+        if (two) tmem_ld16_async(taddr + c0 + 16, r + 16);
+        tmem_ld_wait();
         if (pixel < P) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (chunk * BLOCK_N + c0 + j < I) dst[(int64_t)(c0 + j) * P] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j)
+            if ((j < 16 || two) && chunk * BLOCK_N + c0 + j < I) dst[(int64_t)(c0 + j) * P] = __uint_as_float(r[j]);
         }
       }
       tc_fence_before();
@@ -331,7 +346,7 @@ __device__ __forceinline__ uint32_t make_idesc_kk(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 dynconv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_feat,
                      float* __restrict__ partial, int C, int P, int I, int chunks, int splits, int kb_per_split) {
   extern __shared__ uint8_t smem_raw[];
@@ -526,7 +541,7 @@ extern "C" int bxs_dynconv1x1_backward(const float* feat, const float* kernels, 
     }
     const size_t smem = sizeof(WgSmem) + 1024;
     cudaFuncSetAttribute(dynconv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dynconv_wgrad_kernel<<<dim3((unsigned)splits, (unsigned)(B * chunks)), NUM_THREADS, smem, st>>>(
+    dynconv_wgrad_kernel<<<dim3((unsigned)splits, (unsigned)(B * chunks)), WG_THREADS, smem, st>>>(
         tm_g, tm_f, partial, (int)C, (int)P, (int)I, chunks, splits, kb_per);
     int rc = check_launch();
     if (rc != BXS_OK) return rc;

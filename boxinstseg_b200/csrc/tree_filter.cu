@@ -499,13 +499,52 @@ __global__ void __launch_bounds__(NT) levels_from_parent_kernel(const int32_t* _
 // ---------------------------------------------------------------------------------------
 // tree aggregation
 // ---------------------------------------------------------------------------------------
-// The recursion has one dependent step per tree level (~1700 levels for a 200x256 image MST), so the cost of a
-// level IS the kernel time.  Everything a level needs is therefore (a) made chain-free by parallel pre-passes
-// (values gathered into position order; child weights packed next to the child range) and (b) prefetched into
-// registers PF levels ahead, so that the per-level critical path is shared-memory read -> FMA -> write -> barrier.
-constexpr int PF = 4;                    // software-pipeline depth (levels in flight)
-constexpr int RNT = 256;                 // threads of a refine CTA: a level up to RNT nodes wide is served by the prefetch ring; 64 was
-                                         // measured SLOWER (wide levels fall back to un-prefetched loads: +8 % forward, +30 % backward)
+// The recursion has one dependent step per tree level (~1700 levels for a 200x256 image MST, ~30 nodes each), so the
+// cost of a level IS the kernel time, and a level is the INSTRUCTION STREAM of the one warp that owns its nodes: an
+// in-order warp at ~4-7 cycles per dependent instruction.  History of the level loop:
+//   round 1   : dependent global loads inside the level                             ~1600 cycles / level
+//   round 2a  : register prefetch rings (node data PF levels ahead, bounds 2 PF)     ~500 cycles / level: ~90 warp
+//               instructions, two thirds of them the address arithmetic of the prefetch, four LDS -> FFMA -> BRA steps
+//   round 2b  : this version.  PRODUCER warps (4-7) run the prefetch: per level they read the level's bounds from a
+//               shared-memory window, issue cp.async copies of the node records into a PF-deep shared-memory ring and
+//               retire the group of two levels ahead (cp.async groups complete in order).  CONSUMER warps (0-3; warp 0
+//               alone for a level of <= 32 nodes) only read the ring -- one level ahead, into registers, in the shadow of
+//               the current level's loads -- and do: five shared-memory loads, one FMA chain, one store, the barrier.
+// One __syncthreads per level publishes the consumers' values and the producers' ring slots at once.
+constexpr int PF = 6;                    // levels in flight in the copy ring
+constexpr int RNT = 256;                 // threads of a refine CTA (parallel pre-passes; 4 consumer + 4 producer warps)
+constexpr int RW = 128;                  // ring width = consumer threads; wider levels: the other threads load directly
+constexpr int LWIN = 1024;               // level-bound window (entries), power of two
+constexpr int LCHUNK = 256;              // window refill granularity (two entries per producer thread)
+static_assert(RNT == 2 * RW && LCHUNK == 2 * RW && (LWIN & (LWIN - 1)) == 0 && LWIN >= 4 * LCHUNK, "refine CTA shape");
+
+struct RingSmem {
+  float4 q[PF][RW];                      // up: child weights; sweep: (ind, outd[parent], grad so far)
+  int ia[PF][RW];                        // up: child range; down / sweep: parent position
+  float fa[PF][RW];                      // down / sweep: edge weight
+  int lvl[LWIN];
+};
+struct Rec { float4 q; int ia; float fa; };
+
+#ifdef BXS_TREE_TRACE
+// per-level clock stamps of the first CTA's up pass: [0..2] consumer thread 0 (level top, after its store was issued,
+// at the barrier), [3..5] producer thread RW (level top, copies issued, group wait done)
+__device__ long long g_tree_trace[6][4096];
+#define TREE_TT(k, i) do { if (DIR < 0 && blockIdx.x == 0 && blockIdx.y == 0 && (i) < 4096) g_tree_trace[k][i] = clock64(); } while (0)
+#else
+#define TREE_TT(k, i) do { } while (0)
+#endif
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cpa4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpa16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct TreeView {
   const int32_t* idx;     // [V] position -> vertex
@@ -536,98 +575,182 @@ __global__ void tree_pack_kernel(const float* __restrict__ w, const int32_t* __r
   }
 }
 
-struct UpNode { int s, e, ci; float4 cw; };
-struct DownNode { int s, e, par; float w; };
-
-// Level bounds travel through their own register ring, PF levels AHEAD of the node ring: the node loads of a level
-// depend on its bounds, and a dependent pair inside one fetch would put an L2 round trip on every level's critical
-// path (round 1: ~0.85 us per level).  With the two rings no load is waited for at the point it is issued.
-struct Bnd { int s, e; };
-__device__ __forceinline__ Bnd fetch_bnd(const TreeView& t, int l, int lmin) {
-  Bnd b;
-  b.s = b.e = 0;
-  if (l >= lmin && l < t.L) { b.s = __ldg(t.lvl + l); b.e = __ldg(t.lvl + l + 1); }
-  return b;
-}
-__device__ __forceinline__ UpNode fetch_up(const TreeView& t, const Bnd b) {
-  UpNode n;
-  n.s = b.s; n.e = b.e; n.ci = 0; n.cw = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int p = b.s + threadIdx.x;
-  if (p < b.e) { n.ci = __ldg(t.cinfo + p); n.cw = __ldg(t.cw + p); }
-  return n;
-}
-__device__ __forceinline__ DownNode fetch_down(const TreeView& t, const Bnd b) {
-  DownNode n;
-  n.s = b.s; n.e = b.e; n.par = 0; n.w = 0.f;
-  const int p = b.s + threadIdx.x;
-  if (p < b.e) { n.par = __ldg(t.par + p); n.w = __ldg(t.w + p); }
-  return n;
-}
-
+// PADDED (shared-memory buffer with 4 zeroed floats behind position V-1): the four child slots are read and
+// accumulated unconditionally -- a missing child has weight 0 (tree_pack_kernel) and its slot holds some finite node
+// value, so it adds an exact zero.  The conditional form serialises up to four shared-memory round trips and four
+// branches on the critical path of EVERY level (SASS: LDS -> FFMA -> BRA, four times); this one is four independent
+// loads and one FMA chain.  (A NaN/Inf input makes every output NaN in either form: the down pass spreads the root's
+// aggregate to all nodes.)
+template <bool PADDED>
 __device__ __forceinline__ float up_node(float own, int ci, const float4& cw, const float* buf) {
   const int first = ci & 0x0fffffff, n = ci >> 28;
   float acc = own;
-  if (n > 0) acc = fmaf(buf[first], cw.x, acc);
-  if (n > 1) acc = fmaf(buf[first + 1], cw.y, acc);
-  if (n > 2) acc = fmaf(buf[first + 2], cw.z, acc);
-  if (n > 3) acc = fmaf(buf[first + 3], cw.w, acc);
+  if (PADDED) {
+    const float b0 = buf[first], b1 = buf[first + 1], b2 = buf[first + 2], b3 = buf[first + 3];
+    acc = fmaf(b0, cw.x, acc);
+    acc = fmaf(b1, cw.y, acc);
+    acc = fmaf(b2, cw.z, acc);
+    acc = fmaf(b3, cw.w, acc);
+  } else {
+    if (n > 0) acc = fmaf(buf[first], cw.x, acc);
+    if (n > 1) acc = fmaf(buf[first + 1], cw.y, acc);
+    if (n > 2) acc = fmaf(buf[first + 2], cw.z, acc);
+    if (n > 3) acc = fmaf(buf[first + 3], cw.w, acc);
+  }
   return acc;
 }
 
-// buf[p] holds the node's own input on entry; on exit U[p] = in(p) + sum_children w[c] U[c].  Deepest level first.
-__device__ __forceinline__ void up_pass(const TreeView& t, float* buf, float* __restrict__ save_up) {
-  UpNode ring[PF];
-  Bnd bring[PF];
+// Walk the levels in dependency order (DIR = -1: deepest level .. root, DIR = +1: level 1 .. deepest).
+//   issue(p, slot, i)        producer thread: cp.async copies of the record of position p into ring[slot][i]
+//   compute(p, on, rec)      consumer thread i < RW: position p = level start + i (`on`: p is inside the level), `rec` =
+//                            its record (UNDEFINED when !on: idle threads must not use it for addresses)
+//   direct(p)                any thread: the same work for position p with plain global loads (levels wider than RW)
+template <int DIR, typename Issue, typename Compute, typename Direct>
+__device__ __forceinline__ void level_walk(const TreeView& t, RingSmem& R, Issue issue, Compute compute, Direct direct) {
+  const int tid = threadIdx.x;
+  const bool producer = tid >= RW;
+  const int slot_i = producer ? tid - RW : tid;
+  const int first = DIR > 0 ? 1 : t.L - 1, last = DIR > 0 ? t.L - 1 : 0;
+  __syncthreads();                                          // the previous walk is done with the ring and the window
+  if (DIR > 0 ? first > last : first < last) return;
+  if (DIR > 0) {
+    for (int e = tid; e < LWIN - LCHUNK; e += RNT)
+      if (e <= t.L) cpa4(&R.lvl[e & (LWIN - 1)], t.lvl + e);
+  } else {
+    const int hi = ((t.L - 1) | (LCHUNK - 1)) + 1;
+    for (int k = tid; k < LWIN - LCHUNK; k += RNT) {
+      const int e = hi - k;
+      if (e >= 0 && e <= t.L) cpa4(&R.lvl[e & (LWIN - 1)], t.lvl + e);
+    }
+  }
+  cp_commit();
+  cp_wait<0>();
+  __syncthreads();
+  auto lv = [&](int l) { return R.lvl[l & (LWIN - 1)]; };
+  auto inside = [&](int l) { return DIR > 0 ? l <= last : l >= last; };
+  auto issue_level = [&](int l, int slot) {
+    if (inside(l)) {
+      const int s = lv(l), e = lv(l + 1);
+      if (s + (slot_i & ~31) < e) {                         // warp-uniform: most levels need only the first producer warp
+        const int p = s + slot_i;
+        if (p < e) issue(p, slot, slot_i);
+      }
+    }
+    cp_commit();                                            // one group per level, empty or not: the count is what matters
+  };
+  auto load_rec = [&](int slot) {
+    Rec r;
+    r.q = R.q[slot][slot_i]; r.ia = R.ia[slot][slot_i]; r.fa = R.fa[slot][slot_i];
+    return r;
+  };
+  if (producer) {
 #pragma unroll
-  for (int j = 0; j < PF; ++j) ring[j] = fetch_up(t, fetch_bnd(t, t.L - 1 - j, 0));
-#pragma unroll
-  for (int j = 0; j < PF; ++j) bring[j] = fetch_bnd(t, t.L - 1 - PF - j, 0);
-  for (int l0 = t.L - 1; l0 >= 0; l0 -= PF) {
+    for (int j = 0; j < PF; ++j) issue_level(first + DIR * j, j);
+    cp_wait<PF - 2>();                                      // the first two levels have landed
+  }
+  __syncthreads();
+  Rec rec;
+  rec.q = make_float4(0.f, 0.f, 0.f, 0.f); rec.ia = 0; rec.fa = 0.f;
+  int s = 0, e = 0;
+  if (!producer) {
+    s = lv(first); e = lv(first + 1);
+    rec = load_rec(0);
+  }
+  for (int l0 = first; DIR > 0 ? l0 <= last : l0 >= last; l0 += DIR * PF) {
 #pragma unroll
     for (int j = 0; j < PF; ++j) {
-      const int l = l0 - j;
-      if (l < 0) break;
-      const UpNode nd = ring[j];
-      ring[j] = fetch_up(t, bring[j]);                      // level l - PF: its bounds were loaded PF levels ago
-      bring[j] = fetch_bnd(t, l - 2 * PF, 0);
-      int p = nd.s + threadIdx.x;
-      if (p < nd.e) buf[p] = up_node(buf[p], nd.ci, nd.cw, buf);
-      for (p += RNT; p < nd.e; p += RNT)                    // wide levels: plenty of parallelism, plain loads
-        buf[p] = up_node(buf[p], __ldg(t.cinfo + p), __ldg(t.cw + p), buf);
+      const int l = l0 + DIR * j;
+      if (DIR > 0 ? l > last : l < last) break;
+      if (!producer) {
+        if (tid == 0) TREE_TT(0, DIR * (l - first));
+        const int p = s + tid;
+        compute(p, p < e, rec);
+        if (tid == 0) TREE_TT(1, DIR * (l - first));
+        asm volatile("" ::: "memory");                      // keep the next level's loads BEHIND this level's store
+        // next level's bounds and record (complete since the previous barrier): their latency hides in the barrier.
+        // Loaded unconditionally (no dependent round trip); compute() ignores the record of an idle thread.
+        Rec nrec = rec;
+        int ns = 0, ne = 0;
+        if (inside(l + DIR)) { ns = lv(l + DIR); ne = lv(l + DIR + 1); nrec = load_rec((j + 1) % PF); }
+#pragma unroll 1
+        for (int p2 = p + RNT; p2 < e; p2 += RNT) direct(p2);
+        rec = nrec; s = ns; e = ne;
+        if (tid == 0) TREE_TT(2, DIR * (l - first));
+      } else {
+        if (tid == RW) TREE_TT(3, DIR * (l - first));
+        const int ls = lv(l), le = lv(l + 1);
+#pragma unroll 1
+        for (int p2 = ls + tid; p2 < le; p2 += RNT) direct(p2);            // positions RW.. of a wide level
+        // window refill, two entries per producer thread, rides in this level's group; read 250+ levels later
+        if (DIR > 0) {
+          if ((l & (LCHUNK - 1)) == 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int en = l + LWIN - 2 * LCHUNK + slot_i + h * RW;
+              if (en <= t.L) cpa4(&R.lvl[en & (LWIN - 1)], t.lvl + en);
+            }
+          }
+        } else {
+          if ((l & (LCHUNK - 1)) == LCHUNK - 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int en = l - (2 * LCHUNK - 1) - slot_i - h * RW;
+              if (en >= 0) cpa4(&R.lvl[en & (LWIN - 1)], t.lvl + en);
+            }
+          }
+        }
+        issue_level(l + DIR * PF, j);                       // slot j: its record was read by the consumers a level ago
+        if (tid == RW) TREE_TT(4, DIR * (l - first));
+        cp_wait<PF - 2>();                                  // level l + 2 has landed: visible to the consumers after the barrier
+        if (tid == RW) TREE_TT(5, DIR * (l - first));
+      }
       __syncthreads();
     }
   }
+  if (producer) cp_wait<0>();
+}
+
+// buf[p] holds the node's own input on entry; on exit U[p] = in(p) + sum_children w[c] U[c].  Deepest level first.
+template <bool PADDED>
+__device__ __forceinline__ void up_pass(const TreeView& t, RingSmem& R, float* buf, float* __restrict__ save_up) {
+  level_walk<-1>(
+      t, R,
+      [&](int p, int slot, int i) {
+        cpa4(&R.ia[slot][i], t.cinfo + p);
+        cpa16(&R.q[slot][i], t.cw + p);
+      },
+      [&](int p, bool on, const Rec& r) {
+        if (PADDED) {
+          const int first = on ? (r.ia & 0x0fffffff) : 0;
+          const float own = buf[on ? p : 0], b0 = buf[first], b1 = buf[first + 1], b2 = buf[first + 2], b3 = buf[first + 3];
+          if (on) buf[p] = fmaf(b3, r.q.w, fmaf(b2, r.q.z, fmaf(b1, r.q.y, fmaf(b0, r.q.x, own))));
+        } else {
+          if (on) buf[p] = up_node<false>(buf[p], r.ia, r.q, buf);
+        }
+      },
+      [&](int p) { buf[p] = up_node<PADDED>(buf[p], __ldg(t.cinfo + p), __ldg(t.cw + p), buf); });
   // U of every position is in `buf`: one coalesced sweep instead of a global store on every level's critical path
   if (save_up)
     for (int p = threadIdx.x; p < t.V; p += RNT) save_up[p] = buf[p];
 }
 
 // in place: A[0] = U[0]; A[p] = (1 - w^2) U[p] + w A[par]; writes the vertex-ordered result
-__device__ __forceinline__ void down_pass(const TreeView& t, float* buf, float* __restrict__ out_vertex) {
-  DownNode ring[PF];
-  Bnd bring[PF];
-#pragma unroll
-  for (int j = 0; j < PF; ++j) ring[j] = fetch_down(t, fetch_bnd(t, 1 + j, 1));
-#pragma unroll
-  for (int j = 0; j < PF; ++j) bring[j] = fetch_bnd(t, 1 + PF + j, 1);
-  __syncthreads();
-  for (int l0 = 1; l0 < t.L; l0 += PF) {
-#pragma unroll
-    for (int j = 0; j < PF; ++j) {
-      const int l = l0 + j;
-      if (l >= t.L) break;
-      const DownNode nd = ring[j];
-      ring[j] = fetch_down(t, bring[j]);
-      bring[j] = fetch_bnd(t, l + 2 * PF, 1);
-      int p = nd.s + threadIdx.x;
-      if (p < nd.e) buf[p] = fmaf(buf[nd.par], nd.w, buf[p] * (1.f - nd.w * nd.w));
-      for (p += RNT; p < nd.e; p += RNT) {
+__device__ __forceinline__ void down_pass(const TreeView& t, RingSmem& R, float* buf, float* __restrict__ out_vertex) {
+  level_walk<1>(
+      t, R,
+      [&](int p, int slot, int i) {
+        cpa4(&R.ia[slot][i], t.par + p);
+        cpa4(&R.fa[slot][i], t.w + p);
+      },
+      [&](int p, bool on, const Rec& r) {
+        const float a_par = buf[on ? r.ia : 0], u_own = buf[on ? p : 0];
+        if (on) buf[p] = fmaf(a_par, r.fa, u_own * (1.f - r.fa * r.fa));
+      },
+      [&](int p) {
         const float ew = __ldg(t.w + p);
         buf[p] = fmaf(buf[__ldg(t.par + p)], ew, buf[p] * (1.f - ew * ew));
-      }
-      __syncthreads();
-    }
-  }
+      });
+  __syncthreads();
   // A of every position is in `buf`: scatter to vertex order in one parallel sweep (not level by level)
   if (out_vertex)
     for (int p = threadIdx.x; p < t.V; p += RNT) out_vertex[__ldg(t.idx + p)] = buf[p];
@@ -657,6 +780,7 @@ __global__ void __launch_bounds__(RNT) refine_updown_kernel(const float* __restr
   // the packed child weights and the normaliser Z exist once per image instead of once per instance.
   // norm_only: this launch computes only the normaliser channel (blockIdx.x indexes trees).
   extern __shared__ float s_buf[];
+  __shared__ RingSmem R;
   const int b = blockIdx.x, c = norm_only ? C : blockIdx.y;
   const int tb = tree_of ? __ldg(tree_of + b) : b;
   const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, tb, V);
@@ -671,9 +795,10 @@ __global__ void __launch_bounds__(RNT) refine_updown_kernel(const float* __restr
     const int v = __ldg(t.idx + p);
     buf[p] = norm ? 1.f : (MODE == 1 ? x[v] / z[v] : x[v]);
   }
+  if (SMEM && threadIdx.x < 4) buf[V + threadIdx.x] = 0.f;      // the pad up_node<true> may read
   __syncthreads();
-  up_pass(t, buf, save_up);
-  down_pass(t, buf, out_v);
+  up_pass<SMEM>(t, R, buf, save_up);
+  down_pass(t, R, buf, out_v);
 }
 
 __global__ void refine_div_kernel(const float* __restrict__ aggr, const float* __restrict__ wsum, float* __restrict__ out,
@@ -691,7 +816,6 @@ __global__ void refine_div_kernel(const float* __restrict__ aggr, const float* _
 //   grad[p] += sweep(aggr_up_c, gnU, aggr_c)[p] - sweep(wsum_up, fgU, wsum)[p]
 // sweep: G[0] = gup[0]; for p > 0: grad = gup (outd[v_par] - w ind) + ind (G[par] - w gup); G = gup (1 - w^2) + G[par] w
 // `outd_par` [2][V] is the position-ordered gather outd[idx[par[p]]] for the two data sets (parallel pre-pass).
-struct SweepNode { int s, e, par; float w, ind, outp, gw; };
 
 template <bool SMEM>
 __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
@@ -705,6 +829,7 @@ __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
   // CTAs of an instance run concurrently on different SMs and write separate buffers (grad_w and its twin B*V further),
   // summed by refine_add_kernel -- the dependent-level chain of this backward is 2 passes long instead of 4.
   extern __shared__ float s_buf[];
+  __shared__ RingSmem R;
   const int b = blockIdx.x, nb = gridDim.x, phase = blockIdx.y;
   const int tb = tree_of ? __ldg(tree_of + b) : b;          // tree / weights / normaliser of the instance's image
   const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, tb, V);
@@ -731,46 +856,34 @@ __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
         buf[p] = phase ? gn * o[v] : gn;
         op[p] = p == 0 ? 0.f : outd[__ldg(t.idx + __ldg(t.par + p))];
       }
+      if (SMEM && threadIdx.x < 4) buf[V + threadIdx.x] = 0.f;   // the pad up_node<true> may read
       __syncthreads();
-      up_pass(t, buf, nullptr);
-      // top-down: buf[p] holds gup[p] until visited, then G[p]
-      SweepNode ring[PF];
-      auto fetch = [&](const Bnd b) {
-        SweepNode n;
-        n.s = b.s; n.e = b.e; n.par = 0; n.w = n.ind = n.outp = n.gw = 0.f;
-        const int p = b.s + threadIdx.x;
-        // gw[p] is updated once per (channel, phase) and the phases are separated by barriers: its old value can
-        // travel with the prefetched node instead of being a dependent global load inside the level
-        if (p < b.e) { n.par = __ldg(t.par + p); n.w = __ldg(t.w + p); n.ind = ind[p]; n.outp = op[p]; n.gw = gw[p]; }
-        return n;
-      };
-      Bnd bring[PF];
-#pragma unroll
-      for (int j = 0; j < PF; ++j) ring[j] = fetch(fetch_bnd(t, 1 + j, 1));
-#pragma unroll
-      for (int j = 0; j < PF; ++j) bring[j] = fetch_bnd(t, 1 + PF + j, 1);
-      for (int l0 = 1; l0 < t.L; l0 += PF) {
-#pragma unroll
-        for (int j = 0; j < PF; ++j) {
-          const int l = l0 + j;
-          if (l >= t.L) break;
-          const SweepNode nd = ring[j];
-          ring[j] = fetch(bring[j]);
-          bring[j] = fetch_bnd(t, l + 2 * PF, 1);
-          int p = nd.s + threadIdx.x;
-          if (p < nd.e) {
-            const float gup = buf[p], Gp = buf[nd.par];
-            gw[p] = nd.gw + sign * (gup * (nd.outp - nd.w * nd.ind) + nd.ind * (Gp - nd.w * gup));
-            buf[p] = fmaf(Gp, nd.w, gup * (1.f - nd.w * nd.w));
-          }
-          for (p += RNT; p < nd.e; p += RNT) {
+      up_pass<SMEM>(t, R, buf, nullptr);
+      // top-down: buf[p] holds gup[p] until visited, then G[p].  gw[p] is updated once per (channel, phase) and the
+      // channels are separated by barriers: its old value travels with the prefetched record instead of being a dependent
+      // global load inside the level.
+      level_walk<1>(
+          t, R,
+          [&](int p, int slot, int i) {
+            cpa4(&R.ia[slot][i], t.par + p);
+            cpa4(&R.fa[slot][i], t.w + p);
+            cpa4(&R.q[slot][i].x, ind + p);
+            cpa4(&R.q[slot][i].y, op + p);
+            cpa4(&R.q[slot][i].z, gw + p);
+          },
+          [&](int p, bool on, const Rec& r) {
+            const float gup = buf[on ? p : 0], Gp = buf[on ? r.ia : 0];
+            if (on) {
+              const float ew = r.fa, in_p = r.q.x;
+              buf[p] = fmaf(Gp, ew, gup * (1.f - ew * ew));
+              gw[p] = r.q.z + sign * (gup * (r.q.y - ew * in_p) + in_p * (Gp - ew * gup));
+            }
+          },
+          [&](int p) {
             const float ew = __ldg(t.w + p), in_p = ind[p], gup = buf[p], Gp = buf[__ldg(t.par + p)];
             gw[p] += sign * (gup * (op[p] - ew * in_p) + in_p * (Gp - ew * gup));
             buf[p] = fmaf(Gp, ew, gup * (1.f - ew * ew));
-          }
-          __syncthreads();
-        }
-      }
+          });
     }
   }
 }
@@ -784,6 +897,8 @@ inline int grid_for(int64_t total, int block) {
   return (int)std::max<int64_t>(1, std::min(g, cap));
 }
 constexpr size_t kMaxTreeSmem = 220 * 1024;
+// refine kernels: the position-ordered values (dynamic) next to the copy ring + level window (static)
+constexpr size_t kMaxRefineSmem = 227 * 1024 - sizeof(RingSmem) - 64;
 
 }  // namespace
 }  // namespace bxs
@@ -932,10 +1047,10 @@ extern "C" int bxs_refine_forward(const float* feature, const float* edge_weight
   cudaStream_t st = as_stream(stream);
   RefineScratch rs = carve_refine(scratch, B, C, V);
   pack_tree(edge_weight, sorted_child, rs, B, V, st);
-  const size_t sm = V * sizeof(float);
+  const size_t sm = (V + 4) * sizeof(float);
   const dim3 grid((unsigned)B, (unsigned)(C + 1));
-  if (sm <= kMaxTreeSmem) {
-    cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+  if (sm <= kMaxRefineSmem) {
+    cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
     refine_updown_kernel<0, true><<<grid, RNT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, nullptr, aggr, aggr_up, wsum, wsum_up,
                                                         nullptr, (int)C, (int)V, nullptr, 0);
@@ -960,10 +1075,10 @@ extern "C" int bxs_refine_backward_feature(const float* edge_weight, const int32
   cudaStream_t st = as_stream(stream);
   RefineScratch rs = carve_refine(scratch, B, C, V);
   pack_tree(edge_weight, sorted_child, rs, B, V, st);
-  const size_t sm = V * sizeof(float);
+  const size_t sm = (V + 4) * sizeof(float);
   const dim3 grid((unsigned)B, (unsigned)C);
-  if (sm <= kMaxTreeSmem) {
-    cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+  if (sm <= kMaxRefineSmem) {
+    cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
     refine_updown_kernel<1, true><<<grid, RNT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
                                                         nullptr, nullptr, (int)C, (int)V, nullptr, 0);
@@ -988,9 +1103,9 @@ extern "C" int bxs_refine_backward_weight(const float* edge_weight, const int32_
   cudaStream_t st = as_stream(stream);
   RefineScratch rs = carve_refine(scratch, B, C, V);
   pack_tree(edge_weight, sorted_child, rs, B, V, st);
-  const size_t sm = V * sizeof(float);
-  if (sm <= kMaxTreeSmem) {
-    cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+  const size_t sm = (V + 4) * sizeof(float);
+  if (sm <= kMaxRefineSmem) {
+    cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
     refine_bwd_weight_kernel<true><<<dim3((unsigned)B, 2), RNT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo,
                                                                          rs.cw, level_start, num_levels, feature_out, aggr,
                                                                          aggr_up, wsum, wsum_up, grad_out, rs.gw2, nullptr,
@@ -1022,9 +1137,9 @@ extern "C" int bxs_refine_forward_grouped(const float* feature, const float* edg
   cudaStream_t st = as_stream(stream);
   RefineScratch rs = carve_refine(scratch, std::max(n, G), C, V);
   pack_tree(edge_weight, sorted_child, rs, G, V, st);
-  const size_t sm = V * sizeof(float);
-  if (sm <= kMaxTreeSmem) {
-    cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+  const size_t sm = (V + 4) * sizeof(float);
+  if (sm <= kMaxRefineSmem) {
+    cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
     refine_updown_kernel<0, true><<<dim3((unsigned)G, 1), RNT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent,
                                                                         rs.cinfo, rs.cw, level_start, num_levels, nullptr, aggr,
                                                                         aggr_up, wsum, wsum_up, nullptr, (int)C, (int)V,
@@ -1058,10 +1173,10 @@ extern "C" int bxs_refine_backward_feature_grouped(const float* edge_weight, con
   cudaStream_t st = as_stream(stream);
   RefineScratch rs = carve_refine(scratch, std::max(n, G), C, V);
   pack_tree(edge_weight, sorted_child, rs, G, V, st);
-  const size_t sm = V * sizeof(float);
+  const size_t sm = (V + 4) * sizeof(float);
   const dim3 grid((unsigned)n, (unsigned)C);
-  if (sm <= kMaxTreeSmem) {
-    cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+  if (sm <= kMaxRefineSmem) {
+    cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
     refine_updown_kernel<1, true><<<grid, RNT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
                                                         nullptr, nullptr, (int)C, (int)V, tree_of, 0);
@@ -1088,9 +1203,9 @@ extern "C" int bxs_refine_backward_weight_grouped(const float* edge_weight, cons
   cudaStream_t st = as_stream(stream);
   RefineScratch rs = carve_refine(scratch, std::max(n, G), C, V);
   pack_tree(edge_weight, sorted_child, rs, G, V, st);
-  const size_t sm = V * sizeof(float);
-  if (sm <= kMaxTreeSmem) {
-    cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
+  const size_t sm = (V + 4) * sizeof(float);
+  if (sm <= kMaxRefineSmem) {
+    cudaFuncSetAttribute(refine_bwd_weight_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
     refine_bwd_weight_kernel<true><<<dim3((unsigned)n, 2), RNT, sm, st>>>(edge_weight, sorted_index, sorted_parent, rs.cinfo,
                                                                          rs.cw, level_start, num_levels, feature_out, aggr,
                                                                          aggr_up, wsum, wsum_up, grad_out, rs.gw2, nullptr,
@@ -1105,3 +1220,9 @@ extern "C" int bxs_refine_backward_weight_grouped(const float* edge_weight, cons
   refine_add_kernel<<<grid_for(n * V, 256), 256, 0, st>>>(grad_weight, rs.gw2 + n * V, n * V);
   return check_launch();
 }
+
+#ifdef BXS_TREE_TRACE
+extern "C" int bxs_debug_tree_trace(long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, bxs::g_tree_trace, sizeof(long long) * 6 * 4096) == cudaSuccess ? 0 : -2;
+}
+#endif

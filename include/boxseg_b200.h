@@ -76,6 +76,22 @@ int bxs_boxinst_rects(const float* boxes, int32_t* rects, int64_t G, int64_t Hp,
 int bxs_boxinst_bitmasks(const int32_t* rects, float* bitmasks, int64_t G, int64_t H, int64_t W,
                          bxs_stream_t stream);
 
+/* The whole target build of a batch (bxs_boxinst_lab + bxs_boxinst_rects + the GT -> image index + bxs_boxinst_similarity) in
+ * two launches, with the per-image metadata passed BY VALUE from host arrays (img_hw_host [B,2] = (h, w) of img_shape,
+ * removed_rows_host [B], num_gts_host [B]; B <= 64, else BXS_ERR_UNSUPPORTED): no host-to-device copies, capturable in a CUDA
+ * graph.  boxes [sum num_gts, 4] xyxy (device, image-major), rects [G,4] / gt_img [G] outputs (may be NULL when G == 0);
+ * sim / edge_bits as in bxs_boxinst_similarity.  Replaces CondInstMaskHead.get_targets' host round trip
+ * (condinst_head.py:170-246, 1345-1448). */
+int bxs_boxinst_targets_forward(const float* img, const float* boxes, const int32_t* img_hw_host,
+                                const int32_t* removed_rows_host, const int32_t* num_gts_host, const float* mean3_host,
+                                const float* std3_host, float* lab, uint8_t* valid, float* sim, uint8_t* edge_bits,
+                                int32_t* rects, int32_t* gt_img, int64_t B, int64_t Hp, int64_t Wp, int stride, int size,
+                                int dilation, float thresh, bxs_stream_t stream);
+
+/* CIE-LAB (float64 evaluation of scikit-image's rgb2lab, cast to float32) of n packed uint8 RGB triplets: lab [n,3].
+ * The colour conversion of the target build on its own, so that it can be checked over all 2^24 colours. */
+int bxs_rgb_u8_to_lab(const uint8_t* rgb, float* lab, int64_t n, bxs_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * a6+a7+a8  fused BoxInst mask loss     replaces the arithmetic of CondInstMaskHead.loss
  *     (condinst_head.py:1288-1343): sigmoid, compute_project_term (:134-143), pairwise_nlog,

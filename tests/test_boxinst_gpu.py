@@ -100,6 +100,78 @@ def test_targets_vs_oracle(dev, ragged):
     assert mism == 0
 
 
+def test_targets_by_value_call_equals_separate_kernels(dev):
+    """bxs_boxinst_targets_forward (metadata by value, two launches) against the four separate entry points it fuses,
+    including images without GT boxes and a batch that ends with one."""
+    from boxinstseg_b200 import _lib as L
+    case = boxinst_case(5, B=4, hp=64, wp=96, gts_per_img=3, inst_per_gt=1, ragged=True)
+    case['gt_bboxes'][1] = case['gt_bboxes'][1][:0]
+    case['gt_bboxes'][3] = case['gt_bboxes'][3][:0]
+    t = _targets(case, dev)
+    img = case['img'].to(dev).contiguous()
+    B, _, Hp, Wp = img.shape
+    H, W = Hp // 4, Wp // 4
+    hw = torch.tensor([m['img_shape'][:2] for m in case['metas']], dtype=torch.int32)
+    rem = torch.tensor([int(10 * float(m['img_shape'][0]) / float(m['ori_shape'][0])) for m in case['metas']], dtype=torch.int32)
+    cfg = case['metas'][0]['img_norm_cfg']
+    mean = np.ascontiguousarray(np.asarray(cfg['mean'], np.float32))
+    std = np.ascontiguousarray(np.asarray(cfg['std'], np.float32))
+    lab = torch.empty(B, 3, H, W, device=dev)
+    valid = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
+    sim = torch.empty(B, 8, H, W, device=dev)
+    bits = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
+    lib = L.lib()
+    hw_d, rem_d = hw.to(dev), rem.to(dev)
+    assert lib.bxs_boxinst_lab(L.ptr(img), L.ptr(hw_d), L.ptr(rem_d), mean.ctypes.data, std.ctypes.data, L.ptr(lab),
+                               L.ptr(valid), B, Hp, Wp, 4, L.stream()) == 0
+    assert lib.bxs_boxinst_similarity(L.ptr(lab), L.ptr(valid), L.ptr(sim), L.ptr(bits), B, H, W, 3, 2, 0.3, L.stream()) == 0
+    boxes = torch.cat(case['gt_bboxes']).float().to(dev).contiguous()
+    G = boxes.shape[0]
+    rects = torch.empty(G, 4, dtype=torch.int32, device=dev)
+    assert lib.bxs_boxinst_rects(L.ptr(boxes), L.ptr(rects), G, Hp, Wp, 4, L.stream()) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(t.lab, lab) and torch.equal(t.valid, valid)
+    assert torch.equal(t.similarity, sim) and torch.equal(t.edge_bits, bits)
+    assert torch.equal(t.rects, rects)
+    want_img = np.repeat(np.arange(B), [b.shape[0] for b in case['gt_bboxes']])
+    assert t.gt_img.cpu().tolist() == want_img.tolist()
+    # argument errors of the C entry point
+    ng = np.asarray([b.shape[0] for b in case['gt_bboxes']], np.int32)
+    hw_h, rem_h = hw.numpy(), rem.numpy()
+    gi = torch.empty(G, dtype=torch.int32, device=dev)
+
+    def call(Bx, ngx=ng, lab_=lab):
+        return lib.bxs_boxinst_targets_forward(L.ptr(img), L.ptr(boxes), hw_h.ctypes.data, rem_h.ctypes.data, ngx.ctypes.data,
+                                               mean.ctypes.data, std.ctypes.data, L.ptr(lab_), L.ptr(valid), L.ptr(sim),
+                                               L.ptr(bits), L.ptr(rects), L.ptr(gi), Bx, Hp, Wp, 4, 3, 2, 0.3, L.stream())
+    assert call(B) == 0
+    assert call(65) == -3                                           # more images than the by-value metadata holds
+    assert call(B, lab_=None) == -1
+    assert call(B, ngx=np.asarray([1, -1, 0, 0], np.int32)) == -1
+
+
+def test_lab_of_all_uint8_colours(dev):
+    """The colour conversion of the target build over ALL 2^24 uint8 colours against the oracle's float64 restatement of
+    scikit-image rgb2lab (cast to float32 as condinst_head.py:1413-1414 does).  Both sides evaluate in float64; libm and
+    CUDA pow / cbrt may differ in the last float64 bit, which can move the float32 cast by one ulp in rare cases."""
+    from boxinstseg_b200 import _lib as L
+    from oracle.boxinst import rgb2lab_u8
+    v = torch.arange(1 << 24, dtype=torch.int32)
+    rgb = torch.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], 1).to(torch.uint8)
+    d_rgb = rgb.to(dev).contiguous()
+    lab = torch.empty(1 << 24, 3, device=dev)
+    assert L.lib().bxs_rgb_u8_to_lab(L.ptr(d_rgb), L.ptr(lab), 1 << 24, L.stream()) == 0
+    got = lab.cpu()
+    worst, differing = 0.0, 0
+    for lo in range(0, 1 << 24, 1 << 21):                            # 2M colours at a time (float64 temporaries)
+        ref = torch.from_numpy(rgb2lab_u8(rgb[lo:lo + (1 << 21)].numpy()).astype(np.float32))
+        d = (got[lo:lo + (1 << 21)] - ref).abs()
+        worst = max(worst, float(d.max()))
+        differing += int((d > 0).sum())
+    assert worst <= 1.6e-5, worst                                    # <= 1 float32 ulp at |value| < 128 (2^-17 .. 2^-16)
+    assert differing <= (3 << 24) * 1e-4, differing                 # and rare
+
+
 # ------------------------------------------------------------------ a6+a7+a8 fused loss
 def _oracle_loss(case, warm, dtype=torch.float64):
     from oracle import boxinst as ob
