@@ -628,24 +628,33 @@ __device__ __forceinline__ void level_walk(const TreeView& t, RingSmem& R, Issue
   __syncthreads();
   auto lv = [&](int l) { return R.lvl[l & (LWIN - 1)]; };
   auto inside = [&](int l) { return DIR > 0 ? l <= last : l >= last; };
-  auto issue_level = [&](int l, int slot) {
-    if (inside(l)) {
-      const int s = lv(l), e = lv(l + 1);
-      if (s + (slot_i & ~31) < e) {                         // warp-uniform: most levels need only the first producer warp
-        const int p = s + slot_i;
-        if (p < e) issue(p, slot, slot_i);
-      }
+  // copies of level l (bounds s0, e0) into ring slot `slot`; one group per level, empty or not: the count is what matters
+  auto issue_level = [&](int l, int slot, int s0, int e0) {
+    if (inside(l) && s0 + (slot_i & ~31) < e0) {            // warp-uniform: most levels need only the first producer warp
+      const int p = s0 + slot_i;
+      if (p < e0) issue(p, slot, slot_i);
     }
-    cp_commit();                                            // one group per level, empty or not: the count is what matters
+    cp_commit();
   };
   auto load_rec = [&](int slot) {
     Rec r;
     r.q = R.q[slot][slot_i]; r.ia = R.ia[slot][slot_i]; r.fa = R.fa[slot][slot_i];
     return r;
   };
+  // producer registers: bounds of the level whose copies sit in slot j (its wide-level remainder is done from them PF
+  // levels later), bounds of the next level to issue (read one level ahead, in the shadow of the barrier), and the level
+  // at which the window is refilled next
+  int bs[PF], be[PF], nis = 0, nie = 0;
+  int refill_at = DIR > 0 ? LCHUNK : (((t.L - 1) | (LCHUNK - 1)) + 1) - LCHUNK - 1;
   if (producer) {
 #pragma unroll
-    for (int j = 0; j < PF; ++j) issue_level(first + DIR * j, j);
+    for (int j = 0; j < PF; ++j) {
+      const int l = first + DIR * j;
+      bs[j] = be[j] = 0;
+      if (inside(l)) { bs[j] = lv(l); be[j] = lv(l + 1); }
+      issue_level(l, j, bs[j], be[j]);
+    }
+    if (inside(first + DIR * PF)) { nis = lv(first + DIR * PF); nie = lv(first + DIR * PF + 1); }
     cp_wait<PF - 2>();                                      // the first two levels have landed
   }
   __syncthreads();
@@ -657,6 +666,16 @@ __device__ __forceinline__ void level_walk(const TreeView& t, RingSmem& R, Issue
     rec = load_rec(0);
   }
   for (int l0 = first; DIR > 0 ? l0 <= last : l0 >= last; l0 += DIR * PF) {
+    // window refill (producers, two entries each), once per chunk of LCHUNK levels, up to PF levels early; the copies ride
+    // in the next level's group and are read 250+ levels later
+    if (producer && (DIR > 0 ? l0 + PF > refill_at : l0 - PF < refill_at)) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int en = DIR > 0 ? refill_at + LWIN - 2 * LCHUNK + slot_i + h * RW : refill_at - (2 * LCHUNK - 1) - slot_i - h * RW;
+        if (en >= 0 && en <= t.L) cpa4(&R.lvl[en & (LWIN - 1)], t.lvl + en);
+      }
+      refill_at += DIR * LCHUNK;
+    }
 #pragma unroll
     for (int j = 0; j < PF; ++j) {
       const int l = l0 + DIR * j;
@@ -678,31 +697,16 @@ __device__ __forceinline__ void level_walk(const TreeView& t, RingSmem& R, Issue
         if (tid == 0) TREE_TT(2, DIR * (l - first));
       } else {
         if (tid == RW) TREE_TT(3, DIR * (l - first));
-        const int ls = lv(l), le = lv(l + 1);
 #pragma unroll 1
-        for (int p2 = ls + tid; p2 < le; p2 += RNT) direct(p2);            // positions RW.. of a wide level
-        // window refill, two entries per producer thread, rides in this level's group; read 250+ levels later
-        if (DIR > 0) {
-          if ((l & (LCHUNK - 1)) == 0) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int en = l + LWIN - 2 * LCHUNK + slot_i + h * RW;
-              if (en <= t.L) cpa4(&R.lvl[en & (LWIN - 1)], t.lvl + en);
-            }
-          }
-        } else {
-          if ((l & (LCHUNK - 1)) == LCHUNK - 1) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int en = l - (2 * LCHUNK - 1) - slot_i - h * RW;
-              if (en >= 0) cpa4(&R.lvl[en & (LWIN - 1)], t.lvl + en);
-            }
-          }
-        }
-        issue_level(l + DIR * PF, j);                       // slot j: its record was read by the consumers a level ago
+        for (int p2 = bs[j] + tid; p2 < be[j]; p2 += RNT) direct(p2);      // positions RW.. of a wide level
+        issue_level(l + DIR * PF, j, nis, nie);             // slot j: its record was read by the consumers a level ago
+        bs[j] = nis; be[j] = nie;
         if (tid == RW) TREE_TT(4, DIR * (l - first));
         cp_wait<PF - 2>();                                  // level l + 2 has landed: visible to the consumers after the barrier
         if (tid == RW) TREE_TT(5, DIR * (l - first));
+        const int ln = l + DIR * (PF + 1);                  // the level the next iteration issues
+        nis = nie = 0;
+        if (inside(ln)) { nis = lv(ln); nie = lv(ln + 1); }
       }
       __syncthreads();
     }
