@@ -120,7 +120,7 @@ def ddp_allreduce_leg(dist, dev, world, loss_step, steps):
     NVLink, issued asynchronously so that it overlaps the mask-loss step.  Returns busbw and the exposed time."""
     total_bytes, bucket_bytes = 136 * 2 ** 20, 25 * 2 ** 20
     sizes = [bucket_bytes] * (total_bytes // bucket_bytes) + ([total_bytes % bucket_bytes] if total_bytes % bucket_bytes else [])
-    buckets = [torch.randn(b // 4, device=dev) for b in sizes]
+    buckets = [torch.zeros(b // 4, device=dev) for b in sizes]          # zeros: repeated sums stay finite
 
     def timed(fn, k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

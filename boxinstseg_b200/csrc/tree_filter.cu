@@ -368,7 +368,19 @@ __global__ void __launch_bounds__(NT) bfs_block_kernel(BfsWs ws, int V, int32_t*
 // parent), exactly the order bfs_block_kernel produces, so both paths give the same result.
 // `flags[b]`: 0 = not a grid tree (or too large for shared memory): bfs_block_kernel must run; 1 = done here.
 // ---------------------------------------------------------------------------------------
-constexpr int BFS_FRONT = 2048;         // frontier entries kept in shared memory (wider frontiers re-read sorted_index)
+#ifdef BXS_TREE_TRACE
+// per-level clock stamps of the first CTA's up pass: [0..2] consumer thread 0 (level top, after its store was issued,
+// at the barrier), [3..5] producer thread RW (level top, copies issued, group wait done)
+__device__ long long g_tree_trace[6][4096];
+#define TREE_TT(k, i) do { if (DIR < 0 && blockIdx.x == 0 && blockIdx.y == 0 && (i) < 4096) g_tree_trace[k][i] = clock64(); } while (0)
+#define BFS_TT(k, i) do { if (blockIdx.x == 0 && lane == 0 && (i) < 4096) g_tree_trace[k][i] = clock64(); } while (0)
+#else
+#define TREE_TT(k, i) do { } while (0)
+#define BFS_TT(k, i) do { } while (0)
+#endif
+constexpr int BFS_FRONT = 1024;         // frontier entries kept in shared memory (a wider frontier declines to the generic path)
+constexpr int BFS_BUFS = 4;             // frontier buffers in rotation: level L is written during L-1, expanded during L, and
+                                        // turned into global output by a helper warp during L+1..L+2
 
 __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict__ tree, int V, int32_t* __restrict__ sorted_index,
                                                       int32_t* __restrict__ sorted_parent, int32_t* __restrict__ sorted_child,
@@ -378,8 +390,10 @@ __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict_
   __shared__ int s_wd[NT / 32];
   __shared__ int s_ok;
   unsigned* s_adj = bfs_smem;                                   // V bytes, packed 4 per word
-  int* s_v = reinterpret_cast<int*>(bfs_smem + (V + 3) / 4);   // [2][BFS_FRONT] frontier vertex ids
-  int* s_pv = s_v + 2 * BFS_FRONT;                              // [2][BFS_FRONT] their parents' vertex ids
+  int* s_v = reinterpret_cast<int*>(bfs_smem + (V + 3) / 4);   // [BFS_BUFS][BFS_FRONT] frontier vertex ids
+  int* s_pv = s_v + BFS_BUFS * BFS_FRONT;                       // ... their parents' vertex ids
+  int* s_q = s_pv + BFS_BUFS * BFS_FRONT;                       // ... first child position | child direction bits << 28
+  __shared__ int s_lev[BFS_BUFS][2];                            // [level & 3] = {level start, level end}; start < 0: stop
   const int b = blockIdx.x, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int2* te = reinterpret_cast<const int2*>(tree + (int64_t)b * (V - 1) * 2);
   // ---- prologue, whole CTA: row pitch of the grid (the single non-unit difference of an edge's end points), then the
@@ -410,59 +424,112 @@ __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict_
   }
   if (!ok) s_ok = 0;
   __syncthreads();
-  if (tid >= 32) return;                                        // the level loop is ONE warp: no CTA barrier from here on
-  if (!s_ok) { if (lane == 0) flags[b] = 0; return; }
+  // ---- level loop.  A level is the instruction stream of ONE warp (a frontier is ~30 vertices), so that stream is kept
+  //      to the dependent part -- frontier -> adjacency bits -> ballot scan -> next frontier, all in shared memory -- and
+  //      everything that only PRODUCES OUTPUT (sorted_index / sorted_parent / sorted_child / level_start stores: two thirds of
+  //      the instructions of round 2a's single-warp loop) is done one level later by two helper warps taking alternate
+  //      levels, from the frontier buffer and a per-vertex (first child position | child bits) record.  Warp 0 and the
+  //      helper of a level meet at a 64-thread named barrier; no CTA-wide barrier from here on. ----
+  if (tid >= 96) return;
+  const int warp = tid >> 5;
+  if (!s_ok) { if (tid == 0) flags[b] = 0; return; }
   int32_t* idx = sorted_index + (int64_t)b * V;
   int32_t* par = sorted_parent + (int64_t)b * V;
   int4* chd = reinterpret_cast<int4*>(sorted_child + (int64_t)b * V * 4);
   int32_t* lvl = level_start + (int64_t)b * (V + 1);
-  if (lane == 0) { idx[0] = root; par[0] = 0; lvl[0] = 0; s_v[0] = root; s_pv[0] = -1; }
-  __syncwarp();
-  const unsigned lt_mask = (1u << lane) - 1u;
-  int ls = 0, le = 1, level = 0, cur = 0;
-  while (ls < le) {
-    int next = le;
-    for (int base = ls; base < le; base += 32) {
-      const int p = base + lane;
-      int v = -1, pv = -1, cnt = 0;
-      unsigned bits = 0u;
-      if (p < le) {
-        if (p - ls < BFS_FRONT) { v = s_v[cur * BFS_FRONT + p - ls]; pv = s_pv[cur * BFS_FRONT + p - ls]; }
-        else { v = idx[p]; pv = idx[par[p]]; }                  // very wide frontier: the global copies (written by this warp)
-        bits = (s_adj[v >> 2] >> ((v & 3) * 8)) & 15u;
-        // drop the parent: it is one of the four neighbours
-        if (pv >= 0) bits &= ~(pv == v - Wd ? 1u : (pv == v - 1 ? 2u : (pv == v + 1 ? 4u : 8u)));
-        cnt = __popc(bits);
-      }
-      // exclusive prefix of the child counts (0..3 per lane; the root may have 4): three ballots instead of a shuffle scan
-      const unsigned b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2), b2 = __ballot_sync(kFull, cnt & 4);
-      const int excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
-      const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-      if (p < le) {
-        const int q0 = next + excl;                 // this node's children occupy positions [q0, q0 + cnt)
-        const int rel = q0 - le;
-        int* nv = s_v + (cur ^ 1) * BFS_FRONT;
-        int* npv = s_pv + (cur ^ 1) * BFS_FRONT;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {               // predicated, no divergent branches: the level's latency is the whole cost
-          const bool on = (bits >> k) & 1u;
-          const int j = __popc(bits & ((1u << k) - 1u));
-          const int u = k == 0 ? v - Wd : (k == 1 ? v - 1 : (k == 2 ? v + 1 : v + Wd));
-          if (on) { idx[q0 + j] = u; par[q0 + j] = p; }
-          if (on && rel + j < BFS_FRONT) { nv[rel + j] = u; npv[rel + j] = v; }
+  auto pair_sync = [](int parity) { asm volatile("bar.sync %0, 64;" ::"r"(1 + parity) : "memory"); };
+  if (warp == 0) {
+    if (lane == 0) { idx[0] = root; par[0] = 0; s_v[0] = root; s_pv[0] = -1; }
+    __syncwarp();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int ls = 0, le = 1, level = 0;
+    bool fail = false;
+    while (ls < le && !fail) {
+      const int cur = level & (BFS_BUFS - 1), nxt = (level + 1) & (BFS_BUFS - 1);
+      const int* cv = s_v + cur * BFS_FRONT;
+      const int* cpv = s_pv + cur * BFS_FRONT;
+      int* cq = s_q + cur * BFS_FRONT;
+      int* nv = s_v + nxt * BFS_FRONT;
+      int* npv = s_pv + nxt * BFS_FRONT;
+      int next = le;
+      BFS_TT(0, level);
+      for (int base = ls; base < le; base += 32) {
+        const int i = base - ls + lane;
+        const bool on = base + lane < le;
+        int v = 0, pv = -1;
+        unsigned bits = 0u;
+        if (on) {
+          v = cv[i]; pv = cpv[i];
+          bits = (s_adj[v >> 2] >> ((v & 3) * 8)) & 15u;
+          // drop the parent: it is one of the four neighbours
+          if (pv >= 0) bits &= ~(pv == v - Wd ? 1u : (pv == v - 1 ? 2u : (pv == v + 1 ? 4u : 8u)));
         }
+        const int cnt = __popc(bits);
+        if (cnt >= 0) BFS_TT(1, level);
+        // exclusive prefix of the child counts (0..3 per lane; the root may have 4): three ballots instead of a shuffle scan
+        const unsigned b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2), b2 = __ballot_sync(kFull, cnt & 4);
+        const int excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+        const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        if (next + total - le > BFS_FRONT) { fail = true; break; }      // warp-uniform
+        if (total >= 0) BFS_TT(2, level);
+        if (on) {
+          const int q0 = next + excl;                 // this vertex's children occupy positions [q0, q0 + cnt)
+          int r = q0 - le;
+          cq[i] = q0 | (int)(bits << 28);
+          // children in ascending vertex order: up, left, right, down
+          if (bits & 1u) { nv[r] = v - Wd; npv[r] = v; ++r; }
+          if (bits & 2u) { nv[r] = v - 1; npv[r] = v; ++r; }
+          if (bits & 4u) { nv[r] = v + 1; npv[r] = v; ++r; }
+          if (bits & 8u) { nv[r] = v + Wd; npv[r] = v; }
+        }
+        next += total;
+      }
+      BFS_TT(3, level);
+      if (lane == 0) { s_lev[cur][0] = fail ? -1 : ls; s_lev[cur][1] = le; }
+      pair_sync(level & 1);
+      BFS_TT(4, level);                          // hand level `level` to its helper (which finished level - 2 long ago)
+      if (fail) break;
+      ls = le;
+      le = next;
+      ++level;
+    }
+    // stop markers for both helpers (the failing level already carries one for its own helper)
+    const int stops = fail ? 1 : 2;
+    for (int k = 0; k < stops; ++k) {
+      const int lv2 = level + (fail ? 1 : 0) + k;
+      if (lane == 0) s_lev[lv2 & (BFS_BUFS - 1)][0] = -1;
+      pair_sync(lv2 & 1);
+    }
+    if (lane == 0) {
+      if (!fail) lvl[level] = ls;                    // == V for a spanning tree
+      num_levels[b] = level;
+      flags[b] = (!fail && ls == V) ? 1 : 0;         // every vertex reached <=> a spanning tree; else the generic path runs
+    }
+  } else {
+    // helper of the levels of parity (warp - 1): global output of a level, while warp 0 is one or two levels further on
+    const int parity = warp - 1;
+    for (int level = parity;; level += 2) {
+      pair_sync(parity);
+      const int cur = level & (BFS_BUFS - 1);
+      const int ls = s_lev[cur][0], le = s_lev[cur][1];
+      if (ls < 0) break;
+      if (lane == 0) lvl[level] = ls;
+      const int* cv = s_v + cur * BFS_FRONT;
+      const int* cq = s_q + cur * BFS_FRONT;
+      for (int i = lane; i < le - ls; i += 32) {
+        const int v = cv[i], qb = cq[i], p = ls + i;
+        const int q0 = qb & 0x0fffffff;
+        const unsigned bits = (unsigned)qb >> 28;
+        int q = q0;
+        if (bits & 1u) { idx[q] = v - Wd; par[q] = p; ++q; }
+        if (bits & 2u) { idx[q] = v - 1; par[q] = p; ++q; }
+        if (bits & 4u) { idx[q] = v + 1; par[q] = p; ++q; }
+        if (bits & 8u) { idx[q] = v + Wd; par[q] = p; ++q; }
+        const int cnt = q - q0;
         chd[p] = make_int4(cnt > 0 ? q0 : 0, cnt > 1 ? q0 + 1 : 0, cnt > 2 ? q0 + 2 : 0, cnt > 3 ? q0 + 3 : 0);
       }
-      next += total;
     }
-    __syncwarp();
-    ls = le;
-    le = next;
-    cur ^= 1;
-    ++level;
-    if (lane == 0) lvl[level] = ls;
   }
-  if (lane == 0) { num_levels[b] = level; flags[b] = ls == V ? 1 : 0; }       // every vertex reached <=> a spanning tree
 }
 
 // level boundaries from (level-contiguous) sorted_parent when they were not produced by bfs_block_kernel:
@@ -526,14 +593,7 @@ struct RingSmem {
 };
 struct Rec { float4 q; int ia; float fa; };
 
-#ifdef BXS_TREE_TRACE
-// per-level clock stamps of the first CTA's up pass: [0..2] consumer thread 0 (level top, after its store was issued,
-// at the barrier), [3..5] producer thread RW (level top, copies issued, group wait done)
-__device__ long long g_tree_trace[6][4096];
-#define TREE_TT(k, i) do { if (DIR < 0 && blockIdx.x == 0 && blockIdx.y == 0 && (i) < 4096) g_tree_trace[k][i] = clock64(); } while (0)
-#else
-#define TREE_TT(k, i) do { } while (0)
-#endif
+
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cpa4(void* dst, const void* src) {
@@ -980,7 +1040,7 @@ static int bfs_forward_impl(const int32_t* tree_edges, int32_t* sorted_index, in
   cudaMemsetAsync(ws.deg, 0, sizeof(int) * B * V, st);
   cudaMemsetAsync(err, 0, sizeof(int), st);
   // fast path: 4-connected grid trees with the adjacency bits in shared memory (one warp per tree)
-  const size_t grid_smem = ((size_t)(V + 3) / 4) * 4 + (size_t)4 * BFS_FRONT * sizeof(int);
+  const size_t grid_smem = ((size_t)(V + 3) / 4) * 4 + (size_t)3 * BFS_BUFS * BFS_FRONT * sizeof(int);
   const bool try_grid = grid_smem <= kMaxTreeSmem;
   if (try_grid) {
     cudaFuncSetAttribute(bfs_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
