@@ -190,27 +190,67 @@ mst_cluster_kernel(const int32_t* __restrict__ edge_index, const float* __restri
 }
 
 // tree edges in ascending edge id; one CTA per tree
-__global__ void __launch_bounds__(NT) mst_compact_kernel(const int32_t* __restrict__ edge_index, MstWs ws,
-                                                         int32_t* __restrict__ edge_out, int E, int V) {
-  __shared__ int s_cnt[NT];
-  const int b = blockIdx.x;
-  const int32_t* ei = edge_index + (int64_t)b * E * 2;
-  const uint8_t* in_tree = ws.in_tree + (int64_t)b * E;
-  int32_t* out = edge_out + (int64_t)b * (V - 1) * 2;
-  const int per = (E + NT - 1) / NT;
-  const int lo = min(threadIdx.x * per, E), hi = min(lo + per, E);
-  int cnt = 0;
-  for (int e = lo; e < hi; ++e) cnt += in_tree[e];
-  s_cnt[threadIdx.x] = cnt;
+// The tree's edges in ascending edge id (the edge SET is the reference's; its order is Boruvka discovery order, boruvka.cpp).
+// Two small grids instead of one CTA per image walking 100 edges per thread (134 us at 200x256, 6 % of config D):
+// chunk counts, then an ordered compaction of each 4096-edge chunk behind the sum of the counts before it.
+constexpr int MC_T = 256, MC_PER = 16, MC_CHUNK = MC_T * MC_PER;
+
+__device__ __forceinline__ unsigned mc_mask(const uint8_t* __restrict__ in_tree, int lo, int E) {
+  unsigned mask = 0u;
+#pragma unroll
+  for (int k = 0; k < MC_PER; ++k)
+    if (lo + k < E && in_tree[lo + k]) mask |= 1u << k;
+  return mask;
+}
+
+__global__ void __launch_bounds__(MC_T) mst_count_kernel(MstWs ws, int* __restrict__ counts, int E) {
+  __shared__ int s_w[MC_T / 32];
+  const int c = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int cnt = __popc(mc_mask(ws.in_tree + (int64_t)b * E, c * MC_CHUNK + threadIdx.x * MC_PER, E));
+  cnt = __reduce_add_sync(kFull, cnt);
+  if (lane == 0) s_w[warp] = cnt;
   __syncthreads();
   if (threadIdx.x == 0) {
-    int run = 0;
-    for (int i = 0; i < NT; ++i) { const int v = s_cnt[i]; s_cnt[i] = run; run += v; }
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < MC_T / 32; ++i) t += s_w[i];
+    counts[b * gridDim.x + c] = t;
+  }
+}
+
+__global__ void __launch_bounds__(MC_T) mst_compact_kernel(const int32_t* __restrict__ edge_index, MstWs ws,
+                                                           const int* __restrict__ counts, int32_t* __restrict__ edge_out,
+                                                           int E, int V) {
+  __shared__ int s_w[MC_T / 32];
+  __shared__ int s_before;
+  const int c = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int2* ei = reinterpret_cast<const int2*>(edge_index + (int64_t)b * E * 2);
+  int2* out = reinterpret_cast<int2*>(edge_out + (int64_t)b * (V - 1) * 2);
+  const int lo = c * MC_CHUNK + threadIdx.x * MC_PER;
+  const unsigned mask = mc_mask(ws.in_tree + (int64_t)b * E, lo, E);
+  const int cnt = __popc(mask);
+  int incl = cnt;                                           // inclusive warp scan
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  if (warp == 0) {                                          // tree edges of this image in the chunks before this one
+    int t = 0;
+    for (int i = lane; i < c; i += 32) t += counts[b * gridDim.x + i];
+    t = __reduce_add_sync(kFull, t);
+    if (lane == 0) s_before = t;
   }
   __syncthreads();
-  int pos = s_cnt[threadIdx.x];
-  for (int e = lo; e < hi; ++e)
-    if (in_tree[e] && pos < V - 1) { out[2 * pos] = ei[2 * e]; out[2 * pos + 1] = ei[2 * e + 1]; ++pos; }
+  int pos = s_before + incl - cnt;
+  for (int i = 0; i < warp; ++i) pos += s_w[i];
+#pragma unroll
+  for (int k = 0; k < MC_PER; ++k)
+    if ((mask >> k) & 1u) {
+      if (pos < V - 1) out[pos] = ei[lo + k];
+      ++pos;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -379,6 +419,7 @@ __device__ long long g_tree_trace[6][4096];
 #define BFS_TT(k, i) do { } while (0)
 #endif
 constexpr int BFS_FRONT = 1024;         // frontier entries kept in shared memory (a wider frontier declines to the generic path)
+constexpr int BFS_STRIDE = BFS_FRONT + 32;
 constexpr int BFS_BUFS = 4;             // frontier buffers in rotation: level L is written during L-1, expanded during L, and
                                         // turned into global output by a helper warp during L+1..L+2
 
@@ -390,9 +431,10 @@ __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict_
   __shared__ int s_wd[NT / 32];
   __shared__ int s_ok;
   unsigned* s_adj = bfs_smem;                                   // V bytes, packed 4 per word
-  int* s_v = reinterpret_cast<int*>(bfs_smem + (V + 3) / 4);   // [BFS_BUFS][BFS_FRONT] frontier vertex ids
-  int* s_pv = s_v + BFS_BUFS * BFS_FRONT;                       // ... their parents' vertex ids
-  int* s_q = s_pv + BFS_BUFS * BFS_FRONT;                       // ... first child position | child direction bits << 28
+  // frontier records, [BFS_BUFS][BFS_STRIDE]: vertex id | (direction bit of its PARENT, seen from the vertex) << 28; the 32
+  // entries behind BFS_FRONT are a per-lane dump zone for the unconditional stores of absent children
+  int* s_v = reinterpret_cast<int*>(bfs_smem + (V + 3) / 4);
+  int* s_q = s_v + BFS_BUFS * BFS_STRIDE;                       // [BFS_BUFS][BFS_STRIDE] first child position | child bits << 28
   __shared__ int s_lev[BFS_BUFS][2];                            // [level & 3] = {level start, level end}; start < 0: stop
   const int b = blockIdx.x, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int2* te = reinterpret_cast<const int2*>(tree + (int64_t)b * (V - 1) * 2);
@@ -439,49 +481,46 @@ __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict_
   int32_t* lvl = level_start + (int64_t)b * (V + 1);
   auto pair_sync = [](int parity) { asm volatile("bar.sync %0, 64;" ::"r"(1 + parity) : "memory"); };
   if (warp == 0) {
-    if (lane == 0) { idx[0] = root; par[0] = 0; s_v[0] = root; s_pv[0] = -1; }
+    if (lane == 0) { idx[0] = root; par[0] = 0; s_v[0] = root; }          // the root has no parent bit
     __syncwarp();
     const unsigned lt_mask = (1u << lane) - 1u;
     int ls = 0, le = 1, level = 0;
     bool fail = false;
     while (ls < le && !fail) {
       const int cur = level & (BFS_BUFS - 1), nxt = (level + 1) & (BFS_BUFS - 1);
-      const int* cv = s_v + cur * BFS_FRONT;
-      const int* cpv = s_pv + cur * BFS_FRONT;
-      int* cq = s_q + cur * BFS_FRONT;
-      int* nv = s_v + nxt * BFS_FRONT;
-      int* npv = s_pv + nxt * BFS_FRONT;
+      const int* cv = s_v + cur * BFS_STRIDE;
+      int* cq = s_q + cur * BFS_STRIDE;
+      int* nv = s_v + nxt * BFS_STRIDE;
       int next = le;
       BFS_TT(0, level);
       for (int base = ls; base < le; base += 32) {
-        const int i = base - ls + lane;
+        // Straight-line code: an idle lane expands entry 0 with its bits masked off, absent children are stored into the
+        // lane's dump slot.  (The branchy form of this block -- `if (on)`, a compare chain for the parent, four conditional
+        // child stores -- cost ~900 of the ~1200 cycles of a level: clock-stamp trace, tools/trace_bfs.py.)
         const bool on = base + lane < le;
-        int v = 0, pv = -1;
-        unsigned bits = 0u;
-        if (on) {
-          v = cv[i]; pv = cpv[i];
-          bits = (s_adj[v >> 2] >> ((v & 3) * 8)) & 15u;
-          // drop the parent: it is one of the four neighbours
-          if (pv >= 0) bits &= ~(pv == v - Wd ? 1u : (pv == v - 1 ? 2u : (pv == v + 1 ? 4u : 8u)));
-        }
+        const int i = on ? base - ls + lane : 0;
+        const int rec = cv[i];
+        const int v = rec & 0x0fffffff;
+        unsigned bits = (s_adj[v >> 2] >> ((v & 3) * 8)) & 15u & ~((unsigned)rec >> 28);
+        bits = on ? bits : 0u;
         const int cnt = __popc(bits);
         if (cnt >= 0) BFS_TT(1, level);
-        // exclusive prefix of the child counts (0..3 per lane; the root may have 4): three ballots instead of a shuffle scan
-        const unsigned b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2), b2 = __ballot_sync(kFull, cnt & 4);
-        const int excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
-        const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        // exclusive prefix of the child counts (0..3 per lane; only the root can have 4): ballots instead of a shuffle scan
+        const unsigned b0 = __ballot_sync(kFull, cnt & 1), b1 = __ballot_sync(kFull, cnt & 2);
+        int excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask), total = __popc(b0) + 2 * __popc(b1);
+        if (level == 0) total = __shfl_sync(kFull, cnt, 0);             // the root: lane 0 alone, excl == 0
         if (next + total - le > BFS_FRONT) { fail = true; break; }      // warp-uniform
         if (total >= 0) BFS_TT(2, level);
-        if (on) {
-          const int q0 = next + excl;                 // this vertex's children occupy positions [q0, q0 + cnt)
-          int r = q0 - le;
-          cq[i] = q0 | (int)(bits << 28);
-          // children in ascending vertex order: up, left, right, down
-          if (bits & 1u) { nv[r] = v - Wd; npv[r] = v; ++r; }
-          if (bits & 2u) { nv[r] = v - 1; npv[r] = v; ++r; }
-          if (bits & 4u) { nv[r] = v + 1; npv[r] = v; ++r; }
-          if (bits & 8u) { nv[r] = v + Wd; npv[r] = v; }
-        }
+        const int q0 = next + excl;                   // this vertex's children occupy positions [q0, q0 + cnt)
+        const int r0 = q0 - le, r1 = r0 + (bits & 1u), r2 = r1 + ((bits >> 1) & 1u), r3 = r2 + ((bits >> 2) & 1u);
+        const int dump = BFS_FRONT + lane;
+        cq[on ? i : dump] = q0 | (int)(bits << 28);
+        // children in ascending vertex order (up, left, right, down); the parent of a child reached through direction k is in
+        // direction 3 - k seen from the child
+        nv[(bits & 1u) ? r0 : dump] = (int)((unsigned)(v - Wd) & 0x0fffffffu | (8u << 28));
+        nv[(bits & 2u) ? r1 : dump] = (int)((unsigned)(v - 1) & 0x0fffffffu | (4u << 28));
+        nv[(bits & 4u) ? r2 : dump] = (int)((unsigned)(v + 1) & 0x0fffffffu | (2u << 28));
+        nv[(bits & 8u) ? r3 : dump] = (int)((unsigned)(v + Wd) & 0x0fffffffu | (1u << 28));
         next += total;
       }
       BFS_TT(3, level);
@@ -514,10 +553,10 @@ __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict_
       const int ls = s_lev[cur][0], le = s_lev[cur][1];
       if (ls < 0) break;
       if (lane == 0) lvl[level] = ls;
-      const int* cv = s_v + cur * BFS_FRONT;
-      const int* cq = s_q + cur * BFS_FRONT;
+      const int* cv = s_v + cur * BFS_STRIDE;
+      const int* cq = s_q + cur * BFS_STRIDE;
       for (int i = lane; i < le - ls; i += 32) {
-        const int v = cv[i], qb = cq[i], p = ls + i;
+        const int v = cv[i] & 0x0fffffff, qb = cq[i], p = ls + i;
         const int q0 = qb & 0x0fffffff;
         const unsigned bits = (unsigned)qb >> 28;
         int q = q0;
@@ -995,7 +1034,12 @@ extern "C" int bxs_mst_forward(const int32_t* edge_index, const float* edge_weig
       mst_compress_kernel<<<gv, 256, 0, st>>>(ws, (int)V);
     }
   }
-  mst_compact_kernel<<<(unsigned)B, NT, 0, st>>>(edge_index, ws, edge_out, (int)E, (int)V);
+  {
+    const int nchunks = (int)ceil_div(E, MC_CHUNK);
+    int* counts = reinterpret_cast<int*>(ws.best);          // the Boruvka keys are dead by now: B * nchunks <= B * V ints
+    mst_count_kernel<<<dim3((unsigned)nchunks, (unsigned)B), MC_T, 0, st>>>(ws, counts, (int)E);
+    mst_compact_kernel<<<dim3((unsigned)nchunks, (unsigned)B), MC_T, 0, st>>>(edge_index, ws, counts, edge_out, (int)E, (int)V);
+  }
   return check_launch();
 }
 
@@ -1040,7 +1084,7 @@ static int bfs_forward_impl(const int32_t* tree_edges, int32_t* sorted_index, in
   cudaMemsetAsync(ws.deg, 0, sizeof(int) * B * V, st);
   cudaMemsetAsync(err, 0, sizeof(int), st);
   // fast path: 4-connected grid trees with the adjacency bits in shared memory (one warp per tree)
-  const size_t grid_smem = ((size_t)(V + 3) / 4) * 4 + (size_t)3 * BFS_BUFS * BFS_FRONT * sizeof(int);
+  const size_t grid_smem = ((size_t)(V + 3) / 4) * 4 + (size_t)BFS_BUFS * 2 * BFS_STRIDE * sizeof(int);
   const bool try_grid = grid_smem <= kMaxTreeSmem;
   if (try_grid) {
     cudaFuncSetAttribute(bfs_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTreeSmem);
