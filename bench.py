@@ -583,7 +583,7 @@ def main_cuda(args, rank, world, local_rank):
     x0 = logit_sets[0].detach().clone().requires_grad_(True)
     p0, q0 = boxinst_mask_loss(x0, targets, gt_inds32, it, plan=plan)
     (g0,) = torch.autograd.grad(p0 + q0, x0)
-    line['losses'] = {'loss_prj': float(p0), 'loss_pairwise': float(q0), 'logit_set': 0}
+    line['losses'] = {'loss_prj': float(p0.detach()), 'loss_pairwise': float(q0.detach()), 'logit_set': 0}
     if ms_step_spread is not None:
         line['config']['region_ms_per_step_min_max'] = list(ms_step_spread)
     if cpu_ms is not None:
