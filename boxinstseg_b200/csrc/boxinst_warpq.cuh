@@ -257,6 +257,7 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
   const int W = FULLW ? NCHUNK * 128 : W_rt;
   extern __shared__ __align__(128) unsigned char wq_smem[];
   __shared__ __align__(8) uint64_t s_bar[WQ_STREAMERS][WQ_RING];
+  __shared__ unsigned s_exit;            // warps of this CTA that have finished
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stage_floats = WQ_SUB * W;
 #ifdef BXS_OP_TRACE
@@ -270,7 +271,8 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __syncwarp();
+  if (threadIdx.x == 0) s_exit = 0u;
+  __syncthreads();                                         // the only CTA-wide barrier of this kernel
   asm volatile("griddepcontrol.wait;" ::: "memory");     // the plan, the scheduler state and the workspace may belong to the predecessor
   const WqHeader* hdr = reinterpret_cast<const WqHeader*>(plan);
   const int S = (H + WQ_R - 1) / WQ_R, T = N * S;
@@ -434,7 +436,6 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
   const unsigned long long wtot = __ldg(&hdr->wtot);
   const float scale = fminf(__ldg(iter_ptr) / warmup_iters, 1.f) / fmaxf((float)wtot, 1.f);
   const int n_pair = __ldg(&hdr->n_pair);
-  const unsigned nwarps = gridDim.x * WQ_NW;
   const unsigned n_idle_slots = gridDim.x * WQ_STREAMERS > (unsigned)NS ? gridDim.x * WQ_STREAMERS - (unsigned)NS : 0u;
   const unsigned n_pair_static = gridDim.x * (WQ_NW - WQ_STREAMERS) + n_idle_slots;
   // the first pair item of a warp that did not stream is static; later ones (and a finished streamer's first) come from
@@ -480,8 +481,23 @@ wq_main_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ edg
   //      poll it, and the last of them resets the queue counters) ----
   __syncwarp();
   if (lane == 0) {
-    __threadfence();
+#ifdef BXS_WQ_SC_FENCE
+    __threadfence();                      // fence.sc.gpu + relaxed atomic (round 2a)
     atomicAdd(&sched->done, 1u);
+#elif defined(BXS_WQ_WARP_ARRIVAL)
+    // one RELEASE reduction per warp instead of a sequentially-consistent fence followed by a relaxed atomic
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&sched->done) : "memory");
+#else
+    // Arrival per CTA: the warps count themselves in shared memory (acq_rel at CTA scope), the LAST one adds the whole CTA
+    // to the global counter with one RELEASE reduction at GPU scope -- 592 reductions on one L2 address at the end of the
+    // kernel instead of 4736 (they serialise there, right on the critical path of the finalize kernel's poll), and no
+    // sequentially-consistent fence.  The other warps' stores reach the finalize CTAs by cumulativity: store -> release
+    // (cta) -> acquire (cta) by the last warp -> release (gpu) -> acquire (gpu) by the poll.
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(&s_exit)) : "memory");
+    if (old == WQ_NW - 1)
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(&sched->done), "r"((unsigned)WQ_NW) : "memory");
+#endif
   }
 }
 

@@ -479,7 +479,11 @@ __global__ void __launch_bounds__(NT) bfs_grid_kernel(const int32_t* __restrict_
   int32_t* par = sorted_parent + (int64_t)b * V;
   int4* chd = reinterpret_cast<int4*>(sorted_child + (int64_t)b * V * 4);
   int32_t* lvl = level_start + (int64_t)b * (V + 1);
-  auto pair_sync = [](int parity) { asm volatile("bar.sync %0, 64;" ::"r"(1 + parity) : "memory"); };
+  // named barriers 1 and 2 (immediate ids), 64 participating threads each: warp 0 + the helper of that level parity
+  auto pair_sync = [](int parity) {
+    if (parity) asm volatile("bar.sync 2, 64;" ::: "memory");
+    else asm volatile("bar.sync 1, 64;" ::: "memory");
+  };
   if (warp == 0) {
     if (lane == 0) { idx[0] = root; par[0] = 0; s_v[0] = root; }          // the root has no parent bit
     __syncwarp();
