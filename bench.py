@@ -731,7 +731,7 @@ def main_config(args, rank, world, local_rank):
                     'value': e0.elapsed_time(e1) / iters / imgs, 'unit': 'ms/img', 'iters': iters,
                     'what': "the reference's eager PyTorch path on this GPU around its own compiled tree_filter_cuda (oracle/_ref, "
                             'built by oracle/Makefile from mmdet/ops/tree_filter/src unmodified), restated in bench_configs.py',
-                    'loss_reference': float(rl[0]), 'loss_b200': float(ours_loss)}
+                    'loss_reference': float(rl[0].detach()) if hasattr(rl[0], 'detach') else float(rl[0]), 'loss_b200': float(ours_loss.detach()) if hasattr(ours_loss, 'detach') else float(ours_loss)}
         except Exception as e:  # noqa: BLE001
             line['gpu_reference'] = {'unavailable': f'{type(e).__name__}: {e}'[:300]}
     print(json.dumps(line), flush=True)

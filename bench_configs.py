@@ -112,11 +112,10 @@ def build_E(dev, seed, layers=10, matched=8):
 
     def step():
         trees = head.image_trees(imgs, (256, 256))                                          # once per step, shared by the layers
-        total = 0.0
-        for e in embeds:
-            mp = head.mask_pred(e, feat)[0].index_select(0, sel)                            # box2mask_head.py:343-345 + matching
-            lp, lm = head.mask_loss_single(mp, targets, [matched], imgs, lst, trees=trees)
-            total = total + lp + lm
+        # box2mask_head.py:343-345 + matching, then loss_single, per decoder layer (multi_apply over the layers, :214-227)
+        pairs = head.mask_loss_layers([lambda e=e: head.mask_pred(e, feat)[0].index_select(0, sel) for e in embeds], targets,
+                                      [matched], imgs, lst, trees=trees)
+        total = sum(lp + lm for lp, lm in pairs)
         return total, torch.autograd.grad(total, leaves)
 
     n, V, V96 = matched, 256 * 256, 96 * 96

@@ -203,9 +203,11 @@ struct LsfPixel {
   }
 };
 
-// block-wide sums of NV values, fixed order (warp shuffles, then the warps in order); result in every thread
+// CTA-wide sums of NV values in a fixed order (warp shuffles, then the warps in order): thread i < NV ends up with the CTA's
+// sum of value i in `v[i]`... as `own`; the other threads' values are left untouched.  (Round 2a had every thread add up all
+// NV x 16 warp partials itself: 304 shared-memory loads per thread per pass -- two thirds of the kernel's 11 M instructions.)
 template <int NV>
-__device__ __forceinline__ void lsf_block_sum(float (&v)[NV], float* s_warp /* [NV][LS_NT/32] */) {
+__device__ __forceinline__ float lsf_block_sum(const float (&v)[NV], float* s_warp /* [NV][LS_NT/32] */) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -213,24 +215,24 @@ __device__ __forceinline__ void lsf_block_sum(float (&v)[NV], float* s_warp /* [
     if (lane == 0) s_warp[i * (LS_NT / 32) + wid] = r;
   }
   __syncthreads();
+  float own = 0.f;
+  if (threadIdx.x < NV) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float r = 0.f;
-#pragma unroll
-    for (int k = 0; k < LS_NT / 32; ++k) r += s_warp[i * (LS_NT / 32) + k];
-    v[i] = r;
+    for (int k = 0; k < LS_NT / 32; ++k) own += s_warp[threadIdx.x * (LS_NT / 32) + k];
   }
-  __syncthreads();
+  return own;
 }
 
-template <bool FUSED>
+// MC: compile-time bound of the channel loops (4 for C <= 4, else LS_MAXC): the loops are fully unrolled and predicated on c < C
+template <bool FUSED, int MC>
 __global__ void __cluster_dims__(LS_CL, 1, 1) __launch_bounds__(LS_NT)
 lsf_forward_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ T,
                    const float* __restrict__ pixel_num, int C, int64_t hw, float loss_weight,
                    LsfStats* __restrict__ stats, float* __restrict__ loss) {
-  constexpr int NV1 = 3 + 2 * LS_MAXC, NV2 = 1 + 2 * LS_MAXC;
+  constexpr int NV1 = 3 + 2 * MC, NV2 = 1 + 2 * MC;
   __shared__ float s_warp[NV1 * (LS_NT / 32)];
   __shared__ float s_part[NV1];                 // this CTA's partial sums, read by the whole cluster
+  __shared__ float s_tot[NV1];                  // the cluster's totals of pass 1
   cg::cluster_group cluster = cg::this_cluster();
   const int n = blockIdx.x / LS_CL, rank = (int)cluster.block_rank();
   LsfPixel<FUSED> px;
@@ -247,32 +249,35 @@ lsf_forward_kernel(const float* __restrict__ x, const float* __restrict__ y, con
     px.ab(p, a, b, m);
     acc[0] += a; acc[1] += b; acc[2] += m;
 #pragma unroll
-    for (int c = 0; c < LS_MAXC; ++c)
+    for (int c = 0; c < MC; ++c)
       if (c < C) {
         const float tv = px.tv(c, p, m);
         acc[3 + c] = fmaf(a, tv, acc[3 + c]);
-        acc[3 + LS_MAXC + c] = fmaf(b, tv, acc[3 + LS_MAXC + c]);
+        acc[3 + MC + c] = fmaf(b, tv, acc[3 + MC + c]);
       }
   }
-  lsf_block_sum<NV1>(acc, s_warp);
-  if (threadIdx.x < NV1) s_part[threadIdx.x] = acc[threadIdx.x];
+  {
+    const float own = lsf_block_sum<NV1>(acc, s_warp);
+    if (threadIdx.x < NV1) s_part[threadIdx.x] = own;
+  }
   cluster.sync();
-  // every CTA sums the 8 partials in rank order: identical statistics everywhere, no broadcast needed
+  // thread i < NV1 of every CTA sums value i of the 8 partials in rank order (identical statistics in every CTA, no broadcast
+  // needed) and publishes it to its own CTA
+  if (threadIdx.x < NV1) {
+    float t = 0.f;
+    for (int r = 0; r < LS_CL; ++r) t += cluster.map_shared_rank(s_part, r)[threadIdx.x];
+    s_tot[threadIdx.x] = t;
+  }
+  cluster.sync();                                 // s_part is rewritten below; s_tot is complete
   float tot[NV1];
 #pragma unroll
-  for (int i = 0; i < NV1; ++i) tot[i] = 0.f;
-  for (int r = 0; r < LS_CL; ++r) {
-    const float* rp = cluster.map_shared_rank(s_part, r);
-#pragma unroll
-    for (int i = 0; i < NV1; ++i) tot[i] += rp[i];
-  }
-  cluster.sync();                                 // s_part is rewritten below
-  float den[2], mean[2][LS_MAXC];
+  for (int i = 0; i < NV1; ++i) tot[i] = s_tot[i];
+  float den[2], mean[2][MC];
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     den[k] = fmaxf(tot[k], kLsEps);
 #pragma unroll
-    for (int c = 0; c < LS_MAXC; ++c) mean[k][c] = c < C ? tot[3 + k * LS_MAXC + c] / den[k] : 0.f;
+    for (int c = 0; c < MC; ++c) mean[k][c] = c < C ? tot[3 + k * MC + c] / den[k] : 0.f;
   }
   // ---- pass 2: C * energy, r0[c] = sum (T - m0) a, r1[c] ----
   float acc2[NV2];
@@ -282,34 +287,41 @@ lsf_forward_kernel(const float* __restrict__ x, const float* __restrict__ y, con
     float a, b, m;
     px.ab(p, a, b, m);
 #pragma unroll
-    for (int c = 0; c < LS_MAXC; ++c)
+    for (int c = 0; c < MC; ++c)
       if (c < C) {
         const float tv = px.tv(c, p, m);
         const float d0 = tv - mean[0][c], d1 = tv - mean[1][c];
         acc2[0] = fmaf(d0 * d0, a, acc2[0]);
         acc2[0] = fmaf(d1 * d1, b, acc2[0]);
         acc2[1 + c] = fmaf(d0, a, acc2[1 + c]);
-        acc2[1 + LS_MAXC + c] = fmaf(d1, b, acc2[1 + LS_MAXC + c]);
+        acc2[1 + MC + c] = fmaf(d1, b, acc2[1 + MC + c]);
       }
   }
-  lsf_block_sum<NV2>(acc2, s_warp);
-  if (threadIdx.x < NV2) s_part[threadIdx.x] = acc2[threadIdx.x];
+  {
+    const float own = lsf_block_sum<NV2>(acc2, s_warp);
+    if (threadIdx.x < NV2) s_part[threadIdx.x] = own;
+  }
   cluster.sync();
+  if (rank == 0) {
+    if (threadIdx.x < NV2) {                      // value i of the 8 partials, rank order
+      float t = 0.f;
+      for (int r = 0; r < LS_CL; ++r) t += cluster.map_shared_rank(s_part, r)[threadIdx.x];
+      s_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
   if (rank == 0 && threadIdx.x == 0) {
     float tot2[NV2];
-    for (int i = 0; i < NV2; ++i) tot2[i] = 0.f;
-    for (int r = 0; r < LS_CL; ++r) {
-      const float* rp = cluster.map_shared_rank(s_part, r);
-      for (int i = 0; i < NV2; ++i) tot2[i] += rp[i];
-    }
+    for (int i = 0; i < NV2; ++i) tot2[i] = s_tot[i];
     LsfStats st;
     for (int k = 0; k < 2; ++k) {
       st.z[k] = tot[k];
       st.den[k] = den[k];
       for (int c = 0; c < LS_MAXC; ++c) {
-        st.a[k][c] = c < C ? tot[3 + k * LS_MAXC + c] : 0.f;
-        st.m[k][c] = mean[k][c];
-        st.d[k][c] = c < C ? -2.f / (float)C * tot2[1 + k * LS_MAXC + c] : 0.f;
+        const bool in = c < C && c < MC;
+        st.a[k][c] = in ? tot[3 + k * MC + (c < MC ? c : 0)] : 0.f;
+        st.m[k][c] = in ? mean[k][c < MC ? c : 0] : 0.f;
+        st.d[k][c] = in ? -2.f / (float)C * tot2[1 + k * MC + (c < MC ? c : 0)] : 0.f;
       }
     }
     st.energy = tot2[0] / (float)C;
@@ -435,9 +447,11 @@ extern "C" int bxs_levelset_fused_forward(const float* x, const float* y, const 
   cudaStream_t st = as_stream(stream);
   LsfStats* stats = reinterpret_cast<LsfStats*>(workspace);
   if (mode == 1)
-    lsf_forward_kernel<true><<<(unsigned)(n * LS_CL), LS_NT, 0, st>>>(x, y, T, pixel_num, (int)C, h * w, loss_weight, stats, loss);
+    if (C <= 4) lsf_forward_kernel<true, 4><<<(unsigned)(n * LS_CL), LS_NT, 0, st>>>(x, y, T, pixel_num, (int)C, h * w, loss_weight, stats, loss);
+    else lsf_forward_kernel<true, LS_MAXC><<<(unsigned)(n * LS_CL), LS_NT, 0, st>>>(x, y, T, pixel_num, (int)C, h * w, loss_weight, stats, loss);
   else
-    lsf_forward_kernel<false><<<(unsigned)(n * LS_CL), LS_NT, 0, st>>>(x, y, T, pixel_num, (int)C, h * w, loss_weight, stats, loss);
+    if (C <= 4) lsf_forward_kernel<false, 4><<<(unsigned)(n * LS_CL), LS_NT, 0, st>>>(x, y, T, pixel_num, (int)C, h * w, loss_weight, stats, loss);
+    else lsf_forward_kernel<false, LS_MAXC><<<(unsigned)(n * LS_CL), LS_NT, 0, st>>>(x, y, T, pixel_num, (int)C, h * w, loss_weight, stats, loss);
   return check_launch();
 }
 

@@ -881,15 +881,20 @@ __global__ void __launch_bounds__(RNT) refine_updown_kernel(const float* __restr
                                                            const float* __restrict__ wsum, float* __restrict__ aggr,
                                                            float* __restrict__ aggr_up, float* __restrict__ wsum_out,
                                                            float* __restrict__ wsum_up, float* __restrict__ scratch, int C,
-                                                           int V, const int32_t* __restrict__ tree_of, int norm_only) {
+                                                           int V, const int32_t* __restrict__ tree_of, int norm_from) {
   // tree_of (may be null): the tree / edge weights / normaliser of batch entry b are those of group tree_of[b] -- the
   // instances of one image share one tree (box_solov2_head.py:300-305,353; box2mask_head.py:271-276), so the order,
   // the packed child weights and the normaliser Z exist once per image instead of once per instance.
-  // norm_only: this launch computes only the normaliser channel (blockIdx.x indexes trees).
+  // norm_from >= 0 (grouped forward): CTAs with blockIdx.x >= norm_from compute the normaliser of TREE blockIdx.x - norm_from
+  // (one per tree, blockIdx.y == 0 only) in the same launch as the feature CTAs -- the two are independent until the division,
+  // and as two launches on one stream they cost two level walks back to back.  norm_from < 0: the normaliser is channel C of
+  // every batch entry (grid.y == C + 1).
   extern __shared__ float s_buf[];
   __shared__ RingSmem R;
-  const int b = blockIdx.x, c = norm_only ? C : blockIdx.y;
-  const int tb = tree_of ? __ldg(tree_of + b) : b;
+  const bool split_norm = norm_from >= 0 && (int)blockIdx.x >= norm_from;
+  if (split_norm && blockIdx.y != 0) return;
+  const int b = split_norm ? (int)blockIdx.x - norm_from : (int)blockIdx.x, c = split_norm ? C : (int)blockIdx.y;
+  const int tb = (tree_of && !split_norm) ? __ldg(tree_of + b) : b;
   const TreeView t = make_view(w, idx, par, cinfo, cw, lvl, nlv, tb, V);
   float* buf = SMEM ? s_buf : scratch + ((int64_t)b * (C + 1) + c) * V;
   const bool norm = MODE == 0 && c == C;
@@ -1165,11 +1170,11 @@ extern "C" int bxs_refine_forward(const float* feature, const float* edge_weight
     cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
     refine_updown_kernel<0, true><<<grid, RNT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, nullptr, aggr, aggr_up, wsum, wsum_up,
-                                                        nullptr, (int)C, (int)V, nullptr, 0);
+                                                        nullptr, (int)C, (int)V, nullptr, -1);
   } else {
     refine_updown_kernel<0, false><<<grid, RNT, 0, st>>>(feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, nullptr, aggr, aggr_up, wsum, wsum_up,
-                                                        rs.bufs, (int)C, (int)V, nullptr, 0);
+                                                        rs.bufs, (int)C, (int)V, nullptr, -1);
   }
   refine_div_kernel<<<grid_for(B * C * V, 256), 256, 0, st>>>(aggr, wsum, feature_out, (int)C, (int)V, B * C * V, nullptr);
   return check_launch();
@@ -1193,11 +1198,11 @@ extern "C" int bxs_refine_backward_feature(const float* edge_weight, const int32
     cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
     refine_updown_kernel<1, true><<<grid, RNT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
-                                                        nullptr, nullptr, (int)C, (int)V, nullptr, 0);
+                                                        nullptr, nullptr, (int)C, (int)V, nullptr, -1);
   } else {
     refine_updown_kernel<1, false><<<grid, RNT, 0, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
-                                                        nullptr, rs.bufs, (int)C, (int)V, nullptr, 0);
+                                                        nullptr, rs.bufs, (int)C, (int)V, nullptr, -1);
   }
   return check_launch();
 }
@@ -1252,21 +1257,13 @@ extern "C" int bxs_refine_forward_grouped(const float* feature, const float* edg
   const size_t sm = (V + 4) * sizeof(float);
   if (sm <= kMaxRefineSmem) {
     cudaFuncSetAttribute(refine_updown_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
-    refine_updown_kernel<0, true><<<dim3((unsigned)G, 1), RNT, sm, st>>>(feature, edge_weight, sorted_index, sorted_parent,
-                                                                        rs.cinfo, rs.cw, level_start, num_levels, nullptr, aggr,
-                                                                        aggr_up, wsum, wsum_up, nullptr, (int)C, (int)V,
-                                                                        nullptr, 1);
-    refine_updown_kernel<0, true><<<dim3((unsigned)n, (unsigned)C), RNT, sm, st>>>(
+    refine_updown_kernel<0, true><<<dim3((unsigned)(n + G), (unsigned)C), RNT, sm, st>>>(
         feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw, level_start, num_levels, nullptr, aggr, aggr_up,
-        wsum, wsum_up, nullptr, (int)C, (int)V, tree_of, 0);
+        wsum, wsum_up, nullptr, (int)C, (int)V, tree_of, (int)n);
   } else {
-    refine_updown_kernel<0, false><<<dim3((unsigned)G, 1), RNT, 0, st>>>(feature, edge_weight, sorted_index, sorted_parent,
-                                                                        rs.cinfo, rs.cw, level_start, num_levels, nullptr, aggr,
-                                                                        aggr_up, wsum, wsum_up, rs.bufs, (int)C, (int)V,
-                                                                        nullptr, 1);
-    refine_updown_kernel<0, false><<<dim3((unsigned)n, (unsigned)C), RNT, 0, st>>>(
+    refine_updown_kernel<0, false><<<dim3((unsigned)(n + G), (unsigned)C), RNT, 0, st>>>(
         feature, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw, level_start, num_levels, nullptr, aggr, aggr_up,
-        wsum, wsum_up, rs.bufs, (int)C, (int)V, tree_of, 0);
+        wsum, wsum_up, rs.bufs, (int)C, (int)V, tree_of, (int)n);
   }
   refine_div_kernel<<<grid_for(n * C * V, 256), 256, 0, st>>>(aggr, wsum, feature_out, (int)C, (int)V, n * C * V, tree_of);
   return check_launch();
@@ -1291,11 +1288,11 @@ extern "C" int bxs_refine_backward_feature_grouped(const float* edge_weight, con
     cudaFuncSetAttribute(refine_updown_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxRefineSmem);
     refine_updown_kernel<1, true><<<grid, RNT, sm, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
-                                                        nullptr, nullptr, (int)C, (int)V, tree_of, 0);
+                                                        nullptr, nullptr, (int)C, (int)V, tree_of, -1);
   } else {
     refine_updown_kernel<1, false><<<grid, RNT, 0, st>>>(grad_out, edge_weight, sorted_index, sorted_parent, rs.cinfo, rs.cw,
                                                         level_start, num_levels, wsum, grad_feature, nullptr, nullptr,
-                                                        nullptr, rs.bufs, (int)C, (int)V, tree_of, 0);
+                                                        nullptr, rs.bufs, (int)C, (int)V, tree_of, -1);
   }
   return check_launch();
 }

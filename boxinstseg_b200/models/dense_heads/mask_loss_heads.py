@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from ...ops.dynconv import box2mask_mask_pred, dynconv1x1, solo_dynamic_conv
 from ...ops.resize import bilinear_resize, scale_target as _scale_target   # a18: F.interpolate / _scale_target as kernels
+from ...ops._streams import Forked, run_concurrently
 from ...ops.tree_filter import MinimumSpanningTree, TreeFilter2D
 from ..builder import HEADS, build_loss, register
 from ..losses import LCM, levelset_assembly, mil_loss
@@ -71,27 +72,42 @@ class BoxSOLOv2Head(nn.Module):
         rebuilds identical trees per instance (:300-305,353).  Same losses either way.
         Per level: one sigmoid, BoxProjectionLoss, ONE launch per level-set term (sigmoid / cat / * box / clamp inside,
         ``levelset_assembly``), two tree filters."""
-        loss_project, loss_levelset = [], []
         w_ls = self.loss_levelset.loss_weight
-        for lvl, (ins_pred, box_mask, img_t, lst_t) in enumerate(zip(ins_preds, ins_labels, img_targets, lst_targets)):
-            if ins_pred.size(0) == 0:
-                continue
+
+        def level(lvl, ins_pred, box_mask, img_t, lst_t):
             mask_pred = torch.sigmoid(ins_pred.unsqueeze(1))
             box = box_mask.unsqueeze(1).to(mask_pred.dtype)
-            loss_project.append(self.loss_boxpro(mask_pred, box))
+            l_prj = self.loss_boxpro(mask_pred, box)
             if inst_imgs is not None:
                 ii = inst_imgs[lvl]
                 img_inst = img_t.index_select(0, ii.long())
+                # the second tree and its BFS order do not depend on the first filter: build them on the side stream meanwhile
+                lst = Forked(lambda: self._tree_and_order(lst_t, mask_pred.shape, None), mask_pred.device)
                 f_img = self.tree_filter(mask_pred, img_t, self.mst(img_t), tree_of=ii)
-                f_lst = self.tree_filter(f_img, lst_t, self.mst(lst_t), low_tree=False, tree_of=ii)
+                lst_tree, lst_order = lst.join()
+                f_lst = self.tree_filter(f_img, lst_t, lst_tree, low_tree=False, tree_of=ii, order=lst_order)
             else:
                 img_inst = img_t
+                lst = Forked(lambda: self._tree_and_order(lst_t, mask_pred.shape, shared_trees), mask_pred.device)
                 f_img = self.tree_filter(mask_pred, img_t, self._mst(img_t, shared_trees))
-                f_lst = self.tree_filter(f_img, lst_t, self._mst(lst_t, shared_trees), low_tree=False)
+                lst_tree, lst_order = lst.join()
+                f_lst = self.tree_filter(f_img, lst_t, lst_tree, low_tree=False, order=lst_order)
             loss_img = levelset_assembly(ins_pred, box, img_inst, w_ls) * 0.05             # :341-351
             loss_feat = levelset_assembly(ins_pred, box, torch.cat((f_img, f_lst), dim=1), w_ls) * 5.0   # :357-360
-            loss_levelset.append(loss_img + loss_feat)
+            return l_prj, loss_img + loss_feat
+
+        # the FPN levels are independent (a tree filter is a dependent-level walk on ~20 CTAs): one lane stream per level
+        work = [(lvl, a, b, c, d) for lvl, (a, b, c, d) in enumerate(zip(ins_preds, ins_labels, img_targets, lst_targets))
+                if a.size(0) > 0]
+        dev = work[0][1].device if work else None
+        outs = run_concurrently([lambda w=w: level(*w) for w in work], dev) if work else []
+        loss_project, loss_levelset = [o[0] for o in outs], [o[1] for o in outs]
         return dict(loss_boxpro=torch.cat(loss_project).mean(), loss_levelset=torch.cat(loss_levelset).mean())
+
+    def _tree_and_order(self, guide, shape, shared):
+        """MST of ``guide`` (shared across identical rows when ``shared`` is not None) and the BFS order the filter will use."""
+        tree = self.mst(guide) if shared is None else self._mst(guide, shared)
+        return tree, self.tree_filter.order(tree, shape)
 
     def _mst(self, guide, shared):
         if not shared or guide.size(0) == 1:
@@ -203,7 +219,12 @@ class Box2MaskHead(nn.Module):
         dev = mask_preds.device
         img96_b, lst96_b = _scale_target(norm_img), _scale_target(lst_feat)       # per IMAGE, :269-272
         img_tree = trees if trees is not None else self.mst(img96_b)
-        lst_tree = self.mst(lst96_b)
+        # the second tree and its BFS order depend on nothing computed below: side stream, joined before the second filter
+        def second_tree():
+            tree = self.mst(lst96_b)
+            return tree, self.tree_filter.order(tree, lst96_b.shape)
+
+        lst = Forked(second_tree, lst96_b.device)
         # instance -> image, built from device-side fills only (host ints in, no copy: CUDA-graph capturable)
         tree_of = torch.cat([torch.full((int(c),), i, device=dev, dtype=torch.int32) for i, c in enumerate(num_per_img)])
         box = bilinear_resize(mask_targets.unsqueeze(1).to(mask_preds.dtype), pred_shape)   # :300
@@ -213,11 +234,28 @@ class Box2MaskHead(nn.Module):
         loss_img = levelset_assembly(mask_preds, box, norm_img.index_select(0, tree_of.long()), w_ls).mean() * 0.05   # :305-312
         s96 = _scale_target(s)
         f_img = self.tree_filter(s96, img96_b, img_tree, tree_of=tree_of)                  # :315-322
-        f_lst = self.tree_filter(f_img, lst96_b, lst_tree, low_tree=False, tree_of=tree_of)
+        lst_tree, lst_order = lst.join()
+        f_lst = self.tree_filter(f_img, lst96_b, lst_tree, low_tree=False, tree_of=tree_of, order=lst_order)
         deep = torch.cat((bilinear_resize(f_img, pred_shape), bilinear_resize(f_lst, pred_shape)), dim=1)   # :323-324
         loss_feat = levelset_assembly(mask_preds, box, deep, w_ls).mean() * 5.0            # :325-327
         loss_lcm = 0.2 * LCM(img96_b.index_select(0, tree_of.long()), s96, _scale_target(box))   # :329-331
         return loss_project, loss_img + loss_feat + loss_lcm
+
+    def mask_loss_layers(self, mask_preds_per_layer, mask_targets, num_per_img, norm_img, lst_feat, trees=None):
+        """``mask_loss_single`` of every decoder layer (the reference's ``multi_apply(self.loss_single, ...)`` over the layers,
+        box2mask_head.py:214-227): the layers are independent, so each one runs on its own lane stream.  ``mask_preds_per_layer``
+        : list of [n,h,w] tensors or of callables producing them (e.g. the layer's einsum + matching, run inside the lane).
+        Returns the list of (loss_project, loss_levelset) pairs."""
+        if trees is None:
+            first = mask_preds_per_layer[0]
+            shape = (first() if callable(first) else first).shape[-2:]
+            trees = self.image_trees(norm_img, shape)
+
+        def layer(mp):
+            mp = mp() if callable(mp) else mp
+            return self.mask_loss_single(mp, mask_targets, num_per_img, norm_img, lst_feat, trees=trees)
+
+        return run_concurrently([lambda mp=mp: layer(mp) for mp in mask_preds_per_layer], norm_img.device)
 
     def image_trees(self, norm_img, pred_shape):
         """MST of every image at 96x96 (box2mask_head.py:232,269-272): identical for all decoder layers of a step."""

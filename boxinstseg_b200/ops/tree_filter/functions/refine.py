@@ -7,6 +7,16 @@ from torch.autograd.function import once_differentiable
 
 from .. import tree_filter_cuda as _C
 
+from ..._streams import Forked
+
+
+def _both(device, feature_fn, weight_fn):
+    """-> (feature_fn(), weight_fn()).  d/d feature and d/d edge_weight are independent level walks (two and three dependent
+    passes over ~1000-1900 tree levels) on a handful of SMs each: the second one runs on the side stream."""
+    forked = Forked(weight_fn, device)
+    gf = feature_fn()
+    return gf, forked.join()
+
 
 class _Refine(Function):
     @staticmethod
@@ -26,8 +36,10 @@ class _Refine(Function):
          nlv) = ctx.saved_tensors
         args = (None, edge_weight, sorted_index, sorted_parent, sorted_child, out, aggr, aggr_up, wsum, wsum_up,
                 grad_output.contiguous())
-        grad_feature = _C.refine_backward_feature(*args, levels=(lvl, nlv))
-        grad_weight = None if ctx.low_tree else _C.refine_backward_weight(*args, levels=(lvl, nlv))
+        if ctx.low_tree:
+            return _C.refine_backward_feature(*args, levels=(lvl, nlv)), None, None, None, None, None
+        grad_feature, grad_weight = _both(grad_output.device, lambda: _C.refine_backward_feature(*args, levels=(lvl, nlv)),
+                                          lambda: _C.refine_backward_weight(*args, levels=(lvl, nlv)))
         return grad_feature, grad_weight, None, None, None, None
 
 
@@ -55,12 +67,17 @@ class _RefineGrouped(Function):
     def backward(ctx, grad_output):
         (edge_weight, idx, par, chd, tree_of, out, aggr, aggr_up, wsum, wsum_up, lvl, nlv) = ctx.saved_tensors
         g = grad_output.contiguous()
-        grad_feature = _C.refine_backward_feature_grouped(edge_weight, idx, par, chd, (lvl, nlv), tree_of, wsum, g)
-        grad_weight = None
-        if not ctx.low_tree:
+        def d_feature():
+            return _C.refine_backward_feature_grouped(edge_weight, idx, par, chd, (lvl, nlv), tree_of, wsum, g)
+
+        def d_weight():
             per_inst = _C.refine_backward_weight_grouped(edge_weight, idx, par, chd, (lvl, nlv), tree_of, out, aggr, aggr_up,
                                                          wsum, wsum_up, g)
-            grad_weight = torch.zeros_like(edge_weight).index_add_(0, tree_of.long(), per_inst)
+            return torch.zeros_like(edge_weight).index_add_(0, tree_of.long(), per_inst)
+
+        if ctx.low_tree:
+            return d_feature(), None, None, None, None, None, None
+        grad_feature, grad_weight = _both(g.device, d_feature, d_weight)
         return grad_feature, grad_weight, None, None, None, None, None
 
 

@@ -142,21 +142,27 @@ class TreeFilter2D(nn.Module):
         dist = self.distance_func(src, dst)
         return torch.exp(-dist / self.sigma) if low_tree else torch.exp(-dist)
 
-    def forward(self, feature_in, embed_in, tree, low_tree=True, tree_of=None):
+    def order(self, tree, shape):
+        """The BFS order ``forward`` would compute for ``tree`` (rooted at the centre pixel of ``shape``): lets a caller build
+        it ahead of time, e.g. on a side stream while another filter runs, and pass it back as ``order=``."""
+        return bfs(tree, 4, self._root(shape))
+
+    def forward(self, feature_in, embed_in, tree, low_tree=True, tree_of=None, order=None):
         """``tree_of`` (optional, int32 [n]): feature_in holds n instances that share the G trees / embeddings given
         (embed_in [G,C,h,w], tree [G,V-1,2]); instance i uses tree ``tree_of[i]``.  Same result as repeating the trees
-        and embeddings per instance (what the reference's heads do), computed once per tree."""
+        and embeddings per instance (what the reference's heads do), computed once per tree.
+        ``order`` (optional): ``self.order(tree, feature_in.shape)`` computed by the caller."""
         if tree_of is not None:
             assert self.groups == 1
             shape = feature_in.shape
-            sorted_index, sorted_parent, sorted_child = bfs(tree, 4, self._root(shape))
+            sorted_index, sorted_parent, sorted_child = order if order is not None else bfs(tree, 4, self._root(shape))
             edge_weight = self.build_edge_weight(embed_in, sorted_index, sorted_parent, low_tree, sorted_child)
             feat = feature_in.reshape(shape[0], shape[1], -1).contiguous()
             t_of = tree_of if tree_of.dtype == torch.int32 else tree_of.to(torch.int32)
             return refine_grouped(feat, edge_weight, sorted_index, sorted_parent, sorted_child, t_of.contiguous(),
                                   low_tree).reshape(shape)
         shape = feature_in.shape
-        sorted_index, sorted_parent, sorted_child = bfs(tree, 4, self._root(shape))
+        sorted_index, sorted_parent, sorted_child = order if order is not None else bfs(tree, 4, self._root(shape))
         edge_weight = self.build_edge_weight(embed_in, sorted_index, sorted_parent, low_tree, sorted_child)
         feat = feature_in.reshape(shape[0] * self.groups, shape[1] // self.groups, -1).contiguous()
         if self.groups > 1:                                  # tree_filter.py:110-120 (split_group)

@@ -1,7 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool synccheck --print-limit 6 python tools/sanitize_small.py > gpurun_out/sanitize_synccheck.log 2>&1; grep -v "^=========     \|^  File\|^    " gpurun_out/sanitize_synccheck.log | head -40
-timeout 600 python -m pytest tests/test_boxinst_gpu.py tests/test_config_a_gpu.py tests/test_tree_filter_gpu.py -x -q 2>&1 | tail -3
-for i in 1 2; do python bench.py --steps 200 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+timeout 600 python -m pytest tests/test_tree_filter_gpu.py tests/test_reference_ext_gpu.py tests/test_mask_loss_heads_gpu.py tests/test_losses_gpu.py -x -q 2>&1 | tail -3
+for c in D E; do timeout 600 python bench.py --config $c --steps 10 --warmup 3 > gpurun_out/r2_bench_$c.json 2> gpurun_out/r2_bench_$c.err; tail -3 gpurun_out/r2_bench_$c.err; python - $c <<'PY'
 import json,sys
-d=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('step us', d['ms_per_step']*1e3, 'frac', d['roofline']['frac'])"; done
+c=sys.argv[1]
+d=json.loads(open(f'gpurun_out/r2_bench_{c}.json').read().strip().split('\n')[-1])
+print(c, d['value'], d['ms_per_step'], d['gpu_reference']['value'], d['gpu_reference'].get('loss_reference'), d['gpu_reference'].get('loss_b200'))
+PY
+done
