@@ -273,3 +273,55 @@ def test_discobox_mask_loss_full_size_vs_oracle():
     assert abs(out['loss_ts'].item() - l_ts.item()) <= 1e-3 * abs(l_ts.item())
     assert rel_err(g.cpu(), g_ref) <= 1e-3
     assert float(g[3].abs().max()) == 0.0                       # the dropped instance receives no gradient
+
+
+def test_multi_level_lanes_equal_single_level_calls_and_graph_replay():
+    """The FPN levels of BoxSOLOv2Head.mask_loss run on lane streams (ops/_streams.py): the multi-level call must equal the
+    levels evaluated one call at a time (losses and every gradient, bit for bit -- same kernels, only the streams differ),
+    eagerly AND as a CUDA-graph replay of forward + backward captured with the forks and joins inside."""
+    from boxinstseg_b200.models import build_head
+    gen = torch.Generator().manual_seed(7)
+    sizes = [(40, 48), (40, 48), (24, 32), (12, 16)]
+    n_img, per_img = 2, 3
+    head = build_head(dict(type='BoxSOLOv2Head', num_classes=80, in_channels=256,
+                           loss_boxpro=dict(type='BoxProjectionLoss', loss_weight=3.0),
+                           loss_levelset=dict(type='LevelsetLoss', loss_weight=1.0)))
+    inst = torch.arange(n_img, dtype=torch.int32).repeat_interleave(per_img).to(DEV)
+    preds = [torch.randn(n_img * per_img, h, w, generator=gen).to(DEV).requires_grad_(True) for h, w in sizes]
+    boxes = [_boxes(n_img * per_img, h, w).to(DEV) for h, w in sizes]
+    img_t = [torch.randn(n_img, 3, h, w, generator=gen).to(DEV) for h, w in sizes]
+    lst_t = [(torch.randn(n_img, 5, h, w, generator=gen) * 0.3).to(DEV).requires_grad_(True) for h, w in sizes]
+    leaves = preds + lst_t
+
+    def step():
+        out = head.mask_loss(preds, boxes, img_t, lst_t, inst_imgs=[inst] * len(sizes))
+        return [out['loss_boxpro'], out['loss_levelset']] + list(torch.autograd.grad(out['loss_boxpro'] + out['loss_levelset'],
+                                                                                     leaves))
+
+    got = [t.clone() for t in step()]
+    # one level per call: no lanes involved (a single level runs on the calling stream)
+    prj, ls, grads = [], [], [None] * len(leaves)
+    for k in range(len(sizes)):
+        o = head.mask_loss([preds[k]], [boxes[k]], [img_t[k]], [lst_t[k]], inst_imgs=[inst])
+        prj.append(o['loss_boxpro']); ls.append(o['loss_levelset'])
+    # the multi-level losses are means over the concatenated per-level vectors: equal level sizes -> mean of the means
+    want_prj, want_ls = torch.stack(prj).mean(), torch.stack(ls).mean()
+    g = torch.autograd.grad(want_prj + want_ls, leaves)
+    assert torch.allclose(got[0], want_prj, rtol=1e-6, atol=0) and torch.allclose(got[1], want_ls, rtol=1e-6, atol=0)
+    for a, b in zip(got[2:], g):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-9)
+    # CUDA-graph capture of the whole step, replayed twice
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = step()
+    for _ in range(2):
+        graph.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(out, got):
+            assert torch.equal(a, b)
