@@ -27,4 +27,7 @@ Parity pinning status (see DESIGN.md "Oracle"):
     ``/root/reference`` (scikit-image unpinned; mmcv-full 1.3.17-1.6.0): their published
     algorithms are restated and pinned on known-answer colours + OpenCV's independent
     implementation -> "parity unpinned" for those two functions only.
+  * ``oracle/solo_targets.py`` (SOLO grid targets, box_solov2_head.py:390-472) is pinned on the reference's own METHOD:
+    ``oracle/make_golden_solo.py`` AST-extracts ``BoxSOLOv2Head.solo_target_single``, runs it and asserts equality; its
+    ``mmcv.imrescale`` (third party, absent) is the ``cv2.resize`` call mmcv makes, OpenCV being importable here.
 """
