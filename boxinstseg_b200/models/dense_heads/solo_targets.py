@@ -51,6 +51,25 @@ def cv2_resize_linear_u8(img, new_h, new_w):
     return out.clamp_(0, 255).to(torch.uint8)
 
 
+def _true_div(a, b):
+    """a / b with IEEE division on every device.  (ATen's CUDA kernels divide by a host scalar by multiplying with its
+    reciprocal, which can differ from the quotient by one ulp -- enough to move a grid-cell boundary.  The reference's own
+    float32 box terms go through that path when its boxes are CUDA tensors, so its CUDA and CPU runs can disagree in rare
+    boundary cases; this implementation reproduces its CPU result -- exact division, as numpy does for the float64 terms -- on
+    both devices.)"""
+    return a / torch.full((), b, dtype=a.dtype, device=a.device)
+
+
+def _floor_div(a, b):
+    """Python's float ``a // b`` (CPython float_floor_div, which numpy and ATen's CPU kernel follow), from IEEE primitives."""
+    bt = torch.full((), b, dtype=a.dtype, device=a.device)
+    mod = torch.fmod(a, bt)
+    div = (a - mod) / bt
+    div = torch.where((mod != 0) & ((mod < 0) != (bt < 0)), div - 1, div)
+    fl = torch.floor(div)
+    return torch.where(div - fl > 0.5, fl + 1, fl)
+
+
 def rescale_size(h, w, scale):
     """mmcv.rescale_size: int(dim * scale + 0.5)."""
     return int(h * float(scale) + 0.5), int(w * float(scale) + 0.5)
@@ -101,7 +120,7 @@ def solo_grid_targets(gt_bboxes, gt_labels, gt_masks, featmap_sizes, scale_range
         cell = 1. / grid
 
         def cells(x, size):
-            return torch.div(x / size, cell, rounding_mode='floor').to(torch.int64)
+            return _floor_div(_true_div(x, float(size)), cell).to(torch.int64)
 
         coord_h, coord_w = cells(ch, up_h), cells(cw, up_w)                              # float64 path
         top_box = cells(ch32 - half_h, up_h).clamp(min=0)                                # float32 path
