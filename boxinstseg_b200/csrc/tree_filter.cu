@@ -860,6 +860,7 @@ __device__ __forceinline__ void down_pass(const TreeView& t, RingSmem& R, float*
   __syncthreads();
   // A of every position is in `buf`: scatter to vertex order in one parallel sweep (not level by level)
   if (out_vertex)
+#pragma unroll 8
     for (int p = threadIdx.x; p < t.V; p += RNT) out_vertex[__ldg(t.idx + p)] = buf[p];
 }
 
@@ -903,6 +904,8 @@ __global__ void __launch_bounds__(RNT) refine_updown_kernel(const float* __restr
   float* save_up = MODE == 0 ? (norm ? wsum_up + (int64_t)b * V : aggr_up + ((int64_t)b * C + c) * V) : nullptr;
   float* out_v = MODE == 0 ? (norm ? wsum_out + (int64_t)b * V : aggr + ((int64_t)b * C + c) * V)
                            : aggr + ((int64_t)b * C + c) * V;     // MODE 1: aggr == grad_feature
+  // (dependent index -> value loads with 256 threads per CTA: unrolled so that 8 round trips are in flight per thread)
+#pragma unroll 8
   for (int p = threadIdx.x; p < V; p += RNT) {               // parallel gather of the inputs into position order
     const int v = __ldg(t.idx + p);
     buf[p] = norm ? 1.f : (MODE == 1 ? x[v] / z[v] : x[v]);
@@ -962,6 +965,7 @@ __global__ void __launch_bounds__(RNT) refine_bwd_weight_kernel(
       const float* outd = phase ? z : ag;
       const float sign = phase ? -1.f : 1.f;
       __syncthreads();
+#pragma unroll 4
       for (int p = threadIdx.x; p < V; p += RNT) {           // parallel pre-pass: inputs and parent data, position order
         const int v = __ldg(t.idx + p);
         const float gn = g[v] / z[v];
