@@ -406,6 +406,26 @@ int bxs_levelset_fused_backward(const float* x, const float* y, const float* T, 
                                 const float* g_loss, float* g_x, float* g_T, int64_t n, int64_t C, int64_t h,
                                 int64_t w, float loss_weight, int mode, bxs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * f2  FCOS point assignment    replaces CondInstBoxHead.get_targets + _get_target_single
+ *     (mmdet/models/dense_heads/condinst_head.py:477-548, 550-633) for a whole batch in one launch.
+ * points f32 [P,2] (all levels concatenated, level l = [level_off[l], level_off[l+1])), gt_boxes f32 [sum G,4] and
+ * gt_labels i64 [sum G] (the images' ground truths concatenated; may be null when sum G = 0).  The *_host arrays are HOST
+ * arrays, copied into the kernel parameters (no H2D copy: the call can be captured in a CUDA graph): gt_off_host i64
+ * [B+1] (image b owns [gt_off[b], gt_off[b+1]) of the concatenated list), level_off_host i64 [num_levels+1], and per
+ * level regress_ranges, strides[l] * center_sample_radius (rounded to f32), strides[l].
+ * Outputs in the reference's layout, level-major and image-major inside a level (what torch.cat of its per-level
+ * lists gives): labels i64 [B*P] (num_classes = background), bbox_targets f32 [B*P,4] (divided by the level's stride
+ * when norm_on_bbox), gt_inds i64 [B*P] (index into the CONCATENATED ground truths, -1 = none).
+ * Bit-exact: every value is one correctly rounded fp32 operation of the reference, in its order.  num_levels <= 8,
+ * B <= 256.
+ * --------------------------------------------------------------------------------------- */
+int bxs_fcos_targets(const float* points, const float* gt_boxes, const int64_t* gt_labels, const int64_t* gt_off_host,
+                     int64_t* labels, float* bbox_targets, int64_t* gt_inds, int64_t B, int64_t num_levels,
+                     const int64_t* level_off_host, const float* range_lo_host, const float* range_hi_host,
+                     const float* stride_radius_host, const float* stride_host, int center_sampling,
+                     int norm_on_bbox, int64_t num_classes, bxs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,3 +54,22 @@ def boxinst_case(seed, B, hp, wp, gts_per_img, inst_per_gt, logit_std=2.0, ragge
 def rel_err(a, b):
     a, b = a.double().flatten(), b.double().flatten()
     return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
+
+
+def host_twin(name):
+    """Compiles tests/host_harness/<name>.cpp -- the HOST build of the very header a kernel is made of -- with g++ and
+    returns the ctypes handle (test infrastructure: lets the CPU suite check a kernel's arithmetic and indexing bit for bit
+    against the oracle on a box without a GPU; the product library exports only the CUDA path)."""
+    import ctypes
+    import os
+    import subprocess
+    import tempfile
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, 'host_harness', name + '.cpp')
+    out = os.path.join(tempfile.gettempdir(), f'bxs_{name}_{os.getuid()}_{int(os.path.getmtime(src))}.so')
+    core = os.path.join(here, '..', 'boxinstseg_b200', 'csrc')
+    newest = max(os.path.getmtime(os.path.join(core, f)) for f in os.listdir(core) if f.endswith('.cuh'))
+    if not os.path.exists(out) or os.path.getmtime(out) < max(newest, os.path.getmtime(src)):
+        subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-x', 'c++', src, '-o', out],
+                       check=True)
+    return ctypes.CDLL(out)
