@@ -23,3 +23,24 @@ def test_solo_targets_cuda_equals_cpu(seed):
             assert torch.equal(got[k][lvl].cpu(), want[k][lvl])
         assert torch.allclose(got[3][lvl].cpu(), F.interpolate(img[None], size=fs[lvl], mode='bilinear'), atol=1e-5)
         assert torch.allclose(got[4][lvl].cpu(), F.interpolate(lst[None], size=fs[lvl], mode='bilinear'), atol=1e-5)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2, 6])
+@pytest.mark.parametrize('best', [False, True])
+def test_disco_targets_cuda_equal_oracle_and_golden_cases(seed, best):
+    """DiscoBox's two builders (discobox_head.py:1362-1529) on CUDA tensors against the oracle's loop form (whose golden
+    vectors come from the reference's own methods; seeds 0-2 are the golden cases)."""
+    import numpy as np
+    from boxinstseg_b200.models.dense_heads.disco_targets import disco_target_single
+    from oracle import solo_targets as ost
+    from oracle.make_golden_disco import CFG as DCFG, case
+    boxes, labels, masks, fsize = case(seed) if seed < 5 else case(seed, H=96, W=256, G=14)
+    if seed == 6:
+        gen = torch.Generator().manual_seed(9)
+        masks = masks * (torch.rand(masks.shape, generator=gen) < 0.6).numpy().astype(np.uint8)
+    want = ost.disco_target_single(boxes, labels, masks, fsize, best=best, **DCFG)
+    got = disco_target_single(boxes.to(DEV), labels.to(DEV), torch.from_numpy(masks).to(DEV), fsize, best=best, **DCFG)
+    for k in range(3):
+        for w, g in zip(want[k], got[k]):
+            assert g.is_cuda and w.shape == g.shape and torch.equal(w, g.cpu())
+    assert [list(x) for x in want[3]] == [x.cpu().tolist() for x in got[3]]
