@@ -426,6 +426,25 @@ int bxs_fcos_targets(const float* points, const float* gt_boxes, const int64_t* 
                      const float* stride_radius_host, const float* stride_host, int center_sampling,
                      int norm_on_bbox, int64_t num_classes, bxs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * f4  DiscoBox semantic correspondence    replaces the inner part of SemanticCorrSolver.solve
+ *     (mmdet/models/dense_heads/discobox_head.py:393-410, with pass_message :347-366) and the transfer of
+ *     corr_loss (:1086-1096, with superres_T :851-865).
+ * bxs_corr_solve: Cu f32 [K,P,P] (cosine similarities of the query cells x the cells of K retrieved objects,
+ *   P = h*w) -> T [K,P,P]: C = Cu * window(dist_kernel), then num_iter x { votes = C; num_smooth x (pass_message,
+ *   rows /= sum + 1e-4); C = Cu + votes; rows /= sum + 1e-4 }.  One CTA per object, state in shared memory;
+ *   dist_kernel odd; (2 P^2 + P) * 4 bytes <= 200 KB (P <= 156).
+ * bxs_corr_transfer: T, Cu [K,P,P], m0 f32 [Hm*Wm] (query RoI mask), m1 f32 [K,Hm*Wm] (masks of the objects) ->
+ *   fg_ci, bg_ci f32 [Hm*Wm]: T2 = T * softmax(Cu, 2), rows /= sum + 1e-5, super-resolution h x w -> Hm x Wm of both
+ *   index pairs (x P / (Hm Wm)), contraction with [m0 m1 > .5] clamp(m1, .1, .9) resp. [(1-m0)(1-m1) > .5]
+ *   clamp(1-m1, .1, .9), mean over the K objects (fixed order).  workspace: bxs_corr_transfer_workspace_bytes.
+ * --------------------------------------------------------------------------------------- */
+int bxs_corr_solve(const float* Cu, float* T, int64_t K, int64_t h, int64_t w, int dist_kernel, int num_iter,
+                   int num_smooth, bxs_stream_t stream);
+int64_t bxs_corr_transfer_workspace_bytes(int64_t K, int64_t Hm, int64_t Wm);
+int bxs_corr_transfer(const float* T, const float* Cu, const float* m0, const float* m1, float* fg_ci, float* bg_ci,
+                      void* workspace, int64_t K, int64_t h, int64_t w, int64_t Hm, int64_t Wm, bxs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,97 @@
+"""f4 on the GPU: DiscoBox's semantic-correspondence path through the C ABI (``bxs_corr_solve``, ``bxs_corr_transfer``) and the
+device-resident object bank, against the oracle restatement and the golden vectors of the reference's own classes
+(oracle/make_golden_corr.py).  Tolerances: the regularised table 5e-6 of its scale (row sums in another order than ATen's
+reductions), the transferred maps 2e-5 absolute on values in [0, 1], the InfoNCE term and its gradient 1e-4 relative (north
+star: 1e-3); retrieval indices and the bank contents exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import corr as oc
+from oracle.make_golden_corr import BANK, CH, FEAT, MASK, SOLVER, bank_case, blob, case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _solver():
+    from boxinstseg_b200.models.dense_heads.disco_corr import SemanticCorrSolver
+    return SemanticCorrSolver(**SOLVER)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_solve_and_transfer_match_reference_golden(golden, seed):
+    from types import SimpleNamespace
+    g = golden('corr')
+    f0, f1, m0, m1 = case(seed)
+    s = _solver()
+    Cu, T, fgm, bgm = s.solve(SimpleNamespace(mask=m0.to(DEV)), dict(feature=f1.to(DEV), mask=m1.to(DEV)), f0.to(DEV))
+    assert fgm is None and bgm is None
+    assert np.abs(Cu.cpu().numpy() - g[f's{seed}_Cu']).max() <= 2e-6
+    ref_T = g[f's{seed}_T']
+    # the table computed from the reference's own Cu (isolates the kernel from the GEMM's rounding)
+    T_ref_in = s.votes(torch.from_numpy(g[f's{seed}_Cu']).to(DEV), FEAT, FEAT)
+    assert np.abs(T_ref_in.cpu().numpy() - ref_T).max() <= 5e-6 * np.abs(ref_T).max()
+    assert np.abs(T.cpu().numpy() - ref_T).max() <= 2e-5 * np.abs(ref_T).max()
+    fg, bg = s.transfer(torch.from_numpy(ref_T).to(DEV), torch.from_numpy(g[f's{seed}_Cu']).to(DEV), m0.to(DEV), m1.to(DEV), FEAT, FEAT)
+    assert np.abs(fg.cpu().numpy() - g[f's{seed}_fg']).max() <= 2e-5 and np.abs(bg.cpu().numpy() - g[f's{seed}_bg']).max() <= 2e-5
+    _, fgm, bgm = s.solve(SimpleNamespace(mask=m0.to(DEV)), dict(feature=f1.to(DEV), mask=m1.to(DEV)), f0.to(DEV), return_masks=True)[1:]
+    assert fgm.shape == (5, MASK * MASK, MASK * MASK) and bgm.shape == fgm.shape
+
+
+@pytest.mark.parametrize('seed,shape,dk,iters,smooth,Hm', [(3, (5, 8), 3, 4, 2, 20), (4, (6, 4), 5, 0, 1, 9), (5, (3, 3), 1, 3, 0, 12),
+                                                           (6, (12, 12), 9, 2, 1, 24)])
+def test_other_shapes_against_oracle(seed, shape, dk, iters, smooth, Hm):
+    """Non-square grids, no rounds / no smoothing, window 1, and the largest grid that needs the > 48 KB shared-memory opt-in."""
+    from boxinstseg_b200.models.dense_heads.disco_corr import SemanticCorrSolver
+    h, w = shape
+    f0, f1, m0, m1 = case(seed, K=3, h=h, w=w, Hm=Hm)
+    s = SemanticCorrSolver(1.0, 0.05, 3, 0.3, iters, smooth, dk)
+    Cu = oc.cosine_table(f0, f1)
+    want = oc.solve_votes(Cu, h, w, dk, iters, smooth)
+    got = s.votes(Cu.to(DEV), h, w).cpu()
+    assert (got - want).abs().max() <= 5e-6 * want.abs().max()
+    _, fg, bg = oc.transfer(want, Cu, m0, m1, h, w)
+    gfg, gbg = s.transfer(want.to(DEV), Cu.to(DEV), m0.to(DEV), m1.to(DEV), h, w)
+    assert (gfg.cpu() - fg).abs().max() <= 2e-5 * max(1.0, float(fg.abs().max()))
+    assert (gbg.cpu() - bg).abs().max() <= 2e-5 * max(1.0, float(bg.abs().max()))
+    again = s.votes(Cu.to(DEV), h, w).cpu()
+    assert torch.equal(again, got)                                        # fixed-order sums: run-to-run identical
+
+
+def test_corr_objects_loop_against_oracle():
+    """The per-object body of corr_loss (:1056-1125): a bank pre-filled with similar objects, six query objects of two
+    classes; InfoNCE sum, number of terms, the pasted inter-image maps, the bank after the loop, and d loss / d RoI feature."""
+    from boxinstseg_b200.models.dense_heads.disco_corr import ObjectQueues, corr_objects
+    feats, masks, boxes = bank_case(0)
+    bank_cfg = dict(BANK, len_queue=8)
+    mine, orc = ObjectQueues(num_class=3, **bank_cfg), oc.Queues(num_class=3, **bank_cfg)
+    for i in range(feats.shape[0]):
+        mine.append(1, i, feats.to(DEV), masks.to(DEV), boxes.to(DEV))
+        orc.append(1, i, feats, masks, boxes)
+    gen = torch.Generator().manual_seed(42)
+    n, H, W = 6, 50, 64
+    s_feat = oc.relu_and_l2_norm_feat(feats[:1] + 0.15 * torch.randn(n, CH, FEAT, FEAT, generator=gen))
+    t_feat = oc.relu_and_l2_norm_feat(feats[:1] + 0.15 * torch.randn(n, CH, FEAT, FEAT, generator=gen))
+    s_mask = blob(gen, n, MASK, MASK / 2, MASK / 2, MASK * 0.36, MASK * 0.3)
+    t_mask = blob(gen, n, MASK, MASK / 2, MASK / 2, MASK * 0.36, MASK * 0.3)
+    qboxes = torch.tensor([[2, 3, 44, 41], [10, 5, 52, 43], [0, 0, 42, 40], [20, 8, 30, 18], [5, 5, 47, 45], [1, 2, 43, 42]],
+                          dtype=torch.float32)
+    labels = torch.tensor([1, 1, 2, 1, 1, 2])
+    want_x = s_feat.clone().requires_grad_(True)
+    iiu_o = torch.zeros(2 * n, H, W)
+    lo, no = oc.corr_objects(orc, want_x, t_feat, s_mask, t_mask, qboxes, labels, iiu_o, SOLVER, min_size=32)
+    assert no >= 3
+    (go,) = torch.autograd.grad(lo, want_x)
+    got_x = s_feat.clone().to(DEV).requires_grad_(True)
+    iiu = torch.zeros(2 * n, H, W, device=DEV)
+    lm, nm, qobj = corr_objects(_solver(), mine, None, got_x, t_feat.to(DEV), s_mask.to(DEV), t_mask.to(DEV), qboxes.to(DEV),
+                                labels.to(DEV), iiu, objbank_min_size=32)
+    (gm,) = torch.autograd.grad(lm, got_x)
+    assert nm == no and qobj is not None
+    assert abs(float(lm) - float(lo)) <= 1e-4 * abs(float(lo))
+    assert (gm.cpu() - go).norm() <= 1e-4 * go.norm()
+    assert (iiu.cpu() - iiu_o).abs().max() <= 5e-5 and float(iiu_o.abs().max()) > 0.05
+    for c in (1, 2):
+        assert torch.equal(mine.queues[c].feature.cpu(), orc.banks[c].feature) and mine.queues[c].ptr == orc.banks[c].ptr
+        assert torch.equal(mine.queues[c].mask.cpu(), orc.banks[c].mask) and torch.equal(mine.queues[c].box.cpu(), orc.banks[c].box)
