@@ -60,6 +60,7 @@ SIGNATURES = {
     'bxs_meanfield_kernel': [c_p, c_p] + [c_i64] * 4 + [c_int, c_f, c_f, c_f, c_p],
     'bxs_meanfield_workspace_bytes': [c_i64] * 3,
     'bxs_meanfield_forward': [c_p] * 8 + [c_i64] * 3 + [c_int, c_int, c_p],
+    'bxs_meanfield_forward_inter': [c_p] * 5 + [c_f] + [c_p] * 4 + [c_i64] * 3 + [c_int, c_int, c_p],
     'bxs_mst_workspace_bytes': [c_i64] * 3,
     'bxs_mst_forward': [c_p] * 4 + [c_i64] * 3 + [c_p],
     'bxs_bfs_workspace_bytes': [c_i64] * 2,

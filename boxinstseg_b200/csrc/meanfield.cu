@@ -56,9 +56,12 @@ __global__ void mf_kernel_kernel(const float* __restrict__ feat, float* __restri
 // A pixel whose target is exactly 0 (outside the object's box -- most of the map) comes out 0 whatever its neighbours are:
 // f_fg = exp(-agg_fg) * 0 + 1e-6 (agg_fg >= 0: the unaries are -log of probabilities and K >= 0, so no inf * 0) and
 // f_bg >= 1e-6, hence f_fg / (f_bg + f_fg) <= 0.5, which is not > 0.5.  Skipping it is exact and removes ~85 % of the work.
+// (With the inter-image term of corr_loss, f += iiu * gamma before the target product: still exact for iiu >= 0, which holds
+// for the reference's iiu -- means of products of non-negative numbers, discobox_head.py:1094-1107.)
 template <int KS>
 __device__ __forceinline__ uint8_t mf_update(const float* __restrict__ Kimg, const uint8_t* bits, const float tgt,
-                                             const MfConst& mc, int h, int w, int ks_rt, int y, int x) {
+                                             const MfConst& mc, int h, int w, int ks_rt, int y, int x,
+                                             const float* __restrict__ iiu = nullptr, float gamma = 0.f) {
   if (tgt == 0.f) return 0;
   const int ks = KS > 0 ? KS : ks_rt;
   const int64_t hw = (int64_t)h * w, p = (int64_t)y * w + x;
@@ -78,6 +81,10 @@ __device__ __forceinline__ uint8_t mf_update(const float* __restrict__ Kimg, con
     agg_fg = __fadd_rn(agg_fg, __fmul_rn(efg, kj));
   }
   float f_bg = expf(-agg_bg), f_fg = expf(-agg_fg);
+  if (iiu) {                                                          // f += inter_img_mask * gamma (:643-644); [2,h,w] of the object
+    f_bg = __fadd_rn(f_bg, __fmul_rn(__ldg(iiu + p), gamma));
+    f_fg = __fadd_rn(f_fg, __fmul_rn(__ldg(iiu + hw + p), gamma));
+  }
   f_fg = __fmul_rn(f_fg, tgt);                                        // f[:,1:] *= targets
   f_bg = __fadd_rn(f_bg, 1e-6f);
   f_fg = __fadd_rn(f_fg, 1e-6f);
@@ -90,7 +97,8 @@ template <int KS>
 __global__ void __launch_bounds__(NT) mf_fused_kernel(const float* __restrict__ K, const int32_t* __restrict__ obj_img,
                                                       const float* __restrict__ x, const float* __restrict__ targets,
                                                       MfConst mc, float* __restrict__ ret, float* __restrict__ valid,
-                                                      int h, int w, int ks, int iters) {
+                                                      int h, int w, int ks, int iters, const float* __restrict__ iiu,
+                                                      float gamma) {
   extern __shared__ uint8_t sm_bits[];
   __shared__ int s_redi[NT / 32];
   const int n = blockIdx.x, hw = h * w;
@@ -98,10 +106,11 @@ __global__ void __launch_bounds__(NT) mf_fused_kernel(const float* __restrict__ 
   uint8_t* b = sm_bits + ((hw + 15) / 16) * 16;
   const float* Kimg = K + (int64_t)(obj_img ? obj_img[n] : 0) * ks * ks * hw;
   const float* tg = targets + (int64_t)n * hw;
+  const float* io = iiu ? iiu + (int64_t)n * 2 * hw : nullptr;
   for (int i = threadIdx.x; i < hw; i += NT) a[i] = __fmul_rn(x[(int64_t)n * hw + i], tg[i]) > 0.5f ? 1 : 0;
   __syncthreads();
   for (int it = 0; it < iters; ++it) {
-    for (int i = threadIdx.x; i < hw; i += NT) b[i] = mf_update<KS>(Kimg, a, tg[i], mc, h, w, ks, i / w, i % w);
+    for (int i = threadIdx.x; i < hw; i += NT) b[i] = mf_update<KS>(Kimg, a, tg[i], mc, h, w, ks, i / w, i % w, io, gamma);
     __syncthreads();
     uint8_t* t = a; a = b; b = t;
   }
@@ -124,13 +133,14 @@ __global__ void mf_init_global(const float* __restrict__ x, const float* __restr
 template <int KS>
 __global__ void mf_step_global(const float* __restrict__ K, const int32_t* __restrict__ obj_img,
                                const float* __restrict__ targets, const uint8_t* __restrict__ src,
-                               uint8_t* __restrict__ dst, MfConst mc, int h, int w, int ks, int64_t total) {
+                               uint8_t* __restrict__ dst, MfConst mc, int h, int w, int ks, int64_t total,
+                               const float* __restrict__ iiu, float gamma) {
   const int64_t hw = (int64_t)h * w;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = i / hw;
     const int p = i % hw;
     const float* Kimg = K + (int64_t)(obj_img ? obj_img[n] : 0) * ks * ks * hw;
-    dst[i] = mf_update<KS>(Kimg, src + n * hw, targets[i], mc, h, w, ks, p / w, p % w);
+    dst[i] = mf_update<KS>(Kimg, src + n * hw, targets[i], mc, h, w, ks, p / w, p % w, iiu ? iiu + n * 2 * hw : nullptr, gamma);
   }
 }
 __global__ void __launch_bounds__(256) mf_finish_global(const uint8_t* __restrict__ bits, float* __restrict__ ret,
@@ -180,6 +190,15 @@ extern "C" int64_t bxs_meanfield_workspace_bytes(int64_t n, int64_t h, int64_t w
 extern "C" int bxs_meanfield_forward(const float* K, const int32_t* obj_img, const float* x, const float* targets,
                                      const float* neglog4_host, float* ret, float* valid, void* workspace, int64_t n,
                                      int64_t h, int64_t w, int kernel_size, int num_iter, bxs_stream_t stream) {
+  return bxs_meanfield_forward_inter(K, obj_img, x, targets, nullptr, 0.f, neglog4_host, ret, valid, workspace, n, h, w,
+                                     kernel_size, num_iter, stream);
+}
+
+extern "C" int bxs_meanfield_forward_inter(const float* K, const int32_t* obj_img, const float* x, const float* targets,
+                                           const float* inter_img_mask, float gamma, const float* neglog4_host, float* ret,
+                                           float* valid, void* workspace, int64_t n, int64_t h, int64_t w, int kernel_size,
+                                           int num_iter, bxs_stream_t stream) {
+  const float* iiu = inter_img_mask;
   if (!K || !x || !targets || !neglog4_host || !ret || !valid || n <= 0 || n >= 65536 || h <= 0 || w <= 0 ||
       kernel_size < 1 || !(kernel_size & 1) || num_iter < 0 || h * w >= (int64_t(1) << 30))
     return BXS_ERR_INVALID_ARG;
@@ -197,7 +216,7 @@ extern "C" int bxs_meanfield_forward(const float* K, const int32_t* obj_img, con
   if (per_object) {
     auto fused = kernel_size == 3 ? mf_fused_kernel<3> : mf_fused_kernel<0>;
     cudaFuncSetAttribute(fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxFusedSmem);
-    fused<<<(unsigned)n, NT, sm, st>>>(K, obj_img, x, targets, mc, ret, valid, (int)h, (int)w, kernel_size, num_iter);
+    fused<<<(unsigned)n, NT, sm, st>>>(K, obj_img, x, targets, mc, ret, valid, (int)h, (int)w, kernel_size, num_iter, iiu, gamma);
   } else {
     if (!workspace) return BXS_ERR_INVALID_ARG;
     uint8_t* a = (uint8_t*)workspace;
@@ -206,9 +225,9 @@ extern "C" int bxs_meanfield_forward(const float* K, const int32_t* obj_img, con
     mf_init_global<<<grid_for(total, 256), 256, 0, st>>>(x, targets, a, total);
     for (int it = 0; it < num_iter; ++it) {
       if (kernel_size == 3)
-        mf_step_global<3><<<grid_for(total, 256), 256, 0, st>>>(K, obj_img, targets, a, b, mc, (int)h, (int)w, kernel_size, total);
+        mf_step_global<3><<<grid_for(total, 256), 256, 0, st>>>(K, obj_img, targets, a, b, mc, (int)h, (int)w, kernel_size, total, iiu, gamma);
       else
-        mf_step_global<0><<<grid_for(total, 256), 256, 0, st>>>(K, obj_img, targets, a, b, mc, (int)h, (int)w, kernel_size, total);
+        mf_step_global<0><<<grid_for(total, 256), 256, 0, st>>>(K, obj_img, targets, a, b, mc, (int)h, (int)w, kernel_size, total, iiu, gamma);
       std::swap(a, b);
     }
     mf_finish_global<<<(unsigned)n, 256, 0, st>>>(a, ret, valid, (int)hw);

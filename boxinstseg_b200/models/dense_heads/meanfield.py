@@ -32,8 +32,6 @@ class MeanField(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, targets, inter_img_mask=None, obj_img=None):
-        if inter_img_mask is not None:
-            raise NotImplementedError('inter_img_mask (cross-image correspondence, corr_loss) is out of scope')
         xs = x.contiguous().float()
         tg = targets.contiguous().float()
         L.require_cuda(xs, tg)
@@ -47,8 +45,14 @@ class MeanField(nn.Module):
         if self.kernel.shape[0] > 1:
             assert obj_img is not None, 'a multi-image kernel needs obj_img'
             obj_img = obj_img.to(device=xs.device, dtype=torch.int32).contiguous()
+        iiu = None
+        if inter_img_mask is not None:                                    # corr_loss: [n,2,h,w] (background, foreground), :616,643-644
+            iiu = inter_img_mask.contiguous().float()
+            L.require_cuda(iiu)
+            assert tuple(iiu.shape) == (n, 2, h, w), iiu.shape
         with torch.cuda.device(xs.device):
-            L.check(lib.bxs_meanfield_forward(L.ptr(self.kernel), L.ptr(obj_img), L.ptr(xs), L.ptr(tg),
-                                              self._neglog.ctypes.data, L.ptr(ret), L.ptr(valid), L.ptr(ws), n, h, w,
-                                              self.kernel_size, self.iter, L.stream()), 'meanfield_forward')
+            L.check(lib.bxs_meanfield_forward_inter(L.ptr(self.kernel), L.ptr(obj_img), L.ptr(xs), L.ptr(tg), L.ptr(iiu),
+                                                    float(np.float32(self.gamma)), self._neglog.ctypes.data, L.ptr(ret),
+                                                    L.ptr(valid), L.ptr(ws), n, h, w, self.kernel_size, self.iter,
+                                                    L.stream()), 'meanfield_forward')
         return ret, valid

@@ -252,6 +252,12 @@ int64_t bxs_meanfield_workspace_bytes(int64_t n, int64_t h, int64_t w);
 int bxs_meanfield_forward(const float* K, const int32_t* obj_img, const float* x, const float* targets,
                           const float* neglog4_host, float* ret, float* valid, void* workspace, int64_t n,
                           int64_t h, int64_t w, int kernel_size, int num_iter, bxs_stream_t stream);
+/* same with the inter-image term of corr_loss (discobox_head.py:616,643-644): inter_img_mask f32 [n,2,h,w] (background,
+ * foreground), f += inter_img_mask * gamma before the target product; NULL = the call above. */
+int bxs_meanfield_forward_inter(const float* K, const int32_t* obj_img, const float* x, const float* targets,
+                                const float* inter_img_mask, float gamma, const float* neglog4_host, float* ret,
+                                float* valid, void* workspace, int64_t n, int64_t h, int64_t w, int kernel_size,
+                                int num_iter, bxs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * a12-a15  tree filter      replaces the pybind module tree_filter_cuda

@@ -118,10 +118,11 @@ def meanfield_kernel(feature_map, kernel_size=3, theta0=0.5, theta1=30.0, alpha0
     return torch.stack(taps, 1).flatten(2)
 
 
-def meanfield_forward(kernel, x, targets, kernel_size=3, num_iter=20, base=0.45):
+def meanfield_forward(kernel, x, targets, kernel_size=3, num_iter=20, base=0.45, inter=None, gamma=0.01):
     """x, targets [n,1,h,w]; kernel [1,k*k,h*w] -> (binary pseudo label [n,1,h,w], valid [n]).
 
-    discobox_head.py:616-651 with inter_img_mask=None.
+    discobox_head.py:616-651; ``inter`` [n,2,h,w] is corr_loss's inter_img_mask (background, foreground): added to the
+    two potentials, times gamma, before the target product (:643-644).
     """
     n, _, h, w = x.shape
     r = kernel_size // 2
@@ -135,6 +136,8 @@ def meanfield_forward(kernel, x, targets, kernel_size=3, num_iter=20, base=0.45)
             dy, dx = j // kernel_size - r, j % kernel_size - r
             agg = agg + _shifted(e, dy, dx, 0.0) * kern[:, :, j]
         f = torch.exp(-agg)
+        if inter is not None:
+            f = f + inter * gamma
         f = torch.cat([f[:, :1], f[:, 1:] * targets], 1) + 1e-6
         f = f / f.sum(1, keepdim=True)
         u = (f > 0.5).to(x.dtype) * (1 - 2 * base) + base

@@ -164,6 +164,32 @@ def test_meanfield_golden(golden):
     assert torch.equal(ps.cpu(), T(g['pseudo'])) and torch.equal(va.cpu(), T(g['valid']))     # binary output: exact
 
 
+@pytest.mark.parametrize('seed,gamma', [(0, 0.01), (1, 0.5), (2, 2.0)])
+def test_meanfield_inter_image_term_golden(golden, seed, gamma):
+    """MeanField.forward(x, targets, inter_img_mask) as corr_loss calls it (discobox_head.py:616,643-644): binary output,
+    bit-exact against the golden vectors of the reference's own class; both kernel paths (per-object CTAs / grid-wide rounds)."""
+    import numpy as np
+    from boxinstseg_b200.models.dense_heads import MeanField
+    from oracle.make_golden_meanfield_inter import CFG, case
+    g = golden('meanfield_inter')
+    fm, x, t, iiu = case(seed)
+    mf = MeanField(fm.to(DEV), gamma=gamma, **CFG)
+    ps, va = mf(x.to(DEV), t.to(DEV), iiu.to(DEV))
+    want = np.unpackbits(g[f's{seed}_pseudo'], axis=-1)[..., :ps.shape[-1]]
+    assert np.array_equal(ps.cpu().numpy().astype(np.uint8), want) and np.array_equal(va.cpu().numpy(), g[f's{seed}_valid'])
+    if int(g[f's{seed}_flips']):
+        plain, _ = mf(x.to(DEV), t.to(DEV))
+        assert int((plain != ps).sum()) == int(g[f's{seed}_flips'])
+    # the per-object shared-memory path (chosen for >= 2 objects per SM, or without a workspace): same bits
+    from boxinstseg_b200 import _lib as L
+    xs, tg, ii = x.to(DEV).contiguous(), t.to(DEV).contiguous(), iiu.to(DEV).contiguous()
+    ret, valid = torch.empty_like(xs), torch.empty(xs.shape[0], device=DEV)
+    L.check(L.lib().bxs_meanfield_forward_inter(L.ptr(mf.kernel), None, L.ptr(xs), L.ptr(tg), L.ptr(ii), float(np.float32(gamma)),
+                                                mf._neglog.ctypes.data, L.ptr(ret), L.ptr(valid), None, xs.shape[0],
+                                                xs.shape[2], xs.shape[3], 3, 10, L.stream()), 'meanfield_forward_inter')
+    assert torch.equal(ret, ps) and torch.equal(valid, va)
+
+
 @pytest.mark.parametrize('n,h,w,big', [(6, 50, 64, False), (3, 200, 256, False), (2, 330, 340, True)])
 def test_meanfield_vs_oracle(n, h, w, big):
     from boxinstseg_b200.models.dense_heads import MeanField

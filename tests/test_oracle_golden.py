@@ -180,3 +180,17 @@ def test_rgb2lab_known_answers_and_opencv():
     ref = cv2.cvtColor((img / 255.0).astype(np.float32), cv2.COLOR_RGB2LAB)
     # OpenCV's float path uses an interpolated LUT (~0.3 LAB units); a coarse independent sanity check
     assert np.abs(ob.rgb2lab_u8(img) - ref).max() < 0.5
+
+
+@pytest.mark.parametrize('seed,gamma', [(0, 0.01), (1, 0.5), (2, 2.0)])
+def test_meanfield_with_inter_image_term_reproduces_reference_golden(golden, seed, gamma):
+    """MeanField.forward(x, targets, inter_img_mask) (discobox_head.py:616-651) as corr_loss calls it."""
+    import numpy as np
+    from oracle import levelset as ol
+    from oracle.make_golden_meanfield_inter import case
+    g = golden('meanfield_inter')
+    fm, x, t, iiu = case(seed)
+    k = ol.meanfield_kernel(fm, 3, 0.5, 30.0, 2.0)
+    ps, va = ol.meanfield_forward(k, x, t, 3, 10, 0.1, inter=iiu, gamma=gamma)
+    want = np.unpackbits(g[f's{seed}_pseudo'], axis=-1)[..., :ps.shape[-1]]
+    assert np.array_equal(ps.numpy().astype(np.uint8), want) and np.array_equal(va.numpy(), g[f's{seed}_valid'])
