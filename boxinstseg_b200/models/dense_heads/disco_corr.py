@@ -236,3 +236,97 @@ def corr_objects(solver, queues, qobj, roi_s_feat, roi_t_feat, roi_s_mask, roi_t
         if (x2 - x1) > objbank_min_size and (y2 - y1) > objbank_min_size:   # :1056-1057, 1113-1124
             queues.append(labels[i], i, roi_t_feat, roi_t_mask, boxes.detach())
     return loss, num, qobj
+
+
+def _torchvision_roi_align(out_size):
+    """mmcv.ops.RoIAlign(out_size) with its defaults (spatial_scale 1, adaptive sampling, aligned=True) -- third party to the
+    reference; torchvision ships the same operator."""
+    from torchvision.ops import roi_align
+
+    def run(x, rois):
+        return roi_align(x, rois, out_size, 1.0, 0, True)
+    return run
+
+
+def mask_boxes(target):
+    """The tight box of every non-empty target mask, (min_x, min_y, max_x + 1, max_y + 1) as float (:1029-1035, where the
+    reference loops over the objects with four ``.min()/.max()`` host reads each): four reductions, no synchronisation."""
+    n, H, W = target.shape
+    on = target > 0
+    rows, cols = on.any(2), on.any(1)                                        # [n,H], [n,W]
+    ys = torch.arange(H, device=target.device)
+    xs = torch.arange(W, device=target.device)
+    min_y = torch.where(rows, ys, ys.new_full((), H)).amin(1)
+    max_y = torch.where(rows, ys, ys.new_full((), -1)).amax(1) + 1
+    min_x = torch.where(cols, xs, xs.new_full((), W)).amin(1)
+    max_x = torch.where(cols, xs, xs.new_full((), -1)).amax(1) + 1
+    return torch.stack([min_x, min_y, max_x, max_y], 1).float()
+
+
+class DiscoCorr:
+    """The state and the per-level body of ``DiscoBoxSOLOv2Head.corr_loss`` (:900-1139) after the dynamic convolutions: per
+    level, drop the empty targets, box every target, RoI-align the student / teacher features and masks, run the per-object
+    loop (``corr_objects``), then the mean field WITH the transferred inter-image maps and the dice against its pseudo labels.
+    Built from the head's ``loss_corr`` config dict (:720-749)."""
+
+    def __init__(self, num_classes, loss_corr, roi_align=_torchvision_roi_align):
+        bank = loss_corr['obj_bank']
+        self.solver = SemanticCorrSolver(loss_corr['corr_exp'], loss_corr['corr_eps'], loss_corr['gaussian_filter_size'],
+                                         loss_corr['low_score'], loss_corr['corr_num_iter'], loss_corr['corr_num_smooth_iter'],
+                                         dist_kernel=loss_corr['dist_kernel'])
+        self.object_queues = ObjectQueues(num_class=num_classes, len_queue=bank['len_object_queues'],
+                                          fg_iou_thresh=bank['fg_iou_thresh'], bg_iou_thresh=bank['bg_iou_thresh'],
+                                          ratio_range=bank['ratio_range'], appear_thresh=bank['appear_thresh'],
+                                          max_retrieval_objs=bank['max_retrieval_objs'])
+        self.feat_roi_align = roi_align((bank['feat_height'], bank['feat_width']))
+        self.mask_roi_align = roi_align((bank['mask_height'], bank['mask_width']))
+        self.objbank_min_size = bank['min_size']
+        self.min_objs = 5                                                    # the literal of :1075
+        self.corr_loss_weight = loss_corr['loss_weight']
+        self.qobj = None
+
+    def levels(self, s_ins_pred_list, t_ins_pred_list, img_ind_list, ins_labels, kernel_label_list, s_feat, t_feat, mean_field,
+               use_ind_teacher=False):
+        """Per level l: s_ins_pred_list[l] [n,H,W] student mask LOGITS (None: no object), t_ins_pred_list[l] the teacher's
+        (ignored unless use_ind_teacher), img_ind_list[l] [n], ins_labels[l] [n,H,W] targets, kernel_label_list[l] [n];
+        s_feat / t_feat [B,C,H,W]; mean_field: ONE ``MeanField`` over the batch's colour features (``obj_img`` selects the
+        image; the reference keeps one module per image).  Returns (corr_loss / (num + 1e-4), [per-level dice terms [n_l]])."""
+        total = s_feat.new_zeros(())
+        num = 0
+        loss_ts = []
+        for s_in, t_in, img_inds, target, klabels in zip(s_ins_pred_list, t_ins_pred_list, img_ind_list, ins_labels,
+                                                         kernel_label_list):
+            if s_in is None or s_in.shape[0] == 0:
+                continue
+            keep = (target.flatten(1) != 0).any(1).nonzero().flatten()       # remove all-zero targets (:1024-1028); one sync
+            if keep.numel() == 0:
+                continue
+            s = torch.sigmoid(s_in).index_select(0, keep)
+            t = torch.sigmoid(t_in).index_select(0, keep) if use_ind_teacher else s
+            img_inds = img_inds.to(s.device).index_select(0, keep)
+            target = target.index_select(0, keep)
+            klabels = klabels.index_select(0, keep)
+            n = s.shape[0]
+            boxes = mask_boxes(target)
+            rois = torch.cat([img_inds.to(s_feat)[:, None], boxes], 1)
+            roi_s_feat = relu_and_l2_norm_feat(self.feat_roi_align(s_feat, rois))
+            with torch.no_grad():
+                roi_t_feat = relu_and_l2_norm_feat(self.feat_roi_align(t_feat.detach(), rois))
+                own = torch.cat([torch.arange(n, device=s.device).to(s)[:, None], boxes], 1)
+                roi_s_mask = self.mask_roi_align(s.detach()[:, None], own)[:, 0]
+                roi_t_mask = self.mask_roi_align(t.detach()[:, None], own)[:, 0]
+                iiu = s.new_zeros((2 * n,) + tuple(s.shape[1:]))
+            lvl_loss, lvl_num, self.qobj = corr_objects(self.solver, self.object_queues, self.qobj, roi_s_feat, roi_t_feat,
+                                                        roi_s_mask, roi_t_mask, boxes, klabels, iiu, self.objbank_min_size,
+                                                        self.min_objs)
+            total = total + lvl_loss
+            num += lvl_num
+            iiu = iiu.view(n, 2, *iiu.shape[1:])
+            tf = target.float()
+            enlarged = F.max_pool2d(tf[:, None], kernel_size=3, stride=1, padding=1)[:, 0]                  # :1128
+            pseudo, _ = mean_field(((t + s) / 2)[:, None], tf[:, None], iiu, obj_img=img_inds)              # :1130-1132
+            cropped = s * enlarged
+            cropped = cropped * mean_field.gamma + cropped.detach() * (1 - mean_field.gamma)                # :1134
+            x, p = cropped.flatten(1).float(), pseudo.flatten(1).float()                                    # dice_loss :542-550
+            loss_ts.append(1 - 2 * (x * p).sum(1) / ((x * x).sum(1) + 0.001 + (p * p).sum(1) + 0.001))
+        return total / (num + 1e-4), loss_ts

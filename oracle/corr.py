@@ -148,19 +148,19 @@ class Queues:
 
 
 def corr_objects(queues, roi_s_feat, roi_t_feat, roi_s_mask, roi_t_mask, boxes, kernel_labels, iiu, solver_cfg, min_size,
-                 min_objs=5):
+                 min_objs=5, state=None):
     """The per-object loop of corr_loss (:1056-1125) on CPU tensors with the pieces above; boxes integer valued [n,4].
     Returns (sum of the InfoNCE terms, number of terms); fills iiu [2n,H,W] and updates `queues`."""
     n = roi_s_feat.shape[0]
     h, w = roi_s_feat.shape[2:]
     loss, num = roi_s_feat.new_zeros(()), 0
-    first = True
+    state = {'first': True} if state is None else state       # the head's query holder exists after its very first object
     for i in range(n):
         x1, y1, x2, y2 = [int(v) for v in boxes[i]]
         cls = int(kernel_labels[i])
         qf = roi_s_feat[i:i + 1].detach()
-        if first:                                   # ObjectFactory.create_one re-normalises the very first query (:43)
-            qf, first = relu_and_l2_norm_feat(qf), False
+        if state['first']:                          # ObjectFactory.create_one re-normalises the very first query (:43)
+            qf, state['first'] = relu_and_l2_norm_feat(qf), False
         idx = queues.similar(cls, roi_s_mask[i:i + 1], qf, boxes[i:i + 1])
         if idx is not None and len(idx) >= min_objs:
             bank = queues.banks[cls]
@@ -175,3 +175,51 @@ def corr_objects(queues, roi_s_feat, roi_t_feat, roi_s_mask, roi_t_mask, boxes, 
         if (x2 - x1) > min_size and (y2 - y1) > min_size:
             queues.append(cls, i, roi_t_feat, roi_t_mask, boxes)
     return loss, num
+
+
+def corr_loss_levels(queues, s_ins_pred_list, img_ind_list, ins_labels, kernel_label_list, s_feat, t_feat, color_feats,
+                     solver_cfg, bank_cfg, mf_cfg, roi_align, state=None):
+    """corr_loss :1013-1139 (no independent teacher) on CPU tensors, object by object like the reference.  ``roi_align(x,
+    rois, out_size)`` stands for mmcv's RoIAlign (third party).  mf_cfg: kernel_size, theta0, theta1, alpha0, iter, base,
+    gamma; the mean field of image b uses color_feats[b:b+1].  Returns (corr_loss / (num + 1e-4), [dice terms per (level,
+    image) chunk, concatenated per level])."""
+    from oracle import levelset as ol
+    total, num, loss_ts = s_feat.new_zeros(()), 0, []
+    state = {'first': True} if state is None else state
+    B = color_feats.shape[0]
+    kernels = [ol.meanfield_kernel(color_feats[b:b + 1], mf_cfg['kernel_size'], mf_cfg['theta0'], mf_cfg['theta1'], mf_cfg['alpha0'])
+               for b in range(B)]
+    for s_in, img_inds, target, klabels in zip(s_ins_pred_list, img_ind_list, ins_labels, kernel_label_list):
+        if s_in is None:
+            continue
+        s = torch.sigmoid(s_in)
+        keep = torch.tensor([bool(t.sum()) for t in target])
+        if keep.sum() == 0:
+            continue
+        s, img_inds, target, klabels = s[keep], img_inds[keep], target[keep], klabels[keep]
+        pos = [torch.where(t) for t in target]
+        boxes = torch.tensor([[int(p[1].min()), int(p[0].min()), int(p[1].max()) + 1, int(p[0].max()) + 1] for p in pos]).float()
+        rois = torch.cat([img_inds.float()[:, None], boxes], 1)
+        roi_s_feat = relu_and_l2_norm_feat(roi_align(s_feat, rois, (bank_cfg['feat_height'], bank_cfg['feat_width'])))
+        roi_t_feat = relu_and_l2_norm_feat(roi_align(t_feat.detach(), rois, (bank_cfg['feat_height'], bank_cfg['feat_width']))).detach()
+        own = torch.cat([torch.arange(len(target)).float()[:, None], boxes], 1)
+        roi_mask = roi_align(s.detach()[:, None], own, (bank_cfg['mask_height'], bank_cfg['mask_width']))[:, 0]
+        iiu = torch.zeros(2 * len(target), *s.shape[1:])
+        l, k = corr_objects(queues, roi_s_feat, roi_t_feat, roi_mask, roi_mask, boxes, klabels, iiu, solver_cfg,
+                            bank_cfg['min_size'], state=state)
+        total, num = total + l, num + k
+        iiu = iiu.reshape(-1, 2, *iiu.shape[1:])
+        enlarged = F.max_pool2d(target.float()[:, None], kernel_size=3, stride=1, padding=1)[:, 0]
+        chunks = []
+        for b in range(B):
+            sel = img_inds == b
+            if sel.sum() > 0:
+                pseudo, _ = ol.meanfield_forward(kernels[b], s[sel][:, None].detach(), target[sel][:, None].float(), mf_cfg['kernel_size'],
+                                                 mf_cfg['iter'], mf_cfg['base'], inter=iiu[sel], gamma=mf_cfg['gamma'])
+                cropped = s[sel] * enlarged[sel]
+                cropped = cropped * mf_cfg['gamma'] + cropped.detach() * (1 - mf_cfg['gamma'])
+                chunks.append((sel.nonzero().flatten(), ol.disco_dice_loss(cropped, pseudo)))
+        order = torch.cat([c[0] for c in chunks])
+        vals = torch.cat([c[1] for c in chunks])
+        loss_ts.append(vals[torch.argsort(order)])
+    return total / (num + 1e-4), loss_ts

@@ -138,3 +138,36 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+def levels_case(seed, B=2, H=48, W=64, C=CH, per_level=(5, 4)):
+    """Inputs of the per-level body of corr_loss (oracle.corr.corr_loss_levels / DiscoCorr.levels): two levels of objects of
+    one class with similar boxes (so that retrieval succeeds once the bank holds five of them), one object of another class,
+    one empty target; logits that are high on an ellipse inside the box (so that the RoI masks have both foreground and
+    background: the two IoU tests of the retrieval are 0 / 0 on a mask without background)."""
+    gen = torch.Generator().manual_seed(1000 + seed)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing='ij')
+    pattern = torch.stack([torch.sin(yy / 3 + c) + torch.cos(xx / 4 + 2 * c) for c in range(C)])          # shared texture
+    s_feat = pattern[None] + 0.03 * torch.randn(B, C, H, W, generator=gen)
+    t_feat = pattern[None] + 0.03 * torch.randn(B, C, H, W, generator=gen)
+    color = torch.randn(B, 3, H, W, generator=gen)
+    s_list, img_list, tgt_list, lab_list = [], [], [], []
+    for n in per_level:
+        tg = torch.zeros(n, H, W, dtype=torch.uint8)
+        imgs = torch.randint(0, B, (n,), generator=gen)
+        obj = []
+        for i in range(n):
+            y0, x0 = 8 + int(torch.randint(0, 4, (1,), generator=gen)), 14 + int(torch.randint(0, 4, (1,), generator=gen))
+            bh, bw = 24 + int(torch.randint(0, 2, (1,), generator=gen)), 26 + int(torch.randint(0, 2, (1,), generator=gen))
+            tg[i, y0:y0 + bh, x0:x0 + bw] = 1
+            inside = ((yy - (y0 + bh / 2 - 0.5)) / (0.40 * bh)) ** 2 + ((xx - (x0 + bw / 2 - 0.5)) / (0.40 * bw)) ** 2 < 1
+            obj.append(inside)
+        logits = (torch.stack(obj).float() * 2 - 1) * 4 + 0.7 * torch.randn(n, H, W, generator=gen)
+        labels = torch.full((n,), 1, dtype=torch.int64)
+        labels[-1] = 2
+        s_list.append(logits)
+        img_list.append(imgs)
+        tgt_list.append(tg)
+        lab_list.append(labels)
+    tgt_list[1][0] = 0                                                   # an all-zero target: removed (:1024-1028)
+    return s_feat, t_feat, color, s_list, img_list, tgt_list, lab_list

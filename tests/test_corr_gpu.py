@@ -95,3 +95,56 @@ def test_corr_objects_loop_against_oracle():
     for c in (1, 2):
         assert torch.equal(mine.queues[c].feature.cpu(), orc.banks[c].feature) and mine.queues[c].ptr == orc.banks[c].ptr
         assert torch.equal(mine.queues[c].mask.cpu(), orc.banks[c].mask) and torch.equal(mine.queues[c].box.cpu(), orc.banks[c].box)
+
+
+def test_corr_loss_levels_against_oracle():
+    """The per-level body of corr_loss (:1013-1139) end to end: empty targets dropped, boxes from the masks, RoIAlign
+    (torchvision's, third party on both sides), the per-object loop, the mean field WITH the transferred inter-image maps, dice.
+    The bank is warmed up by one oracle iteration and copied to the device; the compared iteration must give the same loss,
+    per-object dice terms, gradients (RoI feature path and mask path) and the same bank afterwards."""
+    from torchvision.ops import roi_align
+    from boxinstseg_b200.models.dense_heads import MeanField
+    from boxinstseg_b200.models.dense_heads.disco_corr import DiscoCorr, ObjectElements, create_one
+    from oracle.make_golden_corr import levels_case
+    bank = dict(feat_height=7, feat_width=7, mask_height=28, mask_width=28, min_size=8, len_object_queues=10, fg_iou_thresh=0.7,
+                bg_iou_thresh=0.7, ratio_range=[0.9, 1.2], appear_thresh=0.7, max_retrieval_objs=5)
+    mf_cfg = dict(kernel_size=3, theta0=0.5, theta1=30.0, alpha0=2.0, iter=10, base=0.1, gamma=0.5)
+    loss_corr = dict(loss_weight=1.0, corr_exp=1.0, corr_eps=0.05, gaussian_filter_size=3, low_score=0.3, corr_num_iter=10,
+                     corr_num_smooth_iter=1, dist_kernel=9, obj_bank=bank)
+    orc = oc.Queues(num_class=3, **dict(BANK, len_queue=10))
+    ra = lambda x, rois, size: roi_align(x, rois, size, 1.0, 0, True)
+    state = {'first': True}
+    s_feat, t_feat, color, s_list, img_list, tgt_list, lab_list = levels_case(0)
+    oc.corr_loss_levels(orc, s_list, img_list, tgt_list, lab_list, s_feat, t_feat, color, SOLVER, bank, mf_cfg, ra, state=state)
+    dc = DiscoCorr(3, loss_corr)
+    for c, b in enumerate(orc.banks):                                     # the warmed-up bank, copied to the device
+        if b is not None:
+            q = ObjectElements(size=10, feat_size=7, mask_size=28, n_channel=CH, device=DEV, category=c)
+            q.feature.copy_(b.feature); q.mask.copy_(b.mask); q.box.copy_(b.box); q.ptr = b.ptr
+            dc.object_queues.queues[c] = q
+    dc.qobj = create_one(torch.zeros(1, 28, 28, device=DEV), torch.zeros(1, CH, 7, 7, device=DEV), torch.zeros(1, 4, device=DEV), 0)
+    s_feat, t_feat, color, s_list, img_list, tgt_list, lab_list = levels_case(1)
+    # oracle side
+    of = s_feat.clone().requires_grad_(True)
+    ol_ = [s.clone().requires_grad_(True) for s in s_list]
+    lo, tso = oc.corr_loss_levels(orc, ol_, img_list, tgt_list, lab_list, of, t_feat, color, SOLVER, bank, mf_cfg, ra, state=state)
+    obj_o = lo + torch.cat(tso).mean()
+    go = torch.autograd.grad(obj_o, [of] + ol_)
+    # product side
+    gf = s_feat.clone().to(DEV).requires_grad_(True)
+    gl = [s.clone().to(DEV).requires_grad_(True) for s in s_list]
+    mf = MeanField(color.to(DEV), kernel_size=3, theta0=0.5, theta1=30.0, theta2=10, alpha0=2.0, iter=10, base=0.1, gamma=0.5)
+    lm, tsm = dc.levels(gl, [None] * len(gl), [i.to(DEV) for i in img_list], [t.to(DEV) for t in tgt_list],
+                        [l.to(DEV) for l in lab_list], gf, t_feat.to(DEV), mf)
+    obj_m = lm + torch.cat(tsm).mean()
+    gm = torch.autograd.grad(obj_m, [gf] + gl)
+    assert float(lo) > 1.0 and abs(float(lm) - float(lo)) <= 1e-4 * abs(float(lo))
+    for a, b in zip(tsm, tso):
+        assert a.shape == b.shape and (a.cpu() - b).abs().max() <= 1e-5
+    for a, b in zip(gm, go):
+        assert (a.cpu() - b).norm() <= 1e-3 * b.norm() + 1e-9, (float((a.cpu() - b).norm()), float(b.norm()))
+    for c, b in enumerate(orc.banks):
+        if b is not None:
+            q = dc.object_queues.queues[c]
+            assert q.ptr == b.ptr and (q.feature.cpu() - b.feature).abs().max() <= 1e-5 and (q.mask.cpu() - b.mask).abs().max() <= 1e-5
+            assert torch.equal(q.box.cpu(), b.box)
