@@ -123,9 +123,10 @@ class BoxSOLOv2Head(nn.Module):
 
 @register(HEADS, partial=True)
 class DiscoBoxSOLOv2Head(nn.Module):
-    """DiscoBox head: mask-loss path only (corr_loss / object bank out of scope)."""
+    """DiscoBox head: the mask-loss path (a3, a16, a17) and, with a ``loss_corr`` config (discobox_head.py:720-749), the
+    semantic-correspondence loss on top of it (f4: ``corr_loss``, models/dense_heads/disco_corr.py)."""
 
-    def __init__(self, num_classes=80, in_channels=256, loss_ins=None, loss_ts=None, **cfg):
+    def __init__(self, num_classes=80, in_channels=256, loss_ins=None, loss_ts=None, loss_corr=None, **cfg):
         super().__init__()
         self.num_classes = num_classes
         self.in_channels = in_channels
@@ -138,6 +139,44 @@ class DiscoBoxSOLOv2Head(nn.Module):
         self.alpha0, self.theta0, self.theta1 = loss_ts['alpha0'], loss_ts['theta0'], loss_ts['theta1']
         self.theta2 = loss_ts.get('theta2', 10)
         self.mkernel, self.crf_base, self.crf_max_iter = loss_ts['kernel'], loss_ts['base'], loss_ts['max_iter']
+        self._bxs_post_init()
+        if loss_corr is not None:
+            from .disco_corr import DiscoCorr
+            self.corr = DiscoCorr(num_classes, loss_corr)
+
+    def _bxs_post_init(self):
+        """Also runs after the REFERENCE class's ``__init__`` when mmdet is importable (``register(partial=True)``): the
+        correspondence state is then rebuilt from the attributes that constructor leaves behind (:720-749)."""
+        self.corr = None
+        solver, queues = getattr(self, 'semantic_corr_solver', None), getattr(self, 'object_queues', None)
+        if solver is None or queues is None:
+            return
+        from .disco_corr import DiscoCorr
+        self.corr = DiscoCorr(self.num_classes, dict(
+            loss_weight=self.corr_loss_weight, corr_exp=solver.exp, corr_eps=solver.eps,
+            gaussian_filter_size=solver.gaussian_filter_size, low_score=solver.low_score, corr_num_iter=solver.num_iter,
+            corr_num_smooth_iter=solver.num_smooth_iter, dist_kernel=solver.dist_kernel,
+            obj_bank=dict(len_object_queues=queues.len_queue, fg_iou_thresh=queues.fg_iou_thresh,
+                          bg_iou_thresh=queues.bg_iou_thresh, ratio_range=queues.ratio_range,
+                          appear_thresh=queues.appear_thresh, max_retrieval_objs=queues.max_retrieval_objs,
+                          feat_height=self.corr_feat_height, feat_width=self.corr_feat_width,
+                          mask_height=self.corr_mask_height, mask_width=self.corr_mask_width, min_size=self.objbank_min_size)))
+
+    # f4 -- discobox_head.py:1013-1139, 1311-1337
+    def corr_loss_levels(self, s_ins_pred_list, t_ins_pred_list, img_ind_list, ins_labels, kernel_label_list, s_feat, t_feat,
+                         color_feats, use_ind_teacher=False, gamma=0.01):
+        """The part of ``corr_loss`` after the dynamic convolutions (per-level lists as ``mask_loss`` takes them, plus the
+        class of every object and the student / teacher feature maps [B,C,H,W]).  Returns (loss_corr * weight,
+        mean of the correspondence-aware teacher-student dice terms) -- what ``loss`` adds to ``loss_corr`` / ``loss_ts``
+        (:1329-1337).  Stateful: the object bank of ``self.corr`` is updated."""
+        if self.corr is None:
+            raise RuntimeError('DiscoBoxSOLOv2Head was built without loss_corr')
+        mf = MeanField(color_feats, alpha0=self.alpha0, theta0=self.theta0, theta1=self.theta1, theta2=self.theta2,
+                       iter=self.crf_max_iter, kernel_size=self.mkernel, base=self.crf_base, gamma=gamma)
+        loss, ts = self.corr.levels(s_ins_pred_list, t_ins_pred_list or [None] * len(s_ins_pred_list), img_ind_list,
+                                    ins_labels, kernel_label_list, s_feat, t_feat, mf, use_ind_teacher)
+        ts_mean = torch.cat(ts).mean() if ts else loss.new_zeros(())
+        return loss * self.corr.corr_loss_weight, ts_mean
 
     # a3 -- discobox_head.py:1206-1246
     @staticmethod

@@ -148,3 +148,12 @@ def test_corr_loss_levels_against_oracle():
             q = dc.object_queues.queues[c]
             assert q.ptr == b.ptr and (q.feature.cpu() - b.feature).abs().max() <= 1e-5 and (q.mask.cpu() - b.mask).abs().max() <= 1e-5
             assert torch.equal(q.box.cpu(), b.box)
+    # the same through the head (DiscoBoxSOLOv2Head.corr_loss_levels builds the mean field from its own CRF settings), next iteration
+    from boxinstseg_b200.models import build_head
+    head = build_head(dict(type='DiscoBoxSOLOv2Head', num_classes=3, in_channels=CH, loss_corr=loss_corr))
+    head.corr = dc
+    s_feat, t_feat, color, s_list, img_list, tgt_list, lab_list = levels_case(2)
+    lo2, tso2 = oc.corr_loss_levels(orc, s_list, img_list, tgt_list, lab_list, s_feat, t_feat, color, SOLVER, bank, mf_cfg, ra, state=state)
+    l2, ts2 = head.corr_loss_levels([s.to(DEV) for s in s_list], None, [i.to(DEV) for i in img_list], [t.to(DEV) for t in tgt_list],
+                                    [l.to(DEV) for l in lab_list], s_feat.to(DEV), t_feat.to(DEV), color.to(DEV), gamma=0.5)
+    assert abs(float(l2) - float(lo2)) <= 1e-4 * abs(float(lo2)) and abs(float(ts2) - float(torch.cat(tso2).mean())) <= 1e-5

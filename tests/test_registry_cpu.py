@@ -70,3 +70,22 @@ def test_partial_heads_inherit_the_reference_methods():
     assert head.training_sample() == 'ref training_sample' and head.simple_test() == 'ref simple_test'
     for m in ('forward', 'training_sample', 'loss', 'simple_test'):     # detectors/condinst.py:54-90
         assert hasattr(head, m)
+
+
+def test_discobox_head_builds_correspondence_state_from_config():
+    """loss_corr of configs/discobox/discobox_solov2_coco_r50_fpn_3x.py:65-93 -> solver + object bank (f4)."""
+    from boxinstseg_b200.models import build_head
+    bank = dict(img_norm_cfg=None, len_object_queues=100, fg_iou_thresh=0.7, bg_iou_thresh=0.7, ratio_range=[0.9, 1.2],
+                appear_thresh=0.7, min_retrieval_objs=2, max_retrieval_objs=5, feat_height=7, feat_width=7, mask_height=28,
+                mask_width=28, img_height=200, img_width=200, min_size=32, num_gpu_bank=20)
+    head = build_head(dict(type='DiscoBoxSOLOv2Head', num_classes=80, in_channels=256,
+                           loss_corr=dict(type='InfoNCE', loss_weight=1.0, corr_exp=1.0, corr_eps=0.05, gaussian_filter_size=3,
+                                          low_score=0.3, corr_num_iter=10, corr_num_smooth_iter=1, save_corr_img=False,
+                                          dist_kernel=9, obj_bank=bank)))
+    assert head.corr is not None and head.corr.solver.num_iter == 10 and head.corr.object_queues.len_queue == 100
+    assert head.corr.objbank_min_size == 32 and len(head.corr.object_queues.queues) == 80
+    plain = build_head(dict(type='DiscoBoxSOLOv2Head', num_classes=80, in_channels=256))
+    assert plain.corr is None
+    import pytest
+    with pytest.raises(RuntimeError):
+        plain.corr_loss_levels([], [], [], [], [], None, None, None)
