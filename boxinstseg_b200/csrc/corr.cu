@@ -11,7 +11,7 @@
 namespace bxs {
 namespace {
 
-constexpr int NT_SOLVE = 256;
+constexpr int NT_SOLVE = 1024;
 constexpr int NT_XFER = 128;
 constexpr int64_t kMaxSmem = 200 * 1024;
 
@@ -34,12 +34,16 @@ __global__ void __launch_bounds__(NT_XFER) corr_transfer_kernel(const float* __r
   float* mx = rs + P;             // [P]
   float* s_m1 = mx + P;           // [M]
   float* R = s_m1 + M;            // [NT_XFER * P]
+  CorrTap* tapV = reinterpret_cast<CorrTap*>(R + NT_XFER * P);   // [Hm]
+  CorrTap* tapU = tapV + Hm;                                      // [Wm]
+  corr_phase(Hm, [&](int i) { tapV[i] = corr_tap(i, h, Hm); });
+  corr_phase(Wm, [&](int i) { tapU[i] = corr_tap(i, w, Wm); });
   corr_weighted(T + k * PP, Cu + k * PP, t2, rs, mx, P, [](float v) { return expf(v); });
   corr_phase(M, [&](int i) { s_m1[i] = m1[k * M + i]; });
   const int pq = blockIdx.x * NT_XFER + threadIdx.x;
   if (pq < M) {
     float fg, bg;
-    corr_transfer_pixel(t2, m0[pq], s_m1, R + threadIdx.x * P, h, w, Hm, Wm, pq, &fg, &bg);
+    corr_transfer_pixel(t2, m0[pq], s_m1, R + threadIdx.x * P, tapV, tapU, h, w, Hm, Wm, pq, &fg, &bg);
     partial[(k * 2 + 0) * M + pq] = fg;
     partial[(k * 2 + 1) * M + pq] = bg;
   }
@@ -70,7 +74,7 @@ extern "C" int bxs_corr_solve(const float* Cu, float* T, int64_t K, int64_t h, i
   if (!Cu || !T || K <= 0 || h <= 0 || w <= 0 || dist_kernel <= 0 || (dist_kernel & 1) == 0 || num_iter < 0 || num_smooth < 0)
     return BXS_ERR_INVALID_ARG;        // an even window would change the size of the reference's max_pool2d output (:394)
   const int64_t P = h * w;
-  const int64_t smem = (2 * P * P + P) * 4;
+  const int64_t smem = (2 * P * P + (1 + kCorrLanes) * P) * 4;
   if (smem > kMaxSmem || K > 65535) return BXS_ERR_UNSUPPORTED;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(corr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -92,7 +96,7 @@ extern "C" int bxs_corr_transfer(const float* T, const float* Cu, const float* m
   if (!T || !Cu || !m0 || !m1 || !fg_ci || !bg_ci || !workspace || K <= 0 || h <= 0 || w <= 0 || Hm <= 0 || Wm <= 0)
     return BXS_ERR_INVALID_ARG;
   const int64_t P = h * w, M = Hm * Wm;
-  const int64_t smem = (P * P + 2 * P + M + (int64_t)NT_XFER * P) * 4;
+  const int64_t smem = (P * P + 2 * P + M + (int64_t)NT_XFER * P) * 4 + (Hm + Wm) * (int64_t)sizeof(CorrTap);
   if (smem > kMaxSmem || K > 65535 || M > (int64_t(1) << 24)) return BXS_ERR_UNSUPPORTED;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(corr_transfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

@@ -63,8 +63,26 @@ BXS_HD float corr_row_sum(const float* A, int P, int p) {
   return s;
 }
 
+// The same sum in two fixed-order stages (kCorrLanes interleaved partial sums per row, then the partials in order): 1/8 of the
+// dependent additions per phase item, identical on the host and on the device.  part: [kCorrLanes * P].
+constexpr int kCorrLanes = 8;
+BXS_HD void corr_row_sums(const float* A, float* part, float* rs, int P, float eps) {
+  corr_phase(P * kCorrLanes, [&](int i) {
+    const int p = i / kCorrLanes, j = i - p * kCorrLanes;
+    float s = 0.f;
+    for (int q = j; q < P; q += kCorrLanes) s = BXS_FADD(s, A[p * P + q]);
+    part[i] = s;
+  });
+  corr_phase(P, [&](int p) {
+    float s = part[p * kCorrLanes];
+    for (int j = 1; j < kCorrLanes; ++j) s = BXS_FADD(s, part[p * kCorrLanes + j]);
+    rs[p] = BXS_FADD(s, eps);
+  });
+}
+
 // The solve loop for one object.  Cu: [P,P] cosine similarities (global or host memory); a, b: two [P,P] work tables,
-// rs: [P] row sums (shared memory on the device).  The result is left in `out` ([P,P], global).
+// rs: [(1 + kCorrLanes) * P] row sums and their partials (shared memory on the device).  The result is left in `out`
+// ([P,P], global).
 BXS_HD void corr_solve(const float* Cu, float* out, float* a, float* b, float* rs, int h, int w, int dist_kernel, int num_iter,
                        int num_smooth) {
   const int P = h * w, PP = P * P, r = dist_kernel / 2;
@@ -76,12 +94,12 @@ BXS_HD void corr_solve(const float* Cu, float* out, float* a, float* b, float* r
     // C = Cu + votes; C /= C.sum(2) + 1e-4                                                     (:407-408)
     for (int s = 0; s < num_smooth; ++s) {
       corr_phase(PP, [&](int i) { nxt[i] = corr_pass_message(cur, h, w, i); });
-      corr_phase(P, [&](int p) { rs[p] = BXS_FADD(corr_row_sum(nxt, P, p), 1e-4f); });
+      corr_row_sums(nxt, rs + P, rs, P, 1e-4f);
       corr_phase(PP, [&](int i) { nxt[i] = BXS_FDIV(nxt[i], rs[i / P]); });
       float* t = cur; cur = nxt; nxt = t;
     }
     corr_phase(PP, [&](int i) { cur[i] = BXS_FADD(Cu[i], cur[i]); });
-    corr_phase(P, [&](int p) { rs[p] = BXS_FADD(corr_row_sum(cur, P, p), 1e-4f); });
+    corr_row_sums(cur, rs + P, rs, P, 1e-4f);
     corr_phase(PP, [&](int i) { cur[i] = BXS_FDIV(cur[i], rs[i / P]); });
   }
   corr_phase(PP, [&](int i) { out[i] = cur[i]; });
@@ -128,11 +146,12 @@ BXS_HD void corr_weighted(const float* T, const float* Cu, float* t2, float* rs,
 // query mask at pq, m1: [Hm*Wm] mask of the object, R: P floats of scratch owned by the caller.
 //   Tsr[pq][(V,U)] = scale * sum_{v,u} wV wU ( sum_{y,x} wY wX t2[(y,x)][(v,u)] ),   scale = P / (Hm*Wm)   (:851-865)
 //   fg = sum_(V,U) Tsr * [m0q * m1 > 0.5] * clamp(m1, .1, .9),  bg = sum Tsr * [(1-m0q)(1-m1) > 0.5] * clamp(1-m1, .1, .9)
-BXS_HD void corr_transfer_pixel(const float* t2, float m0q, const float* m1, float* R, int h, int w, int Hm, int Wm, int pq,
-                                float* fg_out, float* bg_out) {
+// tapV [Hm], tapU [Wm]: corr_tap(V, h, Hm) / corr_tap(U, w, Wm), computed once per CTA.
+BXS_HD void corr_transfer_pixel(const float* t2, float m0q, const float* m1, float* R, const CorrTap* tapV, const CorrTap* tapU,
+                                int h, int w, int Hm, int Wm, int pq, float* fg_out, float* bg_out) {
   const int P = h * w;
   const int Y = pq / Wm, X = pq - Y * Wm;
-  const CorrTap ty = corr_tap(Y, h, Hm), tx = corr_tap(X, w, Wm);
+  const CorrTap ty = tapV[Y], tx = tapU[X];
   const float* r00 = t2 + (ty.i0 * w + tx.i0) * P;
   const float* r01 = t2 + (ty.i0 * w + tx.i1) * P;
   const float* r10 = t2 + (ty.i1 * w + tx.i0) * P;
@@ -143,9 +162,9 @@ BXS_HD void corr_transfer_pixel(const float* t2, float m0q, const float* m1, flo
   const float n0q = BXS_FSUB(1.f, m0q);
   float fg = 0.f, bg = 0.f;
   for (int V = 0; V < Hm; ++V) {
-    const CorrTap tv = corr_tap(V, h, Hm);
+    const CorrTap tv = tapV[V];
     for (int U = 0; U < Wm; ++U) {
-      const CorrTap tu = corr_tap(U, w, Wm);
+      const CorrTap tu = tapU[U];
       const float val = tv.l0 * (tu.l0 * R[tv.i0 * w + tu.i0] + tu.l1 * R[tv.i0 * w + tu.i1]) +
                         tv.l1 * (tu.l0 * R[tv.i1 * w + tu.i0] + tu.l1 * R[tv.i1 * w + tu.i1]);
       const float m = m1[V * Wm + U], n = BXS_FSUB(1.f, m);
