@@ -178,6 +178,66 @@ class DiscoBoxSOLOv2Head(nn.Module):
         ts_mean = torch.cat(ts).mean() if ts else loss.new_zeros(())
         return loss * self.corr.corr_loss_weight, ts_mean
 
+    def _grid_cfg(self):
+        """(scale_ranges, strides, seg_num_grids, sigma): attributes when the reference constructor ran (:690-700), else the
+        construction kwargs with the reference's defaults (:662-666)."""
+        get = lambda name, key, default: getattr(self, name, None) if getattr(self, name, None) is not None else self.cfg.get(key, default)
+        return (get('scale_ranges', 'scale_ranges', ((8, 32), (16, 64), (32, 128), (64, 256), (128, 512))),
+                get('strides', 'strides', (4, 8, 16, 32, 64)), get('seg_num_grids', 'num_grids', None), get('sigma', 'sigma', 0.2))
+
+    # f2 + a3 -- discobox_head.py:917-1003 (identical in loss(), :1161-1260, with the other target builder)
+    def corr_inputs(self, s_kernel_preds_raw, t_kernel_preds_raw, s_ins_pred, t_ins_pred, gt_bbox_list, gt_label_list, gt_mask_list,
+                    use_ind_teacher=False, best=True, conv=None):
+        """From the raw head outputs to the per-level lists of ``mask_loss`` / ``corr_loss_levels``: SOLO targets of every image
+        (``best_target_single`` for corr_loss, ``solov2_target_single`` with ``best=False``), the dynamic kernels of the covered
+        cells gathered by ``grid_order``, one dynamic convolution per (level, image) with objects (a3: the tcgen05 kernel).
+        ``*_kernel_preds_raw``: per level [B,C,g,g]; ``*_ins_pred`` [B,C,H,W]; ``gt_mask_list``: per image uint8 [G,H',W'] device
+        tensors.  Returns (s_ins_pred_list, t_ins_pred_list, img_ind_list, ins_labels, kernel_label_list) with None for a level
+        without objects.  Plain torch around ``conv`` (default: ``self.dynamic_conv``)."""
+        from .disco_targets import disco_target_single
+        conv = conv or self.dynamic_conv
+        scale_ranges, strides, grids, sigma = self._grid_cfg()
+        fsize = tuple(s_ins_pred.shape[-2:])
+        per_img = [disco_target_single(b, l, m, fsize, scale_ranges, strides, grids, sigma, self.num_classes, best=best)
+                   for b, l, m in zip(gt_bbox_list, gt_label_list, gt_mask_list)]
+        L_, B = len(grids), len(per_img)
+        ins_labels = [torch.cat([per_img[b][0][lv] for b in range(B)], 0) for lv in range(L_)]
+        klabels = [torch.cat([per_img[b][1][lv].reshape(-1)[per_img[b][3][lv]] for b in range(B)], 0) for lv in range(L_)]
+        s_list, t_list, img_list = [], [], []
+        for lv in range(L_):
+            s_lv, t_lv, i_lv = [], [], []
+            for b in range(B):
+                order = per_img[b][3][lv]
+                if order.numel() == 0:
+                    continue
+                sk = s_kernel_preds_raw[lv][b].reshape(s_kernel_preds_raw[lv].shape[1], -1)[:, order]       # [C,I]
+                s_lv.append(conv(s_ins_pred[b], sk))
+                if use_ind_teacher:
+                    tk = t_kernel_preds_raw[lv][b].reshape(t_kernel_preds_raw[lv].shape[1], -1)[:, order]
+                    t_lv.append(conv(t_ins_pred[b], tk))
+                i_lv.append(torch.full((order.numel(),), b, dtype=torch.int64, device=s_ins_pred.device))
+            s_list.append(torch.cat(s_lv, 0) if s_lv else None)
+            t_list.append(torch.cat(t_lv, 0) if t_lv else None)
+            img_list.append(torch.cat(i_lv, 0) if i_lv else None)
+        return s_list, t_list, img_list, ins_labels, klabels
+
+    # f4 -- discobox_head.py:900-1139, the reference's signature
+    def corr_loss(self, cate_preds, s_kernel_preds_raw, t_kernel_preds_raw, s_ins_pred, t_ins_pred, gt_bbox_list, gt_label_list,
+                  gt_mask_list, mean_fields, img_metas, cfg, img=None, gt_bboxes_ignore=None, use_loss_ts=False,
+                  use_ind_teacher=False, s_feat=None, t_feat=None):
+        """Returns (corr_loss / (num + 1e-4), [per-level dice terms]) like the reference.  ``mean_fields``: the reference passes
+        one module per image; here ONE mean field over the batch is built from ``img`` (only ``gamma`` is read from the list)."""
+        if self.corr is None:
+            raise RuntimeError('DiscoBoxSOLOv2Head was built without loss_corr')
+        s_list, t_list, img_list, ins_labels, klabels = self.corr_inputs(
+            s_kernel_preds_raw, t_kernel_preds_raw, s_ins_pred, t_ins_pred, gt_bbox_list, gt_label_list, gt_mask_list,
+            use_ind_teacher=use_ind_teacher, best=True)
+        color_feats = bilinear_resize(img, tuple(s_ins_pred.shape[-2:]), align_corners=True)                    # :957-958
+        gamma = mean_fields[0].gamma if mean_fields else 0.01
+        mf = MeanField(color_feats, alpha0=self.alpha0, theta0=self.theta0, theta1=self.theta1, theta2=self.theta2,
+                       iter=self.crf_max_iter, kernel_size=self.mkernel, base=self.crf_base, gamma=gamma)
+        return self.corr.levels(s_list, t_list, img_list, ins_labels, klabels, s_feat, t_feat, mf, use_ind_teacher)
+
     # a3 -- discobox_head.py:1206-1246
     @staticmethod
     def dynamic_conv(mask_feat_img, kernels):

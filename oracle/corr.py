@@ -223,3 +223,31 @@ def corr_loss_levels(queues, s_ins_pred_list, img_ind_list, ins_labels, kernel_l
         vals = torch.cat([c[1] for c in chunks])
         loss_ts.append(vals[torch.argsort(order)])
     return total / (num + 1e-4), loss_ts
+
+
+def corr_inputs(s_kernel_preds_raw, s_ins_pred, gt_bbox_list, gt_label_list, gt_mask_list, scale_ranges, strides, seg_num_grids,
+                sigma, num_classes, best=True):
+    """discobox_head.py:917-1003 (no independent teacher): per-image SOLO targets, the kernels of the covered cells gathered by
+    grid_order, one F.conv2d per (level, image) with objects.  gt_mask_list: per image uint8 NUMPY [G,H,W].  Returns
+    (s_ins_pred_list, img_ind_list, ins_labels, kernel_label_list); None for a level without objects."""
+    from oracle import solo_targets as ost
+    fsize = tuple(s_ins_pred.shape[-2:])
+    tg = [ost.disco_target_single(b, l, m, fsize, scale_ranges, strides, seg_num_grids, sigma, num_classes, best=best)
+          for b, l, m in zip(gt_bbox_list, gt_label_list, gt_mask_list)]
+    L_, B = len(seg_num_grids), len(tg)
+    ins_labels = [torch.cat([tg[b][0][lv] for b in range(B)], 0) for lv in range(L_)]
+    klabels = [torch.cat([tg[b][1][lv].reshape(-1)[tg[b][3][lv]] for b in range(B)], 0) for lv in range(L_)]
+    s_list, img_list = [], []
+    for lv in range(L_):
+        preds, inds = [], []
+        for b in range(B):
+            kern = s_kernel_preds_raw[lv][b].view(s_kernel_preds_raw[lv].shape[1], -1)[:, tg[b][3][lv]]
+            if kern.size(-1) == 0:
+                continue
+            C, I = kern.shape
+            H, W = s_ins_pred.shape[-2:]
+            preds.append(F.conv2d(s_ins_pred[b][None], kern.permute(1, 0).view(I, -1, 1, 1), stride=1).view(-1, H, W))
+            inds.append(torch.ones(I) * b)
+        s_list.append(torch.cat(preds, 0) if preds else None)
+        img_list.append(torch.cat(inds, 0) if inds else None)
+    return s_list, img_list, ins_labels, klabels

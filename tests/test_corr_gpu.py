@@ -157,3 +157,52 @@ def test_corr_loss_levels_against_oracle():
     l2, ts2 = head.corr_loss_levels([s.to(DEV) for s in s_list], None, [i.to(DEV) for i in img_list], [t.to(DEV) for t in tgt_list],
                                     [l.to(DEV) for l in lab_list], s_feat.to(DEV), t_feat.to(DEV), color.to(DEV), gamma=0.5)
     assert abs(float(l2) - float(lo2)) <= 1e-4 * abs(float(lo2)) and abs(float(ts2) - float(torch.cat(tso2).mean())) <= 1e-5
+
+
+def test_head_corr_loss_with_the_reference_signature():
+    """DiscoBoxSOLOv2Head.corr_loss (discobox_head.py:900-1139) from the raw head outputs: SOLO targets, kernel gathering, the
+    tcgen05 dynamic convolutions (against F.conv2d on the same tensors, TF32 tolerance), the colour features (align_corners=True
+    resize), and two training steps of the level body on top of them (the first fills the bank): finite values, a gradient to the
+    mask features, the kernels and the RoI feature map, the bank advancing."""
+    import torch.nn.functional as F
+    from boxinstseg_b200.models import build_head
+    from boxinstseg_b200.models.dense_heads import MeanField
+    from oracle.make_golden_disco import CFG as DCFG, case as dcase
+    bank = dict(feat_height=7, feat_width=7, mask_height=28, mask_width=28, min_size=2, len_object_queues=16, fg_iou_thresh=0.7,
+                bg_iou_thresh=0.7, ratio_range=[0.9, 1.2], appear_thresh=0.7, max_retrieval_objs=5)
+    loss_corr = dict(loss_weight=1.0, corr_exp=1.0, corr_eps=0.05, gaussian_filter_size=3, low_score=0.3, corr_num_iter=10,
+                     corr_num_smooth_iter=1, dist_kernel=9, obj_bank=bank)
+    B, C = 2, 32
+    head = build_head(dict(type='DiscoBoxSOLOv2Head', num_classes=DCFG['num_classes'], in_channels=C, loss_corr=loss_corr,
+                           scale_ranges=DCFG['scale_ranges'], strides=DCFG['strides'], num_grids=DCFG['seg_num_grids'],
+                           sigma=DCFG['sigma']))
+    gen = torch.Generator().manual_seed(8)
+    cases = [dcase(s) for s in (0, 1)]
+    fsize = cases[0][3]
+    boxes, labels = [c[0].to(DEV) for c in cases], [c[1].to(DEV) for c in cases]
+    masks = [torch.from_numpy(c[2]).to(DEV) for c in cases]
+    kraw = [(0.2 * torch.randn(B, C, g, g, generator=gen)).to(DEV).requires_grad_(True) for g in DCFG['seg_num_grids']]
+    feat = torch.randn(B, C, fsize[0], fsize[1], generator=gen).to(DEV).requires_grad_(True)
+    s_feat = torch.randn(B, 16, fsize[0], fsize[1], generator=gen).to(DEV).requires_grad_(True)
+    img = torch.randn(B, 3, 160, 192, generator=gen).to(DEV)
+    # the front part against F.conv2d on the same tensors
+    got = head.corr_inputs(kraw, None, feat, None, boxes, labels, masks)
+    ref = head.corr_inputs(kraw, None, feat, None, boxes, labels, masks, conv=lambda f, k: F.conv2d(f[None], k.t()[:, :, None, None])[0])
+    n_obj = 0
+    for a, b in zip(got[0], ref[0]):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert (a - b).norm() <= 1e-3 * b.norm()
+            n_obj += a.shape[0]
+    assert n_obj >= 8
+    mfs = [MeanField(F.interpolate(img[b:b + 1], fsize, mode='bilinear', align_corners=True), gamma=0.5) for b in range(B)]
+    for step in range(2):
+        loss, ts = head.corr_loss(None, kraw, None, feat, None, boxes, labels, masks, mfs, None, None, img=img,
+                                  s_feat=s_feat, t_feat=s_feat.detach())
+        assert torch.isfinite(loss) and len(ts) >= 1 and all(torch.isfinite(t).all() for t in ts)
+        assert sum(t.numel() for t in ts) <= n_obj
+        total = loss + torch.cat(ts).mean()
+        grads = torch.autograd.grad(total, [feat] + kraw + [s_feat], allow_unused=True)
+        assert grads[0] is not None and torch.isfinite(grads[0]).all() and float(grads[0].abs().sum()) > 0
+    filled = sum(q.ptr for q in head.corr.object_queues.queues if q is not None)
+    assert filled > 0

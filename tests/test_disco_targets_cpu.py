@@ -58,3 +58,40 @@ def test_no_ground_truth_and_all_masks_empty(best):
             _same(ost.disco_target_single(b, l, m, fsize, best=best, **CFG), got)
         assert all(x.shape == (0, fsize[0], fsize[1]) for x in got[0]) and all(x.numel() == 0 for x in got[3])
         assert all((c == CFG['num_classes']).all() for c in got[1]) and not any(i.any() for i in got[2])
+
+
+@pytest.mark.parametrize('best', [True, False])
+def test_head_inputs_from_raw_outputs_equal_reference_loops(best):
+    """DiscoBoxSOLOv2Head.corr_inputs (discobox_head.py:917-1003 / 1161-1260): targets of every image, kernels gathered by
+    grid_order, one dynamic convolution per (level, image) -- against the oracle's loop form, with F.conv2d standing in for the
+    tcgen05 kernel (the glue is plain torch; the kernel has its own GPU parity tests)."""
+    import torch.nn.functional as F
+    from boxinstseg_b200.models import build_head
+    from oracle import corr as oc
+    gen = torch.Generator().manual_seed(5)
+    B, C = 3, 8
+    cases = [case(s) for s in (0, 1, 2)]
+    cases[1] = (cases[1][0][:0], cases[1][1][:0], cases[1][2][:0], cases[1][3])          # an image without ground truth
+    fsize = cases[0][3]
+    grids = CFG['seg_num_grids']
+    kraw = [torch.randn(B, C, g, g, generator=gen) for g in grids]
+    feat = torch.randn(B, C, fsize[0], fsize[1], generator=gen)
+    head = build_head(dict(type='DiscoBoxSOLOv2Head', num_classes=CFG['num_classes'], in_channels=C, scale_ranges=CFG['scale_ranges'],
+                           strides=CFG['strides'], num_grids=grids, sigma=CFG['sigma']))
+    conv = lambda f, k: F.conv2d(f[None], k.t()[:, :, None, None])[0]
+    got = head.corr_inputs(kraw, None, feat, None, [c[0] for c in cases], [c[1] for c in cases],
+                           [torch.from_numpy(c[2]) for c in cases], best=best, conv=conv)
+    want = oc.corr_inputs(kraw, feat, [c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases], CFG['scale_ranges'],
+                          CFG['strides'], grids, CFG['sigma'], CFG['num_classes'], best=best)
+    s_list, t_list, img_list, ins_labels, klabels = got
+    assert all(t is None for t in t_list)
+    seen = 0
+    for lv in range(len(grids)):
+        assert torch.equal(ins_labels[lv], want[2][lv]) and torch.equal(klabels[lv], want[3][lv])
+        if want[0][lv] is None:
+            assert s_list[lv] is None and img_list[lv] is None
+            continue
+        assert torch.allclose(s_list[lv], want[0][lv], rtol=1e-5, atol=1e-5) and torch.equal(img_list[lv].float(), want[1][lv])
+        assert s_list[lv].shape[0] == ins_labels[lv].shape[0] == klabels[lv].shape[0]
+        seen += s_list[lv].shape[0]
+    assert seen >= 8 and not (torch.cat([i for i in img_list if i is not None]) == 1).any()
