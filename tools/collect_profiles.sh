@@ -15,6 +15,7 @@ for c in C D E; do
 done
 python tools/bench_dynconv.py > gpurun_out/r2_bench_dynconv.log 2>&1; cp gpurun_out/bench_dynconv.json gpurun_out/r2_bench_dynconv.json
 python tools/bench_ops.py > gpurun_out/r2_bench_ops.json 2> gpurun_out/r2_bench_ops.err
+python tools/bench_f_rows.py > gpurun_out/r2_bench_f_rows.json 2> gpurun_out/r2_bench_f_rows.err    # f2 / f4 rows vs the reference's composition
 # full captures -> CSV (raw page = every metric per kernel), reports deleted except the headline one
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'wq_|onepass_backward' -s 24 -c 3 -o gpurun_out/r2_wq_full -f python tools/raw_loop1.py 16 > gpurun_out/ncu_a.log 2>&1
 ncu -i gpurun_out/r2_wq_full.ncu-rep --page raw --csv > gpurun_out/r2_ncu_full_wq.csv 2>/dev/null
