@@ -5,9 +5,10 @@ dynamic-conv call sites (a2-a4), on the kernels of libboxseg_b200:
   ``DiscoBoxSOLOv2Head``  mmdet/models/dense_heads/discobox_head.py:1206-1300 (per-image conv, MIL dice, mean-field teacher)
   ``Box2MaskHead``        mmdet/models/dense_heads/box2mask_head.py:338-359 (mask_pred einsum), :269-335 (loss_single)
 
-Only the mask-loss hot path is implemented here.  The conv towers, SOLO / Hungarian target building,
-category losses, inference and DiscoBox's cross-image correspondence loss are out of scope:
-the classes keep the reference's registry names and accept (and store) the reference's constructor kwargs so
+The mask-loss hot path and its immediate callers are implemented here: the SOLO target builders live in
+``solo_targets.py`` / ``disco_targets.py`` (f2), the Hungarian front half in ``core/assigner.py`` (f1), DiscoBox's
+cross-image correspondence loss in ``disco_corr.py`` (f4; ``DiscoBoxSOLOv2Head.corr_inputs / corr_loss``).  The conv towers,
+category losses and inference are out of scope: the classes keep the reference's registry names and accept (and store) the reference's constructor kwargs so
 the configs build, and expose the hot-path pieces as methods with the tensors the reference passes between
 its own lines.
 """
