@@ -65,3 +65,27 @@ def test_missing_library_is_an_error(lib, monkeypatch):
     monkeypatch.setattr(lib, 'LIB_PATH', '/nonexistent/libboxseg_b200.so')
     with pytest.raises(ImportError):
         lib.lib()
+
+
+def test_argument_validation_of_the_f_row_entry_points(lib):
+    """Host-side checks run before any launch, so they can be exercised without a GPU: null pointers and malformed tables are
+    invalid arguments (-1), shapes outside the kernels' envelopes are unsupported (-3)."""
+    import ctypes
+    h = lib.lib()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    off2 = ctypes.cast((ctypes.c_int64 * 3)(0, 1, 2), ctypes.c_void_p)
+    lvl = ctypes.cast((ctypes.c_int64 * 2)(0, 4), ctypes.c_void_p)
+    assert h.bxs_fcos_targets(None, p, p, off2, p, p, p, 2, 1, lvl, p, p, p, p, 1, 1, 80, None) == -1          # no points
+    assert h.bxs_fcos_targets(p, p, p, off2, p, p, p, 2, 9, lvl, p, p, p, p, 1, 1, 80, None) == -3             # > 8 levels
+    assert h.bxs_fcos_targets(p, p, p, off2, p, p, p, 257, 1, lvl, p, p, p, p, 1, 1, 80, None) == -3           # > 256 images
+    bad = ctypes.cast((ctypes.c_int64 * 3)(0, 2, 1), ctypes.c_void_p)
+    assert h.bxs_fcos_targets(p, p, p, bad, p, p, p, 2, 1, lvl, p, p, p, p, 1, 1, 80, None) == -1              # offsets decrease
+    assert h.bxs_fcos_targets(p, None, None, off2, p, p, p, 2, 1, lvl, p, p, p, p, 1, 1, 80, None) == -1       # GTs without boxes
+    assert h.bxs_corr_solve(None, p, 5, 7, 7, 9, 10, 1, None) == -1
+    assert h.bxs_corr_solve(p, p, 5, 7, 7, 8, 10, 1, None) == -1                                               # even window
+    assert h.bxs_corr_solve(p, p, 5, 16, 16, 9, 10, 1, None) == -3                                             # tables > 200 KB
+    assert h.bxs_corr_transfer_workspace_bytes(5, 28, 28) == 5 * 2 * 784 * 4 and h.bxs_corr_transfer_workspace_bytes(0, 28, 28) == 0
+    assert h.bxs_corr_transfer(p, p, p, p, p, p, None, 5, 7, 7, 28, 28, None) == -1                            # no workspace
+    assert h.bxs_corr_transfer(p, p, p, p, p, p, p, 5, 16, 16, 28, 28, None) == -3
+    assert h.bxs_meanfield_forward_inter(None, None, p, p, p, 0.5, p, p, p, p, 4, 8, 8, 3, 10, None) == -1
