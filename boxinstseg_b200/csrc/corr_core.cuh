@@ -35,7 +35,10 @@ BXS_HD void corr_phase(int n, F f) {
 // pass_message (:347-366) for one element i = p * P + q of a [P,P] = [h,w,h,w] table: the mean over the (dy,dx) in
 // {-1,0,1}^2 for which BOTH the source cell p - (dy,dx) and the target cell q - (dy,dx) exist.  Accumulation order = the
 // reference's loop order (dx outer, dy inner), starting from its zero tensor.
-BXS_HD float corr_pass_message(const float* T, int h, int w, int i) {
+// CH, CW > 0: compile-time grid (the divisions become multiplications; 7 x 7 is the reference's configuration), else h_rt, w_rt.
+template <int CH, int CW>
+BXS_HD float corr_pass_message(const float* T, int h_rt, int w_rt, int i) {
+  const int h = CH > 0 ? CH : h_rt, w = CW > 0 ? CW : w_rt;
   const int P = h * w;
   const int p = i / P, q = i - p * P;
   const int y = p / w, x = p - y * w, v = q / w, u = q - v * w;
@@ -85,8 +88,10 @@ BXS_HD void corr_row_sums(const float* A, float* part, float* rs, int P, float e
 // The solve loop for one object.  Cu: [P,P] cosine similarities (global or host memory); a, b: two [P,P] work tables,
 // rs: [(1 + kCorrLanes) * P] row sums and their partials (shared memory on the device).  The result is left in `out`
 // ([P,P], global).
-BXS_HD void corr_solve(const float* Cu, float* out, float* a, float* b, float* rs, int h, int w, int dist_kernel, int num_iter,
-                       int num_smooth) {
+template <int CH, int CW>
+BXS_HD void corr_solve_t(const float* Cu, float* out, float* a, float* b, float* rs, int h_rt, int w_rt, int dist_kernel,
+                         int num_iter, int num_smooth) {
+  const int h = CH > 0 ? CH : h_rt, w = CW > 0 ? CW : w_rt;
   const int P = h * w, PP = P * P, r = dist_kernel / 2;
   float* cur = a;        // C
   float* nxt = b;
@@ -95,7 +100,7 @@ BXS_HD void corr_solve(const float* Cu, float* out, float* a, float* b, float* r
     // votes = C.clone(); num_smooth x { pass_message; votes /= votes.sum(2) + 1e-4 }          (:399-403)
     // C = Cu + votes; C /= C.sum(2) + 1e-4                                                     (:407-408)
     for (int s = 0; s < num_smooth; ++s) {
-      corr_phase(PP, [&](int i) { nxt[i] = corr_pass_message(cur, h, w, i); });
+      corr_phase(PP, [&](int i) { nxt[i] = corr_pass_message<CH, CW>(cur, h, w, i); });
       corr_row_sums(nxt, rs + P, rs, P, 1e-4f);
       corr_phase(PP, [&](int i) { nxt[i] = BXS_FDIV(nxt[i], rs[i / P]); });
       float* t = cur; cur = nxt; nxt = t;
@@ -105,6 +110,14 @@ BXS_HD void corr_solve(const float* Cu, float* out, float* a, float* b, float* r
     corr_phase(PP, [&](int i) { cur[i] = BXS_FDIV(cur[i], rs[i / P]); });
   }
   corr_phase(PP, [&](int i) { out[i] = cur[i]; });
+}
+
+BXS_HD void corr_solve(const float* Cu, float* out, float* a, float* b, float* rs, int h, int w, int dist_kernel, int num_iter,
+                       int num_smooth) {
+  if (h == 7 && w == 7)                 // obj_bank feat_height / feat_width of the reference's configs
+    corr_solve_t<7, 7>(Cu, out, a, b, rs, h, w, dist_kernel, num_iter, num_smooth);
+  else
+    corr_solve_t<0, 0>(Cu, out, a, b, rs, h, w, dist_kernel, num_iter, num_smooth);
 }
 
 // ATen's align_corners=False linear tap for destination index d of an `in` -> `out` up-sampling (UpSample.h:
