@@ -86,3 +86,34 @@ def test_product_path_has_no_cpu_fallback():
     head = build_head(dict(type='CondInstBoxHead', num_classes=80, in_channels=256))
     with pytest.raises(RuntimeError):
         head.get_targets(points, boxes, labels)
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_boundary_heavy_boxes_on_the_host_build(seed):
+    """Integer-valued boxes whose edges, centre-sampling windows and regress distances land exactly on locations and on the
+    regress-range bounds (64, 128, 256, 512), duplicated boxes (area ties: the first one wins), degenerate (zero-area) boxes:
+    every `> 0` / `>=` / `<=` / `<` of the reference is exercised at equality."""
+    gen = torch.Generator().manual_seed(300 + seed)
+    H, W = 256, 320
+    sizes = [((H + s - 1) // s, (W + s - 1) // s) for s in CFG['strides']]
+    points = oft.grid_points(sizes, CFG['strides'])
+    boxes, labels = [], []
+    for b in range(2):
+        g = 14
+        x1 = torch.randint(0, W // 8, (g,), generator=gen) * 4.0
+        y1 = torch.randint(0, H // 8, (g,), generator=gen) * 4.0
+        span = torch.tensor([8., 12., 64., 128., 136., 256.])
+        bw = span[torch.randint(0, len(span), (g,), generator=gen)]
+        bh = span[torch.randint(0, len(span), (g,), generator=gen)]
+        bx = torch.stack([x1, y1, x1 + bw, y1 + bh], 1)
+        bx[3] = bx[2]                                    # duplicate: equal area, equal geometry
+        bx[5, 2:] = bx[5, :2]                            # zero-area box
+        bx[7] = torch.tensor([4., 4., 132., 132.])       # max regress distance of the location (4, 4)... = 128 exactly
+        boxes.append(bx)
+        labels.append(torch.randint(0, 80, (g,), generator=gen))
+    for flags in (dict(center_sampling=True, norm_on_bbox=True), dict(center_sampling=False, norm_on_bbox=False)):
+        want, got = _oracle(points, boxes, labels, flags), _host(points, boxes, labels, flags)
+        for w_list, g_list in zip(want, got):
+            for w, g in zip(w_list, g_list):
+                assert torch.equal(w, g)
+        assert int((torch.cat(want[2]) >= 0).sum()) > 50
