@@ -1,3 +1,6 @@
+"""Ten-second check of bxs_corr_solve on the GPU box: the regularised tables of the three golden cases against the reference's own
+(tests/golden/corr.npz, scaled max difference) and the device time of one call replayed from a CUDA graph.
+      python tools/quick_corr_check.py"""
 import numpy as np, torch, sys
 sys.path.insert(0, '.')
 from boxinstseg_b200.models.dense_heads.disco_corr import SemanticCorrSolver
