@@ -32,6 +32,9 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = 'mask_loss_fwd_bwd_ms_per_img'
+# the workload both arms name (the reference arm times a bounded per-image sample of it: `cpu_baseline.sample`)
+WORKLOAD = ('BoxInst R-50 mask loss fwd+bwd (config A): batch 2/GPU x (3,800,1024), 8 GT/img, '
+            'N=128 instances, loss grid 200x256, pairwise 3x3 dil 2')
 HP, WP, B_IMG, GTS, INST_PER_GT = 800, 1024, 2, 8, 8
 H, W, K_NEIGH = HP // 4, WP // 4, 8
 N_INST = B_IMG * GTS * INST_PER_GT
@@ -207,7 +210,7 @@ def main_reference(args, rank, world):
     line = {'impl': 'reference', 'metric': METRIC, 'value': ms_img, 'unit': 'ms/img', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_img, 'higher_is_better': False,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'BoxInst R-50 mask loss fwd+bwd, 800x1024, 8 GT/img, 64 inst/img (config A)'},
+            'config': {'workload': WORKLOAD, 'sample': 'one image of the workload per step (the metric is per image): ' + sample},
             'cpu_baseline': {'value': ms_img, 'unit': 'ms/img', 'cores': cores, 'cores_available': os.cpu_count(),
                              'cores_note': 'torch intra-op threads capped at 32: the oracle port (elementwise torch ops on '
                                            '[64,8,200,256] tensors) does not scale beyond that', 'kind': 'port', 'sample': sample},
@@ -540,8 +543,7 @@ def main_cuda(args, rank, world, local_rank):
         'unit': 'ms/img', 'n_gpus': world,
         'steps': steps_timed, 'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': False, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BoxInst R-50 mask loss fwd+bwd (config A): batch 2/GPU x (3,800,1024), 8 GT/img, '
-                               'N=128 instances, loss grid 200x256, pairwise 3x3 dil 2',
+        'config': {'workload': WORKLOAD,
                    'l2': f'inputs rotate over {ROTATE} logit/grad sets ({ROTATE * 52} MB > 126 MB L2)',
                    'launch': mode, 'eager_ms_per_step': ms_eager,
                    'e2e_mode': 'CondInstMaskHead.loss + backward from pinned host buffers, 2 steps in flight on 2 streams',
