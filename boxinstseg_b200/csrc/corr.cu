@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(NT_XFER) corr_transfer_kernel(const float* __r
                                                                 float* __restrict__ partial, int h, int w, int Hm, int Wm) {
   extern __shared__ float sm[];
   const int P = h * w, PP = P * P, M = Hm * Wm;
-  const int64_t k = blockIdx.y, K = gridDim.y;
+  const int64_t k = blockIdx.y;
   float* t2 = sm;                 // [PP]
   float* rs = t2 + PP;            // [P]
   float* mx = rs + P;             // [P]
@@ -47,7 +47,6 @@ __global__ void __launch_bounds__(NT_XFER) corr_transfer_kernel(const float* __r
     partial[(k * 2 + 0) * M + pq] = fg;
     partial[(k * 2 + 1) * M + pq] = bg;
   }
-  (void)K;
 }
 
 // .mean(0) over the objects, in object order
